@@ -1,0 +1,75 @@
+"""ctypes binding of `libavssl_b200.so` (the C-ABI declared in include/avssl_b200.h).
+
+The library is the product: there is no Python/torch fallback.  If the shared
+object is missing the import fails with instructions to build it; if a compute
+entry point is called without a CUDA device the library returns an error that is
+raised here.
+"""
+import ctypes
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libavssl_b200.so")
+
+c_void_p, c_int, c_int64, c_float, c_size_t, c_uint64 = (
+    ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t, ctypes.c_uint64)
+
+
+class AvsslError(RuntimeError):
+    """A C-ABI call returned a non-zero avssl_status."""
+
+
+class EmaChunk(ctypes.Structure):
+    """Mirror of `avssl_ema_chunk` (include/avssl_b200.h)."""
+    _fields_ = [("online", c_void_p), ("hist", c_void_p), ("n", ctypes.c_uint32), ("flags", ctypes.c_uint32)]
+
+
+# name -> (restype, argtypes).  Every function declared in include/avssl_b200.h is
+# listed here; tests/test_abi.py checks the two stay in sync.
+SIGNATURES = {
+    "avssl_abi_version": (c_int, []),
+    "avssl_last_error": (ctypes.c_char_p, []),
+    "avssl_device_sm_count": (c_int, []),
+    "avssl_ema_chunk_elems": (c_int64, []),
+    "avssl_ema_plan_chunks": (c_int64, [c_void_p, c_int]),
+    "avssl_ema_plan_fill": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64]),
+    "avssl_ema_multi_tensor": (c_int, [c_void_p, c_int64, c_float, c_float, c_void_p, c_int, c_void_p, c_void_p]),
+    "avssl_moco_infonce_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "avssl_moco_infonce_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float,
+                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                           c_int, c_void_p]),
+    "avssl_queue_enqueue": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+}
+
+IMPL_AUTO, IMPL_SIMT, IMPL_TC3X, IMPL_TC1X = 0, 1, 2, 3
+MAX_KEYS = 8
+DEVFLAG_QUEUE_OVERRUN = 1
+DEVFLAG_BAD_INDEX = 2
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "advise_video_ssl_b200: %s is missing. Build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` or "
+            "`python advise_video_ssl_b200/build.py` (needs nvcc, targets sm_100a). "
+            "There is no CPU or PyTorch fallback for the contrastive hot path." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so is stale: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def last_error():
+    msg = lib.avssl_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(rc, what):
+    if rc != 0:
+        raise AvsslError("%s failed (status %d): %s" % (what, rc, last_error()))

@@ -1,0 +1,156 @@
+// K1 — multi-tensor momentum EMA (replaces models/contrastive.py:158-172).
+//
+// One launch updates every parameter tensor of the key encoder.  The work list is
+// a device table of fixed-size chunks (pointer pair + length) so the grid is flat:
+// one 256-thread CTA per 4096-element chunk, each thread keeping 8 independent
+// 128-bit loads in flight (4 online + 4 history) before the first use.  Pure
+// HBM-bound streaming: 12 bytes per parameter (read online, read hist, write hist).
+//
+// Bit-exactness: the reference evaluates `online * (1 - m) + hist * m` as three
+// ATen kernels, i.e. three separately rounded fp32 operations.  __fmul_rn/__fadd_rn
+// are never contracted into an FMA by nvcc, so every element matches bit for bit.
+#include "common.cuh"
+
+namespace avssl {
+
+constexpr int kEmaThreads = 256;
+constexpr int kEmaUnroll = 4;
+constexpr int kEmaChunk = kEmaThreads * 4 * kEmaUnroll;  // 4096 floats = 16 KiB per array
+
+__device__ __forceinline__ float ema_blend(float o, float h, float m, float om) {
+  return __fadd_rn(__fmul_rn(o, om), __fmul_rn(h, m));
+}
+__device__ __forceinline__ float4 ema_blend4(const float4& o, const float4& h, float m, float om) {
+  return make_float4(ema_blend(o.x, h.x, m, om), ema_blend(o.y, h.y, m, om),
+                     ema_blend(o.z, h.z, m, om), ema_blend(o.w, h.w, m, om));
+}
+
+__global__ void __launch_bounds__(kEmaThreads)
+ema_multi_tensor_kernel(const avssl_ema_chunk* __restrict__ table, float m, float om,
+                        int64_t* iter, int bump_iter, uint32_t* done_counter) {
+  const avssl_ema_chunk c = table[blockIdx.x];
+  // iter == 0: history := online first (models/contrastive.py:167-169)
+  const bool first = (*reinterpret_cast<volatile int64_t*>(iter) == 0);
+  const int tid = threadIdx.x;
+
+  if ((c.flags & 1u) && c.n == (uint32_t)kEmaChunk) {
+    const float4* o4 = reinterpret_cast<const float4*>(c.online) + tid;
+    float4* h4 = reinterpret_cast<float4*>(c.hist) + tid;
+    float4 o[kEmaUnroll], h[kEmaUnroll];
+#pragma unroll
+    for (int u = 0; u < kEmaUnroll; ++u) o[u] = ldg_stream(o4 + u * kEmaThreads);
+    if (!first) {
+#pragma unroll
+      for (int u = 0; u < kEmaUnroll; ++u) h[u] = ld_stream(h4 + u * kEmaThreads);
+    } else {
+#pragma unroll
+      for (int u = 0; u < kEmaUnroll; ++u) h[u] = o[u];
+    }
+#pragma unroll
+    for (int u = 0; u < kEmaUnroll; ++u) st_stream(h4 + u * kEmaThreads, ema_blend4(o[u], h[u], m, om));
+  } else if (c.flags & 1u) {
+    // aligned tail chunk: vector body + scalar remainder
+    const uint32_t n4 = c.n >> 2;
+    const float4* o4 = reinterpret_cast<const float4*>(c.online);
+    float4* h4 = reinterpret_cast<float4*>(c.hist);
+    for (uint32_t i = tid; i < n4; i += kEmaThreads) {
+      const float4 o = ldg_stream(o4 + i);
+      const float4 h = first ? o : ld_stream(h4 + i);
+      st_stream(h4 + i, ema_blend4(o, h, m, om));
+    }
+    for (uint32_t i = (n4 << 2) + tid; i < c.n; i += kEmaThreads) {
+      const float o = c.online[i];
+      const float h = first ? o : c.hist[i];
+      c.hist[i] = ema_blend(o, h, m, om);
+    }
+  } else {
+    for (uint32_t i = tid; i < c.n; i += kEmaThreads) {
+      const float o = c.online[i];
+      const float h = first ? o : c.hist[i];
+      c.hist[i] = ema_blend(o, h, m, om);
+    }
+  }
+
+  if (bump_iter) {
+    // `self.iter += 1` (models/contrastive.py:314) by the last CTA to finish: every
+    // CTA has read `iter` before it arrives here.
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      const uint32_t prev = atomicAdd(done_counter, 1u);
+      if (prev == gridDim.x - 1) {
+        *iter = *reinterpret_cast<volatile int64_t*>(iter) + 1;
+        *done_counter = 0u;
+        __threadfence();
+      }
+    }
+  }
+}
+
+__global__ void bump_iter_kernel(int64_t* iter) { *iter += 1; }
+
+}  // namespace avssl
+
+using namespace avssl;
+
+extern "C" int64_t avssl_ema_chunk_elems(void) { return kEmaChunk; }
+
+extern "C" int64_t avssl_ema_plan_chunks(const int64_t* numel_host, int n_tensors) {
+  if (!numel_host || n_tensors < 0) return -1;
+  int64_t total = 0;
+  for (int t = 0; t < n_tensors; ++t) {
+    if (numel_host[t] < 0) return -1;
+    total += (numel_host[t] + kEmaChunk - 1) / kEmaChunk;
+  }
+  return total;
+}
+
+extern "C" int avssl_ema_plan_fill(const uint64_t* online_ptrs_host, const uint64_t* hist_ptrs_host,
+                                   const int64_t* numel_host, int n_tensors,
+                                   avssl_ema_chunk* table_host, int64_t n_chunks) {
+  AVSSL_REQUIRE(online_ptrs_host && hist_ptrs_host && numel_host && (table_host || n_chunks == 0),
+                AVSSL_ERR_INVALID_ARGUMENT, "ema_plan_fill: null argument");
+  AVSSL_REQUIRE(avssl_ema_plan_chunks(numel_host, n_tensors) == n_chunks, AVSSL_ERR_INVALID_ARGUMENT,
+                "ema_plan_fill: table has %lld entries, plan needs %lld", (long long)n_chunks,
+                (long long)avssl_ema_plan_chunks(numel_host, n_tensors));
+  int64_t k = 0;
+  for (int t = 0; t < n_tensors; ++t) {
+    const uint64_t po = online_ptrs_host[t], ph = hist_ptrs_host[t];
+    AVSSL_REQUIRE(numel_host[t] == 0 || (po && ph), AVSSL_ERR_INVALID_ARGUMENT,
+                  "ema_plan_fill: tensor %d has a null pointer", t);
+    AVSSL_REQUIRE((po & 3u) == 0 && (ph & 3u) == 0, AVSSL_ERR_INVALID_ARGUMENT,
+                  "ema_plan_fill: tensor %d is not 4-byte aligned", t);
+    for (int64_t off = 0; off < numel_host[t]; off += kEmaChunk) {
+      avssl_ema_chunk& c = table_host[k++];
+      const int64_t n = numel_host[t] - off < kEmaChunk ? numel_host[t] - off : kEmaChunk;
+      c.online = reinterpret_cast<const float*>(po + 4ull * off);
+      c.hist = reinterpret_cast<float*>(ph + 4ull * off);
+      c.n = (uint32_t)n;
+      c.flags = (((po + 4ull * off) | (ph + 4ull * off)) & 15u) == 0 ? 1u : 0u;
+    }
+  }
+  return AVSSL_OK;
+}
+
+extern "C" int avssl_ema_multi_tensor(const avssl_ema_chunk* table_dev, int64_t n_chunks, float m,
+                                      float one_minus_m, int64_t* iter_dev, int bump_iter,
+                                      uint32_t* done_counter_dev, void* stream) {
+  AVSSL_REQUIRE(iter_dev, AVSSL_ERR_INVALID_ARGUMENT, "ema_multi_tensor: iter_dev is null");
+  AVSSL_REQUIRE(n_chunks >= 0 && n_chunks < (1ll << 31), AVSSL_ERR_INVALID_ARGUMENT,
+                "ema_multi_tensor: bad n_chunks %lld", (long long)n_chunks);
+  AVSSL_REQUIRE(!bump_iter || done_counter_dev, AVSSL_ERR_INVALID_ARGUMENT,
+                "ema_multi_tensor: bump_iter needs done_counter_dev");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (n_chunks == 0) {
+    if (bump_iter) {
+      bump_iter_kernel<<<1, 1, 0, s>>>(iter_dev);
+      AVSSL_LAUNCH_OK("bump_iter_kernel");
+    }
+    return AVSSL_OK;
+  }
+  AVSSL_REQUIRE(table_dev, AVSSL_ERR_INVALID_ARGUMENT, "ema_multi_tensor: table_dev is null");
+  ema_multi_tensor_kernel<<<(unsigned)n_chunks, kEmaThreads, 0, s>>>(table_dev, m, one_minus_m, iter_dev,
+                                                                     bump_iter, done_counter_dev);
+  AVSSL_LAUNCH_OK("ema_multi_tensor_kernel");
+  return AVSSL_OK;
+}

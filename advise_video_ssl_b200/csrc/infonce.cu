@@ -1,0 +1,117 @@
+// K2+K3 front door: argument checks, workspace carving, implementation choice.
+#include "infonce.cuh"
+
+using namespace avssl;
+
+namespace {
+
+constexpr size_t kAlign = 256;
+inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
+
+int max_splits() {
+  int sms = sm_count();
+  if (sms <= 0) {
+    cudaGetLastError();
+    sms = 148;
+  }
+  return 2 * sms;
+}
+
+struct Carve {
+  size_t counter, row_loss, part_m, part_l, part_acc, total;
+};
+Carve carve(int B, int D, int n_keys, int S) {
+  Carve c;
+  size_t off = 0;
+  c.counter = off;
+  off += kAlign;
+  c.row_loss = off;
+  off += align_up(sizeof(float) * (size_t)n_keys * B);
+  c.part_m = off;
+  off += align_up(sizeof(float) * (size_t)S * B);
+  c.part_l = off;
+  off += align_up(sizeof(float) * (size_t)S * B);
+  c.part_acc = off;
+  off += align_up(sizeof(float) * (size_t)S * B * D);
+  c.total = off;
+  return c;
+}
+
+}  // namespace
+
+extern "C" size_t avssl_moco_infonce_workspace_bytes(int B, int D, int K, int n_keys) {
+  if (B <= 0 || D <= 0 || K <= 0 || n_keys <= 0) return 0;
+  return carve(B, D, n_keys, max_splits()).total;
+}
+
+extern "C" int avssl_moco_infonce_fwd_bwd(const float* feat_q, const float* const* keys_host, int n_keys,
+                                          const float* queue, int B, int D, int K, float T, float* q_out,
+                                          float* loss_out, float* dfeat_out, float* row_lse_out,
+                                          float* logits_out, void* workspace, size_t workspace_bytes,
+                                          int impl, void* stream) {
+  AVSSL_REQUIRE(feat_q && keys_host && queue && q_out && loss_out && dfeat_out && workspace,
+                AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: null pointer");
+  AVSSL_REQUIRE(B > 0 && D > 0 && K > 0, AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: bad sizes B=%d D=%d K=%d", B, D, K);
+  AVSSL_REQUIRE(n_keys >= 1 && n_keys <= AVSSL_MAX_KEYS, AVSSL_ERR_INVALID_ARGUMENT,
+                "moco_infonce: n_keys=%d outside [1, %d]", n_keys, AVSSL_MAX_KEYS);
+  AVSSL_REQUIRE(T > 0.f, AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: temperature must be positive");
+  AVSSL_REQUIRE((reinterpret_cast<uintptr_t>(feat_q) & 15u) == 0 && (reinterpret_cast<uintptr_t>(queue) & 15u) == 0 &&
+                    (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0,
+                AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: feat_q/queue need 16-byte, workspace 256-byte alignment");
+  const int sms = sm_count();
+  AVSSL_REQUIRE(sms > 0, AVSSL_ERR_CUDA, "moco_infonce: no CUDA device (there is no CPU fallback)");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+
+  InfoNceParams p;
+  p.feat_q = feat_q;
+  for (int k = 0; k < AVSSL_MAX_KEYS; ++k) p.keys[k] = k < n_keys ? keys_host[k] : nullptr;
+  for (int k = 0; k < n_keys; ++k)
+    AVSSL_REQUIRE(p.keys[k], AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: keys[%d] is null", k);
+  p.n_keys = n_keys;
+  p.queue = queue;
+  p.B = B;
+  p.D = D;
+  p.K = K;
+  p.inv_T = 1.0f / T;
+  p.q_out = q_out;
+  p.loss_out = loss_out;
+  p.dfeat_out = dfeat_out;
+  p.row_lse_out = row_lse_out;
+  p.logits_out = logits_out;
+
+  int use = impl;
+  if (use == AVSSL_IMPL_AUTO) use = infonce_tc_supported(B, D, K) ? AVSSL_IMPL_TC3X : AVSSL_IMPL_SIMT;
+  AVSSL_REQUIRE(use == AVSSL_IMPL_SIMT || use == AVSSL_IMPL_TC3X || use == AVSSL_IMPL_TC1X,
+                AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: unknown impl %d", impl);
+
+  // split the queue over the SMs in whole tiles
+  const int tile = (use == AVSSL_IMPL_SIMT) ? 64 : 128;
+  const int n_tiles = (K + tile - 1) / tile;
+  const int row_blocks = (use == AVSSL_IMPL_SIMT) ? (B + 63) / 64 : (B + 127) / 128;
+  int S = sms / row_blocks;
+  if (S < 1) S = 1;
+  if (S > n_tiles) S = n_tiles;
+  const int tiles_per_split = (n_tiles + S - 1) / S;
+  S = (n_tiles + tiles_per_split - 1) / tiles_per_split;  // drop empty splits
+  p.n_splits = S;
+  p.rows_per_split = tiles_per_split * tile;
+
+  const Carve c = carve(B, D, n_keys, S);
+  AVSSL_REQUIRE(workspace_bytes >= c.total, AVSSL_ERR_WORKSPACE,
+                "moco_infonce: workspace of %zu bytes, need %zu", workspace_bytes, c.total);
+  char* w = static_cast<char*>(workspace);
+  p.counter = reinterpret_cast<unsigned*>(w + c.counter);
+  p.row_loss = reinterpret_cast<float*>(w + c.row_loss);
+  p.part_m = reinterpret_cast<float*>(w + c.part_m);
+  p.part_l = reinterpret_cast<float*>(w + c.part_l);
+  p.part_acc = reinterpret_cast<float*>(w + c.part_acc);
+
+  int rc;
+  if (use == AVSSL_IMPL_SIMT) {
+    rc = launch_infonce_simt(p, s);
+  } else {
+    rc = launch_infonce_tc(p, use == AVSSL_IMPL_TC3X ? 1 : 0, s);
+  }
+  if (rc != AVSSL_OK) return rc;
+  return launch_infonce_combine(p, s);
+}

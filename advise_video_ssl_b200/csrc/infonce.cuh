@@ -1,0 +1,55 @@
+// Shared declarations for the MoCo l2-norm + logits + InfoNCE kernels (K2+K3).
+#pragma once
+#include "common.cuh"
+
+namespace avssl {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// Launch-time description shared by the split kernels (SIMT / tcgen05) and the
+// combine kernel.  Partials are kept in the log2 domain:
+//   part_m[s][i]      running max of s_ij * log2e/T over the split's queue rows
+//   part_l[s][i]      sum_j 2^(s2_ij - m)
+//   part_acc[s][i][c] sum_j 2^(s2_ij - m) * queue[j][c]
+struct InfoNceParams {
+  const float* feat_q;
+  const float* keys[AVSSL_MAX_KEYS];
+  int n_keys;
+  const float* queue;
+  int B, D, K;
+  float inv_T;
+  float* q_out;
+  float* loss_out;
+  float* dfeat_out;
+  float* row_lse_out;
+  float* logits_out;
+  // workspace
+  unsigned* counter;
+  float* row_loss;
+  float* part_m;
+  float* part_l;
+  float* part_acc;
+  int n_splits;
+  int rows_per_split;  // queue rows handled by one split (multiple of the tile)
+};
+
+// 1 / ||row|| computed by ONE warp with a fixed summation order, so that every
+// kernel that normalises the same row obtains the same bits.
+__device__ __forceinline__ float warp_row_norm(const float* __restrict__ row, int D, int lane) {
+  float ss = 0.f;
+  for (int c = lane; c < D; c += 32) {
+    const float v = row[c];
+    ss = fmaf(v, v, ss);
+  }
+  ss = warp_sum(ss);
+  return sqrtf(ss);  // Normalize: x / sum(x^2)^(1/2), no eps (models/contrastive.py:929-934)
+}
+
+int launch_infonce_simt(const InfoNceParams& p, cudaStream_t s);
+int launch_infonce_combine(const InfoNceParams& p, cudaStream_t s);
+// tcgen05 path; returns AVSSL_ERR_UNSUPPORTED when the shape does not fit.
+int launch_infonce_tc(const InfoNceParams& p, int three_term, cudaStream_t s);
+bool infonce_tc_supported(int B, int D, int K);
+
+}  // namespace avssl

@@ -1,0 +1,341 @@
+#!/usr/bin/env python3
+"""Benchmark of the contrastive hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (configs[1] of BASELINE.json, head only — SURVEY.md §8(d) cfg2):
+  Slow-R50 MoCo, 2 views per clip, queue 65536, dim 128, batch 64 per GPU.
+  One "step" = momentum EMA over the reference's real Slow-R50+MLP-head parameter
+  list (164 tensors, 36,095,168 fp32) -> [key all_gather when N>1] -> l2-norm +
+  q.[k;queue]^T logits + InfoNCE forward AND backward (df) -> enqueue.  Backbone
+  forward/backward are out of scope and excluded.  Synthetic embeddings, random
+  weights.
+
+`value`  : clips/s = N * 64 / step time, inputs already resident in HBM.
+`e2e`    : same metric through the public module API with pinned HOST embeddings:
+           H2D of the step's inputs and D2H of the loss inside the timed region,
+           one host synchronisation per step.
+`roofline`: the dominant kernel (the EMA, 93 % of the step's bytes): algorithmic
+           bytes 12 B/param per launch / CUDA-event duration of that launch.
+`cpu_baseline` / `--impl reference`: the CPU oracle port of the same step
+           (torch CPU ops, all host threads), bounded sample.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+B_PER_GPU, DIM, QUEUE_LEN, TEMP, MOMENTUM = 64, 128, 65536, 0.1, 0.999
+POOL = 8  # distinct synthetic batches rotated through the steps
+WORKLOAD = ("configs[1] head: Slow-R50 MoCo, 2 views/clip, queue 65536, dim 128, batch 64/GPU; "
+            "EMA(164 tensors, 36.1M fp32) + l2norm + logits + InfoNCE fwd/bwd + enqueue; backbone excluded")
+METRIC, UNIT = "contrastive_head_clips_per_sec", "clips/s"
+
+
+def param_shapes(tag="slow_r50_moco_dim128"):
+    with open(os.path.join(ROOT, "tests", "golden", "slow_r50_param_shapes.json")) as f:
+        return [tuple(s) for _, s in json.load(f)[tag]["shapes"]]
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------ clock sampling
+class ClockSampler:
+    """Samples SM clock and throttle reasons during the timed region (NVML)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr is not None:
+            self._stop.set()
+            self._thr.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------ CPU oracle arm
+def cpu_step_factory(seed=0):
+    from oracle import contrastive_oracle as O
+    g = torch.Generator().manual_seed(seed)
+    online = [torch.randn(s, generator=g) * 0.02 for s in param_shapes()]
+    stdv = 1.0 / (DIM / 3) ** 0.5
+    queue = torch.rand(QUEUE_LEN, DIM, generator=g).mul_(2 * stdv).add_(-stdv)
+    head = O.MoCoHeadStep(online, queue, TEMP, MOMENTUM)
+    feats = [torch.randn(B_PER_GPU, DIM, generator=g) for _ in range(POOL)]
+    keys = [O.l2_normalize(torch.randn(B_PER_GPU, DIM, generator=g)) for _ in range(POOL)]
+
+    def step(i):
+        return head.step(feats[i % POOL], [keys[i % POOL]])
+    return step
+
+
+def run_cpu(steps, warmup, budget_s=None):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_step_factory()
+    for i in range(warmup):
+        step(i)
+    t0 = time.perf_counter()
+    done = 0
+    for i in range(steps):
+        step(warmup + i)
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s and done >= 3:
+            break
+    dt = (time.perf_counter() - t0) / done
+    return dt, done
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps = min(args.steps, 40)
+    warmup = min(args.warmup, 3)
+    dt, done = run_cpu(steps, warmup, budget_s=120.0)
+    val = B_PER_GPU / dt
+    cores = torch.get_num_threads()
+    sample = "%d full steps (EMA 36.1M params + head B=64,K=65536,D=128 fwd/bwd + enqueue) after %d warm-up" % (done, warmup)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": done, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "CPU oracle port (torch CPU ops = the reference's own op sequence), rank 0 only"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+    return 0
+
+
+# ------------------------------------------------------------------------ GPU arm
+def gpu_arm(args):
+    import torch.distributed as dist
+    from advise_video_ssl_b200 import ops, _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the contrastive hot path has no CPU fallback "
+                         "(use --impl reference for the CPU oracle arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
+    n_gpus = world
+
+    g = torch.Generator().manual_seed(1000 + rank)
+    online = [(torch.randn(s, generator=g) * 0.02).to(dev) for s in param_shapes()]
+    hist = [torch.zeros_like(o) for o in online]
+    n_params = sum(o.numel() for o in online)
+    stdv = 1.0 / (DIM / 3) ** 0.5
+    gq = torch.Generator().manual_seed(7)
+    queue = torch.rand(QUEUE_LEN, DIM, generator=gq).mul_(2 * stdv).add_(-stdv).to(dev)
+    feats_h = [torch.randn(B_PER_GPU, DIM, generator=g).pin_memory() for _ in range(POOL)]
+    keys_h = [torch.nn.functional.normalize(torch.randn(B_PER_GPU, DIM, generator=g)).pin_memory() for _ in range(POOL)]
+    feats = [t.to(dev) for t in feats_h]
+    keys = [t.to(dev) for t in keys_h]
+    it = torch.zeros(1, dtype=torch.int64, device=dev)
+    ptr = torch.zeros(1, dtype=torch.int64, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    plan = ops.EmaPlan(online, hist)
+    gathered = torch.empty(world * B_PER_GPU, DIM, device=dev) if world > 1 else None
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    impl = {"auto": _lib.IMPL_AUTO, "simt": _lib.IMPL_SIMT, "tc3x": _lib.IMPL_TC3X, "tc1x": _lib.IMPL_TC1X}[args.kernel]
+    out = {}
+    launches_per_step = 4  # ema, infonce split, infonce combine, enqueue
+    ema_events = []
+
+    def step(i, f, k, time_ema=False):
+        """EMA -> [gather keys] -> fused head -> enqueue (reference order, :308-316, :486-503)."""
+        if time_ema:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        if world > 1:
+            # C3: key all_gather on the comm stream, overlapped with the EMA kernel
+            comm.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(comm):
+                dist.all_gather_into_tensor(gathered, k)
+        plan.run(MOMENTUM, it, bump_iter=True)
+        if time_ema:
+            e1.record()
+            ema_events.append((e0, e1))
+        if world > 1:
+            torch.cuda.current_stream().wait_stream(comm)
+            k = gathered[rank * B_PER_GPU:(rank + 1) * B_PER_GPU]
+        r = ops.moco_infonce(f, [k], queue, TEMP, want_logits=not args.no_logits, impl=impl, out=out)
+        ops.queue_enqueue(queue, ptr, k, status)
+        return r
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident timing (value)
+    for i in range(args.warmup):
+        r = step(i, feats[i % POOL], keys[i % POOL])
+        out = r if not out else out
+    sync_all()
+    sampler = ClockSampler(local)
+    sampler.start()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for i in range(args.steps):
+        step(i, feats[i % POOL], keys[i % POOL], time_ema=True)
+    t_end.record()
+    sync_all()
+    clocks = sampler.stop()
+    ms_total = t_start.elapsed_time(t_end)
+    ema_ms = sum(a.elapsed_time(b) for a, b in ema_events) / len(ema_events)
+    loss_val = float(out["loss"].item())
+    assert int(status.item()) == 0, "device status word set: %d" % int(status.item())
+
+    # ---- end-to-end timing: pinned host inputs, loss read back, one sync per step
+    f_dev = torch.empty(B_PER_GPU, DIM, device=dev)
+    k_dev = torch.empty(B_PER_GPU, DIM, device=dev)
+    loss_h = torch.empty(1).pin_memory()
+    e2e_steps = args.steps
+
+    def e2e_step(i):
+        f_dev.copy_(feats_h[i % POOL], non_blocking=True)
+        k_dev.copy_(keys_h[i % POOL], non_blocking=True)
+        r = step(i, f_dev, k_dev)
+        loss_h.copy_(r["loss"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(loss_h[0])
+
+    for i in range(min(args.warmup, 10)):
+        e2e_step(i)
+    sync_all()
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_start.record()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    e_end.record()
+    sync_all()
+    e2e_ms = e_start.elapsed_time(e_end)
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([ms_total, e2e_ms, ema_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, e2e_ms, ema_ms = (float(x) for x in t.tolist())
+
+    ms_per_step = ms_total / args.steps
+    value = n_gpus * B_PER_GPU / (ms_per_step * 1e-3)
+    e2e_value = n_gpus * B_PER_GPU / (e2e_ms / e2e_steps * 1e-3)
+    peak, peak_src = measured_peaks()
+    ema_bytes = 12 * n_params
+    achieved = ema_bytes / (ema_ms * 1e-3) / 1e9
+    step_bytes = ema_bytes + 4 * QUEUE_LEN * DIM + 4 * B_PER_GPU * DIM * 3 + 8 * B_PER_GPU * DIM
+    if not args.no_logits:
+        step_bytes += 4 * B_PER_GPU * (QUEUE_LEN + 1)
+
+    result = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "step_us": ms_per_step * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B_PER_GPU, "global_batch": n_gpus * B_PER_GPU,
+                   "queue_len": QUEUE_LEN, "dim": DIM, "T": TEMP, "ema_tensors": len(online),
+                   "ema_params": n_params, "logits_materialised": not args.no_logits,
+                   "infonce_kernel": args.kernel,
+                   "parallelism": "dp%d (queue/EMA replicated, batch sharded; key all_gather only)" % n_gpus,
+                   "l2": "no explicit flush: one step streams %.0f MB (> 126 MB L2) so nothing survives between steps" % (step_bytes / 1e6)},
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / e2e_steps,
+                "h2d_bytes_per_step": 2 * 4 * B_PER_GPU * DIM, "d2h_bytes_per_step": 4,
+                "note": "pinned host embeddings -> H2D -> EMA+head+enqueue -> loss D2H, host sync every step"},
+        "gpu_launches": launches_per_step * args.steps,
+        "clocks": clocks,
+        "roofline": {"kernel": "ema_multi_tensor_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "bytes_per_launch": ema_bytes, "us_per_launch": ema_ms * 1e3, "peak_source": peak_src},
+        "step_roofline": {"bytes_per_step": step_bytes, "floor_us": step_bytes / (peak * 1e9) * 1e6,
+                          "frac": (step_bytes / (peak * 1e9) * 1e3) / ms_per_step},
+        "loss": loss_val,
+    }
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+        dt, done = run_cpu(50, 2, budget_s=15.0)
+        result["cpu_baseline"] = {
+            "value": B_PER_GPU / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "ms_per_step": dt * 1e3,
+            "sample": "%d full steps of the same workload on the CPU oracle (torch CPU, all threads) after 2 warm-up" % done}
+    if rank == 0:
+        print(json.dumps(result))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tc3x", "tc1x"])
+    ap.add_argument("--no-logits", action="store_true", help="do not materialise the [B,K+1] logits tensor")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return reference_arm(args)
+    return gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

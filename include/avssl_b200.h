@@ -1,0 +1,135 @@
+/*
+ * avssl_b200.h — C-ABI of the B200-native contrastive hot path.
+ *
+ * Drop-in boundary for the contrastive head of JingwWu/advise-video-ssl
+ * (`models/contrastive.py`, `models/losses.py:15-25`, `utils/distributed.py:79-155`).
+ * The reference is pure Python/torch and has no FFI of its own; these are the
+ * entry points SURVEY.md §8(b) lists for a C-ABI replacement.  Each function
+ * cites the reference lines whose op sequence it replaces.
+ *
+ * Conventions
+ *   - plain C: raw pointers, sizes, `cudaStream_t` passed as `void*`; no torch types.
+ *   - device pointers unless the name ends in `_host`.
+ *   - every call is asynchronous on `stream` and never synchronises unless stated.
+ *   - return value: 0 = AVSSL_OK, otherwise an avssl_status code; the message for
+ *     the calling thread's last failure is available from avssl_last_error().
+ *   - the caller owns all memory; the library keeps no global device state.
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails.
+ *   - fp32 tensors are row-major and contiguous; indices / pointers are int64.
+ */
+#ifndef AVSSL_B200_H_
+#define AVSSL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define AVSSL_API __attribute__((visibility("default")))
+#else
+#define AVSSL_API
+#endif
+
+typedef enum {
+  AVSSL_OK = 0,
+  AVSSL_ERR_INVALID_ARGUMENT = 1,
+  AVSSL_ERR_CUDA = 2,
+  AVSSL_ERR_UNSUPPORTED = 3,
+  AVSSL_ERR_WORKSPACE = 4
+} avssl_status;
+
+/* Bits of the device-side status word written by kernels that replace host asserts. */
+#define AVSSL_DEVFLAG_QUEUE_OVERRUN 1u /* ptr + n > K   (models/contrastive.py:285) */
+#define AVSSL_DEVFLAG_BAD_INDEX 2u     /* bank index out of range                   */
+
+AVSSL_API int avssl_abi_version(void);
+AVSSL_API const char* avssl_last_error(void);
+/* Number of SMs of the current device (grid sizing), or <0 on error. */
+AVSSL_API int avssl_device_sm_count(void);
+
+/* ------------------------------------------------------------------ K1: momentum EMA
+ * Replaces ContrastiveModel._update_history (models/contrastive.py:158-172):
+ *     hist <- online * (1 - m) + hist * m            for every parameter tensor,
+ * three separately rounded fp32 ops (mul, mul, add — no FMA contraction) so the
+ * result is bit-identical to the reference's ATen sequence.  When *iter_dev == 0
+ * the history is first replaced by the online weights (:167-169) and then blended.
+ *
+ * The pointer table is a device array of avssl_ema_chunk built once on the host by
+ * avssl_ema_plan_fill() and reused every step.
+ */
+typedef struct {
+  const float* online; /* start of this chunk in the online (query) encoder tensor */
+  float* hist;         /* same offset in the momentum (key) encoder tensor         */
+  uint32_t n;          /* elements in this chunk (<= chunk_elems)                  */
+  uint32_t flags;      /* bit0: both pointers 16-byte aligned                      */
+} avssl_ema_chunk;
+
+/* Elements per chunk used by the kernel's fast path. */
+AVSSL_API int64_t avssl_ema_chunk_elems(void);
+/* Number of chunks for a parameter list (host; no CUDA). */
+AVSSL_API int64_t avssl_ema_plan_chunks(const int64_t* numel_host, int n_tensors);
+/* Fill a host table of avssl_ema_plan_chunks() entries (host; no CUDA). */
+AVSSL_API int avssl_ema_plan_fill(const uint64_t* online_ptrs_host, const uint64_t* hist_ptrs_host,
+                        const int64_t* numel_host, int n_tensors,
+                        avssl_ema_chunk* table_host, int64_t n_chunks);
+/*
+ * m, one_minus_m: the fp32 roundings of the host doubles m and (1.0 - m), exactly
+ *   what ATen uses for `tensor * python_float`.
+ * iter_dev: int64[1] device-resident step counter (buffer `iter`, :90); read, not
+ *   copied to the host (the reference's int(self.iter) D2H sync, :161, is gone).
+ * bump_iter != 0: also performs `self.iter += 1` (compute_key_feat, :314) after
+ *   every block has read it; needs done_counter (uint32[1], zero-initialised,
+ *   self-resetting).
+ */
+AVSSL_API int avssl_ema_multi_tensor(const avssl_ema_chunk* table_dev, int64_t n_chunks, float m,
+                           float one_minus_m, int64_t* iter_dev, int bump_iter,
+                           uint32_t* done_counter_dev, void* stream);
+
+/* -------------------------------------------- K2+K3: l2-norm + MoCo logits + InfoNCE
+ * Replaces the MoCo score/loss block (models/contrastive.py:462, 486-500) and
+ * ContrastiveLoss.forward (models/losses.py:20-25), forward AND backward in one
+ * pass over the queue:
+ *     q = f / ||f||;  s_ij = q_i . queue_j / T;  s0_ki = q_i . key_ki / T
+ *     loss = mean_{k,i} ( log( e^{s0_ki} + sum_j e^{s_ij} ) - s0_ki )
+ *     dq_i = sum_k ( sum_j p_kij queue_j + p_ki0 key_ki - key_ki ) / (T n_rows)
+ *     df_i = ( dq_i - (dq_i . q_i) q_i ) / ||f_i||
+ * keys_host: host array of n_keys (<= AVSSL_MAX_KEYS) device pointers, each [B, D],
+ *   already normalised and detached (compute_key_feat output).
+ * logits_out: optional [n_keys*B, K+1] (the tensor the reference returns, :498,506);
+ *   NULL skips the 4*n_keys*B*(K+1) bytes of writes.
+ * row_lse_out: optional [n_keys*B] log-sum-exp per logits row.
+ * impl: AVSSL_IMPL_AUTO picks the tcgen05 kernel when the shape allows it.
+ * workspace: avssl_moco_infonce_workspace_bytes() bytes, 256-byte aligned, zero-filled
+ *   ONCE by the caller when it is allocated; the call leaves it reusable.
+ */
+#define AVSSL_MAX_KEYS 8
+#define AVSSL_IMPL_AUTO 0
+#define AVSSL_IMPL_SIMT 1   /* fp32 CUDA-core kernel, any D % 4 == 0, D <= 256 */
+#define AVSSL_IMPL_TC3X 2   /* tcgen05 kind::tf32, 3-term error-compensated (fp32-grade) */
+#define AVSSL_IMPL_TC1X 3   /* tcgen05 kind::tf32, single pass (tf32-grade)    */
+
+AVSSL_API size_t avssl_moco_infonce_workspace_bytes(int B, int D, int K, int n_keys);
+AVSSL_API int avssl_moco_infonce_fwd_bwd(const float* feat_q, const float* const* keys_host, int n_keys,
+                               const float* queue, int B, int D, int K, float T, float* q_out,
+                               float* loss_out, float* dfeat_out, float* row_lse_out,
+                               float* logits_out, void* workspace, size_t workspace_bytes,
+                               int impl, void* stream);
+
+/* --------------------------------------------------------------- K4: queue ring write
+ * Replaces _dequeue_and_enqueue (models/contrastive.py:263-292) for one key tensor:
+ *     queue[ptr:ptr+n] = keys;  ptr = (ptr + n == K) ? 0 : ptr + n
+ * with ptr device-resident (no .item() sync, :265).  The host assert K % n == 0
+ * (:284) is checked by the call; `ptr + n <= K` (:285) is checked on the device:
+ * on violation nothing is written and AVSSL_DEVFLAG_QUEUE_OVERRUN is or-ed into
+ * *status_dev (uint32[1], may be NULL).
+ */
+AVSSL_API int avssl_queue_enqueue(float* queue, int64_t* ptr_dev, const float* keys, int n, int K, int D,
+                        uint32_t* status_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVSSL_B200_H_ */

@@ -1,0 +1,242 @@
+"""-m gpu parity tests of the CUDA kernels, called through the C-ABI, against the
+CPU oracle and the committed golden vectors (which come from the reference)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import recipes
+from oracle import contrastive_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+# fp32 tolerance of north_star: 1e-3 relative for loss and gradients.  The CUDA-core
+# kernel is far inside it; the tighter bounds below are what it actually meets.
+RTOL_LOSS = 1e-5
+RTOL_GRAD = 1e-4
+
+
+def _ops():
+    from advise_video_ssl_b200 import ops
+    return ops
+
+
+def _impls():
+    from advise_video_ssl_b200 import _lib
+    return [("simt", _lib.IMPL_SIMT)]
+
+
+def _grad_close(a, ref, rtol):
+    ref = ref.double()
+    err = (a.double().cpu() - ref).abs().max().item()
+    return err <= rtol * ref.abs().max().item()
+
+
+# ------------------------------------------------------------------------------ EMA
+def test_ema_bit_exact_golden(golden):
+    ops = _ops()
+    g = golden("ema")
+    names = list(g["names"])
+    hist = [g["hist_init/" + n].cuda() for n in names]
+    online = [torch.empty_like(h) for h in hist]
+    plan = ops.EmaPlan(online, hist)
+    it = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for s, ep in enumerate(g["epochs"].tolist()):
+        m = O.momentum_cosine(g.scalar("m0"), ep, int(g.scalar("max_epoch")))
+        for o, n in zip(online, names):
+            o.copy_(g["online%d/%s" % (s, n)])
+        plan.run(m, it, bump_iter=True)
+        for h, n in zip(hist, names):
+            assert torch.equal(h.cpu(), g["hist%d/%s" % (s, n)]), (s, n)
+        assert int(it.item()) == s + 1
+
+
+@pytest.mark.parametrize("m", [0.999, 0.5, 0.0, 1.0])
+def test_ema_bit_exact_oracle_many_shapes(m):
+    ops = _ops()
+    torch.manual_seed(0)
+    shapes = [(1,), (3,), (4096,), (4097,), (8192 + 5,), (64, 3, 1, 7, 7), (2048, 512), (128, 2048), (7, 11, 13)]
+    online_c = [torch.randn(s) for s in shapes]
+    hist_c = [torch.randn(s) for s in shapes]
+    # include a deliberately misaligned view (4-byte aligned only)
+    base_o, base_h = torch.randn(1001 + 1).cuda(), torch.randn(1001 + 1).cuda()
+    online = [t.cuda() for t in online_c] + [base_o[1:]]
+    hist = [t.cuda() for t in hist_c] + [base_h[1:]]
+    online_c.append(base_o[1:].cpu())
+    hist_c.append(base_h[1:].cpu())
+    plan = ops.EmaPlan(online, hist)
+    it = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for step in range(3):
+        hist_c = O.ema_update(online_c, hist_c, m, step)
+        plan.run(m, it, bump_iter=True)
+        for h, hc in zip(hist, hist_c):
+            assert torch.equal(h.cpu(), hc)
+        online_c = [o + 0.01 for o in online_c]
+        for o, oc in zip(online, online_c):
+            o.copy_(oc)
+    # no-bump variant leaves iter alone
+    plan.run(m, it, bump_iter=False)
+    assert int(it.item()) == 3
+
+
+def test_ema_full_size_linearity():
+    """BASELINE cfg2 size (36.1 M params): size-independent property instead of a
+    full CPU compare — with m = 0.5 and hist == online the blend is the identity;
+    spot-check 1 M elements against the oracle as well."""
+    ops = _ops()
+    n = 36_095_168
+    online = torch.randn(n, device="cuda")
+    hist = online.clone()
+    parts_o = list(online.split(1_000_003))
+    parts_h = list(hist.split(1_000_003))
+    plan = ops.EmaPlan(parts_o, parts_h)
+    it = torch.ones(1, dtype=torch.int64, device="cuda")
+    plan.run(0.5, it)
+    assert torch.equal(hist, online)
+    hist.normal_()
+    ref = O.ema_update([online[:1_000_000].cpu()], [hist[:1_000_000].cpu()], 0.996, 1)[0]
+    plan.run(0.996, it)
+    assert torch.equal(hist[:1_000_000].cpu(), ref)
+
+
+# ---------------------------------------------------------------------------- queue
+def test_enqueue_bit_exact_and_wrap(golden):
+    ops = _ops()
+    g = golden("moco_multikey")
+    K, B, D = int(g.scalar("K")), int(g.scalar("B")), int(g.scalar("D"))
+    queue = g["queue0"].cuda()
+    ptr = torch.zeros(1, dtype=torch.int64, device="cuda")
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    qc, pc = g["queue0"].clone(), 0
+    torch.manual_seed(1)
+    for s in range(11):
+        keys = [torch.randn(B, D) for _ in range(2)]
+        pc = O.enqueue(qc, pc, keys, K, multi_view=True)
+        for k in keys:
+            ops.queue_enqueue(queue, ptr, k.cuda(), status)
+        assert torch.equal(queue.cpu(), qc)
+        assert int(ptr.item()) == pc
+    assert int(status.item()) == 0
+    # device-side replacement of `assert ptr + n <= K` (models/contrastive.py:285)
+    ptr.fill_(K - B // 2)
+    before = queue.clone()
+    ops.queue_enqueue(queue, ptr, torch.randn(B, D).cuda(), status)
+    assert int(status.item()) & 1 and torch.equal(queue, before) and int(ptr.item()) == K - B // 2
+    with pytest.raises(AssertionError):  # models/contrastive.py:284
+        ops.queue_enqueue(queue, ptr, torch.randn(5, D).cuda(), status)
+
+
+# -------------------------------------------------------------------------- InfoNCE
+def _check_infonce(out, feat, keys, queue, T, rtol_loss, rtol_grad, logits_atol):
+    f = feat.clone().requires_grad_(True)
+    q, logits, loss = O.moco_head(f, keys, queue, T)
+    loss.backward()
+    cl, cdf, _ = O.moco_head_closed_form(feat, keys, queue, T)
+    # loss = mean(lse - s0): relative to the magnitude of the terms it is made of
+    lse_ref = torch.logsumexp(logits.detach().double(), 1)
+    scale = max(abs(cl.item()), lse_ref.abs().max().item())
+    assert abs(out["loss"].item() - cl.item()) <= rtol_loss * scale
+    assert abs(out["loss"].item() - loss.item()) <= rtol_loss * scale + 2e-6
+    assert _grad_close(out["dfeat"], cdf, rtol_grad)
+    assert _grad_close(out["dfeat"], f.grad, rtol_grad)
+    assert torch.allclose(out["q"].cpu(), q.detach(), rtol=0, atol=3e-7)
+    if out["logits"] is not None:
+        assert out["logits"].shape == logits.shape
+        assert (out["logits"].cpu() - logits.detach()).abs().max().item() <= logits_atol
+    lse = torch.logsumexp(logits.detach().double(), 1)
+    assert (out["lse"].double().cpu() - lse).abs().max().item() <= 1e-5 * lse.abs().max().item()
+
+
+@pytest.mark.parametrize("name,impl", [("simt", 1)])
+def test_infonce_golden_small(golden, name, impl):
+    ops = _ops()
+    g = golden("moco_small")
+    T = g.scalar("T")
+    for s in range(3):
+        queue = g["queue0"] if s == 0 else g["queue_after%d" % (s - 1)]
+        hist = g["Whist_after%d" % s]
+        keys = [O.l2_normalize(F.linear(g["xk%d" % s], hist))]
+        feat = g["featq%d" % s]
+        out = ops.moco_infonce(feat.cuda(), [k.cuda() for k in keys], queue.cuda(), T, True, impl)
+        # against the reference's own numbers
+        assert abs(out["loss"].item() - g["loss%d" % s].item()) <= RTOL_LOSS * abs(g["loss%d" % s].item())
+        assert _grad_close(out["dfeat"], g["dfeatq%d" % s], RTOL_GRAD)
+        assert (out["logits"].cpu() - g["logits%d" % s]).abs().max().item() <= 5e-6
+        _check_infonce(out, feat, keys, queue, T, RTOL_LOSS, RTOL_GRAD, 5e-6)
+
+
+@pytest.mark.parametrize("name,impl", [("simt", 1)])
+def test_infonce_golden_multikey(golden, name, impl):
+    ops = _ops()
+    g = golden("moco_multikey")
+    T = g.scalar("T")
+    for s in range(2):
+        queue = g["queue0"] if s == 0 else g["queue_after%d" % (s - 1)]
+        hist = g["Whist_after%d" % s]
+        keys = [O.l2_normalize(F.linear(g["x%d_%d" % (s, i)], hist)) for i in (1, 2)]
+        feat = g["featq%d" % s]
+        out = ops.moco_infonce(feat.cuda(), [k.cuda() for k in keys], queue.cuda(), T, True, impl)
+        assert abs(out["loss"].item() - g["loss%d" % s].item()) <= RTOL_LOSS * abs(g["loss%d" % s].item())
+        assert _grad_close(out["dfeat"], g["dfeatq%d" % s], RTOL_GRAD)
+        assert (out["logits"].cpu() - g["logits%d" % s]).abs().max().item() <= 5e-6
+
+
+@pytest.mark.parametrize("name,impl", [("simt", 1)])
+def test_infonce_cfg1_full_size(golden, name, impl):
+    """BASELINE configs[0] at full size (B=64, K=65536, D=128, T=0.1) against the
+    reference's golden loss / gradient / logits samples."""
+    ops = _ops()
+    g = golden("moco_cfg1")
+    r = recipes.moco_cfg1()
+    hist = O.ema_update([r["W"]], [r["W"].clone()], r["m"], 0)[0]
+    keys = [O.l2_normalize(F.linear(r["xk"], hist))]
+    feat = g["featq"]
+    out = ops.moco_infonce(feat.cuda(), [k.cuda() for k in keys], r["queue"].cuda(), r["T"], True, impl)
+    assert abs(out["loss"].item() - g["loss"].item()) <= RTOL_LOSS * abs(g["loss"].item())
+    assert _grad_close(out["dfeat"], g["dfeatq"], RTOL_GRAD)
+    lg = out["logits"].cpu()
+    assert (lg[:, :16] - g["logits_head"]).abs().max().item() <= 5e-6
+    assert (lg[:, -16:] - g["logits_tail"]).abs().max().item() <= 5e-6
+    assert (lg.double().sum(1) - g["logits_rowsum"]).abs().max().item() <= 2e-2  # 65537 terms
+    assert (out["lse"].double().cpu() - g["lse"]).abs().max().item() <= 1e-4
+    # no-logits variant gives identical loss and gradient bits
+    out2 = ops.moco_infonce(feat.cuda(), [k.cuda() for k in keys], r["queue"].cuda(), r["T"], False, impl)
+    assert out2["logits"] is None
+    assert torch.equal(out2["loss"], out["loss"]) and torch.equal(out2["dfeat"], out["dfeat"])
+
+
+@pytest.mark.parametrize("name,impl", [("simt", 1)])
+@pytest.mark.parametrize("B,D,K,nk,T", [(1, 4, 1, 1, 0.2), (5, 32, 130, 2, 0.07), (64, 128, 4096, 1, 0.1),
+                                         (96, 256, 1000, 3, 0.5), (130, 64, 777, 1, 0.07), (64, 100, 640, 1, 0.1)])
+def test_infonce_shapes_vs_oracle(name, impl, B, D, K, nk, T):
+    ops = _ops()
+    torch.manual_seed(B * 1000 + K)
+    feat = torch.randn(B, D) * 3
+    keys = [O.l2_normalize(torch.randn(B, D)) for _ in range(nk)]
+    queue = O.l2_normalize(torch.randn(K, D))
+    out = ops.moco_infonce(feat.cuda(), [k.cuda() for k in keys], queue.cuda(), T, True, impl)
+    _check_infonce(out, feat, keys, queue, T, 2e-5, 2e-4, 2e-5)
+
+
+@pytest.mark.parametrize("name,impl", [("simt", 1)])
+def test_infonce_peaked_distribution(name, impl):
+    """Trained-state case: some queue rows nearly equal q (logits up to 1/T)."""
+    ops = _ops()
+    torch.manual_seed(7)
+    B, D, K, T = 64, 128, 8192, 0.07
+    feat = torch.randn(B, D)
+    q = O.l2_normalize(feat)
+    queue = O.l2_normalize(torch.randn(K, D))
+    idx = torch.randint(0, K, (B, 3))
+    for i in range(B):
+        queue[idx[i]] = O.l2_normalize(q[i:i + 1] + 0.05 * torch.randn(3, D))
+    keys = [O.l2_normalize(q + 0.1 * torch.randn(B, D))]
+    out = ops.moco_infonce(feat.cuda(), [k.cuda() for k in keys], queue.cuda(), T, True, impl)
+    _check_infonce(out, feat, keys, queue, T, 2e-5, 2e-4, 3e-5)
+
+
+def test_no_cpu_fallback():
+    ops = _ops()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.moco_infonce(torch.randn(4, 8), [torch.randn(4, 8)], torch.randn(16, 8), 0.1)
