@@ -39,6 +39,28 @@ SIGNATURES = {
                                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                            c_int, c_void_p]),
     "avssl_queue_enqueue": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "avssl_membank_update": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                     c_float, c_float, c_int, c_void_p, c_void_p]),
+    "avssl_membank_gather_dot": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p]),
+    "avssl_l2norm_fwd": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "avssl_l2norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "avssl_byol_simloss_workspace_bytes": (c_size_t, [c_int]),
+    "avssl_byol_simloss_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p, c_void_p,
+                                           c_void_p, c_size_t, c_void_p]),
+    "avssl_ce_target0_workspace_bytes": (c_size_t, [c_int]),
+    "avssl_ce_target0_fwd": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "avssl_ce_target0_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "avssl_ntxent_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "avssl_ntxent_rowsum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_size_t,
+                                    c_void_p]),
+    "avssl_ntxent_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float,
+                                  c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "avssl_sinkhorn_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "avssl_sinkhorn": (c_int, [c_void_p, c_int, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "avssl_swav_ce_workspace_bytes": (c_size_t, [c_int]),
+    "avssl_swav_ce_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 
 IMPL_AUTO, IMPL_SIMT, IMPL_TC3X, IMPL_TC1X = 0, 1, 2, 3

@@ -12,37 +12,9 @@
 // D <= 256, any B, any K) and the fallback for shapes the tcgen05 kernel does not
 // take.  It is FFMA-bound (2.1 GFLOP at cfg1), not HBM-bound.
 #include "infonce.cuh"
+#include "simt_tile.cuh"
 
 namespace avssl {
-
-constexpr int kTileJ = 64;   // queue rows per tile
-constexpr int kTileI = 64;   // query rows per CTA
-constexpr int kSimtThreads = 256;
-constexpr int kPsStride = kTileJ + 4;
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  const int sz = valid ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-template <int DP>
-__device__ __forceinline__ void load_tile(float* ks, const float* __restrict__ queue, int D, int j0, int j_end) {
-  constexpr int KS = DP + 4;
-  constexpr int CH = DP / 4;  // 16-byte chunks per row
-  for (int idx = threadIdx.x; idx < kTileJ * CH; idx += kSimtThreads) {
-    const int r = idx / CH, ch = idx % CH;
-    const int j = j0 + r;
-    const bool valid = (j < j_end) && (ch * 4 < D);
-    const float* src = valid ? queue + (size_t)j * D + ch * 4 : queue;
-    cp_async16(ks + r * KS + ch * 4, src, valid);
-  }
-}
 
 template <int DP>
 __global__ void __launch_bounds__(kSimtThreads, 1) infonce_simt_kernel(const InfoNceParams p) {
@@ -103,27 +75,7 @@ __global__ void __launch_bounds__(kSimtThreads, 1) infonce_simt_kernel(const Inf
 
     // ---- S = q . tile^T : thread owns rows ty*4+ii, columns tx+16*jj
     float s[4][4];
-#pragma unroll
-    for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) s[ii][jj] = 0.f;
-#pragma unroll 4
-    for (int c = 0; c < DP; c += 4) {
-      float4 qv[4], kv[4];
-#pragma unroll
-      for (int ii = 0; ii < 4; ++ii) qv[ii] = *reinterpret_cast<const float4*>(qs + (ty * 4 + ii) * KS + c);
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) kv[jj] = *reinterpret_cast<const float4*>(ks + (tx + 16 * jj) * KS + c);
-#pragma unroll
-      for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          s[ii][jj] = fmaf(qv[ii].x, kv[jj].x, s[ii][jj]);
-          s[ii][jj] = fmaf(qv[ii].y, kv[jj].y, s[ii][jj]);
-          s[ii][jj] = fmaf(qv[ii].z, kv[jj].z, s[ii][jj]);
-          s[ii][jj] = fmaf(qv[ii].w, kv[jj].w, s[ii][jj]);
-        }
-    }
+    simt_s_tile<DP>(qs, ks, ty, tx, s);
 
     const int jt0 = j_begin + t * kTileJ;
     // optional logits materialisation (models/contrastive.py:498: logits / T)
@@ -184,29 +136,7 @@ __global__ void __launch_bounds__(kSimtThreads, 1) infonce_simt_kernel(const Inf
         acc[ii][cc].z *= alpha[ii];
         acc[ii][cc].w *= alpha[ii];
       }
-#pragma unroll 2
-    for (int j0 = 0; j0 < kTileJ; j0 += 4) {
-      float4 pv[4];
-#pragma unroll
-      for (int ii = 0; ii < 4; ++ii) pv[ii] = *reinterpret_cast<const float4*>(ps + (ty * 4 + ii) * kPsStride + j0);
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        float4 kv[CC];
-#pragma unroll
-        for (int cc = 0; cc < CC; ++cc) kv[cc] = *reinterpret_cast<const float4*>(ks + (j0 + jj) * KS + tx * 4 + 64 * cc);
-#pragma unroll
-        for (int ii = 0; ii < 4; ++ii) {
-          const float pj = jj == 0 ? pv[ii].x : jj == 1 ? pv[ii].y : jj == 2 ? pv[ii].z : pv[ii].w;
-#pragma unroll
-          for (int cc = 0; cc < CC; ++cc) {
-            acc[ii][cc].x = fmaf(pj, kv[cc].x, acc[ii][cc].x);
-            acc[ii][cc].y = fmaf(pj, kv[cc].y, acc[ii][cc].y);
-            acc[ii][cc].z = fmaf(pj, kv[cc].z, acc[ii][cc].z);
-            acc[ii][cc].w = fmaf(pj, kv[cc].w, acc[ii][cc].w);
-          }
-        }
-      }
-    }
+    simt_pv_tile<DP>(ps, ks, ty, tx, acc);
     __syncthreads();
   }
 

@@ -1,0 +1,315 @@
+// K6 — SimCLR NT-Xent over THIS rank's rows against all gathered columns
+// (replaces models/contrastive.py:770-792 and the gradient bookkeeping of
+//  AllGatherWithGradient, utils/distributed.py:131-155).
+//
+//   out = [q_all ; q2_all]  (2N unit rows),  s_rc = out_r . out_c / T
+//   Z_r  = sum_{c != r} e^{s_rc - 1/T}                       (pass 1, "rowsum")
+//   loss = mean_r( log Z_r + 1/T - s_{r,r+} )                 (r+ = partner row)
+//   G_r  = [ sum_{c != r} e^{s_rc-1/T} (1/Z_r + 1/Z_c) out_c - 2 out_{r+} ] / (2N T)   (pass 2)
+//
+// The reference materialises the 2N x 2N matrix (and four same-sized temporaries) on
+// every rank; here each rank touches only its 2*B_local rows, never stores a tile of
+// the matrix, and the 1/T shift (|s| <= 1/T for unit rows) keeps exp() in range
+// where the reference's raw exp overflows for T < 0.0113.
+// Both passes are split over column ranges; partials are reduced in a fixed order.
+// CUDA-core kernels (fp32 exact); the tcgen05 variant shares K3's mainloop.
+#include "simt_tile.cuh"
+
+namespace avssl {
+
+constexpr float kLog2eN = 1.4426950408889634f;
+
+struct NtxArgs {
+  const float* out;     // [N2, D] unit rows, global order
+  const int* rows;      // [n_loc] global row ids handled here
+  const float* z_all;   // [N2] (pass 2)
+  int N2, D, n_loc;
+  float inv_T;
+  int n_splits, cols_per_split;
+  float* part_z;        // [n_splits][n_loc]
+  float* part_g;        // [n_splits][n_loc][D]
+};
+
+template <int DP>
+__device__ __forceinline__ void ntx_load_rows(float* qs, const NtxArgs& a, int i_base) {
+  constexpr int KS = DP + 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int r = warp; r < kTileI; r += kSimtThreads / 32) {
+    const int i = i_base + r;
+    const float* src = (i < a.n_loc) ? a.out + (size_t)a.rows[i] * a.D : nullptr;
+    for (int c = lane; c < DP; c += 32) qs[r * KS + c] = (src && c < a.D) ? src[c] : 0.f;
+  }
+}
+
+template <int DP, bool kGrad>
+__global__ void __launch_bounds__(kSimtThreads, 1) ntxent_pass_kernel(const NtxArgs a) {
+  constexpr int KS = DP + 4;
+  constexpr int CC = DP / 64;
+  extern __shared__ __align__(16) float smem[];
+  float* qs = smem;
+  float* ks0 = qs + kTileI * KS;
+  float* ps = ks0 + 2 * kTileJ * KS;  // only when kGrad
+  __shared__ int s_rowid[kTileI];
+  __shared__ float s_invz[kTileI];
+
+  const int tid = threadIdx.x;
+  const int split = blockIdx.x;
+  const int i_base = blockIdx.y * kTileI;
+  const int j_begin = split * a.cols_per_split;
+  const int j_end = min(a.N2, j_begin + a.cols_per_split);
+  const int n_tiles = (j_end - j_begin + kTileJ - 1) / kTileJ;
+
+  if (n_tiles > 0) {
+    load_tile<DP>(ks0, a.out, a.D, j_begin, j_end);
+    cp_async_commit();
+  }
+  ntx_load_rows<DP>(qs, a, i_base);
+  if (tid < kTileI) {
+    const int i = i_base + tid;
+    s_rowid[tid] = i < a.n_loc ? a.rows[i] : -1;
+    if (kGrad) s_invz[tid] = i < a.n_loc ? 1.f / a.z_all[a.rows[i]] : 0.f;
+  }
+
+  const int ty = tid >> 4, tx = tid & 15;
+  const float scale2 = a.inv_T * kLog2eN;
+  float zsum[4] = {0.f, 0.f, 0.f, 0.f};
+  float4 acc[4][CC];
+#pragma unroll
+  for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+    for (int cc = 0; cc < CC; ++cc) acc[ii][cc] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (int t = 0; t < n_tiles; ++t) {
+    float* ks = ks0 + (t & 1) * kTileJ * KS;
+    if (t + 1 < n_tiles) {
+      load_tile<DP>(ks0 + ((t + 1) & 1) * kTileJ * KS, a.out, a.D, j_begin + (t + 1) * kTileJ, j_end);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+
+    float s[4][4];
+    simt_s_tile<DP>(qs, ks, ty, tx, s);
+    const int jt0 = j_begin + t * kTileJ;
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+      const int rid = s_rowid[ty * 4 + ii];
+      const float invz_r = kGrad ? s_invz[ty * 4 + ii] : 0.f;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = jt0 + tx + 16 * jj;
+        const bool valid = (j < j_end) && (j != rid) && (rid >= 0);
+        // e^{(s - 1)/T}: unit rows give s <= 1, so the exponent is <= 0
+        const float e = valid ? exp2f((s[ii][jj] - 1.f) * scale2) : 0.f;
+        if (kGrad) {
+          const float w = valid ? e * (invz_r + 1.f / a.z_all[j]) : 0.f;
+          ps[(ty * 4 + ii) * kPsStride + tx + 16 * jj] = w;
+        } else {
+          zsum[ii] += e;
+        }
+      }
+    }
+    if (kGrad) {
+      __syncthreads();
+      simt_pv_tile<DP>(ps, ks, ty, tx, acc);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int ii = 0; ii < 4; ++ii) {
+    const int i = i_base + ty * 4 + ii;
+    if (kGrad) {
+      if (i < a.n_loc) {
+#pragma unroll
+        for (int cc = 0; cc < CC; ++cc) {
+          const int c = tx * 4 + 64 * cc;
+          if (c < a.D) *reinterpret_cast<float4*>(a.part_g + ((size_t)split * a.n_loc + i) * a.D + c) = acc[ii][cc];
+        }
+      }
+    } else {
+      float z = zsum[ii];
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+      if (tx == 0 && i < a.n_loc) a.part_z[(size_t)split * a.n_loc + i] = z;
+    }
+  }
+}
+
+__global__ void ntxent_sum_z_kernel(const float* __restrict__ part_z, int n_splits, int n_loc, float* __restrict__ z_loc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_loc) return;
+  float z = 0.f;
+  for (int s = 0; s < n_splits; ++s) z += part_z[(size_t)s * n_loc + i];
+  z_loc[i] = z;
+}
+
+// One warp per local row: merge the gradient partials, subtract the positive term,
+// apply 1/(2N T) and the world-size factor, then chain through the l2-normalisation.
+__global__ void __launch_bounds__(256)
+ntxent_combine_kernel(const NtxArgs a, const float* __restrict__ norm_loc, float gscale, float* __restrict__ dfeat) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= a.n_loc) return;
+  const int r = a.rows[i];
+  const int half = a.N2 / 2;
+  const int rp = r < half ? r + half : r - half;
+  const float* o = a.out + (size_t)r * a.D;
+  const float* op = a.out + (size_t)rp * a.D;
+  float dot = 0.f;
+  for (int c = lane; c < a.D; c += 32) {
+    float g = 0.f;
+    for (int s = 0; s < a.n_splits; ++s) g += a.part_g[((size_t)s * a.n_loc + i) * a.D + c];
+    g = (g - 2.f * op[c]) * gscale;
+    dot = fmaf(g, o[c], dot);
+  }
+  dot = warp_sum(dot);
+  const float nrm = norm_loc[i];
+  for (int c = lane; c < a.D; c += 32) {
+    float g = 0.f;
+    for (int s = 0; s < a.n_splits; ++s) g += a.part_g[((size_t)s * a.n_loc + i) * a.D + c];
+    g = (g - 2.f * op[c]) * gscale;
+    dfeat[(size_t)i * a.D + c] = (g - dot * o[c]) / nrm;
+  }
+}
+
+// loss = mean_r( log Z_r + 1/T - out_r . out_{r+} / T ) over all 2N rows.
+__global__ void __launch_bounds__(256)
+ntxent_loss_kernel(const float* __restrict__ out, const float* __restrict__ z_all, int N2, int D, float inv_T,
+                   float* loss_out, float* row_term, unsigned* counter) {
+  __shared__ float s_red[32];
+  __shared__ unsigned s_last;
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r < N2) {
+    const int half = N2 / 2;
+    const int rp = r < half ? r + half : r - half;
+    float dot = 0.f;
+    for (int c = lane; c < D; c += 32) dot = fmaf(out[(size_t)r * D + c], out[(size_t)rp * D + c], dot);
+    dot = warp_sum(dot);
+    if (lane == 0) row_term[r] = logf(z_all[r]) + inv_T - dot * inv_T;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    float tot = 0.f;
+    for (int i = threadIdx.x; i < N2; i += blockDim.x) tot += reinterpret_cast<volatile float*>(row_term)[i];
+    tot = block_sum(tot, s_red);
+    if (threadIdx.x == 0) {
+      *loss_out = tot / (float)N2;
+      *counter = 0u;
+    }
+  }
+}
+
+template <int DP, bool kGrad>
+static int launch_pass(const NtxArgs& a, cudaStream_t s) {
+  const size_t smem = simt_smem_bytes(DP, kGrad);
+  static bool configured = false;
+  if (!configured) {
+    AVSSL_CUDA_OK(cudaFuncSetAttribute(ntxent_pass_kernel<DP, kGrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  dim3 grid(a.n_splits, (a.n_loc + kTileI - 1) / kTileI);
+  ntxent_pass_kernel<DP, kGrad><<<grid, kSimtThreads, smem, s>>>(a);
+  AVSSL_LAUNCH_OK("ntxent_pass_kernel");
+  return AVSSL_OK;
+}
+
+template <bool kGrad>
+static int launch_pass_d(const NtxArgs& a, cudaStream_t s) {
+  if (a.D <= 64) return launch_pass<64, kGrad>(a, s);
+  if (a.D <= 128) return launch_pass<128, kGrad>(a, s);
+  return launch_pass<256, kGrad>(a, s);
+}
+
+static int plan_splits(int N2, int n_loc, int* n_splits, int* cols_per_split) {
+  int sms = sm_count();
+  if (sms <= 0) return -1;
+  const int row_blocks = (n_loc + kTileI - 1) / kTileI;
+  const int n_tiles = (N2 + kTileJ - 1) / kTileJ;
+  int S = (2 * sms + row_blocks - 1) / row_blocks;
+  if (S < 1) S = 1;
+  if (S > n_tiles) S = n_tiles;
+  if (S > 64) S = 64;
+  const int tps = (n_tiles + S - 1) / S;
+  *n_splits = (n_tiles + tps - 1) / tps;
+  *cols_per_split = tps * kTileJ;
+  return 0;
+}
+
+}  // namespace avssl
+
+using namespace avssl;
+
+extern "C" size_t avssl_ntxent_workspace_bytes(int N2, int D, int n_loc) {
+  if (N2 <= 0 || D <= 0 || n_loc <= 0) return 0;
+  // counter | row_term[N2] | part_z[64][n_loc] | part_g[64][n_loc][D]
+  return 256 + 4 * ((size_t)N2 + 64) + 4 * 64 * ((size_t)n_loc + 64) + 4 * 64 * (size_t)n_loc * D + 1024;
+}
+
+static int ntx_setup(NtxArgs& a, const float* out, const int* rows, const float* z_all, int N2, int D, int n_loc,
+                     float T, void* workspace, size_t workspace_bytes, const char* who) {
+  AVSSL_REQUIRE(out && rows && workspace, AVSSL_ERR_INVALID_ARGUMENT, "%s: null pointer", who);
+  AVSSL_REQUIRE(N2 > 0 && (N2 % 2) == 0 && n_loc > 0 && n_loc <= N2 && T > 0.f, AVSSL_ERR_INVALID_ARGUMENT,
+                "%s: bad sizes N2=%d n_loc=%d", who, N2, n_loc);
+  AVSSL_REQUIRE(D % 4 == 0 && D >= 4 && D <= 256, AVSSL_ERR_UNSUPPORTED, "%s: D=%d unsupported (D %% 4 == 0, D <= 256)", who, D);
+  AVSSL_REQUIRE(workspace_bytes >= avssl_ntxent_workspace_bytes(N2, D, n_loc), AVSSL_ERR_WORKSPACE, "%s: workspace too small", who);
+  a.out = out;
+  a.rows = rows;
+  a.z_all = z_all;
+  a.N2 = N2;
+  a.D = D;
+  a.n_loc = n_loc;
+  a.inv_T = 1.f / T;
+  AVSSL_REQUIRE(plan_splits(N2, n_loc, &a.n_splits, &a.cols_per_split) == 0, AVSSL_ERR_CUDA, "%s: no CUDA device", who);
+  char* w = static_cast<char*>(workspace);
+  size_t off = 256 + 4 * ((size_t)N2 + 64);
+  off = (off + 255) / 256 * 256;
+  a.part_z = reinterpret_cast<float*>(w + off);
+  off += 4 * 64 * ((size_t)n_loc + 64);
+  off = (off + 255) / 256 * 256;
+  a.part_g = reinterpret_cast<float*>(w + off);
+  return AVSSL_OK;
+}
+
+extern "C" int avssl_ntxent_rowsum(const float* out, const int* rows, int N2, int D, int n_loc, float T,
+                                   float* z_loc_out, void* workspace, size_t workspace_bytes, void* stream) {
+  NtxArgs a;
+  int rc = ntx_setup(a, out, rows, nullptr, N2, D, n_loc, T, workspace, workspace_bytes, "ntxent_rowsum");
+  if (rc) return rc;
+  AVSSL_REQUIRE(z_loc_out, AVSSL_ERR_INVALID_ARGUMENT, "ntxent_rowsum: null output");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  rc = launch_pass_d<false>(a, s);
+  if (rc) return rc;
+  ntxent_sum_z_kernel<<<(n_loc + 255) / 256, 256, 0, s>>>(a.part_z, a.n_splits, n_loc, z_loc_out);
+  AVSSL_LAUNCH_OK("ntxent_sum_z_kernel");
+  return AVSSL_OK;
+}
+
+extern "C" int avssl_ntxent_grad(const float* out, const int* rows, const float* z_all, const float* norm_loc, int N2,
+                                 int D, int n_loc, float T, float grad_scale, float* loss_out, float* dfeat_out,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  NtxArgs a;
+  int rc = ntx_setup(a, out, rows, z_all, N2, D, n_loc, T, workspace, workspace_bytes, "ntxent_grad");
+  if (rc) return rc;
+  AVSSL_REQUIRE(z_all && norm_loc && loss_out && dfeat_out, AVSSL_ERR_INVALID_ARGUMENT, "ntxent_grad: null pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  rc = launch_pass_d<true>(a, s);
+  if (rc) return rc;
+  const float gscale = grad_scale * a.inv_T / (float)N2;
+  ntxent_combine_kernel<<<(n_loc + 7) / 8, 256, 0, s>>>(a, norm_loc, gscale, dfeat_out);
+  AVSSL_LAUNCH_OK("ntxent_combine_kernel");
+  unsigned* counter = static_cast<unsigned*>(workspace);
+  float* row_term = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
+  ntxent_loss_kernel<<<(N2 + 7) / 8, 256, 0, s>>>(out, z_all, N2, D, a.inv_T, loss_out, row_term, counter);
+  AVSSL_LAUNCH_OK("ntxent_loss_kernel");
+  return AVSSL_OK;
+}

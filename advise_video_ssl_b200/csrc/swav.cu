@@ -1,0 +1,293 @@
+// K10 / K11 — SwAV: single-launch Sinkhorn-Knopp and the fused soft-target
+// cross-entropy (forward + backward).
+//   sinkhorn            models/contrastive.py:872-887 (+ exp(out/eps).t(), :665-666)
+//   swap-prediction CE  models/contrastive.py:672-679, KLDivLoss :912-916
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace avssl {
+
+// ------------------------------------------------------------------ Sinkhorn-Knopp
+// The reference rewrites the whole [P, B] matrix ~2 times per iteration (~25 launches
+// per call).  Sinkhorn only ever rescales rows and columns, so the result is
+//     code[b][k] = alpha_k * Q0[b][k] * beta_b,   Q0 = exp(score / eps)
+// and the iterations only update the two scaling vectors:
+//     row step: alpha_k = (1/P) / sum_b Q0[b][k] beta_b
+//     col step: beta_b  = (1/B) / sum_k alpha_k Q0[b][k]
+//     final   : beta_b  =   1   / sum_k alpha_k Q0[b][k]
+// (the initial Q /= sum(Q) is a uniform scale that the first row step removes).
+// One cooperative launch: every CTA keeps its samples' Q0 rows resident in shared
+// memory for all passes; column sums are CTA-local (warp-shuffle reductions), row sums
+// are combined across CTAs through a [grid][P] scratch and two grid barriers per
+// iteration, in a fixed order (deterministic).
+struct SinkArgs {
+  const float* scores;  // [Btot, P]
+  int Btot, P;
+  float inv_eps;
+  int iters, keep_last;
+  float* out;           // [keep_last, P]
+  float* g_part;        // [grid][P]
+  float* g_alpha;       // [P]
+  unsigned* bar;        // [2] count, generation (zero-initialised once)
+  int spc;              // samples per CTA
+  int slab_in_smem;
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    volatile unsigned* gen = bar + 1;
+    const unsigned g = *gen;
+    __threadfence();
+    if (atomicAdd(bar, 1u) == nblocks - 1) {
+      bar[0] = 0u;
+      __threadfence();
+      atomicAdd(bar + 1, 1u);
+    } else {
+      while (*gen == g) {
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256, 1) sinkhorn_kernel(const SinkArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  float* alpha = sm;                 // [P]
+  float* beta = alpha + a.P;         // [spc]
+  float* slab = beta + ((a.spc + 3) & ~3);  // [spc][P] when it fits
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int b0 = blockIdx.x * a.spc;
+  const int nb = max(0, min(a.spc, a.Btot - b0));
+  const int P = a.P;
+
+  // Q0 rows of this CTA
+  if (a.slab_in_smem) {
+    for (int b = 0; b < nb; ++b) {
+      const float* src = a.scores + (size_t)(b0 + b) * P;
+      for (int k = tid; k < P; k += blockDim.x) slab[b * P + k] = expf(src[k] * a.inv_eps);
+    }
+  }
+  for (int b = tid; b < nb; b += blockDim.x) beta[b] = 1.f;
+  for (int k = tid; k < P; k += blockDim.x) alpha[k] = 1.f;
+  __syncthreads();
+  auto q0 = [&](int b, int k) -> float {
+    return a.slab_in_smem ? slab[b * P + k] : expf(a.scores[(size_t)(b0 + b) * P + k] * a.inv_eps);
+  };
+
+  const float r = 1.f / (float)P, c = 1.f / (float)a.Btot;
+  const int kp = (P + gridDim.x - 1) / gridDim.x;
+  for (int it = 0; it < a.iters; ++it) {
+    // row step, part 1: partial row sums over this CTA's samples
+    for (int k = tid; k < P; k += blockDim.x) {
+      float s = 0.f;
+      for (int b = 0; b < nb; ++b) s = fmaf(q0(b, k), beta[b], s);
+      a.g_part[(size_t)blockIdx.x * P + k] = s;
+    }
+    grid_barrier(a.bar, gridDim.x);
+    // row step, part 2: this CTA finishes a slice of k (one warp per k, lanes over CTAs)
+    for (int kk = warp; kk < kp; kk += nw) {
+      const int k = blockIdx.x * kp + kk;
+      if (k < P) {
+        float s = 0.f;
+        for (int g = lane; g < (int)gridDim.x; g += 32) s += __ldcg(a.g_part + (size_t)g * P + k);
+        s = warp_sum(s);
+        if (lane == 0) a.g_alpha[k] = r / s;
+      }
+    }
+    grid_barrier(a.bar, gridDim.x);
+    for (int k = tid; k < P; k += blockDim.x) alpha[k] = __ldcg(a.g_alpha + k);
+    __syncthreads();
+    if (it < a.iters - 1) {
+      // col step (local): one warp per sample
+      for (int b = warp; b < nb; b += nw) {
+        float s = 0.f;
+        for (int k = lane; k < P; k += 32) s = fmaf(alpha[k], q0(b, k), s);
+        s = warp_sum(s);
+        if (lane == 0) beta[b] = c / s;
+      }
+      __syncthreads();
+    }
+  }
+  // final column normalisation + output of the kept rows
+  const int first_keep = a.Btot - a.keep_last;
+  for (int b = warp; b < nb; b += nw) {
+    const int gb = b0 + b;
+    if (gb < first_keep) continue;
+    float s = 0.f;
+    for (int k = lane; k < P; k += 32) s = fmaf(alpha[k], q0(b, k), s);
+    s = warp_sum(s);
+    const float bb = 1.f / s;
+    float* dst = a.out + (size_t)(gb - first_keep) * P;
+    for (int k = lane; k < P; k += 32) dst[k] = alpha[k] * q0(b, k) * bb;
+  }
+}
+
+// ------------------------------------------------------- soft-target cross-entropy
+// One CTA per score row (crop v, sample r).  For every code set `a` with weight
+// w[a][v] != 0:   loss += w * ( lse * sum_k code - sum_k code * s/T )
+//                 dscore[k] += w * ( softmax_k * sum_k code - code_k ) / T
+// (log(softmax(.)) of the reference == s/T - lse.)
+constexpr int kMaxAssign = 4, kMaxCrops = 16;
+struct SwavCeArgs {
+  const float* scores;  // [n_crops*bs, P]
+  const float* codes;   // [n_assign, bs, P]
+  int n_crops, n_assign, bs, P;
+  float inv_T;
+  float w[kMaxAssign * kMaxCrops];
+  float* loss_out;
+  float* dscores;       // may be null
+  float* row_loss;      // [n_crops*bs]
+  unsigned* counter;
+};
+
+__global__ void __launch_bounds__(256) swav_ce_kernel(const SwavCeArgs a) {
+  __shared__ float s_red[32];
+  __shared__ unsigned s_last;
+  const int row = blockIdx.x;
+  const int v = row / a.bs, r = row % a.bs;
+  const int P = a.P, tid = threadIdx.x;
+  const float* s = a.scores + (size_t)row * P;
+
+  float mx = -INFINITY;
+  for (int k = tid; k < P; k += blockDim.x) mx = fmaxf(mx, s[k] * a.inv_T);
+  mx = warp_max(mx);
+  __syncthreads();
+  if ((tid & 31) == 0) s_red[tid >> 5] = mx;
+  __syncthreads();
+  mx = s_red[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, s_red[w]);
+  float se = 0.f;
+  for (int k = tid; k < P; k += blockDim.x) se += expf(s[k] * a.inv_T - mx);
+  se = block_sum(se, s_red);
+  const float lse = mx + logf(se);
+
+  float loss = 0.f, wsum = 0.f;  // wsum = sum_a w * sum_k code
+  for (int as = 0; as < a.n_assign; ++as) {
+    const float w = a.w[as * a.n_crops + v];
+    if (w == 0.f) continue;
+    const float* code = a.codes + ((size_t)as * a.bs + r) * P;
+    float dot = 0.f, sq = 0.f;
+    for (int k = tid; k < P; k += blockDim.x) {
+      const float cq = code[k];
+      dot = fmaf(cq, s[k] * a.inv_T, dot);
+      sq += cq;
+    }
+    dot = block_sum(dot, s_red);
+    sq = block_sum(sq, s_red);
+    loss += w * (lse * sq - dot);
+    wsum += w * sq;
+  }
+  if (a.dscores) {
+    float* d = a.dscores + (size_t)row * P;
+    for (int k = tid; k < P; k += blockDim.x) {
+      float g = expf(s[k] * a.inv_T - lse) * wsum;
+      for (int as = 0; as < a.n_assign; ++as) {
+        const float w = a.w[as * a.n_crops + v];
+        if (w != 0.f) g -= w * a.codes[((size_t)as * a.bs + r) * P + k];
+      }
+      d[k] = g * a.inv_T;
+    }
+  }
+  if (tid == 0) a.row_loss[row] = loss;
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    s_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    float tot = 0.f;
+    const int n = a.n_crops * a.bs;
+    for (int i = tid; i < n; i += blockDim.x) tot += reinterpret_cast<volatile float*>(a.row_loss)[i];
+    tot = block_sum(tot, s_red);
+    if (tid == 0) {
+      *a.loss_out = tot;
+      *a.counter = 0u;
+    }
+  }
+}
+
+}  // namespace avssl
+
+using namespace avssl;
+
+static int sink_grid(int Btot) {
+  int sms = sm_count();
+  if (sms <= 0) return -1;
+  return Btot < sms ? Btot : sms;
+}
+
+extern "C" size_t avssl_sinkhorn_workspace_bytes(int Btot, int P) {
+  if (Btot <= 0 || P <= 0) return 0;
+  int g = sink_grid(Btot);
+  if (g <= 0) {
+    cudaGetLastError();
+    g = Btot < 148 ? Btot : 148;
+  }
+  return 256 + 4 * (size_t)P + 256 + 4 * (size_t)g * P + 256;
+}
+
+extern "C" int avssl_sinkhorn(const float* scores, int Btot, int P, float eps, int iters, int keep_last,
+                              float* codes_out, void* workspace, size_t workspace_bytes, void* stream) {
+  AVSSL_REQUIRE(scores && codes_out && workspace, AVSSL_ERR_INVALID_ARGUMENT, "sinkhorn: null pointer");
+  AVSSL_REQUIRE(Btot > 0 && P > 0 && eps > 0.f && iters >= 0 && keep_last > 0 && keep_last <= Btot,
+                AVSSL_ERR_INVALID_ARGUMENT, "sinkhorn: bad arguments Btot=%d P=%d keep=%d", Btot, P, keep_last);
+  const int grid = sink_grid(Btot);
+  AVSSL_REQUIRE(grid > 0, AVSSL_ERR_CUDA, "sinkhorn: no CUDA device (there is no CPU fallback)");
+  AVSSL_REQUIRE(workspace_bytes >= avssl_sinkhorn_workspace_bytes(Btot, P), AVSSL_ERR_WORKSPACE, "sinkhorn: workspace too small");
+  SinkArgs a;
+  a.scores = scores;
+  a.Btot = Btot;
+  a.P = P;
+  a.inv_eps = 1.f / eps;
+  a.iters = iters;
+  a.keep_last = keep_last;
+  a.out = codes_out;
+  char* w = static_cast<char*>(workspace);
+  a.bar = reinterpret_cast<unsigned*>(w);
+  a.g_alpha = reinterpret_cast<float*>(w + 256);
+  a.g_part = reinterpret_cast<float*>(w + 256 + ((4 * (size_t)P + 255) / 256) * 256);
+  a.spc = (Btot + grid - 1) / grid;
+  const int grid_used = (Btot + a.spc - 1) / a.spc;
+  const size_t fixed = sizeof(float) * ((size_t)P + ((a.spc + 3) & ~3));
+  const size_t slab = sizeof(float) * (size_t)a.spc * P;
+  a.slab_in_smem = (fixed + slab <= 200 * 1024) ? 1 : 0;
+  const size_t smem = fixed + (a.slab_in_smem ? slab : 0);
+  AVSSL_REQUIRE(fixed <= 200 * 1024, AVSSL_ERR_UNSUPPORTED, "sinkhorn: P=%d too large", P);
+  AVSSL_CUDA_OK(cudaFuncSetAttribute(sinkhorn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+  void* args[] = {&a};
+  AVSSL_CUDA_OK(cudaLaunchCooperativeKernel((void*)sinkhorn_kernel, dim3(grid_used), dim3(256), args, smem,
+                                            static_cast<cudaStream_t>(stream)));
+  return AVSSL_OK;
+}
+
+extern "C" size_t avssl_swav_ce_workspace_bytes(int n_rows) { return 256 + 4 * (size_t)(n_rows > 0 ? n_rows : 0); }
+
+extern "C" int avssl_swav_ce_fwd_bwd(const float* scores, const float* codes, int n_crops, int n_assign, int bs, int P,
+                                     float T, const float* pair_w_host, float* loss_out, float* dscores_out,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
+  AVSSL_REQUIRE(scores && codes && pair_w_host && loss_out && workspace, AVSSL_ERR_INVALID_ARGUMENT, "swav_ce: null pointer");
+  AVSSL_REQUIRE(n_crops > 0 && n_crops <= kMaxCrops && n_assign > 0 && n_assign <= kMaxAssign && bs > 0 && P > 0 && T > 0.f,
+                AVSSL_ERR_INVALID_ARGUMENT, "swav_ce: bad sizes (n_crops <= %d, n_assign <= %d)", kMaxCrops, kMaxAssign);
+  AVSSL_REQUIRE(workspace_bytes >= avssl_swav_ce_workspace_bytes(n_crops * bs), AVSSL_ERR_WORKSPACE, "swav_ce: workspace too small");
+  SwavCeArgs a;
+  a.scores = scores;
+  a.codes = codes;
+  a.n_crops = n_crops;
+  a.n_assign = n_assign;
+  a.bs = bs;
+  a.P = P;
+  a.inv_T = 1.f / T;
+  for (int i = 0; i < kMaxAssign * kMaxCrops; ++i) a.w[i] = i < n_assign * n_crops ? pair_w_host[i] : 0.f;
+  a.loss_out = loss_out;
+  a.dscores = dscores_out;
+  a.counter = static_cast<unsigned*>(workspace);
+  a.row_loss = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
+  swav_ce_kernel<<<n_crops * bs, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  AVSSL_LAUNCH_OK("swav_ce_kernel");
+  return AVSSL_OK;
+}

@@ -172,3 +172,242 @@ def queue_enqueue(queue, ptr, keys, status=None):
     check(lib.avssl_queue_enqueue(queue.data_ptr(), ptr.data_ptr(), keys.data_ptr(), n, K, D,
                                   status.data_ptr() if status is not None else None, _stream()),
           "avssl_queue_enqueue")
+
+
+# ------------------------------------------------------------------------ K5 / K14
+def _bank_dims(bank):
+    if bank.dim() == 3:
+        return bank.shape[0], bank.shape[1], bank.shape[2]
+    if bank.dim() == 2:
+        return bank.shape[0], 1, bank.shape[1]
+    raise ValueError("bank must be [L, duration, D] or [L, D]")
+
+
+def membank_update(bank, mem, ind, time, momentum, interp=False, status=None):
+    """bank[ind, time] <- l2norm(mem*m + old*(1-m)); last duplicate wins (K5)."""
+    _req(bank, "bank")
+    L, dur, D = _bank_dims(bank)
+    mem = _req(mem.reshape(mem.shape[0], -1), "mem")
+    if mem.shape[1] != D:
+        raise ValueError("mem dim %d != bank dim %d" % (mem.shape[1], D))
+    n = mem.shape[0]
+    ind = _req(ind.reshape(-1).long().contiguous(), "ind", torch.int64)
+    if ind.numel() != n:
+        raise ValueError("ind has %d entries for %d rows" % (ind.numel(), n))
+    ti = tf = None
+    if interp:
+        tf = _req(time.reshape(-1).float().contiguous(), "time", _f32)
+    elif time is not None:
+        ti = _req(time.reshape(-1).long().contiguous(), "time", torch.int64)
+    if status is not None:
+        _req(status, "status", torch.int32)
+    m = float(momentum)
+    check(lib.avssl_membank_update(bank.data_ptr(), L, dur, D, mem.data_ptr(), ind.data_ptr(),
+                                   ti.data_ptr() if ti is not None else None,
+                                   tf.data_ptr() if tf is not None else None, n, m, 1.0 - m,
+                                   1 if interp else 0, status.data_ptr() if status is not None else None,
+                                   _stream()), "avssl_membank_update")
+
+
+def membank_gather_dot(bank, q, ind, time, T, interp=False, status=None):
+    """prod[n,k] = q_n . bank[ind[n,k], time[n,k]] / T (K14)."""
+    _req(bank, "bank")
+    _req(q, "q")
+    L, dur, D = _bank_dims(bank)
+    B = q.shape[0]
+    ind = _req(ind.reshape(B, -1).long().contiguous(), "ind", torch.int64)
+    Kp = ind.shape[1]
+    ti = tf = None
+    if interp:
+        tf = _req(time.reshape(B, -1).float().contiguous(), "time", _f32)
+    elif time is not None:
+        ti = _req(time.reshape(B, -1).long().contiguous(), "time", torch.int64)
+    prod = torch.empty(B, Kp, dtype=_f32, device=q.device)
+    check(lib.avssl_membank_gather_dot(bank.data_ptr(), L, dur, D, q.data_ptr(), ind.data_ptr(),
+                                       ti.data_ptr() if ti is not None else None,
+                                       tf.data_ptr() if tf is not None else None, B, Kp, float(T),
+                                       1 if interp else 0, prod.data_ptr(),
+                                       status.data_ptr() if status is not None else None, _stream()),
+          "avssl_membank_gather_dot")
+    return prod
+
+
+# ------------------------------------------------------------------------- K2 / K7
+def l2norm_fwd(x, eps=0.0):
+    _req(x, "x")
+    n, D = x.shape
+    y = torch.empty_like(x)
+    nrm = torch.empty(n, dtype=_f32, device=x.device)
+    check(lib.avssl_l2norm_fwd(x.data_ptr(), n, D, float(eps), y.data_ptr(), nrm.data_ptr(), _stream()),
+          "avssl_l2norm_fwd")
+    return y, nrm
+
+
+def l2norm_bwd(y, nrm, dy, eps=0.0):
+    _req(y, "y")
+    _req(nrm, "norm")
+    dy = _req(dy.contiguous(), "dy")
+    n, D = y.shape
+    dx = torch.empty_like(y)
+    check(lib.avssl_l2norm_bwd(y.data_ptr(), nrm.data_ptr(), dy.data_ptr(), n, D, float(eps), dx.data_ptr(),
+                               _stream()), "avssl_l2norm_bwd")
+    return dx
+
+
+def byol_simloss(pred, key, T, normalize=True, want_grad=True):
+    """loss = -mean(p.k)/T with p = pred/||pred|| when `normalize` (K7). Returns (loss[1], dpred|None)."""
+    _req(pred, "pred")
+    _req(key, "key")
+    if pred.shape != key.shape or pred.dim() != 2:
+        raise ValueError("pred and key must both be [B, D]")
+    n, D = pred.shape
+    loss = torch.empty(1, dtype=_f32, device=pred.device)
+    dpred = torch.empty_like(pred) if want_grad else None
+    ws = _workspace(pred.device, lib.avssl_byol_simloss_workspace_bytes(n))
+    check(lib.avssl_byol_simloss_fwd_bwd(pred.data_ptr(), key.data_ptr(), n, D, float(T), 1 if normalize else 0,
+                                         loss.data_ptr(), dpred.data_ptr() if want_grad else None,
+                                         ws.data_ptr(), ws.numel(), _stream()), "avssl_byol_simloss_fwd_bwd")
+    return loss, dpred
+
+
+def ce_target0_fwd(logits):
+    """Mean cross-entropy against class 0 (ContrastiveLoss). Returns (loss[1], row_lse[n])."""
+    _req(logits, "logits")
+    n, C = logits.shape
+    loss = torch.empty(1, dtype=_f32, device=logits.device)
+    lse = torch.empty(n, dtype=_f32, device=logits.device)
+    ws = _workspace(logits.device, lib.avssl_ce_target0_workspace_bytes(n))
+    check(lib.avssl_ce_target0_fwd(logits.data_ptr(), n, C, loss.data_ptr(), lse.data_ptr(), ws.data_ptr(),
+                                   ws.numel(), _stream()), "avssl_ce_target0_fwd")
+    return loss, lse
+
+
+def ce_target0_bwd(logits, lse, grad_out):
+    _req(logits, "logits")
+    _req(lse, "row_lse")
+    g = _req(grad_out.reshape(1).contiguous(), "grad_out")
+    n, C = logits.shape
+    d = torch.empty_like(logits)
+    check(lib.avssl_ce_target0_bwd(logits.data_ptr(), lse.data_ptr(), n, C, g.data_ptr(), d.data_ptr(), _stream()),
+          "avssl_ce_target0_bwd")
+    return d
+
+
+# ----------------------------------------------------------------------------- K6
+def ntxent(feat1, feat2, T, gather=None):
+    """SimCLR NT-Xent (K6) with the cross-rank gather (C4) and the reduce-scatter-
+    equivalent gradient (C5) folded in.  feat1/feat2: this rank's raw [B, D] features.
+    Returns (loss[1], dfeat1, dfeat2); the gradients carry the reference's world-size
+    factor (utils/distributed.py:142-155)."""
+    import torch.distributed as dist
+    _req(feat1, "feat1")
+    _req(feat2, "feat2")
+    if feat1.shape != feat2.shape or feat1.dim() != 2:
+        raise ValueError("feat1 and feat2 must both be [B, D]")
+    B, D = feat1.shape
+    dev = feat1.device
+    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    if gather is None:
+        gather = world > 1
+    if not gather:
+        world = 1
+    rank = dist.get_rank() if world > 1 else 0
+    y, nrm = l2norm_fwd(torch.cat([feat1, feat2], 0), 0.0)  # [2B, D] unit rows, local
+    if world > 1:
+        allq = torch.empty(world, 2, B, D, dtype=_f32, device=dev)
+        dist.all_gather_into_tensor(allq.view(world * 2 * B, D), y)
+        out = allq.permute(1, 0, 2, 3).reshape(2 * world * B, D).contiguous()  # [q_all ; q2_all]
+    else:
+        out = y
+    N = world * B
+    rows = torch.cat([torch.arange(rank * B, (rank + 1) * B, dtype=torch.int32, device=dev),
+                      torch.arange(N + rank * B, N + (rank + 1) * B, dtype=torch.int32, device=dev)])
+    n_loc = 2 * B
+    ws = _workspace(dev, lib.avssl_ntxent_workspace_bytes(2 * N, D, n_loc))
+    z_loc = torch.empty(n_loc, dtype=_f32, device=dev)
+    check(lib.avssl_ntxent_rowsum(out.data_ptr(), rows.data_ptr(), 2 * N, D, n_loc, float(T), z_loc.data_ptr(),
+                                  ws.data_ptr(), ws.numel(), _stream()), "avssl_ntxent_rowsum")
+    if world > 1:
+        zg = torch.empty(world, 2, B, dtype=_f32, device=dev)
+        dist.all_gather_into_tensor(zg.view(-1), z_loc)
+        z_all = zg.permute(1, 0, 2).reshape(-1).contiguous()
+    else:
+        z_all = z_loc
+    loss = torch.empty(1, dtype=_f32, device=dev)
+    dfeat = torch.empty(n_loc, D, dtype=_f32, device=dev)
+    check(lib.avssl_ntxent_grad(out.data_ptr(), rows.data_ptr(), z_all.data_ptr(), nrm.data_ptr(), 2 * N, D, n_loc,
+                                float(T), float(world), loss.data_ptr(), dfeat.data_ptr(), ws.data_ptr(),
+                                ws.numel(), _stream()), "avssl_ntxent_grad")
+    return loss, dfeat[:B], dfeat[B:]
+
+
+# ---------------------------------------------------------------------- K10 / K11
+def sinkhorn(scores, eps, iters, keep_last=None):
+    """codes = sinkhorn(exp(scores/eps)) (K10).  scores [Btot, P]; returns the last
+    `keep_last` rows (default all), each summing to 1."""
+    _req(scores, "scores")
+    Btot, P = scores.shape
+    keep = Btot if keep_last is None else int(keep_last)
+    out = torch.empty(keep, P, dtype=_f32, device=scores.device)
+    ws = _workspace(scores.device, lib.avssl_sinkhorn_workspace_bytes(Btot, P))
+    check(lib.avssl_sinkhorn(scores.data_ptr(), Btot, P, float(eps), int(iters), keep, out.data_ptr(),
+                             ws.data_ptr(), ws.numel(), _stream()), "avssl_sinkhorn")
+    return out
+
+
+def sinkhorn_distributed(Q, iters):
+    """distributed_sinkhorn (models/contrastive.py:889-910), multi-node only
+    (cfg.NUM_SHARDS > 1; never taken on one 8-GPU box).  Q: [P, B_local]
+    = exp(scores/eps)^T on the device.  Cold path: device tensor ops with the row-sum
+    all_reduce between the half-steps; the single-box hot path is `sinkhorn`."""
+    import torch.distributed as dist
+    if not Q.is_cuda:
+        raise RuntimeError("Q must be a CUDA tensor: the contrastive hot path has no CPU fallback")
+    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+    def allsum(t):
+        if world > 1:
+            dist.all_reduce(t)
+        return t
+    Q = Q / allsum(torch.sum(Q))
+    r = 1.0 / Q.shape[0]
+    c = 1.0 / (world * Q.shape[1])
+    cur = allsum(torch.sum(Q, dim=1))
+    for _ in range(iters):
+        Q = Q * (r / cur).unsqueeze(1)
+        Q = Q * (c / torch.sum(Q, dim=0)).unsqueeze(0)
+        cur = allsum(torch.sum(Q, dim=1))
+    return (Q / torch.sum(Q, dim=0, keepdim=True)).t().float()
+
+
+def swav_pair_weights(n_crops, n_assign, bs):
+    """w[a][v] of models/contrastive.py:672-679: mean over bs, /(n_crops-1), /n_assign;
+    assign crop a is crop a (swav_crops_for_assign = arange(2))."""
+    w = np.zeros((n_assign, n_crops), dtype=np.float32)
+    for a in range(n_assign):
+        for v in range(n_crops):
+            if v != a:
+                w[a, v] = 1.0 / (bs * (n_crops - 1) * n_assign)
+    return w
+
+
+def swav_ce(scores, codes, n_crops, bs, T, pair_w=None, want_grad=True):
+    """SwAV swapped-prediction cross-entropy, forward + backward (K11).
+    scores [n_crops*bs, P]; codes [n_assign, bs, P].  Returns (loss[1], dscores|None)."""
+    _req(scores, "scores")
+    codes = _req(codes.contiguous(), "codes")
+    n_assign = codes.shape[0]
+    P = scores.shape[1]
+    if scores.shape[0] != n_crops * bs or tuple(codes.shape[1:]) != (bs, P):
+        raise ValueError("scores %s / codes %s do not match n_crops=%d bs=%d" %
+                         (tuple(scores.shape), tuple(codes.shape), n_crops, bs))
+    if pair_w is None:
+        pair_w = swav_pair_weights(n_crops, n_assign, bs) if n_crops > 1 else np.full((1, 1), 1.0 / bs, np.float32)
+    pair_w = np.ascontiguousarray(pair_w, dtype=np.float32)
+    loss = torch.empty(1, dtype=_f32, device=scores.device)
+    d = torch.empty_like(scores) if want_grad else None
+    ws = _workspace(scores.device, lib.avssl_swav_ce_workspace_bytes(n_crops * bs))
+    check(lib.avssl_swav_ce_fwd_bwd(scores.data_ptr(), codes.data_ptr(), n_crops, n_assign, bs, P, float(T),
+                                    pair_w.ctypes.data, loss.data_ptr(), d.data_ptr() if want_grad else None,
+                                    ws.data_ptr(), ws.numel(), _stream()), "avssl_swav_ce_fwd_bwd")
+    return loss, d

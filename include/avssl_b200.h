@@ -129,6 +129,100 @@ AVSSL_API int avssl_moco_infonce_fwd_bwd(const float* feat_q, const float* const
 AVSSL_API int avssl_queue_enqueue(float* queue, int64_t* ptr_dev, const float* keys, int n, int K, int D,
                         uint32_t* status_dev, void* stream);
 
+/* ----------------------------------------------------- K5: memory-bank update (scatter)
+ * Replaces Memory.update (models/contrastive.py:989-1036), Memory1D.update (:1066-1080)
+ * and knn_mem_update (:131-140), after the all_gather of (mem, ind, time):
+ *   interp == 0:  bank[ind, time] <- l2norm( mem * m + bank[ind, time] * (1 - m) )
+ *   interp != 0:  the two-row time-interpolated update of :995-1026 (float times).
+ * bank is [L, duration, D] (Memory1D: duration = 1).  Indices are applied bit-exactly;
+ * duplicate targets resolve like the reference's CPU index_put (all updates computed
+ * from the old rows, last occurrence wins).  Out-of-range indices set
+ * AVSSL_DEVFLAG_BAD_INDEX in *status_dev and are skipped.  time_i64 may be NULL (= 0).
+ */
+AVSSL_API int avssl_membank_update(float* bank, int64_t L, int duration, int D, const float* mem,
+                         const int64_t* ind, const int64_t* time_i64, const float* time_f32, int n,
+                         float momentum, float one_minus_momentum, int interp, uint32_t* status_dev,
+                         void* stream);
+
+/* ------------------------------------------------- K14: mem-mode logits (fused gather-dot)
+ * Replaces Memory.get + einsum + div (models/contrastive.py:429-433, :966-987):
+ *   prod[n, k] = q_n . bank[ind[n,k], time[n,k]] / T        (never builds [B, K+1, D])
+ */
+AVSSL_API int avssl_membank_gather_dot(const float* bank, int64_t L, int duration, int D, const float* q,
+                             const int64_t* ind, const int64_t* time_i64, const float* time_f32, int B,
+                             int Kp, float T, int interp, float* prod, uint32_t* status_dev, void* stream);
+
+/* --------------------------------------------------------- K2: row l2-normalisation
+ * y = x / max(||x||, eps) per row of x [n, D].  eps = 0 is Normalize
+ * (models/contrastive.py:923-934); eps = 1e-12 is F.normalize (:617-621, :850, :867).
+ * norm_out [n] receives ||x|| (needed by the backward).
+ */
+AVSSL_API int avssl_l2norm_fwd(const float* x, int n, int D, float eps, float* y, float* norm_out, void* stream);
+AVSSL_API int avssl_l2norm_bwd(const float* y, const float* norm, const float* dy, int n, int D, float eps,
+                     float* dx, void* stream);
+
+/* ------------------------------------------------------- K7: BYOL similarity loss
+ * Replaces sim_loss (models/contrastive.py:243-249) fused with the predictor
+ * l2-norm (:533) when normalize != 0:  loss = -mean_n( p_n . key_n ) / T, and
+ * dpred_out (optional) = d loss / d pred.  workspace: zero-filled once, reusable.
+ */
+AVSSL_API size_t avssl_byol_simloss_workspace_bytes(int n);
+AVSSL_API int avssl_byol_simloss_fwd_bwd(const float* pred, const float* key, int n, int D, float T, int normalize,
+                               float* loss_out, float* dpred_out, void* workspace, size_t workspace_bytes,
+                               void* stream);
+
+/* ------------------------------------------ ContrastiveLoss on materialised logits
+ * Replaces ContrastiveLoss.forward (models/losses.py:15-25) for callers that hold a
+ * logits tensor (mem mode, models/contrastive.py:436): mean cross-entropy against
+ * class 0.  bwd: dlogits = (softmax - onehot0) * (*grad_out_dev) / n.
+ */
+AVSSL_API size_t avssl_ce_target0_workspace_bytes(int n);
+AVSSL_API int avssl_ce_target0_fwd(const float* logits, int n, int C, float* loss_out, float* row_lse_out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+AVSSL_API int avssl_ce_target0_bwd(const float* logits, const float* row_lse, int n, int C,
+                         const float* grad_out_dev, float* dlogits, void* stream);
+
+/* ------------------------------------------------------------- K6: SimCLR NT-Xent
+ * Replaces the live SimCLR branch (models/contrastive.py:770-792) and the gradient
+ * bookkeeping of AllGatherWithGradient (utils/distributed.py:131-155), computing
+ * only the rows this rank owns.  out = [q_all ; q2_all] is [N2, D] with unit rows
+ * (already gathered); rows[n_loc] are the global row ids of this rank.
+ *   avssl_ntxent_rowsum : z_loc[i] = sum_{c != r_i} exp((out_r . out_c - 1) / T)
+ *   avssl_ntxent_grad   : given z for ALL rows, loss = mean_r(log z_r + 1/T - s_{r,r+})
+ *       and dfeat[i] = grad_scale * dLoss/dout_{r_i} chained through the row
+ *       l2-normalisation (norm_loc[i] = ||f_i||).  grad_scale = world size reproduces
+ *       the reference's all_reduce(SUM)-then-slice backward.
+ * workspace: avssl_ntxent_workspace_bytes(), zero-filled once, reusable.
+ */
+AVSSL_API size_t avssl_ntxent_workspace_bytes(int N2, int D, int n_loc);
+AVSSL_API int avssl_ntxent_rowsum(const float* out, const int* rows, int N2, int D, int n_loc, float T,
+                        float* z_loc_out, void* workspace, size_t workspace_bytes, void* stream);
+AVSSL_API int avssl_ntxent_grad(const float* out, const int* rows, const float* z_all, const float* norm_loc,
+                      int N2, int D, int n_loc, float T, float grad_scale, float* loss_out,
+                      float* dfeat_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------- K10: Sinkhorn-Knopp
+ * Replaces `q = exp(out / eps).t(); sinkhorn(q.t(), iters)[-keep_last:]`
+ * (models/contrastive.py:665-671, 872-887) with ONE cooperative launch.
+ * scores [Btot, P] are the raw prototype scores; codes_out is [keep_last, P], every
+ * row summing to 1.  workspace: avssl_sinkhorn_workspace_bytes(), zero-filled once.
+ */
+AVSSL_API size_t avssl_sinkhorn_workspace_bytes(int Btot, int P);
+AVSSL_API int avssl_sinkhorn(const float* scores, int Btot, int P, float eps, int iters, int keep_last,
+                   float* codes_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------ K11: SwAV swapped-prediction loss
+ * Replaces models/contrastive.py:672-679 (and KLDivLoss, :912-916), forward and
+ * backward: loss = sum_{a,v} w[a][v] * sum_r ( - sum_k code[a][r][k] *
+ * log softmax(scores[v*bs + r] / T)[k] ).  pair_w_host is the host array
+ * w[n_assign][n_crops] (the reference's 1/(bs (n_crops-1) n_assign) for v != crop(a)).
+ * dscores_out (optional) = d loss / d scores.
+ */
+AVSSL_API size_t avssl_swav_ce_workspace_bytes(int n_rows);
+AVSSL_API int avssl_swav_ce_fwd_bwd(const float* scores, const float* codes, int n_crops, int n_assign, int bs,
+                          int P, float T, const float* pair_w_host, float* loss_out, float* dscores_out,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

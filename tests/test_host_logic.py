@@ -1,0 +1,99 @@
+"""CPU-only tests of the host-side logic: EMA chunk planning, the fp32 arithmetic
+specification of the EMA kernel against the reference's golden vectors, swav pair
+weights, cfg-driven module construction."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import make_cfg, register_backbones
+
+
+def test_ema_plan_table():
+    from advise_video_ssl_b200 import ops
+    numels = [1, 4096, 4097, 0, 10000]
+    base_o, base_h = 0x10000000, 0x20000000
+    optr, hptr, off = [], [], 0
+    for n in numels:
+        optr.append(base_o + 4 * off)
+        hptr.append(base_h + 4 * off)
+        off += n
+    t = ops.ema_plan_table(optr, hptr, numels)
+    assert len(t) == 1 + 1 + 2 + 0 + 3
+    assert int(t["n"].sum()) == sum(numels)
+    assert list(t["n"]) == [1, 4096, 4096, 1, 4096, 4096, 1808]
+    # chunk k of a tensor starts 16 KiB after chunk k-1, in both arrays
+    assert t["online"][1] - t["online"][0] == 4 and t["online"][3] - t["online"][2] == 4096 * 4
+    assert t["hist"][5] - t["hist"][4] == 4096 * 4
+    # alignment flag: tensor 0 is 16-byte aligned; tensor 1 starts 4 bytes later
+    assert t["flags"][0] == 1 and t["flags"][1] == 0
+    with pytest.raises(Exception):
+        ops.ema_plan_table([base_o + 1], [base_h], [8])  # not 4-byte aligned
+
+
+def test_ema_arithmetic_spec_matches_reference(golden):
+    """The kernel computes fadd(fmul(o, f32(1-m)), fmul(h, f32(m))) with the scalars
+    rounded once from the host doubles; emulate that in numpy float32 and compare
+    bit-for-bit with what the reference's ATen ops produced."""
+    g = golden("ema")
+    names = list(g["names"])
+    hist = {n: g["hist_init/" + n].numpy() for n in names}
+    for s in range(len(g["epochs"])):
+        m = g.scalar("mmt%d" % s)
+        mf, omf = np.float32(m), np.float32(1.0 - m)
+        for n in names:
+            o = g["online%d/%s" % (s, n)].numpy()
+            h = o if s == 0 else hist[n]
+            new = (o * omf).astype(np.float32) + (h * mf).astype(np.float32)
+            assert np.array_equal(new, g["hist%d/%s" % (s, n)].numpy()), (s, n)
+            hist[n] = new
+
+
+def test_swav_pair_weights():
+    from advise_video_ssl_b200 import ops
+    w = ops.swav_pair_weights(6, 2, 256)
+    assert w.shape == (2, 6) and w[0, 0] == 0 and w[1, 1] == 0
+    assert np.isclose(w.sum(), 1.0 / 256)
+    assert np.allclose(w[0, 1:], 1.0 / (256 * 5 * 2))
+
+
+def test_module_builds_on_cpu_and_rejects_cpu_compute():
+    C = register_backbones()
+    for typ, extra in (("moco", {}), ("byol", {"CONTRASTIVE__PREDICTOR_DEPTHS": [1]}), ("swav", {}), ("simclr", {}),
+                       ("mem", {"CONTRASTIVE__LENGTH": 20})):
+        cfg = make_cfg(CONTRASTIVE__TYPE=typ, CONTRASTIVE__DIM=16, CONTRASTIVE__QUEUE_LEN=32, **extra)
+        m = C.ContrastiveModel(cfg)
+        assert m.type == typ
+    cfg = make_cfg(CONTRASTIVE__TYPE="moco", CONTRASTIVE__DIM=16, CONTRASTIVE__QUEUE_LEN=32)
+    m = C.ContrastiveModel(cfg).train()
+    assert m.ptr.dtype == torch.int64 and m.iter.dtype == torch.int64 and m.queue_x.shape == (32, 16)
+    assert m._batch_shuffle_on
+    cfg2 = make_cfg(CONTRASTIVE__TYPE="moco", CONTRASTIVE__DIM=16, CONTRASTIVE__QUEUE_LEN=32,
+                    BN__NORM_TYPE="sync_batchnorm", BN__NUM_SYNC_DEVICES=1)
+    assert not C.ContrastiveModel(cfg2)._batch_shuffle_on  # sync BN over all GPUs (:91-99)
+    if not torch.cuda.is_available():
+        x = torch.randn(4, 16)
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            m([[x], [x]], torch.arange(4), torch.zeros(4, 2, 1), 0.0)
+    with pytest.raises(NotImplementedError):
+        bad = C.ContrastiveModel(make_cfg(CONTRASTIVE__TYPE="self", CONTRASTIVE__DIM=16, CONTRASTIVE__QUEUE_LEN=32))
+        bad([[torch.randn(2, 16)]], torch.arange(2))
+
+
+def test_momentum_anneal_matches_oracle():
+    from oracle import contrastive_oracle as O
+    C = register_backbones()
+    cfg = make_cfg(CONTRASTIVE__TYPE="moco", CONTRASTIVE__DIM=16, CONTRASTIVE__QUEUE_LEN=32, CONTRASTIVE__MOMENTUM=0.99,
+                   CONTRASTIVE__MOMENTUM_ANNEALING=True, SOLVER__MAX_EPOCH=200)
+    m = C.ContrastiveModel(cfg)
+    for ep in (0.0, 1.5, 77.7, 200.0):
+        m.momentum_anneal_cosine(ep)
+        assert m.mmt == O.momentum_cosine(0.99, ep, 200)
+
+
+def test_queue_divisibility_assert():
+    """K % n == 0 stays a host AssertionError (models/contrastive.py:284)."""
+    C = register_backbones()
+    cfg = make_cfg(CONTRASTIVE__TYPE="moco", CONTRASTIVE__DIM=16, CONTRASTIVE__QUEUE_LEN=32)
+    m = C.ContrastiveModel(cfg)
+    with pytest.raises(AssertionError):
+        m._dequeue_and_enqueue([torch.randn(5, 16)])
