@@ -33,7 +33,7 @@ SIGNATURES = {
     "avssl_ema_chunk_elems": (c_int64, []),
     "avssl_ema_plan_chunks": (c_int64, [c_void_p, c_int]),
     "avssl_ema_plan_fill": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64]),
-    "avssl_ema_multi_tensor": (c_int, [c_void_p, c_int64, c_float, c_float, c_void_p, c_int, c_void_p, c_void_p]),
+    "avssl_ema_multi_tensor": (c_int, [c_void_p, c_int64, c_float, c_float, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "avssl_moco_infonce_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "avssl_moco_infonce_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float,
                                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,

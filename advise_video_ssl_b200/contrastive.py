@@ -191,6 +191,7 @@ class ContrastiveModel(nn.Module):
         self.materialize_logits = True
         self.infonce_impl = _lib.IMPL_AUTO
         self._ema_plan = None
+        self._iter_mirror = None
         self._dummy_logits = None
         self.register_buffer("_status", torch.zeros(1, dtype=torch.int32), persistent=False)
 
@@ -242,6 +243,7 @@ class ContrastiveModel(nn.Module):
     def _apply(self, fn, *args, **kwargs):
         # .cuda()/.to()/.float() move parameter storage: drop cached pointer tables
         self._ema_plan = None
+        self._iter_mirror = None
         self._dummy_logits = None
         return super(ContrastiveModel, self)._apply(fn, *args, **kwargs)
 
@@ -308,7 +310,15 @@ class ContrastiveModel(nn.Module):
         if self._ema_plan is None:
             o_list, h_list = self._ema_lists()
             self._ema_plan = ops.EmaPlan(o_list, h_list)
-        self._ema_plan.run(self.mmt, self.iter, bump_iter=_bump_iter)
+        # host mirror of `iter`: our kernels bump the buffer through its raw pointer, which leaves
+        # the tensor's version counter alone; any torch-side write (load_state_dict, zero_(), ...)
+        # changes it and forces one re-read.  Steady state: no D2H sync at all.
+        key = (self.iter.data_ptr(), self.iter._version)
+        if self._iter_mirror is None or self._iter_mirror[0] != key:
+            self._iter_mirror = [key, int(self.iter.item())]
+        self._ema_plan.run(self.mmt, self.iter, bump_iter=_bump_iter, first_iter=self._iter_mirror[1] == 0)
+        if _bump_iter:
+            self._iter_mirror[1] += 1
 
     # ------------------------------------------------------ shuffle BN (A6, C1-C3)
     @torch.no_grad()

@@ -25,13 +25,19 @@ __device__ __forceinline__ float4 ema_blend4(const float4& o, const float4& h, f
                      ema_blend(o.z, h.z, m, om), ema_blend(o.w, h.w, m, om));
 }
 
+// kFirstMode: 0 = not the first step, 1 = first step (host knows `iter`), 2 = read `iter` on
+// the device.  kBump (only with a host-known `iter`): CTA 0 performs `self.iter += 1`
+// (models/contrastive.py:314) -- nobody reads `iter` inside the kernel then, so there is no
+// ordering to enforce.
+template <int kFirstMode, bool kBump>
 __global__ void __launch_bounds__(kEmaThreads)
 ema_multi_tensor_kernel(const avssl_ema_chunk* __restrict__ table, float m, float om,
-                        int64_t* iter, int bump_iter, uint32_t* done_counter) {
+                        int64_t* iter, uint32_t* done_counter) {
   const avssl_ema_chunk c = table[blockIdx.x];
   // iter == 0: history := online first (models/contrastive.py:167-169)
-  const bool first = (*reinterpret_cast<volatile int64_t*>(iter) == 0);
+  const bool first = kFirstMode == 2 ? (*reinterpret_cast<volatile int64_t*>(iter) == 0) : (kFirstMode == 1);
   const int tid = threadIdx.x;
+  if (kBump && kFirstMode != 2 && blockIdx.x == 0 && tid == 0) *iter += 1;
 
   if ((c.flags & 1u) && c.n == (uint32_t)kEmaChunk) {
     const float4* o4 = reinterpret_cast<const float4*>(c.online) + tid;
@@ -71,9 +77,9 @@ ema_multi_tensor_kernel(const avssl_ema_chunk* __restrict__ table, float m, floa
     }
   }
 
-  if (bump_iter) {
-    // `self.iter += 1` (models/contrastive.py:314) by the last CTA to finish: every
-    // CTA has read `iter` before it arrives here.
+  if (kBump && kFirstMode == 2) {
+    // device-read mode: `self.iter += 1` by the last CTA to finish (every CTA has read `iter`
+    // before it arrives here)
     __syncthreads();
     if (tid == 0) {
       __threadfence();
@@ -133,13 +139,14 @@ extern "C" int avssl_ema_plan_fill(const uint64_t* online_ptrs_host, const uint6
 }
 
 extern "C" int avssl_ema_multi_tensor(const avssl_ema_chunk* table_dev, int64_t n_chunks, float m,
-                                      float one_minus_m, int64_t* iter_dev, int bump_iter,
+                                      float one_minus_m, int64_t* iter_dev, int first_iter, int bump_iter,
                                       uint32_t* done_counter_dev, void* stream) {
   AVSSL_REQUIRE(iter_dev, AVSSL_ERR_INVALID_ARGUMENT, "ema_multi_tensor: iter_dev is null");
+  AVSSL_REQUIRE(first_iter >= -1 && first_iter <= 1, AVSSL_ERR_INVALID_ARGUMENT, "ema_multi_tensor: first_iter must be -1, 0 or 1");
   AVSSL_REQUIRE(n_chunks >= 0 && n_chunks < (1ll << 31), AVSSL_ERR_INVALID_ARGUMENT,
                 "ema_multi_tensor: bad n_chunks %lld", (long long)n_chunks);
-  AVSSL_REQUIRE(!bump_iter || done_counter_dev, AVSSL_ERR_INVALID_ARGUMENT,
-                "ema_multi_tensor: bump_iter needs done_counter_dev");
+  AVSSL_REQUIRE(!(bump_iter && first_iter < 0) || done_counter_dev, AVSSL_ERR_INVALID_ARGUMENT,
+                "ema_multi_tensor: bump_iter with a device-read iter needs done_counter_dev");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (n_chunks == 0) {
     if (bump_iter) {
@@ -149,8 +156,17 @@ extern "C" int avssl_ema_multi_tensor(const avssl_ema_chunk* table_dev, int64_t 
     return AVSSL_OK;
   }
   AVSSL_REQUIRE(table_dev, AVSSL_ERR_INVALID_ARGUMENT, "ema_multi_tensor: table_dev is null");
-  ema_multi_tensor_kernel<<<(unsigned)n_chunks, kEmaThreads, 0, s>>>(table_dev, m, one_minus_m, iter_dev,
-                                                                     bump_iter, done_counter_dev);
+  const unsigned grid = (unsigned)n_chunks;
+#define AVSSL_EMA_LAUNCH(MODE, BUMP) \
+  ema_multi_tensor_kernel<MODE, BUMP><<<grid, kEmaThreads, 0, s>>>(table_dev, m, one_minus_m, iter_dev, done_counter_dev)
+  if (first_iter < 0) {
+    if (bump_iter) AVSSL_EMA_LAUNCH(2, true); else AVSSL_EMA_LAUNCH(2, false);
+  } else if (first_iter == 1) {
+    if (bump_iter) AVSSL_EMA_LAUNCH(1, true); else AVSSL_EMA_LAUNCH(1, false);
+  } else {
+    if (bump_iter) AVSSL_EMA_LAUNCH(0, true); else AVSSL_EMA_LAUNCH(0, false);
+  }
+#undef AVSSL_EMA_LAUNCH
   AVSSL_LAUNCH_OK("ema_multi_tensor_kernel");
   return AVSSL_OK;
 }

@@ -85,7 +85,7 @@ extern "C" int avssl_moco_infonce_fwd_bwd(const float* feat_q, const float* cons
                 AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: unknown impl %d", impl);
 
   // split the queue over the SMs in whole tiles
-  const int tile = (use == AVSSL_IMPL_SIMT) ? 64 : 128;
+  const int tile = (use == AVSSL_IMPL_SIMT) ? kSimtTileRows : kTcTileRows;
   const int n_tiles = (K + tile - 1) / tile;
   const int row_blocks = (use == AVSSL_IMPL_SIMT) ? (B + 63) / 64 : (B + 127) / 128;
   int S = sms / row_blocks;

@@ -6,6 +6,8 @@ namespace avssl {
 
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
+constexpr int kSimtTileRows = 64;  // queue rows per tile, CUDA-core kernel
+constexpr int kTcTileRows = 64;    // queue rows per tile, tcgen05 kernel
 
 // Launch-time description shared by the split kernels (SIMT / tcgen05) and the
 // combine kernel.  Partials are kept in the log2 domain:

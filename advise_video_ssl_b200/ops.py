@@ -90,12 +90,15 @@ class EmaPlan:
     def matches(self, online, hist):
         return self.ptr_key == tuple((o.data_ptr(), h.data_ptr()) for o, h in zip(online, hist))
 
-    def run(self, m, iter_buf, bump_iter=False):
-        """hist <- online*(1-m) + hist*m, bit-exact with the reference's fp32 ops."""
+    def run(self, m, iter_buf, bump_iter=False, first_iter=None):
+        """hist <- online*(1-m) + hist*m, bit-exact with the reference's fp32 ops.
+        first_iter: True/False when the caller mirrors `iter` on the host, None to let the
+        kernel read it from the device."""
         _req(iter_buf, "iter", torch.int64)
         m = float(m)
+        fi = -1 if first_iter is None else (1 if first_iter else 0)
         check(lib.avssl_ema_multi_tensor(self.table.data_ptr(), self.n_chunks, m, 1.0 - m,
-                                         iter_buf.data_ptr(), 1 if bump_iter else 0,
+                                         iter_buf.data_ptr(), fi, 1 if bump_iter else 0,
                                          self.done.data_ptr(), _stream()), "avssl_ema_multi_tensor")
 
     @property

@@ -194,6 +194,7 @@ def gpu_arm(args):
     comm = torch.cuda.Stream(device=dev) if world > 1 else None
     impl = {"auto": _lib.IMPL_AUTO, "simt": _lib.IMPL_SIMT, "tc3x": _lib.IMPL_TC3X, "tc1x": _lib.IMPL_TC1X}[args.kernel]
     out = {}
+    state = {"n": 0}
     launches_per_step = 4  # ema, infonce split, infonce combine, enqueue
     ema_events = []
 
@@ -207,7 +208,8 @@ def gpu_arm(args):
             comm.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(comm):
                 dist.all_gather_into_tensor(gathered, k)
-        plan.run(MOMENTUM, it, bump_iter=True)
+        plan.run(MOMENTUM, it, bump_iter=True, first_iter=state["n"] == 0)  # host mirror of `iter`, as the module keeps
+        state["n"] += 1
         if time_ema:
             e1.record()
             ema_events.append((e0, e1))

