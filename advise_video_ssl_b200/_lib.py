@@ -38,6 +38,9 @@ SIGNATURES = {
     "avssl_moco_infonce_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float,
                                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                            c_int, c_void_p]),
+    "avssl_moco_infonce_fwd_bwd_enqueue": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                                   c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                   c_void_p, c_size_t, c_int, c_void_p]),
     "avssl_queue_enqueue": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "avssl_membank_update": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                      c_float, c_float, c_int, c_void_p, c_void_p]),

@@ -102,9 +102,11 @@ class _MocoInfoNceFn(torch.autograd.Function):
     """Fused l2-norm + logits + InfoNCE, forward and backward in one pass (K2+K3)."""
 
     @staticmethod
-    def forward(ctx, feat_q, queue, T, want_logits, impl, *keys):
+    def forward(ctx, feat_q, queue, T, want_logits, impl, enqueue, *keys):
+        # enqueue = (ptr, status) folds K4 for keys[0] into the same launch (after the loss
+        # has been computed against the old queue, models/contrastive.py:486-503)
         out = ops.moco_infonce(feat_q.detach().contiguous(), [k.detach().contiguous() for k in keys],
-                               queue, T, want_logits=want_logits, impl=impl)
+                               queue, T, want_logits=want_logits, impl=impl, enqueue=enqueue)
         ctx.save_for_backward(out["dfeat"])
         logits = out["logits"] if want_logits else feat_q.new_empty(0)
         ctx.mark_non_differentiable(logits, out["q"])
@@ -113,7 +115,7 @@ class _MocoInfoNceFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss, g_logits, g_q):
         (dfeat,) = ctx.saved_tensors
-        return (dfeat * g_loss,) + (None,) * 4 + (None,) * (len(ctx.needs_input_grad) - 5)
+        return (dfeat * g_loss,) + (None,) * (len(ctx.needs_input_grad) - 1)
 
 
 class _ByolSimFn(torch.autograd.Function):
@@ -562,11 +564,18 @@ class ContrastiveModel(nn.Module):
             auto_enqueue_keys = False
 
         # K2+K3: q = l2norm(feat_q); logits = [q.k, q.queue^T]/T; InfoNCE fwd + bwd
+        # K4 rides in the same launch when exactly keys[0] is enqueued (the default,
+        # CONTRASTIVE.MOCO_MULTI_VIEW_QUEUE off): the ring write happens behind a grid-wide
+        # barrier after the last read of the queue.
+        enqueue_here = self.training and auto_enqueue_keys
+        fused = (enqueue_here and not self.cfg.CONTRASTIVE.MOCO_MULTI_VIEW_QUEUE
+                 and keys[0].shape == feat_q.shape and self.k % int(keys[0].size(0)) == 0)
         loss, logits, q = _MocoInfoNceFn.apply(feat_q, self.queue_x, self.T, self.materialize_logits,
-                                               self.infonce_impl, *keys)
+                                               self.infonce_impl, (self.ptr, self._status) if fused else None,
+                                               *keys)
         if not self.materialize_logits:
             logits = None
-        if self.training and auto_enqueue_keys:
+        if enqueue_here and not fused:
             self._dequeue_and_enqueue(keys)
         self.knn_mem_update(q, index)
         return logits, loss

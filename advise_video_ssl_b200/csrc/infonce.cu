@@ -44,11 +44,12 @@ extern "C" size_t avssl_moco_infonce_workspace_bytes(int B, int D, int K, int n_
   return carve(B, D, n_keys, max_splits()).total;
 }
 
-extern "C" int avssl_moco_infonce_fwd_bwd(const float* feat_q, const float* const* keys_host, int n_keys,
-                                          const float* queue, int B, int D, int K, float T, float* q_out,
-                                          float* loss_out, float* dfeat_out, float* row_lse_out,
-                                          float* logits_out, void* workspace, size_t workspace_bytes,
-                                          int impl, void* stream) {
+namespace {
+
+int moco_infonce_run(const float* feat_q, const float* const* keys_host, int n_keys, const float* queue,
+                     float* queue_rw, int64_t* ptr_dev, uint32_t* status_dev, int B, int D, int K, float T,
+                     float* q_out, float* loss_out, float* dfeat_out, float* row_lse_out, float* logits_out,
+                     void* workspace, size_t workspace_bytes, int impl, void* stream) {
   AVSSL_REQUIRE(feat_q && keys_host && queue && q_out && loss_out && dfeat_out && workspace,
                 AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: null pointer");
   AVSSL_REQUIRE(B > 0 && D > 0 && K > 0, AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: bad sizes B=%d D=%d K=%d", B, D, K);
@@ -78,6 +79,15 @@ extern "C" int avssl_moco_infonce_fwd_bwd(const float* feat_q, const float* cons
   p.dfeat_out = dfeat_out;
   p.row_lse_out = row_lse_out;
   p.logits_out = logits_out;
+  p.queue_rw = queue_rw;
+  p.enq_ptr = reinterpret_cast<long long*>(ptr_dev);
+  p.enq_status = status_dev;
+  if (ptr_dev) {
+    // models/contrastive.py:284  assert self.k % num_items == 0
+    AVSSL_REQUIRE(K % B == 0, AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: K=%d is not a multiple of the key batch %d", K, B);
+    AVSSL_REQUIRE(queue_rw && (reinterpret_cast<uintptr_t>(p.keys[0]) & 15u) == 0 && D % 4 == 0,
+                  AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: fused enqueue needs a writable queue and 16-byte aligned keys[0]");
+  }
 
   int use = impl;
   if (use == AVSSL_IMPL_AUTO) use = infonce_tc_supported(B, D, K) ? AVSSL_IMPL_TC3X : AVSSL_IMPL_SIMT;
@@ -106,12 +116,34 @@ extern "C" int avssl_moco_infonce_fwd_bwd(const float* feat_q, const float* cons
   p.part_l = reinterpret_cast<float*>(w + c.part_l);
   p.part_acc = reinterpret_cast<float*>(w + c.part_acc);
 
-  int rc;
-  if (use == AVSSL_IMPL_SIMT) {
-    rc = launch_infonce_simt(p, s);
-  } else {
-    rc = launch_infonce_tc(p, use == AVSSL_IMPL_TC3X ? 1 : 0, s);
+  if (use != AVSSL_IMPL_SIMT) {
+    // one cooperative launch: sweep + grid barrier + merge (+ the queue ring write of K4)
+    return launch_infonce_tc(p, use == AVSSL_IMPL_TC3X ? 1 : 0, s);
   }
+  int rc = launch_infonce_simt(p, s);
   if (rc != AVSSL_OK) return rc;
-  return launch_infonce_combine(p, s);
+  rc = launch_infonce_combine(p, s);
+  if (rc != AVSSL_OK || !ptr_dev) return rc;
+  return avssl_queue_enqueue(queue_rw, ptr_dev, p.keys[0], B, K, D, status_dev, stream);
+}
+
+}  // namespace
+
+extern "C" int avssl_moco_infonce_fwd_bwd(const float* feat_q, const float* const* keys_host, int n_keys,
+                                          const float* queue, int B, int D, int K, float T, float* q_out,
+                                          float* loss_out, float* dfeat_out, float* row_lse_out,
+                                          float* logits_out, void* workspace, size_t workspace_bytes,
+                                          int impl, void* stream) {
+  return moco_infonce_run(feat_q, keys_host, n_keys, queue, nullptr, nullptr, nullptr, B, D, K, T, q_out, loss_out,
+                          dfeat_out, row_lse_out, logits_out, workspace, workspace_bytes, impl, stream);
+}
+
+extern "C" int avssl_moco_infonce_fwd_bwd_enqueue(const float* feat_q, const float* const* keys_host, int n_keys,
+                                                  float* queue, int64_t* ptr_dev, uint32_t* status_dev, int B,
+                                                  int D, int K, float T, float* q_out, float* loss_out,
+                                                  float* dfeat_out, float* row_lse_out, float* logits_out,
+                                                  void* workspace, size_t workspace_bytes, int impl, void* stream) {
+  AVSSL_REQUIRE(ptr_dev, AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce_enqueue: ptr_dev is null");
+  return moco_infonce_run(feat_q, keys_host, n_keys, queue, queue, ptr_dev, status_dev, B, D, K, T, q_out, loss_out,
+                          dfeat_out, row_lse_out, logits_out, workspace, workspace_bytes, impl, stream);
 }

@@ -27,13 +27,18 @@ struct InfoNceParams {
   float* row_lse_out;
   float* logits_out;
   // workspace
-  unsigned* counter;
+  unsigned* counter;  // [0] finish counter, [1] grid-barrier counter; zero between launches
   float* row_loss;
   float* part_m;
   float* part_l;
   float* part_acc;
   int n_splits;
   int rows_per_split;  // queue rows handled by one split (multiple of the tile)
+  // optional fused K4 (models/contrastive.py:263-292): queue[ptr:ptr+B] = keys[0], ptr advanced,
+  // performed after every CTA has finished reading the queue.  enq_ptr == nullptr: no enqueue.
+  float* queue_rw;
+  long long* enq_ptr;
+  uint32_t* enq_status;
 };
 
 // 1 / ||row|| computed by ONE warp with a fixed summation order, so that every

@@ -12,6 +12,7 @@
 // D <= 256, any B, any K) and the fallback for shapes the tcgen05 kernel does not
 // take.  It is FFMA-bound (2.1 GFLOP at cfg1), not HBM-bound.
 #include "infonce.cuh"
+#include "infonce_combine.cuh"
 #include "simt_tile.cuh"
 
 namespace avssl {
@@ -159,163 +160,14 @@ __global__ void __launch_bounds__(kSimtThreads, 1) infonce_simt_kernel(const Inf
 }
 
 // --------------------------------------------------------------------- combine
-// One CTA per query row.  Deterministic: partials are merged in a fixed order and the
-// mean over rows is taken by the last CTA in row order.  512 threads = 16 groups of 32
-// lanes; a group reads one split-partial row as float4 per lane, 4 rows in flight per
-// group, so ~32 KB of independent loads are outstanding per CTA (the partials sit in L2:
-// ~5 MB at 147 splits).
+// One CTA per query row (infonce_combine.cuh); the mean over rows is taken by the last
+// CTA to finish, in row order.
 constexpr int kCombineThreads = 512;
-constexpr int kCombineCols = 128;
-constexpr int kCombineGroups = kCombineThreads / 32;
-constexpr int kMaxSplits = 1024;
 
 __global__ void __launch_bounds__(kCombineThreads) infonce_combine_kernel(const InfoNceParams p) {
-  __shared__ float s_w[kMaxSplits];
-  __shared__ float s_red[32];
-  __shared__ float s_bcast[4];
-  __shared__ __align__(16) float s_acc[kCombineGroups][2 * kCombineCols];
-  __shared__ unsigned s_is_last;
-  const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int col = tid % kCombineCols;
-  const int grp = tid >> 5;  // split group (warp) for the accumulator merge
-  const int D = p.D, B = p.B, S = p.n_splits;
-  constexpr int MAXC = 2;  // D <= 256
-  const float* f = p.feat_q + (size_t)i * D;
-
-  if (warp == 0) {
-    const float nrm = warp_row_norm(f, D, lane);
-    if (lane == 0) s_bcast[0] = nrm;
-  }
-  // global max over the splits
-  float mloc = -INFINITY;
-  for (int s = tid; s < S; s += kCombineThreads) mloc = fmaxf(mloc, p.part_m[(size_t)s * B + i]);
-  mloc = warp_max(mloc);
-  if (lane == 0) s_red[warp] = mloc;
-  __syncthreads();
-  float M = s_red[0];
-  for (int w = 1; w < kCombineThreads / 32; ++w) M = fmaxf(M, s_red[w]);
-  const float nrm = s_bcast[0];
-  __syncthreads();
-  float lloc = 0.f;
-  for (int s = tid; s < S; s += kCombineThreads) {
-    const float w = exp2f(p.part_m[(size_t)s * B + i] - M);
-    s_w[s] = w;
-    lloc += w * p.part_l[(size_t)s * B + i];
-  }
-  const float L = block_sum(lloc, s_red);  // (order fixed by the launch geometry)
-  __syncthreads();
-
-  // merge the accumulators: warp g takes splits g, g+G, ...; lane l owns columns 4l..4l+3
-  // (+128 for D > 128), four split rows in flight
-  {
-    const size_t stride = (size_t)B * D;
-#pragma unroll
-    for (int u = 0; u < MAXC; ++u) {
-      const int c = lane * 4 + u * kCombineCols;
-      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
-      if (c < D) {
-        const float* base = p.part_acc + (size_t)i * D + c;
-        auto ld = [&](int s) { return __ldcg(reinterpret_cast<const float4*>(base + (size_t)s * stride)); };
-        auto fma4 = [](float w, const float4& v, float4& a) {
-          a.x = fmaf(w, v.x, a.x);
-          a.y = fmaf(w, v.y, a.y);
-          a.z = fmaf(w, v.z, a.z);
-          a.w = fmaf(w, v.w, a.w);
-        };
-        int s = grp;
-        for (; s + 3 * kCombineGroups < S; s += 4 * kCombineGroups) {
-          const float4 v0 = ld(s), v1 = ld(s + kCombineGroups), v2 = ld(s + 2 * kCombineGroups),
-                       v3 = ld(s + 3 * kCombineGroups);
-          fma4(s_w[s], v0, a0);
-          fma4(s_w[s + kCombineGroups], v1, a1);
-          fma4(s_w[s + 2 * kCombineGroups], v2, a2);
-          fma4(s_w[s + 3 * kCombineGroups], v3, a3);
-        }
-        for (; s < S; s += kCombineGroups) fma4(s_w[s], ld(s), a0);
-      }
-      float4 r;
-      r.x = (a0.x + a1.x) + (a2.x + a3.x);
-      r.y = (a0.y + a1.y) + (a2.y + a3.y);
-      r.z = (a0.z + a1.z) + (a2.z + a3.z);
-      r.w = (a0.w + a1.w) + (a2.w + a3.w);
-      *reinterpret_cast<float4*>(&s_acc[grp][c]) = r;
-    }
-  }
-  __syncthreads();
-
-  const bool owner = tid < kCombineCols;  // these 128 threads own the columns from here on
-  float q[MAXC], acc[MAXC], dq[MAXC];
-#pragma unroll
-  for (int u = 0; u < MAXC; ++u) {
-    const int c = col + u * kCombineCols;
-    q[u] = acc[u] = dq[u] = 0.f;
-    if (owner && c < D) {
-      q[u] = f[c] / nrm;
-      float a = s_acc[0][c];
-#pragma unroll
-      for (int g = 1; g < kCombineGroups; ++g) a += s_acc[g][c];
-      acc[u] = a;
-      p.q_out[(size_t)i * D + c] = q[u];
-    }
-  }
-
-  const int n_rows = p.n_keys * B;
-  const float gscale = p.inv_T / (float)n_rows;
-  for (int k = 0; k < p.n_keys; ++k) {
-    const float* key = p.keys[k] + (size_t)i * D;
-    float kv[MAXC], dot = 0.f;
-#pragma unroll
-    for (int u = 0; u < MAXC; ++u) {
-      const int c = col + u * kCombineCols;
-      kv[u] = (owner && c < D) ? key[c] : 0.f;
-      dot = fmaf(q[u], kv[u], dot);
-    }
-    dot = block_sum(dot, s_red);
-    const float s0 = dot * p.inv_T;         // positive logit (column 0)
-    const float s0_2 = s0 * kLog2e;
-    const float Mk = fmaxf(M, s0_2);
-    const float e0 = exp2f(s0_2 - Mk);
-    const float wq = exp2f(M - Mk);
-    const float Z = e0 + L * wq;
-    const float lse = (Mk + log2f(Z)) * kLn2;
-    const float p0 = e0 / Z;
-    const float pq = wq / Z;  // scales acc to sum_j p_kij queue_j
-#pragma unroll
-    for (int u = 0; u < MAXC; ++u) dq[u] += (pq * acc[u] + p0 * kv[u] - kv[u]) * gscale;
-    if (tid == 0) {
-      p.row_loss[(size_t)k * B + i] = lse - s0;
-      if (p.row_lse_out) p.row_lse_out[(size_t)k * B + i] = lse;
-      if (p.logits_out) p.logits_out[((size_t)k * B + i) * (size_t)(p.K + 1)] = s0;
-    }
-  }
-  // gradient through the normalisation: df = (dq - (dq.q) q) / ||f||
-  float dd = 0.f;
-#pragma unroll
-  for (int u = 0; u < MAXC; ++u) dd = fmaf(dq[u], q[u], dd);
-  dd = block_sum(dd, s_red);
-#pragma unroll
-  for (int u = 0; u < MAXC; ++u) {
-    const int c = col + u * kCombineCols;
-    if (owner && c < D) p.dfeat_out[(size_t)i * D + c] = (dq[u] - dd * q[u]) / nrm;
-  }
-
-  // mean over all logits rows, by the last CTA, in row order
-  __syncthreads();
-  if (tid == 0) {
-    __threadfence();
-    s_is_last = (atomicAdd(p.counter, 1u) == gridDim.x - 1) ? 1u : 0u;
-  }
-  __syncthreads();
-  if (s_is_last) {
-    __threadfence();
-    float tot = 0.f;
-    for (int r = tid; r < n_rows; r += kCombineThreads) tot += reinterpret_cast<volatile float*>(p.row_loss)[r];
-    tot = block_sum(tot, s_red);
-    if (tid == 0) {
-      *p.loss_out = tot / (float)n_rows;
-      *p.counter = 0u;
-    }
-  }
+  __shared__ CombineSmem<kCombineThreads> sm;
+  infonce_combine_row<kCombineThreads, 2>(p, blockIdx.x, sm);
+  infonce_finish<kCombineThreads>(p, gridDim.x, sm);
 }
 
 template <int DP>

@@ -9,17 +9,25 @@
 // so loss statistics (m, l) AND the gradient term sum_j p_ij queue_j come out of the
 // same sweep.  tf32 operands that are MN-major (the second GEMM reads the tile with the
 // queue-row index as K) must use the 128B-swizzle-with-32B-atoms shared-memory layout,
-// while the K-major operand of the first GEMM needs the plain 128B swizzle, so TMA lands
-// every tile twice (two tensor maps over the same global rows; the second read is an L2
-// hit): the "S tile" ring feeds the first GEMM, the "V tile" ring the second.  An S slot is
-// recycled as soon as its S GEMM retires, a V slot when its PV GEMM retires.
+// while the K-major operand of the first GEMM needs the plain 128B swizzle, so every tile
+// exists twice in shared memory: the "S tile" ring feeds the first GEMM, the "V tile" ring
+// the second.  An S slot is recycled as soon as its S GEMM retires, a V slot when its PV
+// GEMM retires.
 //
-// fp32-grade accuracy on tf32 tensor cores (kThreeTerm): four helper warps split the S
-// tile in shared memory into hi = rn_tf32(x) and lo = x - hi, q likewise (in TMEM), and
-// S = q_lo.k_hi + q_hi.k_lo + q_hi.k_hi (error ~2^-22, no truncation bias); four more
-// warps round the V tile to tf32 (round-to-nearest instead of the hardware's truncation).
-// Without the split (kThreeTerm = false) the hardware truncates the queue operand to 10
-// mantissa bits: 3x fewer S MMAs, tf32-grade logits.
+// fp32-grade accuracy on tf32 tensor cores (kThreeTerm): the tensor core reads an fp32
+// operand as tf32 by ignoring its low 13 mantissa bits, so with k_hi = trunc(k) (what the
+// hardware sees in the RAW tile), k_lo = k - k_hi (exact), q_hi = rn_tf32(q), q_lo = q - q_hi:
+//     S = q_hi.k_hi  (kind::tf32, raw tile)  +  [q_lo | q] . [k | k_lo]   (kind::f16, bf16)
+// The two correction terms are ~2^-11 of S, so bf16 operands (2^-9) keep them to ~2^-20, and
+// they ride in ONE bf16 MMA pass with the contraction length doubled (A = [q_lo | q] packed
+// in TMEM, B = the "correction tile" [bf16(k) | bf16(k_lo)] that four helper warps write
+// into the second half of the S slot).  Shared-memory bandwidth (128 B/clk/SM, shared by
+// TMA writes, the helper warps and the tensor core's operand reads) bounds the sweep, so
+// every byte is touched as few times as possible: the tile is landed ONCE by TMA, the
+// helper warps read it once, write the correction tile and -- from registers, once PV(t-2)
+// has released the slot -- the V tile rounded to nearest tf32 (unbiased, unlike truncation)
+// in the 32B-atom layout.  Without the split (kThreeTerm = false) TMA lands both layouts and
+// the hardware truncates: tf32-grade logits.
 //
 // Measured on B200 (tools/microbench): one thread issues a tcgen05.mma every ~55 cycles at
 // best and an M=128, N=64, K=8 tf32 MMA occupies the tensor pipe for 32 cycles, so the issue
@@ -27,25 +35,23 @@
 // unrolled.
 //
 // Warp roles (448 threads, 1 CTA / SM):  0 TMA producer | 1 MMA issuer + TMEM allocator |
-// 2-5 S-tile hi/lo split | 6-9 V-tile rounding | 10-13 softmax + epilogue (thread = query row).
-// TMEM columns: [0,D) q_hi | [D,2D) q_lo | [2D,2D+128) S/P double buffer | [2D+128,3D+128) acc.
+// 2-5 S-tile hi/lo split | 6-9 V-tile rounding + coalesced logits writer | 10-13 softmax +
+// epilogue (thread = query row).
+// TMEM columns: [0,D) q_hi | [D,2D) [q_lo | q] as packed bf16 | [2D,2D+128) S/P double buffer |
+// [2D+128,3D+128) acc.
+//
+// The launch is cooperative (grid <= number of SMs, all CTAs co-resident): after the sweep
+// every CTA writes its partial (m, l, acc), the grid meets at a barrier, and the CTAs then
+// merge the partials one query row each (infonce_combine.cuh), take the mean loss and --
+// optionally -- perform the queue ring write of K4 (models/contrastive.py:263-292), which
+// is safe there because no CTA reads the queue any more.  One launch per step instead of
+// three (split, combine, enqueue).
 #include "infonce.cuh"
+#include "tc_trace.cuh"
+#include "infonce_combine.cuh"
 #include "sm100_ptx.cuh"
 
 namespace avssl {
-
-#ifdef AVSSL_TC_TRACE
-// developer build only (tools/microbench/tc_trace.cu): per-role timestamps of CTA (0,0)
-__device__ long long g_tc_trace[16][64];
-#define TC_TRACE(ev, t)                                                                \
-  do {                                                                                 \
-    if (blockIdx.x == 0 && blockIdx.y == 0 && (t) < 64) g_tc_trace[ev][t] = clock64(); \
-  } while (0)
-#else
-#define TC_TRACE(ev, t) \
-  do {                  \
-  } while (0)
-#endif
 
 namespace {
 
@@ -55,6 +61,8 @@ constexpr int kTcThreads = 448;
 constexpr int kGroupThreads = 128;    // split / round / softmax groups
 constexpr float kRescaleThreshold = 8.f;  // log2 units: P stays below 2^8
 constexpr int kMaxSlots = 3;
+constexpr int kStageRows = 64;             // query rows per CTA whose logits go through the staging tile
+constexpr int kStagePitch = kBlockJ + 1;   // floats; +1 keeps row-wise writes and column-wise reads conflict-free
 
 template <int D, bool kThreeTerm>
 struct TcCfg {
@@ -66,10 +74,11 @@ struct TcCfg {
   static constexpr int kVSlots = kThreeTerm ? 2 : 3;
   static constexpr int kSRingBytes = kSSlots * kSSlotBytes;
   static constexpr int kVRingBytes = kVSlots * kTileBytes;
-  static constexpr int kScratchBytes = 4 * 32 * 33 * 4;  // q transpose scratch, one [32][33] per softmax warp
+  static constexpr int kScratchBytes = kStageRows * kStagePitch * 4;  // logits staging tile [64][65]
   static constexpr int kColQhi = 0, kColQlo = D, kColS = 2 * D, kColAcc = 2 * D + 2 * kBlockJ;
   static constexpr int kTmemCols = 512;
   static_assert(3 * D + 2 * kBlockJ <= 512, "TMEM budget");
+  static_assert(kSRingBytes >= (int)sizeof(CombineSmem<kTcThreads>), "merge scratch aliases the S ring");
   static constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kSRingBytes + kVRingBytes + kScratchBytes + 512;
 };
 
@@ -78,8 +87,15 @@ struct TcBarriers {
   uint64_t v_full[kMaxSlots], v_op[kMaxSlots], v_free[kMaxSlots];
   uint64_t s_ready[2], p_ready[2], pv_done[2];
   uint64_t q_ready, acc_done;
+  uint64_t stage_full, stage_free;
   uint32_t tmem_base;
 };
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 
 template <int D, bool kThreeTerm>
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -91,15 +107,35 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_ring = smem;
   uint8_t* v_ring = smem + C::kSRingBytes;
-  float* scratch = reinterpret_cast<float*>(smem + C::kSRingBytes + C::kVRingBytes);
+  float* stage = reinterpret_cast<float*>(smem + C::kSRingBytes + C::kVRingBytes);
   TcBarriers* bar = reinterpret_cast<TcBarriers*>(smem + C::kSRingBytes + C::kVRingBytes + C::kScratchBytes);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) TC_TRACE(14, 0);
   const int split = blockIdx.x;
   const int i_base = blockIdx.y * kM;
   const int j_begin = split * p.rows_per_split;
   const int j_end = min(p.K, j_begin + p.rows_per_split);
   const int n_tiles = (j_end - j_begin + kBlockJ - 1) / kBlockJ;
+  // The query rows travel global -> registers (coalesced 128-bit loads by the four softmax
+  // warps, requested before the set-up barrier) -> shared memory (the V ring + logits staging
+  // area, which nobody else touches before q is in TMEM) -> one row per thread.  The 16-byte
+  // row padding keeps the per-thread row reads free of bank conflicts.
+  constexpr int kQPitch = D * 4 + 16;
+  constexpr int kRowF4 = D / 4;                              // float4 per query row
+  constexpr int kQHalf = (kM / 2) * kRowF4 / kGroupThreads;  // float4 per thread for 64 rows
+  static_assert(kM * kQPitch <= C::kVRingBytes + C::kScratchBytes, "q staging aliases the V ring + logits staging tile");
+  uint8_t* q_stage = v_ring;
+  const int q_total = min(kM, p.B - i_base) * kRowF4;  // float4 to stage
+  const float4* q_gsrc = reinterpret_cast<const float4*>(p.feat_q + (size_t)i_base * D);
+  float4 q_buf[kQHalf];
+  if (warp >= 10) {
+#pragma unroll
+    for (int n = 0; n < kQHalf; ++n) {
+      const int idx = (tid - 320) + n * kGroupThreads;
+      q_buf[n] = idx < q_total ? __ldg(q_gsrc + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
 
   // ------------------------------------------------------------------ one-time setup
   if (warp == 0 && lane == 0) {
@@ -120,6 +156,8 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
     }
     ptx::mbar_init(&bar->q_ready, kGroupThreads);
     ptx::mbar_init(&bar->acc_done, 1);
+    ptx::mbar_init(&bar->stage_full, 2 * 32);        // softmax warps 10 and 11 (rows 0..63 of the CTA tile)
+    ptx::mbar_init(&bar->stage_free, kGroupThreads);  // the four writer warps
     ptx::mbar_fence_init();
   }
   if (warp == 1) ptx::tmem_alloc(&bar->tmem_base, C::kTmemCols);
@@ -127,24 +165,40 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = bar->tmem_base;
+  if (tid == 0) TC_TRACE(14, 1);
 
   if (warp == 0) {
     // ================================================================ TMA producer
+    // The S tile of tile t+1 is requested before the V tile of tile t: an S slot is
+    // released when S(t-1) retires, a V slot only when PV(t-2) retires (later), and the
+    // hi/lo split of the next S tile must not wait behind the V ring.
     if (lane == 0) {
-      for (int t = 0; t < n_tiles; ++t) {
-        const int ss = t % C::kSSlots, vs = t % C::kVSlots;
-        const int j0 = j_begin + t * kBlockJ;
+      auto load_s = [&](int t) {
+        const int ss = t % C::kSSlots;
         if (t >= C::kSSlots) ptx::mbar_wait(&bar->s_free[ss], ((t / C::kSSlots) - 1) & 1);
         TC_TRACE(0, t);
         ptx::mbar_arrive_expect_tx(&bar->s_full[ss], C::kTileBytes);
         uint8_t* dst = s_ring + (size_t)ss * C::kSSlotBytes;
 #pragma unroll
-        for (int kb = 0; kb < C::kKB; ++kb) ptx::tma_load_2d(dst + kb * C::kBoxBytes, &tmap, &bar->s_full[ss], kb * 32, j0);
+        for (int kb = 0; kb < C::kKB; ++kb)
+          ptx::tma_load_2d(dst + kb * C::kBoxBytes, &tmap, &bar->s_full[ss], kb * 32, j_begin + t * kBlockJ);
+      };
+      auto load_v = [&](int t) {
+        const int vs = t % C::kVSlots;
         if (t >= C::kVSlots) ptx::mbar_wait(&bar->v_free[vs], ((t / C::kVSlots) - 1) & 1);
         ptx::mbar_arrive_expect_tx(&bar->v_full[vs], C::kTileBytes);
-        dst = v_ring + (size_t)vs * C::kTileBytes;
+        uint8_t* dst = v_ring + (size_t)vs * C::kTileBytes;
 #pragma unroll
-        for (int kb = 0; kb < C::kKB; ++kb) ptx::tma_load_2d(dst + kb * C::kBoxBytes, &tmap_v, &bar->v_full[vs], kb * 32, j0);
+        for (int kb = 0; kb < C::kKB; ++kb)
+          ptx::tma_load_2d(dst + kb * C::kBoxBytes, &tmap_v, &bar->v_full[vs], kb * 32, j_begin + t * kBlockJ);
+      };
+      if (n_tiles > 0) load_s(0);
+      for (int t = 0; t < n_tiles; ++t) {
+        if (t + 1 < n_tiles) load_s(t + 1);
+        if (!kThreeTerm) {
+          if (t == 0) ptx::mbar_wait(&bar->q_ready, 0);  // the V ring doubles as the q staging area
+          load_v(t);
+        }
       }
     }
   } else if (warp == 1) {
@@ -153,6 +207,7 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
     // instructions, so descriptors and TMEM addresses stay in uniform registers.
     constexpr uint32_t idesc_s = ptx::umma_idesc_tf32(kM, kBlockJ, 0, 0);  // B = tile, K-major
     constexpr uint32_t idesc_pv = ptx::umma_idesc_tf32(kM, D, 0, 1);       // B = tile, MN-major
+    constexpr uint32_t idesc_c = ptx::umma_idesc_bf16(kM, kBlockJ, 0, 0);  // B = correction tile, K-major
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
     const uint32_t s_ring0 = __shfl_sync(0xffffffffu, ptx::smem_u32(s_ring), 0);
     const uint32_t v_ring0 = __shfl_sync(0xffffffffu, ptx::smem_u32(v_ring), 0);
@@ -189,16 +244,13 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
       const uint64_t lo0 = hi0 + (uint64_t)(C::kTileBytes >> 4);
       const uint32_t d_s = tm + C::kColS + b * kBlockJ;
       if (ptx::elect_one()) {
-        // smallest contributions first: q_lo.k_hi, q_hi.k_lo, then q_hi.k_hi
+        // smallest contributions first: the bf16 correction pass [q_lo | q].[k | k_lo] (2D bf16 per
+        // row = the same D/32 boxes of 128 B, 16 k per MMA = 32 B per step), then q_hi.k_hi
         if (kThreeTerm) {
 #pragma unroll
           for (int ks = 0; ks < D / 8; ++ks)
-            ptx::mma_tf32_ts(d_s, tm + C::kColQlo + ks * 8, hi0 + (uint64_t)(((ks >> 2) * C::kBoxBytes + (ks & 3) * 32) >> 4),
-                             idesc_s, ks > 0 ? 1u : 0u);
-#pragma unroll
-          for (int ks = 0; ks < D / 8; ++ks)
-            ptx::mma_tf32_ts(d_s, tm + C::kColQhi + ks * 8, lo0 + (uint64_t)(((ks >> 2) * C::kBoxBytes + (ks & 3) * 32) >> 4),
-                             idesc_s, 1u);
+            ptx::mma_f16_ts(d_s, tm + C::kColQlo + ks * 8, lo0 + (uint64_t)(((ks >> 2) * C::kBoxBytes + (ks & 3) * 32) >> 4),
+                            idesc_c, ks > 0 ? 1u : 0u);
         }
 #pragma unroll
         for (int ks = 0; ks < D / 8; ++ks)
@@ -215,54 +267,76 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
     if (ptx::elect_one()) ptx::tc_commit(&bar->acc_done);
     __syncwarp();
   } else if (warp < 6) {
-    // ===================================================== S-tile hi/lo split (3-term only)
+    // ============================ S-tile split + V tile (3-term only): one read of the raw tile
     if (kThreeTerm) {
       const int st = tid - 64;  // 0..127
+      constexpr int kPer = C::kTileBytes / 16 / kGroupThreads;  // float4 per thread and tile (D / 8)
       for (int t = 0; t < n_tiles; ++t) {
-        const int ss = t % C::kSSlots;
+        const int ss = t % C::kSSlots, vs = t % C::kVSlots;
         ptx::mbar_wait_relaxed(&bar->s_full[ss], (t / C::kSSlots) & 1);
         if (st == 0) TC_TRACE(1, t);
-        float4* hi = reinterpret_cast<float4*>(s_ring + (size_t)ss * C::kSSlotBytes);
-        float4* lo = reinterpret_cast<float4*>(s_ring + (size_t)ss * C::kSSlotBytes + C::kTileBytes);
-#pragma unroll 8
-        for (int e = st; e < C::kTileBytes / 16; e += kGroupThreads) {
-          const float4 x = hi[e];
-          float4 h, l;
-          h.x = ptx::round_tf32(x.x);
-          h.y = ptx::round_tf32(x.y);
-          h.z = ptx::round_tf32(x.z);
-          h.w = ptx::round_tf32(x.w);
-          l.x = x.x - h.x;
-          l.y = x.y - h.y;
-          l.z = x.z - h.z;
-          l.w = x.w - h.w;
-          hi[e] = h;
-          lo[e] = l;
+        const float4* raw = reinterpret_cast<const float4*>(s_ring + (size_t)ss * C::kSSlotBytes);
+        uint8_t* corr = s_ring + (size_t)ss * C::kSSlotBytes + C::kTileBytes;  // [bf16(k) | bf16(k_lo)], K-major, 128B swizzle
+        float4 h[kPer];
+#pragma unroll
+        for (int n = 0; n < kPer; ++n) {
+          const int e = st + n * kGroupThreads;
+          const float4 x = raw[e];
+          // S layout (128B swizzle): box kb, row j, physical 16-byte chunk c' = c ^ (j & 7); columns d0..d0+3
+          const int kb = e >> 9, j = (e >> 3) & 63, c = (e & 7) ^ (j & 7);
+          const int d0 = kb * 32 + c * 4;
+          uint2 kk, ll;
+          kk.x = ptx::pack_bf16x2(x.x, x.y);
+          kk.y = ptx::pack_bf16x2(x.z, x.w);
+          // k_lo = k - trunc(k): exact in fp32, what the tf32 pass does not see
+          ll.x = ptx::pack_bf16x2(x.x - ptx::trunc_tf32(x.x), x.y - ptx::trunc_tf32(x.y));
+          ll.y = ptx::pack_bf16x2(x.z - ptx::trunc_tf32(x.z), x.w - ptx::trunc_tf32(x.w));
+          // byte offset bo of element kappa in a correction-tile row: 2*kappa; box bo >> 7, chunk (bo & 127) >> 4
+          auto put = [&](int bo, const uint2& v) {
+            *reinterpret_cast<uint2*>(corr + (bo >> 7) * C::kBoxBytes + j * 128 + ((((bo & 127) >> 4) ^ (j & 7)) << 4) + (bo & 8)) = v;
+          };
+          put(2 * d0, kk);
+          put(2 * D + 2 * d0, ll);
+          h[n] = make_float4(ptx::round_tf32(x.x), ptx::round_tf32(x.y), ptx::round_tf32(x.z), ptx::round_tf32(x.w));
         }
         ptx::fence_proxy_async_smem();
         if (st == 0) TC_TRACE(2, t);
         ptx::mbar_arrive(&bar->s_op[ss]);
-      }
-    }
-  } else if (warp < 10) {
-    // ======================= V-tile rounding (3-term only): unbiased rn instead of truncation
-    if (kThreeTerm) {
-      const int st = tid - 192;  // 0..127
-      for (int t = 0; t < n_tiles; ++t) {
-        const int vs = t % C::kVSlots;
-        ptx::mbar_wait_relaxed(&bar->v_full[vs], (t / C::kVSlots) & 1);
+        // V tile = rn_tf32(k) in the 32B-atom layout, written from registers once PV(t - kVSlots)
+        // has released the slot (and, for the first tiles, once q has left the aliased staging area)
+        if (t == 0) ptx::mbar_wait_relaxed(&bar->q_ready, 0);
+        if (t >= C::kVSlots) ptx::mbar_wait_relaxed(&bar->v_free[vs], ((t / C::kVSlots) - 1) & 1);
         float4* vt = reinterpret_cast<float4*>(v_ring + (size_t)vs * C::kTileBytes);
-#pragma unroll 8
-        for (int e = st; e < C::kTileBytes / 16; e += kGroupThreads) {
-          float4 x = vt[e];
-          x.x = ptx::round_tf32(x.x);
-          x.y = ptx::round_tf32(x.y);
-          x.z = ptx::round_tf32(x.z);
-          x.w = ptx::round_tf32(x.w);
-          vt[e] = x;
+#pragma unroll
+        for (int n = 0; n < kPer; ++n) {
+          const int e = st + n * kGroupThreads;
+          // S layout (128B swizzle): box kb, row j, physical 16-byte chunk c' = c ^ (j & 7)
+          const int kb = e >> 9, j = (e >> 3) & 63, c = (e & 7) ^ (j & 7);
+          // V layout (Swizzle<2,5,2>): 32-byte chunk (c >> 1) ^ (j & 3), same half
+          vt[(kb << 9) | (j << 3) | ((((c >> 1) ^ (j & 3)) << 1) | (c & 1))] = h[n];
         }
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&bar->v_op[vs]);
+      }
+    }
+  } else if (warp < 10) {
+    // ====================================== coalesced logits stores from the staging tile
+    const int vwarp = warp - 6;
+    const int rows_staged = min(kStageRows, p.B - i_base);
+    if (p.logits_out) {
+      for (int t = 0; t < n_tiles; ++t) {  // logits / T of tile t (models/contrastive.py:498), rows [0,64) of the CTA tile
+        ptx::mbar_wait_relaxed(&bar->stage_full, t & 1);
+        const int j0 = j_begin + t * kBlockJ;
+        const int valid = min(kBlockJ, j_end - j0);
+        for (int rr = vwarp; rr < rows_staged; rr += 4) {
+          const float v0 = stage[rr * kStagePitch + lane], v1 = stage[rr * kStagePitch + 32 + lane];
+          for (int k = 0; k < p.n_keys; ++k) {
+            float* dst = p.logits_out + ((size_t)k * p.B + i_base + rr) * (size_t)(p.K + 1) + 1 + j0;
+            if (lane < valid) dst[lane] = v0;
+            if (32 + lane < valid) dst[32 + lane] = v1;
+          }
+        }
+        ptx::mbar_arrive(&bar->stage_free);
       }
     }
   } else {
@@ -276,83 +350,71 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
 
     // ---- A operand of the S GEMM: the RAW query features f, split into (hi, lo), go to TMEM;
     // the l2-normalisation q = f/||f|| is folded into this thread's softmax scale (the thread
-    // owns row i, so s_ij = (f_i . k_j) / ||f_i||).  Cooperative and coalesced: lanes stride the
-    // columns of one row at a time (the summation order of warp_row_norm(), so the norm is
-    // bit-identical to the combine kernel's), a [32][33] shared-memory transpose hands every
-    // thread its own row for tcgen05.st, and the next 32-column block is loaded while the current
-    // one is transposed.  The MMA warp is released before the norms are reduced.
+    // owns row i, so s_ij = (f_i . k_j) / ||f_i||).  Every thread streams its own 512-byte row
+    // with 128-bit loads (32 columns in flight ahead of the tcgen05.st of the current 32).
     float inv_norm = 0.f;
     {
-      float* sc = scratch + sub * (32 * 33);
-      const int row0 = i_base + sub * 32;
-      float ssq[32], fv[32], fn[32];
+      {
+        const int stid = tid - 320;  // 0..127
+        auto put = [&](int idx, const float4& v) {
+          *reinterpret_cast<float4*>(q_stage + (size_t)(idx / kRowF4) * kQPitch + (idx % kRowF4) * 16) = v;
+        };
 #pragma unroll
-      for (int rr = 0; rr < 32; ++rr) ssq[rr] = 0.f;
-      if (warp_valid) {
+        for (int n = 0; n < kQHalf; ++n) put(stid + n * kGroupThreads, q_buf[n]);
+        if (q_total > kQHalf * kGroupThreads) {  // rows 64..127 of the CTA tile (B > 64)
 #pragma unroll
-        for (int rr = 0; rr < 32; ++rr)  // rows past B re-read the last valid row (branch-free) and are masked below
-          fv[rr] = __ldg(p.feat_q + (size_t)min(row0 + rr, p.B - 1) * D + lane);
+          for (int n = 0; n < kQHalf; ++n) {
+            const int idx = stid + (kQHalf + n) * kGroupThreads;
+            q_buf[n] = idx < q_total ? __ldg(q_gsrc + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int n = 0; n < kQHalf; ++n) put(stid + (kQHalf + n) * kGroupThreads, q_buf[n]);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four softmax warps
       }
+      if (r == 0) TC_TRACE(15, 1);
+      const float4* q_src = reinterpret_cast<const float4*>(q_stage + (size_t)r * kQPitch);
+      float4 ss = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int cb = 0; cb < D / 32; ++cb) {
-        uint32_t v[32];
-        if (warp_valid) {
-          if (cb + 1 < D / 32) {
+        uint32_t vh[32], vlo[16], vq[16];
 #pragma unroll
-            for (int rr = 0; rr < 32; ++rr)
-              fn[rr] = __ldg(p.feat_q + (size_t)min(row0 + rr, p.B - 1) * D + (cb + 1) * 32 + lane);
-          }
-#pragma unroll
-          for (int rr = 0; rr < 32; ++rr) {
-            ssq[rr] = fmaf(fv[rr], fv[rr], ssq[rr]);
-            sc[rr * 33 + lane] = (row0 + rr) < p.B ? fv[rr] : 0.f;
-          }
-          __syncwarp();
-#pragma unroll
-          for (int c = 0; c < 32; ++c) v[c] = __float_as_uint(ptx::round_tf32(sc[lane * 33 + c]));
-        } else {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) v[c] = 0u;
+        for (int k = 0; k < 8; ++k) {
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);  // rows past B feed zeros to the tensor core
+          if (row_valid) x = q_src[cb * 8 + k];
+          ss.x = fmaf(x.x, x.x, ss.x);
+          ss.y = fmaf(x.y, x.y, ss.y);
+          ss.z = fmaf(x.z, x.z, ss.z);
+          ss.w = fmaf(x.w, x.w, ss.w);
+          const float hx = ptx::round_tf32(x.x), hy = ptx::round_tf32(x.y), hz = ptx::round_tf32(x.z),
+                      hw = ptx::round_tf32(x.w);
+          vh[4 * k + 0] = __float_as_uint(hx);
+          vh[4 * k + 1] = __float_as_uint(hy);
+          vh[4 * k + 2] = __float_as_uint(hz);
+          vh[4 * k + 3] = __float_as_uint(hw);
+          vlo[2 * k + 0] = ptx::pack_bf16x2(x.x - hx, x.y - hy);
+          vlo[2 * k + 1] = ptx::pack_bf16x2(x.z - hz, x.w - hw);
+          vq[2 * k + 0] = ptx::pack_bf16x2(x.x, x.y);
+          vq[2 * k + 1] = ptx::pack_bf16x2(x.z, x.w);
         }
-        ptx::tmem_st32(lane_base + C::kColQhi + cb * 32, v);
-        if (kThreeTerm) {
-          if (warp_valid) {
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const float x = sc[lane * 33 + c];
-              v[c] = __float_as_uint(x - ptx::round_tf32(x));
-            }
-          }
-          ptx::tmem_st32(lane_base + C::kColQlo + cb * 32, v);
+        ptx::tmem_st32(lane_base + C::kColQhi + cb * 32, vh);
+        if (kThreeTerm) {  // A of the correction pass: k in [0,D) -> q_lo (meets bf16(k)), k in [D,2D) -> q (meets bf16(k_lo))
+          ptx::tmem_st16(lane_base + C::kColQlo + cb * 16, vlo);
+          ptx::tmem_st16(lane_base + C::kColQlo + D / 2 + cb * 16, vq);
         }
-        if (warp_valid) {
-          __syncwarp();
-#pragma unroll
-          for (int rr = 0; rr < 32; ++rr) fv[rr] = fn[rr];
-        }
+        if (r == 0) TC_TRACE(15, 2 + cb);
       }
       ptx::tc_wait_st();
+      if (r == 0) TC_TRACE(15, 6);
       ptx::tc_fence_before();
       if (r == 0) TC_TRACE(12, 0);
       ptx::mbar_arrive(&bar->q_ready);
-      if (warp_valid) {
-        // transpose the per-lane partial sums, then every lane reduces ITS row with the same
-        // 16-8-4-2-1 pairing as warp_sum()'s xor butterfly (bit-identical to warp_row_norm)
-#pragma unroll
-        for (int rr = 0; rr < 32; ++rr) sc[rr * 33 + lane] = ssq[rr];
-        __syncwarp();
-#pragma unroll
-        for (int c = 0; c < 32; ++c) ssq[c] = sc[lane * 33 + c];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-          for (int l = 0; l < o; ++l) ssq[l] = ssq[l] + ssq[l + o];
-        inv_norm = row_valid ? 1.f / sqrtf(ssq[0]) : 0.f;
-      }
+      inv_norm = row_valid ? 1.f / sqrtf((ss.x + ss.y) + (ss.z + ss.w)) : 0.f;
       if (r == 0) TC_TRACE(11, 0);
     }
-    const float scale2 = p.inv_T * kLog2e * inv_norm;  // log2-domain logit scale of this row
+    const float scale2 = p.inv_T * kLog2e * inv_norm;  // log2-domain logit scale of this row (>= 0)
     const float logit_scale = p.inv_T * inv_norm;
+    const bool staged = sub < 2;  // warp-uniform: rows [0,64) of the CTA tile use the staging tile
 
     float m_run = -INFINITY, l_run = 0.f;
     for (int t = 0; t < n_tiles; ++t) {
@@ -362,29 +424,45 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
       ptx::mbar_wait(&bar->s_ready[b], (t >> 1) & 1);
       ptx::tc_fence_after();
       if (r == 0) TC_TRACE(6, t);
+      const uint32_t s_col = lane_base + C::kColS + b * kBlockJ;
+      uint32_t sv[2 * 32];
       if (warp_valid) {
-        const uint32_t s_col = lane_base + C::kColS + b * kBlockJ;
         // one TMEM round trip for the whole 64-column row of S
-        uint32_t sv[2][32];
-        ptx::tmem_ld32(s_col, sv[0]);
-        ptx::tmem_ld32(s_col + 32, sv[1]);
+        ptx::tmem_ld32(s_col, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+        ptx::tmem_ld32(s_col + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
         ptx::tc_wait_ld();
-        if (p.logits_out && row_valid) {  // logits / T (models/contrastive.py:498)
+      }
+      if (p.logits_out) {  // logits / T (models/contrastive.py:498)
+        if (staged) {
+          if (t > 0) ptx::mbar_wait(&bar->stage_free, (t - 1) & 1);
+          if (warp_valid) {
+#pragma unroll
+            for (int c = 0; c < kBlockJ; ++c) stage[r * kStagePitch + c] = __uint_as_float(sv[c]) * logit_scale;
+          }
+          ptx::mbar_arrive(&bar->stage_full);
+        } else if (row_valid) {
           for (int k = 0; k < p.n_keys; ++k) {
             float* dst = p.logits_out + ((size_t)k * p.B + i) * (size_t)(p.K + 1) + 1 + j0;
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
-#pragma unroll
-              for (int c = 0; c < 32; ++c)
-                if (h * 32 + c < valid) dst[h * 32 + c] = __uint_as_float(sv[h][c]) * logit_scale;
+            for (int c = 0; c < kBlockJ; ++c)
+              if (c < valid) dst[c] = __uint_as_float(sv[c]) * logit_scale;
           }
         }
-        float tmax = -INFINITY;
+      }
+      if (warp_valid) {
+        if (valid < kBlockJ) {  // ragged last tile: columns past the queue end never win the max and get P = 0
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+          for (int c = 0; c < kBlockJ; ++c)
+            if (c >= valid) sv[c] = 0xff800000u;  // -inf
+        }
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-          for (int c = 0; c < 32; ++c)
-            if (h * 32 + c < valid) tmax = fmaxf(tmax, __uint_as_float(sv[h][c]) * scale2);
+        for (int c = 0; c < kBlockJ; c += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) mx[u] = fmaxf(mx[u], __uint_as_float(sv[c + u]));
+        }
+        // scale2 >= 0, so the maximum commutes with the scaling (rows past B have scale2 = 0)
+        const float tmax = row_valid ? fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * scale2 : 0.f;
         if (r == 0) TC_TRACE(8, t);
         // lazy rescale: keep the reference maximum unless it falls more than 2^8 behind
         const bool need = tmax > m_run + kRescaleThreshold;
@@ -411,21 +489,21 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
         }
         if (r == 0) TC_TRACE(9, t);
         // P = 2^(s2 - m), rounded to tf32, written over S
-        float psum = 0.f;
+        float ps[4] = {0.f, 0.f, 0.f, 0.f};
         const float neg_m = -m_run;
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int c = 0; c < kBlockJ; c += 4) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
+          for (int u = 0; u < 4; ++u) {
             float pv;
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pv) : "f"(fmaf(__uint_as_float(sv[h][c]), scale2, neg_m)));
-            pv = (h * 32 + c < valid) ? pv : 0.f;
-            psum += pv;
-            sv[h][c] = __float_as_uint(ptx::round_tf32(pv));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pv) : "f"(fmaf(__uint_as_float(sv[c + u]), scale2, neg_m)));
+            ps[u] += pv;
+            sv[c + u] = __float_as_uint(ptx::round_tf32(pv));
           }
-        ptx::tmem_st32(s_col, sv[0]);
-        ptx::tmem_st32(s_col + 32, sv[1]);
-        l_run += psum;
+        }
+        ptx::tmem_st32(s_col, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+        ptx::tmem_st32(s_col + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+        l_run += (ps[0] + ps[1]) + (ps[2] + ps[3]);
         ptx::tc_wait_st();
       }
       ptx::tc_fence_before();
@@ -451,19 +529,66 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
           float4* dst = reinterpret_cast<float4*>(p.part_acc + row * D + cb * 32);
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4)
-            dst[c4] = make_float4(__uint_as_float(av[c4 * 4]), __uint_as_float(av[c4 * 4 + 1]),
-                                  __uint_as_float(av[c4 * 4 + 2]), __uint_as_float(av[c4 * 4 + 3]));
+            __stcg(dst + c4, make_float4(__uint_as_float(av[c4 * 4]), __uint_as_float(av[c4 * 4 + 1]),
+                                         __uint_as_float(av[c4 * 4 + 2]), __uint_as_float(av[c4 * 4 + 3])));
         }
       }
     }
   }
 
-  // -------------------------------------------------------------------- teardown
+  // ------------------------------------------------- teardown of the tensor-core sweep
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem, C::kTmemCols);
+  }
+
+  // --------------------------------------------------------------------- grid barrier
+  // Cooperative launch: all CTAs are co-resident, so spinning on a global counter is safe.
+  const unsigned n_ctas = gridDim.x * gridDim.y;
+  if (tid == 0) TC_TRACE(14, 2);
+  if (tid == 0) {
+    __threadfence();  // this CTA's partials (ordered before by the barrier above) are visible GPU-wide
+    atomicAdd(p.counter + 1, 1u);
+    while (ld_acquire_u32(p.counter + 1) < n_ctas) __nanosleep(40);
+  }
+  __syncthreads();
+
+  // ------------------------------------------- merge: one query row per CTA, then the mean
+  CombineSmem<kTcThreads>& csm = *reinterpret_cast<CombineSmem<kTcThreads>*>(smem);  // the rings are dead
+  if (tid == 0) TC_TRACE(14, 3);
+  const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+  long long enq_ptr = 0;
+  bool enq_ok = false;
+  if (p.enq_ptr) {
+    enq_ptr = *reinterpret_cast<volatile long long*>(p.enq_ptr);  // advanced only after every CTA arrived below
+    enq_ok = enq_ptr >= 0 && enq_ptr + p.B <= p.K;               // models/contrastive.py:285
+  }
+  for (int i = cta; i < p.B; i += (int)n_ctas) {
+    infonce_combine_row<kTcThreads, 1>(p, i, csm);
+    if (enq_ok) {  // K4: queue[ptr + i] = keys[0][i]; no CTA reads the queue after the grid barrier
+      const float4* src = reinterpret_cast<const float4*>(p.keys[0] + (size_t)i * D);
+      float4* dst = reinterpret_cast<float4*>(p.queue_rw + (size_t)(enq_ptr + i) * D);
+      for (int c4 = tid; c4 < D / 4; c4 += kTcThreads) dst[c4] = src[c4];
+    }
+  }
+  if (tid == 0) TC_TRACE(14, 4);
+  const bool last_cta = infonce_finish<kTcThreads>(p, n_ctas, csm);
+  if (tid == 0) TC_TRACE(14, 5);
+  if (last_cta) {
+    if (tid == 0) {
+      p.counter[1] = 0u;  // every CTA is past the barrier: it incremented counter[0] afterwards
+      if (p.enq_ptr) {
+        if (enq_ok) {
+          long long np = enq_ptr + p.B;
+          if (np == p.K) np = 0;  // wrap only when landing exactly on K (:290-291)
+          *p.enq_ptr = np;
+        } else if (p.enq_status) {
+          atomicOr(p.enq_status, AVSSL_DEVFLAG_QUEUE_OVERRUN);
+        }
+      }
+    }
   }
 }
 
@@ -521,16 +646,25 @@ int launch_tc(const InfoNceParams& p, cudaStream_t s) {
     configured = true;
   }
   dim3 grid(p.n_splits, (p.B + kM - 1) / kM);
-  infonce_tc_kernel<D, kThreeTerm><<<grid, kTcThreads, C::kSmemBytes, s>>>(p, cache.s, cache.v);
-  AVSSL_LAUNCH_OK("infonce_tc_kernel");
+  AVSSL_REQUIRE((int)(grid.x * grid.y) <= sm_count(), AVSSL_ERR_INVALID_ARGUMENT,
+                "moco_infonce: %u CTAs cannot be co-resident on %d SMs", grid.x * grid.y, sm_count());
+  // cooperative: the kernel contains a grid-wide barrier (all CTAs must be co-resident)
+  InfoNceParams pc = p;
+  void* args[] = {&pc, &cache.s, &cache.v};
+  cudaError_t le = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&infonce_tc_kernel<D, kThreeTerm>), grid,
+                                               dim3(kTcThreads), args, C::kSmemBytes, s);
+  if (le != cudaSuccess) {
+    set_error("cooperative launch of infonce_tc_kernel failed: %s", cudaGetErrorString(le));
+    return AVSSL_ERR_CUDA;
+  }
   return AVSSL_OK;
 }
 
 }  // namespace
 
 bool infonce_tc_supported(int B, int D, int K) {
-  (void)B;
-  return (D == 32 || D == 64 || D == 96 || D == 128) && K >= 1;
+  // one CTA per 128 query rows and queue split; the cooperative grid must fit the SMs
+  return (D == 32 || D == 64 || D == 96 || D == 128) && K >= 1 && (B + kM - 1) / kM <= sm_count();
 }
 
 int launch_infonce_tc(const InfoNceParams& p, int three_term, cudaStream_t s) {

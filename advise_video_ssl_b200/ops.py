@@ -119,11 +119,14 @@ def _workspace(device, nbytes):
     return ws
 
 
-def moco_infonce(feat_q, keys, queue, T, want_logits=True, impl=_lib.IMPL_AUTO, out=None):
+def moco_infonce(feat_q, keys, queue, T, want_logits=True, impl=_lib.IMPL_AUTO, out=None, enqueue=None):
     """Fused l2-norm + logits + InfoNCE forward/backward (K2+K3).
 
     Returns dict(loss[1], dfeat[B,D], q[B,D], lse[n_keys*B], logits[n_keys*B,K+1] or None).
     `out` may carry preallocated tensors under the same names (CUDA-graph replay).
+    `enqueue=(ptr, status)` additionally performs K4 for keys[0] after the loss has been
+    computed against the old queue: queue[ptr:ptr+B] = keys[0], ptr advanced on the device
+    (same launch with the tcgen05 kernels); `status` may be None.
     """
     _req(feat_q, "feat_q")
     _req(queue, "queue")
@@ -150,11 +153,25 @@ def moco_infonce(feat_q, keys, queue, T, want_logits=True, impl=_lib.IMPL_AUTO, 
     nbytes = lib.avssl_moco_infonce_workspace_bytes(B, D, K, n_keys)
     ws = _workspace(dev, nbytes)
     key_ptrs = (ctypes.c_void_p * n_keys)(*[k.data_ptr() for k in keys])
-    check(lib.avssl_moco_infonce_fwd_bwd(
-        feat_q.data_ptr(), ctypes.addressof(key_ptrs), n_keys, queue.data_ptr(), B, D, K, float(T),
-        q.data_ptr(), loss.data_ptr(), dfeat.data_ptr(), lse.data_ptr(),
-        logits.data_ptr() if logits is not None else None, ws.data_ptr(), ws.numel(), int(impl), _stream()),
-        "avssl_moco_infonce_fwd_bwd")
+    if enqueue is None:
+        check(lib.avssl_moco_infonce_fwd_bwd(
+            feat_q.data_ptr(), ctypes.addressof(key_ptrs), n_keys, queue.data_ptr(), B, D, K, float(T),
+            q.data_ptr(), loss.data_ptr(), dfeat.data_ptr(), lse.data_ptr(),
+            logits.data_ptr() if logits is not None else None, ws.data_ptr(), ws.numel(), int(impl), _stream()),
+            "avssl_moco_infonce_fwd_bwd")
+    else:
+        ptr, status = enqueue
+        _req(ptr, "ptr", torch.int64)
+        if status is not None:
+            _req(status, "status", torch.int32)
+        # models/contrastive.py:284 — same exception type as the reference's assert
+        assert K % B == 0, "queue length %d is not a multiple of the key batch %d" % (K, B)
+        check(lib.avssl_moco_infonce_fwd_bwd_enqueue(
+            feat_q.data_ptr(), ctypes.addressof(key_ptrs), n_keys, queue.data_ptr(), ptr.data_ptr(),
+            status.data_ptr() if status is not None else None, B, D, K, float(T),
+            q.data_ptr(), loss.data_ptr(), dfeat.data_ptr(), lse.data_ptr(),
+            logits.data_ptr() if logits is not None else None, ws.data_ptr(), ws.numel(), int(impl), _stream()),
+            "avssl_moco_infonce_fwd_bwd_enqueue")
     return {"loss": loss, "dfeat": dfeat, "q": q, "lse": lse, "logits": logits}
 
 

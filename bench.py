@@ -195,7 +195,7 @@ def gpu_arm(args):
     impl = {"auto": _lib.IMPL_AUTO, "simt": _lib.IMPL_SIMT, "tc3x": _lib.IMPL_TC3X, "tc1x": _lib.IMPL_TC1X}[args.kernel]
     out = {}
     state = {"n": 0}
-    launches_per_step = 4  # ema, infonce split, infonce combine, enqueue
+    launches_per_step = 2 if args.kernel != "simt" else 4  # ema + fused head (simt: ema, split, combine, enqueue)
     ema_events = []
 
     def step(i, f, k, time_ema=False):
@@ -216,9 +216,9 @@ def gpu_arm(args):
         if world > 1:
             torch.cuda.current_stream().wait_stream(comm)
             k = gathered[rank * B_PER_GPU:(rank + 1) * B_PER_GPU]
-        r = ops.moco_infonce(f, [k], queue, TEMP, want_logits=not args.no_logits, impl=impl, out=out)
-        ops.queue_enqueue(queue, ptr, k, status)
-        return r
+        # K2+K3+K4 in one cooperative launch: loss/grad against the old queue, then the ring write
+        return ops.moco_infonce(f, [k], queue, TEMP, want_logits=not args.no_logits, impl=impl, out=out,
+                                enqueue=(ptr, status))
 
     def sync_all():
         torch.cuda.synchronize()

@@ -119,6 +119,19 @@ AVSSL_API int avssl_moco_infonce_fwd_bwd(const float* feat_q, const float* const
                                float* loss_out, float* dfeat_out, float* row_lse_out,
                                float* logits_out, void* workspace, size_t workspace_bytes,
                                int impl, void* stream);
+/* Same, followed by the queue ring write of K4 for keys_host[0] (the non-multi-view
+ * `_dequeue_and_enqueue(keys)` of models/contrastive.py:502-503, 263-292):
+ *     queue[ptr:ptr+B] = keys[0];  ptr = (ptr + B == K) ? 0 : ptr + B
+ * The logits, loss and gradient are computed against the queue BEFORE the write, as in
+ * the reference.  With the tcgen05 kernels the write happens inside the same launch, after
+ * a grid-wide barrier behind the last read of the queue; ptr_dev / status_dev as in
+ * avssl_queue_enqueue (requires K % B == 0; ptr + B <= K is checked on the device).
+ */
+AVSSL_API int avssl_moco_infonce_fwd_bwd_enqueue(const float* feat_q, const float* const* keys_host, int n_keys,
+                                       float* queue, int64_t* ptr_dev, uint32_t* status_dev, int B, int D,
+                                       int K, float T, float* q_out, float* loss_out, float* dfeat_out,
+                                       float* row_lse_out, float* logits_out, void* workspace,
+                                       size_t workspace_bytes, int impl, void* stream);
 
 /* --------------------------------------------------------------- K4: queue ring write
  * Replaces _dequeue_and_enqueue (models/contrastive.py:263-292) for one key tensor:

@@ -256,6 +256,62 @@ def test_infonce_peaked_distribution(name, impl):
     _check_infonce(out, feat, keys, queue, T, lt, gt if name != "tc1x" else 2e-2, at)
 
 
+@pytest.mark.parametrize("name,impl", IMPLS)
+@pytest.mark.parametrize("B,D,K,nk", [(64, 128, 4096, 1), (32, 64, 640, 2), (256, 128, 2048, 1), (8, 32, 64, 1)])
+def test_infonce_fused_enqueue(name, impl, B, D, K, nk):
+    """K3 + K4 in one call: loss/grad/logits against the OLD queue, then queue[ptr:ptr+B] =
+    keys[0] and the pointer advance, bit-exact with O.enqueue (models/contrastive.py:263-292,
+    486-503); repeated until the pointer wraps."""
+    ops = _ops()
+    torch.manual_seed(B + K)
+    T = 0.1
+    queue_c = O.l2_normalize(torch.randn(K, D))
+    queue = queue_c.clone().cuda()
+    ptr = torch.zeros(1, dtype=torch.int64, device="cuda")
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    pc = 0
+    steps = min(K // B + 1, 6)
+    if K // B > 6:  # start near the end so the wrap is exercised
+        pc = K - 2 * B
+        ptr.fill_(pc)
+    for s in range(steps):
+        feat = torch.randn(B, D)
+        keys = [O.l2_normalize(torch.randn(B, D)) for _ in range(nk)]
+        out = ops.moco_infonce(feat.cuda(), [k.cuda() for k in keys], queue, T, True, impl, enqueue=(ptr, status))
+        _check_infonce(out, feat, keys, queue_c, T, *TOL[name])  # against the queue BEFORE the write
+        pc = O.enqueue(queue_c, pc, keys, K)
+        assert torch.equal(queue.cpu(), queue_c), "step %d" % s
+        assert int(ptr.item()) == pc
+    assert int(status.item()) == 0
+    # device-side replacement of `assert ptr + n <= K`: nothing written, flag raised, loss still valid
+    if K >= 2 * B:
+        ptr.fill_(K - B // 2 if B > 1 else K)
+        before, pbefore = queue.clone(), int(ptr.item())
+        feat = torch.randn(B, D)
+        keys = [O.l2_normalize(torch.randn(B, D)) for _ in range(nk)]
+        out = ops.moco_infonce(feat.cuda(), [k.cuda() for k in keys], queue, T, False, impl, enqueue=(ptr, status))
+        _check_infonce(out, feat, keys, queue_c, T, *TOL[name])
+        assert int(status.item()) & 1 and torch.equal(queue, before) and int(ptr.item()) == pbefore
+    with pytest.raises(AssertionError):  # models/contrastive.py:284
+        ops.moco_infonce(torch.randn(7, D).cuda(), [torch.randn(7, D).cuda()], queue, T, False, impl,
+                         enqueue=(ptr, status))
+
+
+def test_infonce_repeated_launches_are_deterministic():
+    """The cooperative kernel's counters reset themselves: 20 back-to-back launches on the same
+    inputs give identical bits (no floating-point atomics anywhere on the path)."""
+    ops = _ops()
+    torch.manual_seed(3)
+    feat = torch.randn(64, 128).cuda()
+    keys = [O.l2_normalize(torch.randn(64, 128)).cuda()]
+    queue = O.l2_normalize(torch.randn(65536, 128)).cuda()
+    ref = ops.moco_infonce(feat, keys, queue, 0.1, True)
+    for _ in range(20):
+        out = ops.moco_infonce(feat, keys, queue, 0.1, True)
+        assert torch.equal(out["loss"], ref["loss"]) and torch.equal(out["dfeat"], ref["dfeat"])
+        assert torch.equal(out["logits"], ref["logits"])
+
+
 def test_no_cpu_fallback():
     ops = _ops()
     with pytest.raises(RuntimeError, match="no CPU fallback"):

@@ -7,7 +7,8 @@ using namespace avssl;
 int main(int argc, char** argv) {
   const int three = argc > 1 ? atoi(argv[1]) : 1;
   const int B = 64, D = 128, K = 65536;
-  float *f, *q, *pm, *pl, *pa;
+  float *f, *q, *pm, *pl, *pa, *o;
+  unsigned* cnt;
   cudaMalloc(&f, B * D * 4); cudaMalloc(&q, (size_t)K * D * 4);
   std::vector<float> h((size_t)K * D);
   for (size_t i = 0; i < h.size(); ++i) h[i] = ((i * 2654435761u) % 1000) / 1000.f - 0.5f;
@@ -20,6 +21,9 @@ int main(int argc, char** argv) {
   p.n_splits = S; p.rows_per_split = tps * 64;
   cudaMalloc(&pm, S * B * 4); cudaMalloc(&pl, S * B * 4); cudaMalloc(&pa, (size_t)S * B * D * 4);
   p.part_m = pm; p.part_l = pl; p.part_acc = pa;
+  cudaMalloc(&cnt, 256); cudaMemset(cnt, 0, 256); p.counter = cnt;
+  cudaMalloc(&o, (size_t)B * (D * 2 + 8) * 4);
+  p.q_out = o; p.dfeat_out = o + B * D; p.row_loss = o + 2 * B * D; p.loss_out = o + 2 * B * D + B; p.keys[0] = f;
   for (int rep = 0; rep < 3; ++rep) {
     int rc = launch_infonce_tc(p, three, 0);
     cudaError_t e = cudaDeviceSynchronize();
@@ -35,6 +39,20 @@ int main(int argc, char** argv) {
     for (int ev = 0; ev < 8; ++ev) printf(" %s=%lld", names[ev], tr[ev][t] - t0);
     printf(" | pass1_done=%lld rescale_done=%lld\n", tr[8][t] - t0, tr[9][t] - t0);
   }
+  printf("phases (cycles rel. first TMA issue): entry=%lld setup_done=%lld sweep_done=%lld barrier_passed=%lld rows_merged=%lld finish=%lld\n",
+         tr[14][0] - t0, tr[14][1] - t0, tr[14][2] - t0, tr[14][3] - t0, tr[14][4] - t0, tr[14][5] - t0);
+  {
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    for (int rep = 0; rep < 50; ++rep) launch_infonce_tc(p, three, 0);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    printf("50 back-to-back launches (queue L2-resident): %.2f us per launch\n", ms * 20.f);
+  }
+  printf("merge row 0: enter=%lld loads_issued=%lld max_done=%lld L_done=%lld acc_merged=%lld keys_done=%lld end=%lld\n", tr[10][0] - t0,
+         tr[10][1] - t0, tr[10][2] - t0, tr[10][3] - t0, tr[10][4] - t0, tr[10][5] - t0, tr[10][6] - t0);
+  printf("q prologue: enter=%lld q_full=%lld cb0=%lld cb1=%lld cb2=%lld cb3=%lld wait_st=%lld\n", tr[15][0] - t0, tr[15][1] - t0,
+         tr[15][2] - t0, tr[15][3] - t0, tr[15][4] - t0, tr[15][5] - t0, tr[15][6] - t0);
   printf("prologue: normsA_done=%lld q_in_tmem=%lld mma_saw_q=%lld\n", tr[11][0] - t0, tr[12][0] - t0, tr[13][0] - t0);
   return 0;
 }
