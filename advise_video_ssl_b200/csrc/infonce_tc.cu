@@ -35,8 +35,8 @@
 // unrolled.
 //
 // Warp roles (448 threads, 1 CTA / SM):  0 TMA producer | 1 MMA issuer + TMEM allocator |
-// 2-5 S-tile hi/lo split | 6-9 V-tile rounding + coalesced logits writer | 10-13 softmax +
-// epilogue (thread = query row).
+// 2-9 helper warps (correction + V tile) | 10-13 softmax + epilogue (thread = query row; warp
+// w owns TMEM lanes 32*(w%4)..; warps without rows store the staged logits).
 // TMEM columns: [0,D) q_hi | [D,2D) [q_lo | q] as packed bf16 | [2D,2D+128) S/P double buffer |
 // [2D+128,3D+128) acc.
 //
@@ -58,11 +58,13 @@ namespace {
 constexpr int kBlockJ = kTcTileRows;  // 64 queue rows per tile
 constexpr int kM = 128;               // query rows per CTA
 constexpr int kTcThreads = 448;
-constexpr int kGroupThreads = 128;    // split / round / softmax groups
+constexpr int kGroupThreads = 128;    // softmax warps
+constexpr int kHelperThreads = 256;   // helper warps 2..9
 constexpr float kRescaleThreshold = 8.f;  // log2 units: P stays below 2^8
 constexpr int kMaxSlots = 3;
-constexpr int kStageRows = 64;             // query rows per CTA whose logits go through the staging tile
-constexpr int kStagePitch = kBlockJ + 1;   // floats; +1 keeps row-wise writes and column-wise reads conflict-free
+constexpr int kStageRows = 64;   // query rows per CTA whose logits go through the staging tile
+constexpr int kStageCarry = 8;   // columns carried over from the previous tile (one 32-byte sector of floats)
+constexpr int kStagePitch = kStageCarry + kBlockJ + 1;  // floats; odd pitch: row- and column-wise accesses conflict-free
 
 template <int D, bool kThreeTerm>
 struct TcCfg {
@@ -74,7 +76,7 @@ struct TcCfg {
   static constexpr int kVSlots = kThreeTerm ? 2 : 3;
   static constexpr int kSRingBytes = kSSlots * kSSlotBytes;
   static constexpr int kVRingBytes = kVSlots * kTileBytes;
-  static constexpr int kScratchBytes = kStageRows * kStagePitch * 4;  // logits staging tile [64][65]
+  static constexpr int kScratchBytes = kStageRows * kStagePitch * 4;  // logits staging tile [64][8 + 64 (+1)]
   static constexpr int kColQhi = 0, kColQlo = D, kColS = 2 * D, kColAcc = 2 * D + 2 * kBlockJ;
   static constexpr int kTmemCols = 512;
   static_assert(3 * D + 2 * kBlockJ <= 512, "TMEM budget");
@@ -103,8 +105,10 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
                   const __grid_constant__ CUtensorMap tmap_v) {
   using C = TcCfg<D, kThreeTerm>;
   extern __shared__ uint8_t smem_raw[];
-  // swizzled operands need 1024-byte aligned tiles
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // swizzled operands need 1024-byte aligned tiles.  The offset is added to the __shared__ array itself
+  // (no integer round trip), so the compiler keeps the shared address space and emits LDS/STS instead
+  // of generic loads and stores.
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_ring = smem;
   uint8_t* v_ring = smem + C::kSRingBytes;
   float* stage = reinterpret_cast<float*>(smem + C::kSRingBytes + C::kVRingBytes);
@@ -143,10 +147,10 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
     ptx::tma_prefetch_desc(&tmap_v);
     for (int s = 0; s < kMaxSlots; ++s) {
       ptx::mbar_init(&bar->s_full[s], 1);
-      ptx::mbar_init(&bar->s_op[s], kGroupThreads);
+      ptx::mbar_init(&bar->s_op[s], kHelperThreads);
       ptx::mbar_init(&bar->s_free[s], 1);
       ptx::mbar_init(&bar->v_full[s], 1);
-      ptx::mbar_init(&bar->v_op[s], kGroupThreads);
+      ptx::mbar_init(&bar->v_op[s], kHelperThreads);
       ptx::mbar_init(&bar->v_free[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -156,8 +160,8 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
     }
     ptx::mbar_init(&bar->q_ready, kGroupThreads);
     ptx::mbar_init(&bar->acc_done, 1);
-    ptx::mbar_init(&bar->stage_full, 2 * 32);        // softmax warps 10 and 11 (rows 0..63 of the CTA tile)
-    ptx::mbar_init(&bar->stage_free, kGroupThreads);  // the four writer warps
+    ptx::mbar_init(&bar->stage_full, 2 * 32);  // the two softmax warps of rows 0..63 of the CTA tile
+    ptx::mbar_init(&bar->stage_free, 2 * 32);  // the other two softmax warps, which store the staged logits
     ptx::mbar_fence_init();
   }
   if (warp == 1) ptx::tmem_alloc(&bar->tmem_base, C::kTmemCols);
@@ -229,8 +233,10 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
         for (int ks = 0; ks < kBlockJ / 8; ++ks)
           ptx::mma_tf32_ts(tm + C::kColAcc, a0 + ks * 8, bd0 + (uint64_t)(ks * 1024 >> 4), idesc_pv,
                            (t > 0 || ks > 0) ? 1u : 0u);
+        TC_TRACE(13, 1 + t);
         ptx::tc_commit(&bar->v_free[vs]);  // V tile consumed -> TMA may refill the slot
         ptx::tc_commit(&bar->pv_done[b]);
+        TC_TRACE(12, 1 + t);
       }
       __syncwarp();
     };
@@ -244,9 +250,12 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
       const uint64_t lo0 = hi0 + (uint64_t)(C::kTileBytes >> 4);
       const uint32_t d_s = tm + C::kColS + b * kBlockJ;
       if (ptx::elect_one()) {
-        // smallest contributions first: the bf16 correction pass [q_lo | q].[k | k_lo] (2D bf16 per
-        // row = the same D/32 boxes of 128 B, 16 k per MMA = 32 B per step), then q_hi.k_hi
+        // Smallest contributions first: the tensor core's fp32 accumulation is not round-to-nearest,
+        // so adding the ~2^-11 correction terms onto the finished q_hi.k_hi sum costs ~2x the error
+        // of summing them first (measured: 3.8e-5 vs 1.7e-5 max logit error at T = 0.07).
         if (kThreeTerm) {
+          // bf16 correction pass [q_lo | q].[k | k_lo]: 2D bf16 per row = the same D/32 boxes of 128 B,
+          // 16 k per MMA = 32 B per step
 #pragma unroll
           for (int ks = 0; ks < D / 8; ++ks)
             ptx::mma_f16_ts(d_s, tm + C::kColQlo + ks * 8, lo0 + (uint64_t)(((ks >> 2) * C::kBoxBytes + (ks & 3) * 32) >> 4),
@@ -257,7 +266,7 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
           ptx::mma_tf32_ts(d_s, tm + C::kColQhi + ks * 8, hi0 + (uint64_t)(((ks >> 2) * C::kBoxBytes + (ks & 3) * 32) >> 4),
                            idesc_s, (kThreeTerm || ks > 0) ? 1u : 0u);
         ptx::tc_commit(&bar->s_ready[b]);
-        ptx::tc_commit(&bar->s_free[ss]);  // S tile consumed -> TMA may refill the slot
+        ptx::tc_commit(&bar->s_free[ss]);  // raw + correction tile consumed -> TMA / helper warps may refill the slot
       }
       __syncwarp();
       TC_TRACE(4, t);
@@ -266,37 +275,48 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
     if (n_tiles > 0) issue_pv(n_tiles - 1);
     if (ptx::elect_one()) ptx::tc_commit(&bar->acc_done);
     __syncwarp();
-  } else if (warp < 6) {
-    // ============================ S-tile split + V tile (3-term only): one read of the raw tile
+  } else if (warp < 10) {
+    // ============================ helper warps 2..9 (3-term only): one read of the raw tile ->
+    // correction tile [bf16(k) | bf16(k_lo)] and, from registers, the V tile rn_tf32(k)
     if (kThreeTerm) {
-      const int st = tid - 64;  // 0..127
-      constexpr int kPer = C::kTileBytes / 16 / kGroupThreads;  // float4 per thread and tile (D / 8)
+      // st in [0,256) indexes the float4 this thread owns: a warp takes rows {w, w+4, w+8, w+12} of a
+      // 16-row group (8 lanes per row) so that its 8-byte correction-tile stores land in both 64-byte
+      // halves of the swizzled rows (no bank conflicts); whole rows keep the 128-bit raw loads and V
+      // stores conflict-free too.
+      const int hw = warp - 2;
+      const int st = (((hw & 3) + 4 * (lane >> 3) + 16 * (hw >> 2)) << 3) | (lane & 7);
+      constexpr int kPer = C::kTileBytes / 16 / kHelperThreads;  // float4 per thread and tile (D / 16)
+      // Thread st owns the float4 e = st + 256 n of the raw tile (n < kPer).  In the S layout (128B
+      // swizzle) e sits in box e >> 9 = n >> 1, row j = (st >> 3) + 32 (n & 1), physical 16-byte chunk
+      // st & 7 = logical chunk c ^ (j & 7) -- so c, j & 7 and every swizzle term are per-thread
+      // constants and the addresses below are "thread base + compile-time offset".
+      const int jl = st >> 3, jc = jl & 7, c = (st & 7) ^ jc;
+      // correction tile: element kappa of row j at byte 2 kappa = kbv * 64 + c * 8 (kbv = box of the fp32
+      // column block, + D/32 for the k_lo half): box kbv >> 1, logical chunk (kbv & 1) * 4 + (c >> 1)
+      const int corr_t = jl * 128 + (((c >> 1) ^ (jc & 3)) << 4) + (c & 1) * 8;
+      const int corr_b[2] = {corr_t + ((jc & 4) << 4), corr_t + (((jc & 4) ^ 4) << 4)};
+      // V layout (Swizzle<2,5,2>): 32-byte chunk (c >> 1) ^ (j & 3), same half
+      const int v_t = (jl << 3) | ((((c >> 1) ^ (jl & 3)) << 1) | (c & 1));
       for (int t = 0; t < n_tiles; ++t) {
         const int ss = t % C::kSSlots, vs = t % C::kVSlots;
         ptx::mbar_wait_relaxed(&bar->s_full[ss], (t / C::kSSlots) & 1);
         if (st == 0) TC_TRACE(1, t);
-        const float4* raw = reinterpret_cast<const float4*>(s_ring + (size_t)ss * C::kSSlotBytes);
+        const float4* raw = reinterpret_cast<const float4*>(s_ring + (size_t)ss * C::kSSlotBytes) + st;
         uint8_t* corr = s_ring + (size_t)ss * C::kSSlotBytes + C::kTileBytes;  // [bf16(k) | bf16(k_lo)], K-major, 128B swizzle
         float4 h[kPer];
 #pragma unroll
         for (int n = 0; n < kPer; ++n) {
-          const int e = st + n * kGroupThreads;
-          const float4 x = raw[e];
-          // S layout (128B swizzle): box kb, row j, physical 16-byte chunk c' = c ^ (j & 7); columns d0..d0+3
-          const int kb = e >> 9, j = (e >> 3) & 63, c = (e & 7) ^ (j & 7);
-          const int d0 = kb * 32 + c * 4;
+          const float4 x = raw[n * kHelperThreads];
           uint2 kk, ll;
           kk.x = ptx::pack_bf16x2(x.x, x.y);
           kk.y = ptx::pack_bf16x2(x.z, x.w);
           // k_lo = k - trunc(k): exact in fp32, what the tf32 pass does not see
           ll.x = ptx::pack_bf16x2(x.x - ptx::trunc_tf32(x.x), x.y - ptx::trunc_tf32(x.y));
           ll.y = ptx::pack_bf16x2(x.z - ptx::trunc_tf32(x.z), x.w - ptx::trunc_tf32(x.w));
-          // byte offset bo of element kappa in a correction-tile row: 2*kappa; box bo >> 7, chunk (bo & 127) >> 4
-          auto put = [&](int bo, const uint2& v) {
-            *reinterpret_cast<uint2*>(corr + (bo >> 7) * C::kBoxBytes + j * 128 + ((((bo & 127) >> 4) ^ (j & 7)) << 4) + (bo & 8)) = v;
-          };
-          put(2 * d0, kk);
-          put(2 * D + 2 * d0, ll);
+          constexpr int kRowOff = 32 * 128;  // 32 rows further per (n & 1)
+          const int kb = n >> 1, kbl = kb + C::kKB;
+          *reinterpret_cast<uint2*>(corr + (kb >> 1) * C::kBoxBytes + (n & 1) * kRowOff + corr_b[kb & 1]) = kk;
+          *reinterpret_cast<uint2*>(corr + (kbl >> 1) * C::kBoxBytes + (n & 1) * kRowOff + corr_b[kbl & 1]) = ll;
           h[n] = make_float4(ptx::round_tf32(x.x), ptx::round_tf32(x.y), ptx::round_tf32(x.z), ptx::round_tf32(x.w));
         }
         ptx::fence_proxy_async_smem();
@@ -306,37 +326,11 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
         // has released the slot (and, for the first tiles, once q has left the aliased staging area)
         if (t == 0) ptx::mbar_wait_relaxed(&bar->q_ready, 0);
         if (t >= C::kVSlots) ptx::mbar_wait_relaxed(&bar->v_free[vs], ((t / C::kVSlots) - 1) & 1);
-        float4* vt = reinterpret_cast<float4*>(v_ring + (size_t)vs * C::kTileBytes);
+        float4* vt = reinterpret_cast<float4*>(v_ring + (size_t)vs * C::kTileBytes) + v_t;
 #pragma unroll
-        for (int n = 0; n < kPer; ++n) {
-          const int e = st + n * kGroupThreads;
-          // S layout (128B swizzle): box kb, row j, physical 16-byte chunk c' = c ^ (j & 7)
-          const int kb = e >> 9, j = (e >> 3) & 63, c = (e & 7) ^ (j & 7);
-          // V layout (Swizzle<2,5,2>): 32-byte chunk (c >> 1) ^ (j & 3), same half
-          vt[(kb << 9) | (j << 3) | ((((c >> 1) ^ (j & 3)) << 1) | (c & 1))] = h[n];
-        }
+        for (int n = 0; n < kPer; ++n) vt[(n >> 1) * 512 + (n & 1) * 256] = h[n];
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&bar->v_op[vs]);
-      }
-    }
-  } else if (warp < 10) {
-    // ====================================== coalesced logits stores from the staging tile
-    const int vwarp = warp - 6;
-    const int rows_staged = min(kStageRows, p.B - i_base);
-    if (p.logits_out) {
-      for (int t = 0; t < n_tiles; ++t) {  // logits / T of tile t (models/contrastive.py:498), rows [0,64) of the CTA tile
-        ptx::mbar_wait_relaxed(&bar->stage_full, t & 1);
-        const int j0 = j_begin + t * kBlockJ;
-        const int valid = min(kBlockJ, j_end - j0);
-        for (int rr = vwarp; rr < rows_staged; rr += 4) {
-          const float v0 = stage[rr * kStagePitch + lane], v1 = stage[rr * kStagePitch + 32 + lane];
-          for (int k = 0; k < p.n_keys; ++k) {
-            float* dst = p.logits_out + ((size_t)k * p.B + i_base + rr) * (size_t)(p.K + 1) + 1 + j0;
-            if (lane < valid) dst[lane] = v0;
-            if (32 + lane < valid) dst[32 + lane] = v1;
-          }
-        }
-        ptx::mbar_arrive(&bar->stage_free);
       }
     }
   } else {
@@ -414,7 +408,11 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
     }
     const float scale2 = p.inv_T * kLog2e * inv_norm;  // log2-domain logit scale of this row (>= 0)
     const float logit_scale = p.inv_T * inv_norm;
-    const bool staged = sub < 2;  // warp-uniform: rows [0,64) of the CTA tile use the staging tile
+    // Logits of a CTA tile with at most 64 query rows (the MoCo case) go through the padded staging
+    // tile: the two softmax warps that own rows write their 64 values per row, the two warps whose
+    // rows do not exist store them as full 128-byte lines.  Larger tiles store directly.
+    const bool staged_cta = p.logits_out != nullptr && (p.B - i_base) <= kStageRows;
+    const bool drainer = staged_cta && sub >= 2;  // warp-uniform
 
     float m_run = -INFINITY, l_run = 0.f;
     for (int t = 0; t < n_tiles; ++t) {
@@ -432,12 +430,88 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
         ptx::tmem_ld32(s_col + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
         ptx::tc_wait_ld();
       }
+      if (drainer) {
+        // rows of this warp do not exist: release PV, then store the staged logits / T of tile t
+        // (models/contrastive.py:498) as whole lines; 32 rows per warp
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&bar->p_ready[b]);
+        ptx::mbar_wait(&bar->stage_full, t & 1);
+        if (sub == 2 && lane == 0) TC_TRACE(11, 1 + t);
+        // Row r of the logits tensor starts (K+1)*4*r + 4 bytes into the buffer, so a tile's 64 columns
+        // are never sector aligned and a straight copy would end both ends of every row chunk with a
+        // partial 32-byte sector (read-modify-write in the memory system; measured 3x slower).  Each
+        // row is therefore written as a stream: the window of 64 floats that ENDS at the last sector
+        // boundary inside the tile = the s floats held back from the previous tile (kept in the carry
+        // columns of the staging tile) + the first 64 - s floats of this one.  Only the first and last
+        // tile of a split touch partial sectors.
+        // The SM keeps only a few store instructions per warp in flight, so stores are made as wide as
+        // possible: one 128-bit store per lane covers two rows (lanes 0-15 / 16-31) x 64 floats.
+        const int rr0 = (sub - 2) * 32;
+        const int n_rows = min(32, p.B - i_base - rr0);  // staged rows of this warp (may be <= 0)
+        const size_t row_pitch = (size_t)(p.K + 1);
+        const bool last_tile = t == n_tiles - 1;
+        const int half = lane >> 4, q4 = (lane & 15) * 4;
+        for (int k = 0; k < p.n_keys; ++k) {
+          // element index of (row rr0 + half, column j0) in the logits tensor; two rows per store, four
+          // stores in flight per trip (the address -> shared load -> store chain of one row pair is
+          // ~170 cycles long, so independent pairs are interleaved by hand; trips are not unrolled to
+          // keep the body resident in the instruction cache)
+          const size_t ge0 = ((size_t)k * p.B + i_base + rr0 + half) * row_pitch + 1 + j0;
+          const float* srow0 = stage + (rr0 + half) * kStagePitch + kStageCarry + q4;
+#pragma unroll 1
+          for (int r4 = 0; r4 < 32; r4 += 8) {
+            int sh[4];
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const size_t ge = ge0 + (size_t)(r4 + 2 * u) * row_pitch;
+              sh[u] = (int)(ge & 7);  // floats held back per tile for this row
+              const float* src = srow0 + (r4 + 2 * u) * kStagePitch - sh[u];
+              v[u] = make_float4(src[0], src[1], src[2], src[3]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int row = r4 + 2 * u + half;
+              if (row < n_rows) {
+                const size_t ge = ge0 + (size_t)(r4 + 2 * u) * row_pitch;
+                float* dst = p.logits_out + ge - sh[u] + q4;  // 16-byte aligned
+                const int c0 = q4 - sh[u];                    // tile column of v.x; negative = carried from the previous tile
+                if ((c0 >= 0 || t > 0) && c0 + 3 < valid) {
+                  *reinterpret_cast<float4*>(dst) = v[u];
+                } else {
+                  if ((c0 >= 0 || t > 0) && c0 < valid) dst[0] = v[u].x;
+                  if ((c0 + 1 >= 0 || t > 0) && c0 + 1 < valid) dst[1] = v[u].y;
+                  if ((c0 + 2 >= 0 || t > 0) && c0 + 2 < valid) dst[2] = v[u].z;
+                  if ((c0 + 3 >= 0 || t > 0) && c0 + 3 < valid) dst[3] = v[u].w;
+                }
+                // the held-back tail of the last tile: window floats 64 .. 64 + sh - 1
+                if (last_tile && (lane & 15) < sh[u] && 64 - sh[u] + (lane & 15) < valid)
+                  dst[64 - q4 + (lane & 15)] = (srow0 + (r4 + 2 * u) * kStagePitch - sh[u])[64 - q4 + (lane & 15)];
+              }
+            }
+          }
+        }
+        if (sub == 2 && lane == 0) TC_TRACE(14, 8 + t);
+        __syncwarp();
+        // carry the last 8 columns of this tile over to the front of the next one
+        {
+          float cv[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) cv[q] = stage[(rr0 + (lane >> 3) + 4 * q) * kStagePitch + kBlockJ + (lane & 7)];
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) stage[(rr0 + (lane >> 3) + 4 * q) * kStagePitch + (lane & 7)] = cv[q];
+        }
+        if (sub == 2 && lane == 0) TC_TRACE(11, 32 + t);
+        ptx::mbar_arrive(&bar->stage_free);
+        continue;
+      }
       if (p.logits_out) {  // logits / T (models/contrastive.py:498)
-        if (staged) {
+        if (staged_cta) {
           if (t > 0) ptx::mbar_wait(&bar->stage_free, (t - 1) & 1);
           if (warp_valid) {
 #pragma unroll
-            for (int c = 0; c < kBlockJ; ++c) stage[r * kStagePitch + c] = __uint_as_float(sv[c]) * logit_scale;
+            for (int c = 0; c < kBlockJ; ++c) stage[r * kStagePitch + kStageCarry + c] = __uint_as_float(sv[c]) * logit_scale;
           }
           ptx::mbar_arrive(&bar->stage_full);
         } else if (row_valid) {
@@ -651,6 +725,12 @@ int launch_tc(const InfoNceParams& p, cudaStream_t s) {
   // cooperative: the kernel contains a grid-wide barrier (all CTAs must be co-resident)
   InfoNceParams pc = p;
   void* args[] = {&pc, &cache.s, &cache.v};
+#ifdef AVSSL_TC_TRACE
+  if (getenv("AVSSL_TC_PLAIN_LAUNCH")) {  // developer probe: cost of the cooperative launch itself
+    infonce_tc_kernel<D, kThreeTerm><<<grid, kTcThreads, C::kSmemBytes, s>>>(pc, cache.s, cache.v);
+    return AVSSL_OK;
+  }
+#endif
   cudaError_t le = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&infonce_tc_kernel<D, kThreeTerm>), grid,
                                                dim3(kTcThreads), args, C::kSmemBytes, s);
   if (le != cudaSuccess) {

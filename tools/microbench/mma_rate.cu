@@ -10,7 +10,7 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d, uint64_t a, uint64_t b, u
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
-__device__ __forceinline__ void mma_f16_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+__device__ __forceinline__ void mma_f16_ts_local(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
                ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
@@ -43,7 +43,7 @@ __global__ void bench(int mode, int N, int dpat, int bmn, int iters, long long* 
       if (mode == 0) mma_tf32_ss(d, ad, bd, idesc, 1);
       else if (mode == 1) mma_tf32_ts(d, tmem + 480, bd, idesc, 1);
       else if (mode == 2) mma_f16_ss(d, ad, bd, idesc, 1);
-      else mma_f16_ts(d, tmem + 480, bd, idesc, 1);
+      else mma_f16_ts_local(d, tmem + 480, bd, idesc, 1);
     }
     tc_commit(&bar);
     mbar_wait(&bar, 0);

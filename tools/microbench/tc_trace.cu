@@ -6,6 +6,7 @@
 using namespace avssl;
 int main(int argc, char** argv) {
   const int three = argc > 1 ? atoi(argv[1]) : 1;
+  const int want_logits = argc > 2 ? atoi(argv[2]) : 0;
   const int B = 64, D = 128, K = 65536;
   float *f, *q, *pm, *pl, *pa, *o;
   unsigned* cnt;
@@ -23,7 +24,9 @@ int main(int argc, char** argv) {
   p.part_m = pm; p.part_l = pl; p.part_acc = pa;
   cudaMalloc(&cnt, 256); cudaMemset(cnt, 0, 256); p.counter = cnt;
   cudaMalloc(&o, (size_t)B * (D * 2 + 8) * 4);
+  if (want_logits) { float* lg; cudaMalloc(&lg, (size_t)B * (K + 1) * 4); p.logits_out = lg; }
   p.q_out = o; p.dfeat_out = o + B * D; p.row_loss = o + 2 * B * D; p.loss_out = o + 2 * B * D + B; p.keys[0] = f;
+  { int pr = argc > 3 ? atoi(argv[3]) : 0; cudaMemcpyToSymbol(g_tc_probe, &pr, sizeof(int)); }
   for (int rep = 0; rep < 3; ++rep) {
     int rc = launch_infonce_tc(p, three, 0);
     cudaError_t e = cudaDeviceSynchronize();
@@ -37,7 +40,7 @@ int main(int argc, char** argv) {
   for (int t = 0; t < tps; ++t) {
     printf("tile %d:", t);
     for (int ev = 0; ev < 8; ++ev) printf(" %s=%lld", names[ev], tr[ev][t] - t0);
-    printf(" | pass1_done=%lld rescale_done=%lld\n", tr[8][t] - t0, tr[9][t] - t0);
+    printf(" | pass1_done=%lld rescale_done=%lld | PV_mma_issued=%lld PV_committed=%lld | drain %lld..(loop end %lld)..%lld\n", tr[8][t] - t0, tr[9][t] - t0, tr[13][1 + t] - t0, tr[12][1 + t] - t0, tr[11][1 + t] - t0, tr[14][8 + t] - t0, tr[11][32 + t] - t0);
   }
   printf("phases (cycles rel. first TMA issue): entry=%lld setup_done=%lld sweep_done=%lld barrier_passed=%lld rows_merged=%lld finish=%lld\n",
          tr[14][0] - t0, tr[14][1] - t0, tr[14][2] - t0, tr[14][3] - t0, tr[14][4] - t0, tr[14][5] - t0);
