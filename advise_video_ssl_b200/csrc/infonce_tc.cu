@@ -34,9 +34,9 @@
 // loop is kept warp-uniform (descriptors in uniform registers, one elected lane) and fully
 // unrolled.
 //
-// Warp roles (448 threads, 1 CTA / SM):  0 TMA producer | 1 MMA issuer + TMEM allocator |
+// Warp roles (512 threads, 1 CTA / SM):  0 TMA producer | 1 MMA issuer + TMEM allocator |
 // 2-9 helper warps (correction + V tile) | 10-13 softmax + epilogue (thread = query row; warp
-// w owns TMEM lanes 32*(w%4)..; warps without rows store the staged logits).
+// w owns TMEM lanes 32*(w%4)..) | 14-15 logits writers (with the softmax warps that own no rows).
 // TMEM columns: [0,D) q_hi | [D,2D) [q_lo | q] as packed bf16 | [2D,2D+128) S/P double buffer |
 // [2D+128,3D+128) acc.
 //
@@ -57,14 +57,14 @@ namespace {
 
 constexpr int kBlockJ = kTcTileRows;  // 64 queue rows per tile
 constexpr int kM = 128;               // query rows per CTA
-constexpr int kTcThreads = 448;
+constexpr int kTcThreads = 512;
 constexpr int kGroupThreads = 128;    // softmax warps
 constexpr int kHelperThreads = 256;   // helper warps 2..9
 constexpr float kRescaleThreshold = 8.f;  // log2 units: P stays below 2^8
 constexpr int kMaxSlots = 3;
-constexpr int kStageRows = 64;   // query rows per CTA whose logits go through the staging tile
-constexpr int kStageCarry = 8;   // columns carried over from the previous tile (one 32-byte sector of floats)
-constexpr int kStagePitch = kStageCarry + kBlockJ + 1;  // floats; odd pitch: row- and column-wise accesses conflict-free
+constexpr int kStageRows = 64;            // query rows per CTA whose logits go through the staging tiles
+constexpr int kStagePitch = kBlockJ + 1;  // floats; odd pitch: row- and column-wise accesses conflict-free
+constexpr int kDrainWarps = 4;            // warps 10, 11 (softmax warps without rows), 14, 15
 
 template <int D, bool kThreeTerm>
 struct TcCfg {
@@ -76,7 +76,8 @@ struct TcCfg {
   static constexpr int kVSlots = kThreeTerm ? 2 : 3;
   static constexpr int kSRingBytes = kSSlots * kSSlotBytes;
   static constexpr int kVRingBytes = kVSlots * kTileBytes;
-  static constexpr int kScratchBytes = kStageRows * kStagePitch * 4;  // logits staging tile [64][8 + 64 (+1)]
+  static constexpr int kStageBytes = kStageRows * kStagePitch * 4;  // one logits staging tile [64][65]
+  static constexpr int kScratchBytes = 2 * kStageBytes;            // double-buffered
   static constexpr int kColQhi = 0, kColQlo = D, kColS = 2 * D, kColAcc = 2 * D + 2 * kBlockJ;
   static constexpr int kTmemCols = 512;
   static_assert(3 * D + 2 * kBlockJ <= 512, "TMEM budget");
@@ -89,7 +90,7 @@ struct TcBarriers {
   uint64_t v_full[kMaxSlots], v_op[kMaxSlots], v_free[kMaxSlots];
   uint64_t s_ready[2], p_ready[2], pv_done[2];
   uint64_t q_ready, acc_done;
-  uint64_t stage_full, stage_free;
+  uint64_t stage_full[2], stage_free[2];
   uint32_t tmem_base;
 };
 
@@ -160,8 +161,10 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
     }
     ptx::mbar_init(&bar->q_ready, kGroupThreads);
     ptx::mbar_init(&bar->acc_done, 1);
-    ptx::mbar_init(&bar->stage_full, 2 * 32);  // the two softmax warps of rows 0..63 of the CTA tile
-    ptx::mbar_init(&bar->stage_free, 2 * 32);  // the other two softmax warps, which store the staged logits
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&bar->stage_full[b], 2 * 32);            // the two softmax warps of rows 0..63 of the CTA tile
+      ptx::mbar_init(&bar->stage_free[b], kDrainWarps * 32);  // the warps that store the staged logits
+    }
     ptx::mbar_fence_init();
   }
   if (warp == 1) ptx::tmem_alloc(&bar->tmem_base, C::kTmemCols);
@@ -170,6 +173,34 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
   ptx::tc_fence_after();
   const uint32_t tmem = bar->tmem_base;
   if (tid == 0) TC_TRACE(14, 1);
+
+  // Logits of a CTA tile with at most 64 query rows (the MoCo case) go through two padded staging
+  // tiles: the two softmax warps that own rows write their 64 values per row, and kDrainWarps
+  // other warps (the two softmax warps whose rows do not exist + warps 14, 15) store tile t as
+  // whole 128-byte row segments while the softmax already works on tile t+1.  Larger CTA tiles
+  // store directly from the softmax threads.
+  const bool staged_cta = p.logits_out != nullptr && (p.B - i_base) <= kStageRows;
+  auto drain_tile = [&](int t, int dw) {  // dw = 0..kDrainWarps-1; logits / T of tile t (models/contrastive.py:498)
+    const int b = t & 1;
+    ptx::mbar_wait(&bar->stage_full[b], (t >> 1) & 1);
+    if (dw == 0 && lane == 0) TC_TRACE(11, 1 + t);
+    const int j0 = j_begin + t * kBlockJ;
+    const int valid = min(kBlockJ, j_end - j0);
+    const int rows_staged = p.B - i_base;
+    const float* st = stage + b * (kStageRows * kStagePitch) + lane;
+    const size_t row_pitch = (size_t)(p.K + 1);
+    for (int k = 0; k < p.n_keys; ++k) {
+      float* dst = p.logits_out + ((size_t)k * p.B + i_base) * row_pitch + 1 + j0 + lane;
+#pragma unroll 4
+      for (int rr = dw; rr < rows_staged; rr += kDrainWarps) {
+        const float v0 = st[rr * kStagePitch], v1 = st[rr * kStagePitch + 32];
+        if (lane < valid) dst[(size_t)rr * row_pitch] = v0;
+        if (32 + lane < valid) dst[(size_t)rr * row_pitch + 32] = v1;
+      }
+    }
+    if (dw == 0 && lane == 0) TC_TRACE(11, 32 + t);
+    ptx::mbar_arrive(&bar->stage_free[b]);
+  };
 
   if (warp == 0) {
     // ================================================================ TMA producer
@@ -333,6 +364,11 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
         ptx::mbar_arrive(&bar->v_op[vs]);
       }
     }
+  } else if (warp >= 14) {
+    // ============================================================ logits writers 14, 15
+    if (staged_cta) {
+      for (int t = 0; t < n_tiles; ++t) drain_tile(t, warp - 12);
+    }
   } else {
     // ==================================================== softmax + epilogue (thread = row)
     const int sub = warp & 3;                   // TMEM sub-partition of this warp
@@ -408,11 +444,7 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
     }
     const float scale2 = p.inv_T * kLog2e * inv_norm;  // log2-domain logit scale of this row (>= 0)
     const float logit_scale = p.inv_T * inv_norm;
-    // Logits of a CTA tile with at most 64 query rows (the MoCo case) go through the padded staging
-    // tile: the two softmax warps that own rows write their 64 values per row, the two warps whose
-    // rows do not exist store them as full 128-byte lines.  Larger tiles store directly.
-    const bool staged_cta = p.logits_out != nullptr && (p.B - i_base) <= kStageRows;
-    const bool drainer = staged_cta && sub >= 2;  // warp-uniform
+    const bool drainer = staged_cta && sub >= 2;  // warp-uniform: this warp's rows do not exist
 
     float m_run = -INFINITY, l_run = 0.f;
     for (int t = 0; t < n_tiles; ++t) {
@@ -431,89 +463,21 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
         ptx::tc_wait_ld();
       }
       if (drainer) {
-        // rows of this warp do not exist: release PV, then store the staged logits / T of tile t
-        // (models/contrastive.py:498) as whole lines; 32 rows per warp
+        // rows of this warp do not exist: release PV, then help storing the staged logits of tile t
         ptx::tc_fence_before();
         ptx::mbar_arrive(&bar->p_ready[b]);
-        ptx::mbar_wait(&bar->stage_full, t & 1);
-        if (sub == 2 && lane == 0) TC_TRACE(11, 1 + t);
-        // Row r of the logits tensor starts (K+1)*4*r + 4 bytes into the buffer, so a tile's 64 columns
-        // are never sector aligned and a straight copy would end both ends of every row chunk with a
-        // partial 32-byte sector (read-modify-write in the memory system; measured 3x slower).  Each
-        // row is therefore written as a stream: the window of 64 floats that ENDS at the last sector
-        // boundary inside the tile = the s floats held back from the previous tile (kept in the carry
-        // columns of the staging tile) + the first 64 - s floats of this one.  Only the first and last
-        // tile of a split touch partial sectors.
-        // The SM keeps only a few store instructions per warp in flight, so stores are made as wide as
-        // possible: one 128-bit store per lane covers two rows (lanes 0-15 / 16-31) x 64 floats.
-        const int rr0 = (sub - 2) * 32;
-        const int n_rows = min(32, p.B - i_base - rr0);  // staged rows of this warp (may be <= 0)
-        const size_t row_pitch = (size_t)(p.K + 1);
-        const bool last_tile = t == n_tiles - 1;
-        const int half = lane >> 4, q4 = (lane & 15) * 4;
-        for (int k = 0; k < p.n_keys; ++k) {
-          // element index of (row rr0 + half, column j0) in the logits tensor; two rows per store, four
-          // stores in flight per trip (the address -> shared load -> store chain of one row pair is
-          // ~170 cycles long, so independent pairs are interleaved by hand; trips are not unrolled to
-          // keep the body resident in the instruction cache)
-          const size_t ge0 = ((size_t)k * p.B + i_base + rr0 + half) * row_pitch + 1 + j0;
-          const float* srow0 = stage + (rr0 + half) * kStagePitch + kStageCarry + q4;
-#pragma unroll 1
-          for (int r4 = 0; r4 < 32; r4 += 8) {
-            int sh[4];
-            float4 v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const size_t ge = ge0 + (size_t)(r4 + 2 * u) * row_pitch;
-              sh[u] = (int)(ge & 7);  // floats held back per tile for this row
-              const float* src = srow0 + (r4 + 2 * u) * kStagePitch - sh[u];
-              v[u] = make_float4(src[0], src[1], src[2], src[3]);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int row = r4 + 2 * u + half;
-              if (row < n_rows) {
-                const size_t ge = ge0 + (size_t)(r4 + 2 * u) * row_pitch;
-                float* dst = p.logits_out + ge - sh[u] + q4;  // 16-byte aligned
-                const int c0 = q4 - sh[u];                    // tile column of v.x; negative = carried from the previous tile
-                if ((c0 >= 0 || t > 0) && c0 + 3 < valid) {
-                  *reinterpret_cast<float4*>(dst) = v[u];
-                } else {
-                  if ((c0 >= 0 || t > 0) && c0 < valid) dst[0] = v[u].x;
-                  if ((c0 + 1 >= 0 || t > 0) && c0 + 1 < valid) dst[1] = v[u].y;
-                  if ((c0 + 2 >= 0 || t > 0) && c0 + 2 < valid) dst[2] = v[u].z;
-                  if ((c0 + 3 >= 0 || t > 0) && c0 + 3 < valid) dst[3] = v[u].w;
-                }
-                // the held-back tail of the last tile: window floats 64 .. 64 + sh - 1
-                if (last_tile && (lane & 15) < sh[u] && 64 - sh[u] + (lane & 15) < valid)
-                  dst[64 - q4 + (lane & 15)] = (srow0 + (r4 + 2 * u) * kStagePitch - sh[u])[64 - q4 + (lane & 15)];
-              }
-            }
-          }
-        }
-        if (sub == 2 && lane == 0) TC_TRACE(14, 8 + t);
-        __syncwarp();
-        // carry the last 8 columns of this tile over to the front of the next one
-        {
-          float cv[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) cv[q] = stage[(rr0 + (lane >> 3) + 4 * q) * kStagePitch + kBlockJ + (lane & 7)];
-          __syncwarp();
-#pragma unroll
-          for (int q = 0; q < 8; ++q) stage[(rr0 + (lane >> 3) + 4 * q) * kStagePitch + (lane & 7)] = cv[q];
-        }
-        if (sub == 2 && lane == 0) TC_TRACE(11, 32 + t);
-        ptx::mbar_arrive(&bar->stage_free);
+        drain_tile(t, sub - 2);
         continue;
       }
       if (p.logits_out) {  // logits / T (models/contrastive.py:498)
         if (staged_cta) {
-          if (t > 0) ptx::mbar_wait(&bar->stage_free, (t - 1) & 1);
+          if (t >= 2) ptx::mbar_wait(&bar->stage_free[b], ((t >> 1) - 1) & 1);  // tile t-2 has left this buffer
           if (warp_valid) {
+            float* st_row = stage + b * (kStageRows * kStagePitch) + r * kStagePitch;
 #pragma unroll
-            for (int c = 0; c < kBlockJ; ++c) stage[r * kStagePitch + kStageCarry + c] = __uint_as_float(sv[c]) * logit_scale;
+            for (int c = 0; c < kBlockJ; ++c) st_row[c] = __uint_as_float(sv[c]) * logit_scale;
           }
-          ptx::mbar_arrive(&bar->stage_full);
+          ptx::mbar_arrive(&bar->stage_full[b]);
         } else if (row_valid) {
           for (int k = 0; k < p.n_keys; ++k) {
             float* dst = p.logits_out + ((size_t)k * p.B + i) * (size_t)(p.K + 1) + 1 + j0;

@@ -40,7 +40,7 @@ int main(int argc, char** argv) {
   for (int t = 0; t < tps; ++t) {
     printf("tile %d:", t);
     for (int ev = 0; ev < 8; ++ev) printf(" %s=%lld", names[ev], tr[ev][t] - t0);
-    printf(" | pass1_done=%lld rescale_done=%lld | PV_mma_issued=%lld PV_committed=%lld | drain %lld..(loop end %lld)..%lld\n", tr[8][t] - t0, tr[9][t] - t0, tr[13][1 + t] - t0, tr[12][1 + t] - t0, tr[11][1 + t] - t0, tr[14][8 + t] - t0, tr[11][32 + t] - t0);
+    printf(" | pass1_done=%lld rescale_done=%lld | PV_mma_issued=%lld PV_committed=%lld | drain %lld..%lld\n", tr[8][t] - t0, tr[9][t] - t0, tr[13][1 + t] - t0, tr[12][1 + t] - t0, tr[11][1 + t] - t0, tr[11][32 + t] - t0);
   }
   printf("phases (cycles rel. first TMA issue): entry=%lld setup_done=%lld sweep_done=%lld barrier_passed=%lld rows_merged=%lld finish=%lld\n",
          tr[14][0] - t0, tr[14][1] - t0, tr[14][2] - t0, tr[14][3] - t0, tr[14][4] - t0, tr[14][5] - t0);
