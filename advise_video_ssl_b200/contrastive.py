@@ -138,15 +138,15 @@ class _NtXentFn(torch.autograd.Function):
     """SimCLR NT-Xent over this rank's rows against all gathered columns (K6 + C4/C5)."""
 
     @staticmethod
-    def forward(ctx, feat1, feat2, T):
-        loss, d1, d2 = ops.ntxent(feat1.detach().contiguous(), feat2.detach().contiguous(), T)
+    def forward(ctx, feat1, feat2, T, impl):
+        loss, d1, d2 = ops.ntxent(feat1.detach().contiguous(), feat2.detach().contiguous(), T, impl=impl)
         ctx.save_for_backward(d1, d2)
         return loss.reshape(())
 
     @staticmethod
     def backward(ctx, g):
         d1, d2 = ctx.saved_tensors
-        return d1 * g, d2 * g, None
+        return d1 * g, d2 * g, None, None
 
 
 class _SwavCeFn(torch.autograd.Function):
@@ -192,6 +192,7 @@ class ContrastiveModel(nn.Module):
         # B200-path knobs (not in the reference)
         self.materialize_logits = True
         self.infonce_impl = _lib.IMPL_AUTO
+        self.ntxent_impl = _lib.IMPL_AUTO  # tcgen05 (tf32, both operands rounded to nearest) when D allows; IMPL_SIMT = exact fp32
         self._ema_plan = None
         self._iter_mirror = None
         self._dummy_logits = None
@@ -694,7 +695,7 @@ class ContrastiveModel(nn.Module):
         feat_q2 = self.backbone(clips[1])
         # K6 (+C4/C5): l2-norm, all_gather, NT-Xent rows of this rank, gradient incl. the
         # reference's world-size factor (utils/distributed.py:142-155)
-        loss = _NtXentFn.apply(feat_q, feat_q2, self.T)
+        loss = _NtXentFn.apply(feat_q, feat_q2, self.T, self.ntxent_impl)
         with torch.no_grad():
             q_knn = self.l2_norm(feat_q.detach())
         self.knn_mem_update(q_knn, index)

@@ -12,23 +12,13 @@
 // the matrix, and the 1/T shift (|s| <= 1/T for unit rows) keeps exp() in range
 // where the reference's raw exp overflows for T < 0.0113.
 // Both passes are split over column ranges; partials are reduced in a fixed order.
-// CUDA-core kernels (fp32 exact); the tcgen05 variant shares K3's mainloop.
+// CUDA-core kernels (fp32 exact) = AVSSL_IMPL_SIMT; the tcgen05 kernels are in ntxent_tc.cu.
+#include "ntxent.cuh"
 #include "simt_tile.cuh"
 
 namespace avssl {
 
 constexpr float kLog2eN = 1.4426950408889634f;
-
-struct NtxArgs {
-  const float* out;     // [N2, D] unit rows, global order
-  const int* rows;      // [n_loc] global row ids handled here
-  const float* z_all;   // [N2] (pass 2)
-  int N2, D, n_loc;
-  float inv_T;
-  int n_splits, cols_per_split;
-  float* part_z;        // [n_splits][n_loc]
-  float* part_g;        // [n_splits][n_loc][D]
-};
 
 template <int DP>
 __device__ __forceinline__ void ntx_load_rows(float* qs, const NtxArgs& a, int i_base) {
@@ -256,7 +246,7 @@ extern "C" size_t avssl_ntxent_workspace_bytes(int N2, int D, int n_loc) {
 }
 
 static int ntx_setup(NtxArgs& a, const float* out, const int* rows, const float* z_all, int N2, int D, int n_loc,
-                     float T, void* workspace, size_t workspace_bytes, const char* who) {
+                     float T, void* workspace, size_t workspace_bytes, int impl, bool* use_tc, const char* who) {
   AVSSL_REQUIRE(out && rows && workspace, AVSSL_ERR_INVALID_ARGUMENT, "%s: null pointer", who);
   AVSSL_REQUIRE(N2 > 0 && (N2 % 2) == 0 && n_loc > 0 && n_loc <= N2 && T > 0.f, AVSSL_ERR_INVALID_ARGUMENT,
                 "%s: bad sizes N2=%d n_loc=%d", who, N2, n_loc);
@@ -269,7 +259,15 @@ static int ntx_setup(NtxArgs& a, const float* out, const int* rows, const float*
   a.D = D;
   a.n_loc = n_loc;
   a.inv_T = 1.f / T;
-  AVSSL_REQUIRE(plan_splits(N2, n_loc, &a.n_splits, &a.cols_per_split) == 0, AVSSL_ERR_CUDA, "%s: no CUDA device", who);
+  AVSSL_REQUIRE(impl == AVSSL_IMPL_AUTO || impl == AVSSL_IMPL_SIMT || impl == AVSSL_IMPL_TC1X, AVSSL_ERR_INVALID_ARGUMENT,
+                "%s: impl must be AVSSL_IMPL_AUTO, AVSSL_IMPL_SIMT or AVSSL_IMPL_TC1X (got %d)", who, impl);
+  *use_tc = impl != AVSSL_IMPL_SIMT && ntxent_tc_supported(N2, D, n_loc) &&
+            (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+  AVSSL_REQUIRE(*use_tc || impl != AVSSL_IMPL_TC1X, AVSSL_ERR_UNSUPPORTED,
+                "%s: the tcgen05 kernel needs D in {32,64,96,128,256} and a 16-byte aligned `out` (D=%d)", who, D);
+  AVSSL_REQUIRE((*use_tc ? ntxent_tc_plan(N2, n_loc, &a.n_splits, &a.cols_per_split)
+                         : plan_splits(N2, n_loc, &a.n_splits, &a.cols_per_split)) == 0,
+                AVSSL_ERR_CUDA, "%s: no CUDA device", who);
   char* w = static_cast<char*>(workspace);
   size_t off = 256 + 4 * ((size_t)N2 + 64);
   off = (off + 255) / 256 * 256;
@@ -281,13 +279,14 @@ static int ntx_setup(NtxArgs& a, const float* out, const int* rows, const float*
 }
 
 extern "C" int avssl_ntxent_rowsum(const float* out, const int* rows, int N2, int D, int n_loc, float T,
-                                   float* z_loc_out, void* workspace, size_t workspace_bytes, void* stream) {
+                                   float* z_loc_out, void* workspace, size_t workspace_bytes, int impl, void* stream) {
   NtxArgs a;
-  int rc = ntx_setup(a, out, rows, nullptr, N2, D, n_loc, T, workspace, workspace_bytes, "ntxent_rowsum");
+  bool use_tc = false;
+  int rc = ntx_setup(a, out, rows, nullptr, N2, D, n_loc, T, workspace, workspace_bytes, impl, &use_tc, "ntxent_rowsum");
   if (rc) return rc;
   AVSSL_REQUIRE(z_loc_out, AVSSL_ERR_INVALID_ARGUMENT, "ntxent_rowsum: null output");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  rc = launch_pass_d<false>(a, s);
+  rc = use_tc ? launch_ntxent_tc(a, false, s) : launch_pass_d<false>(a, s);
   if (rc) return rc;
   ntxent_sum_z_kernel<<<(n_loc + 255) / 256, 256, 0, s>>>(a.part_z, a.n_splits, n_loc, z_loc_out);
   AVSSL_LAUNCH_OK("ntxent_sum_z_kernel");
@@ -296,13 +295,14 @@ extern "C" int avssl_ntxent_rowsum(const float* out, const int* rows, int N2, in
 
 extern "C" int avssl_ntxent_grad(const float* out, const int* rows, const float* z_all, const float* norm_loc, int N2,
                                  int D, int n_loc, float T, float grad_scale, float* loss_out, float* dfeat_out,
-                                 void* workspace, size_t workspace_bytes, void* stream) {
+                                 void* workspace, size_t workspace_bytes, int impl, void* stream) {
   NtxArgs a;
-  int rc = ntx_setup(a, out, rows, z_all, N2, D, n_loc, T, workspace, workspace_bytes, "ntxent_grad");
+  bool use_tc = false;
+  int rc = ntx_setup(a, out, rows, z_all, N2, D, n_loc, T, workspace, workspace_bytes, impl, &use_tc, "ntxent_grad");
   if (rc) return rc;
   AVSSL_REQUIRE(z_all && norm_loc && loss_out && dfeat_out, AVSSL_ERR_INVALID_ARGUMENT, "ntxent_grad: null pointer");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  rc = launch_pass_d<true>(a, s);
+  rc = use_tc ? launch_ntxent_tc(a, true, s) : launch_pass_d<true>(a, s);
   if (rc) return rc;
   const float gscale = grad_scale * a.inv_T / (float)N2;
   ntxent_combine_kernel<<<(n_loc + 7) / 8, 256, 0, s>>>(a, norm_loc, gscale, dfeat_out);

@@ -1,0 +1,403 @@
+// K6 on the 5th-generation tensor cores: SimCLR NT-Xent for THIS rank's rows against all
+// gathered columns (models/contrastive.py:770-792; see ntxent.cu for the math and the
+// CUDA-core reference kernels, whose partial layout and finalisation kernels are reused).
+//
+// One CTA = 128 local rows x one range of columns.  Per 64-column tile of `out`:
+//     S  = Q . tile^T                       (M=128 x N=64, K=D, kind::tf32, A = Q in TMEM)
+//     e  = 2^((S - 1) log2e / T)            (softmax warps: tcgen05.ld -> exp2; diagonal masked)
+//   pass 1 (rowsum):  z_r += sum_c e_rc
+//   pass 2 (grad):    P = e (1/Z_r + 1/Z_c) -> TMEM;  acc += P . tile   (M=128 x N<=128, K=64)
+// With D = 256 the accumulator of pass 2 (256 TMEM columns) does not fit beside Q (256) and the
+// double-buffered S/P tile (128), so pass 2 sweeps the columns once per 128-wide half of D and
+// recomputes S for the second half (tensor time is cheap here: 28 k cycles per CTA at cfg3).
+//
+// Precision: single-pass tf32 with BOTH operands rounded to nearest (Q when it is written to
+// TMEM, the tiles in place in shared memory by eight helper warps), so there is no truncation
+// bias; measured errors are ~1e-5 (loss) and ~3e-4 (gradient), inside the 1e-3 fp32 tolerance.
+// The CUDA-core kernels (AVSSL_IMPL_SIMT) remain the exact-fp32 reference.
+//
+// Warp roles (448 threads, 1 CTA / SM): 0 TMA producer | 1 MMA issuer + TMEM allocator |
+// 2-9 helper warps (round tiles to tf32, stage 1/Z_c) | 10-13 softmax + epilogue (thread = row).
+#include "ntxent.cuh"
+#include "sm100_ptx.cuh"
+
+namespace avssl {
+
+namespace {
+
+constexpr int kBJ = 64;    // columns of `out` per tile
+constexpr int kMt = 128;   // local rows per CTA
+constexpr int kNtThreads = 448;
+constexpr int kSoftmax = 128, kHelpers = 256;
+constexpr int kSlots = 2;
+constexpr float kLog2eT = 1.4426950408889634f;
+
+template <int D, bool kGrad>
+struct NtCfg {
+  static constexpr int kKB = D / 32;                 // 128-byte k-blocks per row
+  static constexpr int kBoxBytes = kBJ * 128;        // one TMA box: 64 rows x 128 B
+  static constexpr int kTileBytes = kKB * kBoxBytes; // S tile: 64 KiB at D = 256
+  static constexpr int kAcc = D < 128 ? D : 128;     // accumulator columns per sweep
+  static constexpr int kHalves = kGrad ? D / kAcc : 1;
+  static constexpr int kVBytes = kGrad ? (kAcc / 32) * kBoxBytes : 0;  // V tile of one half
+  static constexpr int kColQ = 0, kColS = D, kColAcc = D + 2 * kBJ;
+  static constexpr int kColsNeeded = D + 2 * kBJ + (kGrad ? kAcc : 0);
+  static constexpr int kTmemCols = kColsNeeded <= 128 ? 128 : (kColsNeeded <= 256 ? 256 : 512);
+  static_assert(kColsNeeded <= 512, "TMEM budget");
+  static constexpr size_t kSmemBytes = 1024 + (size_t)kSlots * (kTileBytes + kVBytes) + 4 * kBJ * 4 + 512;
+};
+
+struct NtBarriers {
+  uint64_t s_full[kSlots], s_op[kSlots], s_free[kSlots];
+  uint64_t v_full[kSlots], v_op[kSlots], v_free[kSlots];
+  uint64_t s_ready[2], p_ready[2];
+  uint64_t q_ready, acc_done;
+  uint32_t tmem_base;
+};
+
+template <int D, bool kGrad>
+__global__ void __launch_bounds__(kNtThreads, 1)
+ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_v) {
+  using C = NtCfg<D, kGrad>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
+  uint8_t* s_ring = smem;
+  uint8_t* v_ring = smem + kSlots * C::kTileBytes;
+  float* invz_c = reinterpret_cast<float*>(smem + kSlots * (C::kTileBytes + C::kVBytes));  // [4][64]
+  NtBarriers* bar = reinterpret_cast<NtBarriers*>(smem + kSlots * (C::kTileBytes + C::kVBytes) + 4 * kBJ * 4);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int split = blockIdx.x;
+  const int i_base = blockIdx.y * kMt;
+  const int j_begin = split * a.cols_per_split;
+  const int j_end = min(a.N2, j_begin + a.cols_per_split);
+  const int n_tiles = (j_end - j_begin + kBJ - 1) / kBJ;
+  const int n_steps = n_tiles * C::kHalves;  // pass 2 with D = 256: every tile is visited once per half of D
+
+  if (warp == 0 && lane == 0) {
+    ptx::tma_prefetch_desc(&tmap);
+    if (kGrad) ptx::tma_prefetch_desc(&tmap_v);
+    for (int s = 0; s < kSlots; ++s) {
+      ptx::mbar_init(&bar->s_full[s], 1);
+      ptx::mbar_init(&bar->s_op[s], kHelpers);
+      ptx::mbar_init(&bar->s_free[s], 1);
+      ptx::mbar_init(&bar->v_full[s], 1);
+      ptx::mbar_init(&bar->v_op[s], kHelpers);
+      ptx::mbar_init(&bar->v_free[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&bar->s_ready[b], 1);
+      ptx::mbar_init(&bar->p_ready[b], kSoftmax);
+    }
+    ptx::mbar_init(&bar->q_ready, kSoftmax);
+    ptx::mbar_init(&bar->acc_done, 1);
+    ptx::mbar_fence_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(&bar->tmem_base, C::kTmemCols);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = bar->tmem_base;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      for (int u = 0; u < n_steps; ++u) {
+        const int t = u % n_tiles, h = u / n_tiles, sl = u % kSlots;
+        const int j0 = j_begin + t * kBJ;
+        if (u >= kSlots) ptx::mbar_wait(&bar->s_free[sl], ((u / kSlots) - 1) & 1);
+        ptx::mbar_arrive_expect_tx(&bar->s_full[sl], C::kTileBytes);
+        uint8_t* dst = s_ring + (size_t)sl * C::kTileBytes;
+#pragma unroll
+        for (int kb = 0; kb < C::kKB; ++kb) ptx::tma_load_2d(dst + kb * C::kBoxBytes, &tmap, &bar->s_full[sl], kb * 32, j0);
+        if (kGrad) {
+          if (u >= kSlots) ptx::mbar_wait(&bar->v_free[sl], ((u / kSlots) - 1) & 1);
+          ptx::mbar_arrive_expect_tx(&bar->v_full[sl], C::kVBytes);
+          uint8_t* dv = v_ring + (size_t)sl * C::kVBytes;
+#pragma unroll
+          for (int kb = 0; kb < C::kAcc / 32; ++kb)
+            ptx::tma_load_2d(dv + kb * C::kBoxBytes, &tmap_v, &bar->v_full[sl], (h * (C::kAcc / 32) + kb) * 32, j0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================== MMA issuer
+    constexpr uint32_t idesc_s = ptx::umma_idesc_tf32(kMt, kBJ, 0, 0);      // B = tile, K-major
+    constexpr uint32_t idesc_pv = ptx::umma_idesc_tf32(kMt, C::kAcc, 0, 1);  // B = tile half, MN-major
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t s_ring0 = __shfl_sync(0xffffffffu, ptx::smem_u32(s_ring), 0);
+    const uint32_t v_ring0 = __shfl_sync(0xffffffffu, ptx::smem_u32(v_ring), 0);
+    ptx::mbar_wait_relaxed(&bar->q_ready, 0);
+    ptx::tc_fence_after();
+    auto issue_pv = [&](int u) {
+      const int sl = u % kSlots, b = u & 1, t = u % n_tiles;
+      ptx::mbar_wait(&bar->v_op[sl], (u / kSlots) & 1);
+      ptx::mbar_wait(&bar->p_ready[b], (u >> 1) & 1);
+      ptx::tc_fence_after();
+      // MN-major, 32B-atom swizzle: 8 rows per k-step (1024 B) = two 4-row atoms 512 B apart (SBO);
+      // the 32-float column blocks (one TMA box each) are kBoxBytes apart (LBO)
+      const uint64_t bd0 = ptx::umma_smem_desc(v_ring0 + sl * C::kVBytes, C::kBoxBytes, 512, ptx::kUmmaSwizzle128BBase32B);
+      const uint32_t a0 = tm + C::kColS + b * kBJ;
+      if (ptx::elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < kBJ / 8; ++ks)
+          ptx::mma_tf32_ts(tm + C::kColAcc, a0 + ks * 8, bd0 + (uint64_t)(ks * 1024 >> 4), idesc_pv, (t > 0 || ks > 0) ? 1u : 0u);
+        ptx::tc_commit(&bar->v_free[sl]);
+        if (t == n_tiles - 1) ptx::tc_commit(&bar->acc_done);  // this half of the accumulator is complete
+      }
+      __syncwarp();
+    };
+    for (int u = 0; u < n_steps; ++u) {
+      const int sl = u % kSlots, b = u & 1;
+      ptx::mbar_wait(&bar->s_op[sl], (u / kSlots) & 1);
+      // S(u) overwrites the TMEM buffer of step u-2: its exponentials must have been read (pass 2 gets
+      // this ordering for free from PV(u-2), which waited for the same barrier)
+      if (!kGrad && u >= 2) ptx::mbar_wait(&bar->p_ready[b], ((u - 2) >> 1) & 1);
+      ptx::tc_fence_after();
+      const uint64_t sd0 = ptx::umma_smem_desc(s_ring0 + sl * C::kTileBytes, 16, 1024, ptx::kUmmaSwizzle128B);
+      const uint32_t d_s = tm + C::kColS + b * kBJ;
+      if (ptx::elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < D / 8; ++ks)
+          ptx::mma_tf32_ts(d_s, tm + C::kColQ + ks * 8, sd0 + (uint64_t)(((ks >> 2) * C::kBoxBytes + (ks & 3) * 32) >> 4), idesc_s,
+                           ks > 0 ? 1u : 0u);
+        ptx::tc_commit(&bar->s_ready[b]);
+        ptx::tc_commit(&bar->s_free[sl]);
+      }
+      __syncwarp();
+      if (kGrad && u > 0) issue_pv(u - 1);
+    }
+    if (kGrad && n_steps > 0) issue_pv(n_steps - 1);
+  } else if (warp < 10) {
+    // ============================ helper warps: round the tiles to tf32 in place (unbiased), stage 1/Z_c
+    const int ht = tid - 64;  // 0..255
+    for (int u = 0; u < n_steps; ++u) {
+      const int t = u % n_tiles, sl = u % kSlots;
+      ptx::mbar_wait_relaxed(&bar->s_full[sl], (u / kSlots) & 1);
+      float4* st = reinterpret_cast<float4*>(s_ring + (size_t)sl * C::kTileBytes);
+#pragma unroll 4
+      for (int e = ht; e < C::kTileBytes / 16; e += kHelpers) {
+        float4 x = st[e];
+        x.x = ptx::round_tf32(x.x);
+        x.y = ptx::round_tf32(x.y);
+        x.z = ptx::round_tf32(x.z);
+        x.w = ptx::round_tf32(x.w);
+        st[e] = x;
+      }
+      if (kGrad && ht < kBJ) {
+        const int j = j_begin + t * kBJ + ht;
+        invz_c[(u & 3) * kBJ + ht] = j < j_end ? 1.f / __ldg(a.z_all + j) : 0.f;
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(&bar->s_op[sl]);
+      if (kGrad) {
+        ptx::mbar_wait_relaxed(&bar->v_full[sl], (u / kSlots) & 1);
+        float4* vt = reinterpret_cast<float4*>(v_ring + (size_t)sl * C::kVBytes);
+#pragma unroll 4
+        for (int e = ht; e < C::kVBytes / 16; e += kHelpers) {
+          float4 x = vt[e];
+          x.x = ptx::round_tf32(x.x);
+          x.y = ptx::round_tf32(x.y);
+          x.z = ptx::round_tf32(x.z);
+          x.w = ptx::round_tf32(x.w);
+          vt[e] = x;
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(&bar->v_op[sl]);
+      }
+    }
+  } else {
+    // ==================================================== softmax + epilogue (thread = local row)
+    const int sub = warp & 3;
+    const int r = sub * 32 + lane;
+    const int i = i_base + r;
+    const bool row_valid = i < a.n_loc;
+    const uint32_t lane_base = tmem + ((uint32_t)(sub * 32) << 16);
+    const int rid = row_valid ? __ldg(a.rows + i) : -1;  // global row id: the diagonal column of this row
+    const float invz_r = (kGrad && row_valid) ? 1.f / __ldg(a.z_all + rid) : 0.f;
+
+    // ---- A operand: this row of `out` (already unit length), rounded to tf32, into TMEM
+    {
+      const float4* src = reinterpret_cast<const float4*>(a.out + (size_t)(row_valid ? rid : 0) * D);
+#pragma unroll 1
+      for (int cb = 0; cb < D / 32; ++cb) {
+        uint32_t v[32];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row_valid) x = __ldg(src + cb * 8 + k);
+          v[4 * k + 0] = __float_as_uint(ptx::round_tf32(x.x));
+          v[4 * k + 1] = __float_as_uint(ptx::round_tf32(x.y));
+          v[4 * k + 2] = __float_as_uint(ptx::round_tf32(x.z));
+          v[4 * k + 3] = __float_as_uint(ptx::round_tf32(x.w));
+        }
+        ptx::tmem_st32(lane_base + C::kColQ + cb * 32, v);
+      }
+      ptx::tc_wait_st();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&bar->q_ready);
+    }
+    const float scale2 = a.inv_T * kLog2eT;
+    float zs[4] = {0.f, 0.f, 0.f, 0.f};
+
+    for (int u = 0; u < n_steps; ++u) {
+      const int t = u % n_tiles, h = u / n_tiles, b = u & 1;
+      const int j0 = j_begin + t * kBJ;
+      ptx::mbar_wait(&bar->s_ready[b], (u >> 1) & 1);
+      ptx::tc_fence_after();
+      const uint32_t s_col = lane_base + C::kColS + b * kBJ;
+      uint32_t sv[kBJ];
+      ptx::tmem_ld32(s_col, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+      ptx::tmem_ld32(s_col + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+      ptx::tc_wait_ld();
+      const int diag = rid - j0;            // column of this tile that is the row itself (masked), if in [0, 64)
+      const int valid = row_valid ? min(kBJ, j_end - j0) : 0;
+      const float* iz = invz_c + (u & 3) * kBJ;
+#pragma unroll
+      for (int c = 0; c < kBJ; ++c) {
+        // e^{(s - 1)/T}: unit rows give s <= 1, so the exponent is <= 0
+        float e;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((__uint_as_float(sv[c]) - 1.f) * scale2));
+        e = (c < valid && c != diag) ? e : 0.f;
+        if (kGrad) {
+          sv[c] = __float_as_uint(ptx::round_tf32(e * (invz_r + iz[c])));
+        } else {
+          zs[c & 3] += e;
+        }
+      }
+      if (kGrad) {
+        ptx::tmem_st32(s_col, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+        ptx::tmem_st32(s_col + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+        ptx::tc_wait_st();
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&bar->p_ready[b]);
+
+      if (kGrad && t == n_tiles - 1) {
+        // ---- this half of the gradient partial is complete once its last PV retires
+        ptx::mbar_wait(&bar->acc_done, h & 1);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int cb = 0; cb < C::kAcc / 32; ++cb) {
+          uint32_t av[32];
+          ptx::tmem_ld32(lane_base + C::kColAcc + cb * 32, av);
+          ptx::tc_wait_ld();
+          if (row_valid) {
+            float4* dst = reinterpret_cast<float4*>(a.part_g + ((size_t)split * a.n_loc + i) * D + h * C::kAcc + cb * 32);
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4)
+              dst[c4] = make_float4(__uint_as_float(av[c4 * 4]), __uint_as_float(av[c4 * 4 + 1]),
+                                    __uint_as_float(av[c4 * 4 + 2]), __uint_as_float(av[c4 * 4 + 3]));
+          }
+        }
+        ptx::tc_fence_before();
+      }
+    }
+    if (!kGrad && row_valid) a.part_z[(size_t)split * a.n_loc + i] = (zs[0] + zs[1]) + (zs[2] + zs[3]);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, C::kTmemCols);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn nt_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+struct NtTmapCache {
+  const float* out = nullptr;
+  int N2 = 0, D = 0;
+  CUtensorMap s, v;
+};
+
+template <int D, bool kGrad>
+int launch_nt(const NtxArgs& a, cudaStream_t st) {
+  using C = NtCfg<D, kGrad>;
+  static thread_local NtTmapCache cache;
+  if (cache.out != a.out || cache.N2 != a.N2 || cache.D != D) {
+    EncodeTiledFn enc = nt_encode_fn();
+    AVSSL_REQUIRE(enc, AVSSL_ERR_CUDA, "ntxent: cuTensorMapEncodeTiled is not available from the driver");
+    const cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)a.N2};
+    const cuuint64_t gstride[1] = {(cuuint64_t)D * sizeof(float)};
+    const cuuint32_t box[2] = {32u, (cuuint32_t)kBJ};
+    const cuuint32_t estride[2] = {1u, 1u};
+    CUresult r = enc(&cache.s, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a.out), gdim, gstride, box, estride,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    AVSSL_REQUIRE(r == CUDA_SUCCESS, AVSSL_ERR_CUDA, "ntxent: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    r = enc(&cache.v, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a.out), gdim, gstride, box, estride,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    AVSSL_REQUIRE(r == CUDA_SUCCESS, AVSSL_ERR_CUDA, "ntxent: cuTensorMapEncodeTiled (32B atoms) failed (%d)", (int)r);
+    cache.out = a.out;
+    cache.N2 = a.N2;
+    cache.D = D;
+  }
+  static bool configured = false;
+  if (!configured) {
+    AVSSL_CUDA_OK(cudaFuncSetAttribute(ntxent_tc_kernel<D, kGrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes));
+    configured = true;
+  }
+  dim3 grid(a.n_splits, (a.n_loc + kMt - 1) / kMt);
+  ntxent_tc_kernel<D, kGrad><<<grid, kNtThreads, C::kSmemBytes, st>>>(a, cache.s, cache.v);
+  AVSSL_LAUNCH_OK("ntxent_tc_kernel");
+  return AVSSL_OK;
+}
+
+}  // namespace
+
+bool ntxent_tc_supported(int N2, int D, int n_loc) {
+  (void)n_loc;
+  return (D == 32 || D == 64 || D == 96 || D == 128 || D == 256) && N2 >= 2;
+}
+
+// Column split of the tcgen05 kernels: whole 64-column tiles, at most 64 splits (workspace layout),
+// about one CTA per SM.
+int ntxent_tc_plan(int N2, int n_loc, int* n_splits, int* cols_per_split) {
+  const int sms = sm_count();
+  if (sms <= 0) return -1;
+  const int row_blocks = (n_loc + kMt - 1) / kMt;
+  const int n_tiles = (N2 + kBJ - 1) / kBJ;
+  int S = sms / row_blocks;
+  if (S < 1) S = 1;
+  if (S > n_tiles) S = n_tiles;
+  if (S > 64) S = 64;
+  const int tps = (n_tiles + S - 1) / S;
+  *n_splits = (n_tiles + tps - 1) / tps;
+  *cols_per_split = tps * kBJ;
+  return 0;
+}
+
+int launch_ntxent_tc(const NtxArgs& a, bool grad, cudaStream_t s) {
+#define AVSSL_NT_CASE(DD) \
+  case DD:                \
+    return grad ? launch_nt<DD, true>(a, s) : launch_nt<DD, false>(a, s);
+  switch (a.D) {
+    AVSSL_NT_CASE(32)
+    AVSSL_NT_CASE(64)
+    AVSSL_NT_CASE(96)
+    AVSSL_NT_CASE(128)
+    AVSSL_NT_CASE(256)
+  }
+#undef AVSSL_NT_CASE
+  return AVSSL_ERR_UNSUPPORTED;
+}
+
+}  // namespace avssl

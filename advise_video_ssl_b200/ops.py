@@ -314,7 +314,7 @@ def ce_target0_bwd(logits, lse, grad_out):
 
 
 # ----------------------------------------------------------------------------- K6
-def ntxent(feat1, feat2, T, gather=None):
+def ntxent(feat1, feat2, T, gather=None, impl=_lib.IMPL_AUTO):
     """SimCLR NT-Xent (K6) with the cross-rank gather (C4) and the reduce-scatter-
     equivalent gradient (C5) folded in.  feat1/feat2: this rank's raw [B, D] features.
     Returns (loss[1], dfeat1, dfeat2); the gradients carry the reference's world-size
@@ -346,7 +346,7 @@ def ntxent(feat1, feat2, T, gather=None):
     ws = _workspace(dev, lib.avssl_ntxent_workspace_bytes(2 * N, D, n_loc))
     z_loc = torch.empty(n_loc, dtype=_f32, device=dev)
     check(lib.avssl_ntxent_rowsum(out.data_ptr(), rows.data_ptr(), 2 * N, D, n_loc, float(T), z_loc.data_ptr(),
-                                  ws.data_ptr(), ws.numel(), _stream()), "avssl_ntxent_rowsum")
+                                  ws.data_ptr(), ws.numel(), int(impl), _stream()), "avssl_ntxent_rowsum")
     if world > 1:
         zg = torch.empty(world, 2, B, dtype=_f32, device=dev)
         dist.all_gather_into_tensor(zg.view(-1), z_loc)
@@ -357,7 +357,7 @@ def ntxent(feat1, feat2, T, gather=None):
     dfeat = torch.empty(n_loc, D, dtype=_f32, device=dev)
     check(lib.avssl_ntxent_grad(out.data_ptr(), rows.data_ptr(), z_all.data_ptr(), nrm.data_ptr(), 2 * N, D, n_loc,
                                 float(T), float(world), loss.data_ptr(), dfeat.data_ptr(), ws.data_ptr(),
-                                ws.numel(), _stream()), "avssl_ntxent_grad")
+                                ws.numel(), int(impl), _stream()), "avssl_ntxent_grad")
     return loss, dfeat[:B], dfeat[B:]
 
 

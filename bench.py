@@ -34,6 +34,7 @@ import torch  # noqa: E402
 
 B_PER_GPU, DIM, QUEUE_LEN, TEMP, MOMENTUM = 64, 128, 65536, 0.1, 0.999
 POOL = 8  # distinct synthetic batches rotated through the steps
+EMA_DRAM_TRAFFIC = 385_177_600  # bytes per launch of the EMA kernel measured by ncu (289.0 MB read + 96.2 MB written)
 WORKLOAD = ("configs[1] head: Slow-R50 MoCo, 2 views/clip, queue 65536, dim 128, batch 64/GPU; "
             "EMA(164 tensors, 36.1M fp32) + l2norm + logits + InfoNCE fwd/bwd + enqueue; backbone excluded")
 METRIC, UNIT = "contrastive_head_clips_per_sec", "clips/s"
@@ -198,27 +199,36 @@ def gpu_arm(args):
     launches_per_step = 2 if args.kernel != "simt" else 4  # ema + fused head (simt: ema, split, combine, enqueue)
     ema_events = []
 
-    def step(i, f, k, time_ema=False):
-        """EMA -> [gather keys] -> fused head -> enqueue (reference order, :308-316, :486-503)."""
+    def ema_part(k_for_gather, time_ema=False, after=None):
+        """K1 (+ the key all_gather C3 on the side stream when N > 1)."""
         if time_ema:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         if world > 1:
             # C3: key all_gather on the comm stream, overlapped with the EMA kernel
             comm.wait_stream(torch.cuda.current_stream())
+            if after is not None:
+                comm.wait_event(after)
             with torch.cuda.stream(comm):
-                dist.all_gather_into_tensor(gathered, k)
+                dist.all_gather_into_tensor(gathered, k_for_gather)
         plan.run(MOMENTUM, it, bump_iter=True, first_iter=state["n"] == 0)  # host mirror of `iter`, as the module keeps
         state["n"] += 1
         if time_ema:
             e1.record()
             ema_events.append((e0, e1))
+
+    def head_part(f, k):
+        """K2+K3+K4 in one cooperative launch: loss/grad against the old queue, then the ring write."""
         if world > 1:
             torch.cuda.current_stream().wait_stream(comm)
             k = gathered[rank * B_PER_GPU:(rank + 1) * B_PER_GPU]
-        # K2+K3+K4 in one cooperative launch: loss/grad against the old queue, then the ring write
         return ops.moco_infonce(f, [k], queue, TEMP, want_logits=not args.no_logits, impl=impl, out=out,
                                 enqueue=(ptr, status))
+
+    def step(i, f, k, time_ema=False):
+        """EMA -> [gather keys] -> fused head + enqueue (reference order, :308-316, :486-503)."""
+        ema_part(k, time_ema)
+        return head_part(f, k)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -251,12 +261,24 @@ def gpu_arm(args):
     loss_h = torch.empty(1).pin_memory()
     e2e_steps = args.steps
 
+    h2d = torch.cuda.Stream(device=dev)
+    copied = torch.cuda.Event()
+
     def e2e_step(i):
-        f_dev.copy_(feats_h[i % POOL], non_blocking=True)
-        k_dev.copy_(keys_h[i % POOL], non_blocking=True)
-        r = step(i, f_dev, k_dev)
+        # The momentum update does not depend on this step's inputs, so the host->device copies run on
+        # a copy stream underneath it; the head (and, for N > 1, the key all_gather) waits for them.
+        if world == 1:
+            ema_part(k_dev)  # launched first: the GPU starts on it while the host enqueues the copies
+        with torch.cuda.stream(h2d):
+            k_dev.copy_(keys_h[i % POOL], non_blocking=True)
+            f_dev.copy_(feats_h[i % POOL], non_blocking=True)
+            copied.record()
+        if world > 1:
+            ema_part(k_dev, after=copied)  # the key all_gather needs this step's keys
+        torch.cuda.current_stream().wait_event(copied)
+        r = head_part(f_dev, k_dev)
         loss_h.copy_(r["loss"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        torch.cuda.current_stream().synchronize()  # also orders the next step's copies after this step's reads
         return float(loss_h[0])
 
     for i in range(min(args.warmup, 10)):
@@ -299,11 +321,13 @@ def gpu_arm(args):
                    "l2": "no explicit flush: one step streams %.0f MB (> 126 MB L2) so nothing survives between steps" % (step_bytes / 1e6)},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / e2e_steps,
                 "h2d_bytes_per_step": 2 * 4 * B_PER_GPU * DIM, "d2h_bytes_per_step": 4,
-                "note": "pinned host embeddings -> H2D -> EMA+head+enqueue -> loss D2H, host sync every step"},
+                "note": "pinned host embeddings -> H2D on a copy stream (under the EMA) -> head+enqueue -> loss D2H, host sync every step"},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
         "roofline": {"kernel": "ema_multi_tensor_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": EMA_DRAM_TRAFFIC,
+                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch "
+                                       "(profiles/r1_ema_ncu.md)",
                      "bytes_per_launch": ema_bytes, "us_per_launch": ema_ms * 1e3, "peak_source": peak_src},
         "step_roofline": {"bytes_per_step": step_bytes, "floor_us": step_bytes / (peak * 1e9) * 1e6,
                           "frac": (step_bytes / (peak * 1e9) * 1e3) / ms_per_step},

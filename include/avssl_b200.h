@@ -207,14 +207,17 @@ AVSSL_API int avssl_ce_target0_bwd(const float* logits, const float* row_lse, in
  *       and dfeat[i] = grad_scale * dLoss/dout_{r_i} chained through the row
  *       l2-normalisation (norm_loc[i] = ||f_i||).  grad_scale = world size reproduces
  *       the reference's all_reduce(SUM)-then-slice backward.
+ * impl: AVSSL_IMPL_AUTO picks the tcgen05 kernels (single-pass tf32 with both operands rounded
+ *   to nearest: loss ~1e-5, gradient ~3e-4 relative, inside the 1e-3 fp32 tolerance) when
+ *   D is 32/64/96/128/256; AVSSL_IMPL_SIMT forces the exact-fp32 CUDA-core kernels.
  * workspace: avssl_ntxent_workspace_bytes(), zero-filled once, reusable.
  */
 AVSSL_API size_t avssl_ntxent_workspace_bytes(int N2, int D, int n_loc);
 AVSSL_API int avssl_ntxent_rowsum(const float* out, const int* rows, int N2, int D, int n_loc, float T,
-                        float* z_loc_out, void* workspace, size_t workspace_bytes, void* stream);
+                        float* z_loc_out, void* workspace, size_t workspace_bytes, int impl, void* stream);
 AVSSL_API int avssl_ntxent_grad(const float* out, const int* rows, const float* z_all, const float* norm_loc,
                       int N2, int D, int n_loc, float T, float grad_scale, float* loss_out,
-                      float* dfeat_out, void* workspace, size_t workspace_bytes, void* stream);
+                      float* dfeat_out, void* workspace, size_t workspace_bytes, int impl, void* stream);
 
 /* ---------------------------------------------------------- K10: Sinkhorn-Knopp
  * Replaces `q = exp(out / eps).t(); sinkhorn(q.t(), iters)[-keep_last:]`
