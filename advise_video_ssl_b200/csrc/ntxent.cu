@@ -136,10 +136,12 @@ __global__ void ntxent_sum_z_kernel(const float* __restrict__ part_z, int n_spli
   z_loc[i] = z;
 }
 
-// One warp per local row: merge the gradient partials, subtract the positive term,
-// apply 1/(2N T) and the world-size factor, then chain through the l2-normalisation.
+// One warp per local row: merge the gradient partials (one pass, all loads of a split row
+// in flight together), subtract the positive term, apply 1/(2N T) and the world-size factor,
+// then chain through the l2-normalisation.  D <= 256: each lane owns up to 8 columns c = lane + 32 u.
 __global__ void __launch_bounds__(256)
 ntxent_combine_kernel(const NtxArgs a, const float* __restrict__ norm_loc, float gscale, float* __restrict__ dfeat) {
+  constexpr int kU = 8;
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= a.n_loc) return;
@@ -148,38 +150,61 @@ ntxent_combine_kernel(const NtxArgs a, const float* __restrict__ norm_loc, float
   const int rp = r < half ? r + half : r - half;
   const float* o = a.out + (size_t)r * a.D;
   const float* op = a.out + (size_t)rp * a.D;
+  float g[kU], ov[kU], pv[kU];
+#pragma unroll
+  for (int u = 0; u < kU; ++u) {
+    const int c = lane + 32 * u;
+    g[u] = 0.f;
+    ov[u] = c < a.D ? __ldg(o + c) : 0.f;
+    pv[u] = c < a.D ? __ldg(op + c) : 0.f;
+  }
+  const float* pg = a.part_g + (size_t)i * a.D + lane;
+  const size_t sstride = (size_t)a.n_loc * a.D;
+  for (int s = 0; s < a.n_splits; ++s) {  // fixed order: deterministic
+#pragma unroll
+    for (int u = 0; u < kU; ++u)
+      if (lane + 32 * u < a.D) g[u] += __ldcg(pg + (size_t)s * sstride + 32 * u);
+  }
   float dot = 0.f;
-  for (int c = lane; c < a.D; c += 32) {
-    float g = 0.f;
-    for (int s = 0; s < a.n_splits; ++s) g += a.part_g[((size_t)s * a.n_loc + i) * a.D + c];
-    g = (g - 2.f * op[c]) * gscale;
-    dot = fmaf(g, o[c], dot);
+#pragma unroll
+  for (int u = 0; u < kU; ++u) {
+    g[u] = (g[u] - 2.f * pv[u]) * gscale;
+    dot = fmaf(g[u], ov[u], dot);
   }
   dot = warp_sum(dot);
-  const float nrm = norm_loc[i];
-  for (int c = lane; c < a.D; c += 32) {
-    float g = 0.f;
-    for (int s = 0; s < a.n_splits; ++s) g += a.part_g[((size_t)s * a.n_loc + i) * a.D + c];
-    g = (g - 2.f * op[c]) * gscale;
-    dfeat[(size_t)i * a.D + c] = (g - dot * o[c]) / nrm;
+  const float rn = 1.f / norm_loc[i];
+#pragma unroll
+  for (int u = 0; u < kU; ++u) {
+    const int c = lane + 32 * u;
+    if (c < a.D) dfeat[(size_t)i * a.D + c] = (g[u] - dot * ov[u]) * rn;
   }
 }
 
-// loss = mean_r( log Z_r + 1/T - out_r . out_{r+} / T ) over all 2N rows.
+// loss = mean_r( log Z_r + 1/T - out_r . out_{r+} / T ) over all 2N rows.  One warp per PAIR
+// (r, r+): both rows share the same dot product.
 __global__ void __launch_bounds__(256)
 ntxent_loss_kernel(const float* __restrict__ out, const float* __restrict__ z_all, int N2, int D, float inv_T,
                    float* loss_out, float* row_term, unsigned* counter) {
   __shared__ float s_red[32];
   __shared__ unsigned s_last;
   const int lane = threadIdx.x & 31;
-  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r < N2) {
-    const int half = N2 / 2;
-    const int rp = r < half ? r + half : r - half;
-    float dot = 0.f;
-    for (int c = lane; c < D; c += 32) dot = fmaf(out[(size_t)r * D + c], out[(size_t)rp * D + c], dot);
-    dot = warp_sum(dot);
-    if (lane == 0) row_term[r] = logf(z_all[r]) + inv_T - dot * inv_T;
+  const int half = N2 / 2;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // pair index
+  if (r < half) {
+    const float* x = out + (size_t)r * D;
+    const float* y = out + (size_t)(r + half) * D;
+    float d0 = 0.f, d1 = 0.f;
+    int c = lane;
+    for (; c + 32 < D; c += 64) {
+      d0 = fmaf(__ldg(x + c), __ldg(y + c), d0);
+      d1 = fmaf(__ldg(x + c + 32), __ldg(y + c + 32), d1);
+    }
+    if (c < D) d0 = fmaf(__ldg(x + c), __ldg(y + c), d0);
+    const float dot = warp_sum(d0 + d1);
+    if (lane == 0) {
+      row_term[r] = logf(z_all[r]) + inv_T - dot * inv_T;
+      row_term[r + half] = logf(z_all[r + half]) + inv_T - dot * inv_T;
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -190,7 +215,7 @@ ntxent_loss_kernel(const float* __restrict__ out, const float* __restrict__ z_al
   if (s_last) {
     __threadfence();
     float tot = 0.f;
-    for (int i = threadIdx.x; i < N2; i += blockDim.x) tot += reinterpret_cast<volatile float*>(row_term)[i];
+    for (int i = threadIdx.x; i < N2; i += blockDim.x) tot += __ldcg(row_term + i);
     tot = block_sum(tot, s_red);
     if (threadIdx.x == 0) {
       *loss_out = tot / (float)N2;
@@ -309,7 +334,7 @@ extern "C" int avssl_ntxent_grad(const float* out, const int* rows, const float*
   AVSSL_LAUNCH_OK("ntxent_combine_kernel");
   unsigned* counter = static_cast<unsigned*>(workspace);
   float* row_term = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
-  ntxent_loss_kernel<<<(N2 + 7) / 8, 256, 0, s>>>(out, z_all, N2, D, a.inv_T, loss_out, row_term, counter);
+  ntxent_loss_kernel<<<(N2 / 2 + 7) / 8, 256, 0, s>>>(out, z_all, N2, D, a.inv_T, loss_out, row_term, counter);
   AVSSL_LAUNCH_OK("ntxent_loss_kernel");
   return AVSSL_OK;
 }

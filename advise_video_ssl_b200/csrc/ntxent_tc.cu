@@ -219,19 +219,28 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
     // ---- A operand: this row of `out` (already unit length), rounded to tf32, into TMEM
     {
       const float4* src = reinterpret_cast<const float4*>(a.out + (size_t)(row_valid ? rid : 0) * D);
+      float4 cur[8], nxt[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cur[k] = __ldg(src + k);
 #pragma unroll 1
       for (int cb = 0; cb < D / 32; ++cb) {
+        if (cb + 1 < D / 32) {  // next 32 columns in flight while this chunk goes to TMEM
+#pragma unroll
+          for (int k = 0; k < 8; ++k) nxt[k] = __ldg(src + (cb + 1) * 8 + k);
+        }
         uint32_t v[32];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row_valid) x = __ldg(src + cb * 8 + k);
+          if (row_valid) x = cur[k];
           v[4 * k + 0] = __float_as_uint(ptx::round_tf32(x.x));
           v[4 * k + 1] = __float_as_uint(ptx::round_tf32(x.y));
           v[4 * k + 2] = __float_as_uint(ptx::round_tf32(x.z));
           v[4 * k + 3] = __float_as_uint(ptx::round_tf32(x.w));
         }
         ptx::tmem_st32(lane_base + C::kColQ + cb * 32, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cur[k] = nxt[k];
       }
       ptx::tc_wait_st();
       ptx::tc_fence_before();

@@ -29,6 +29,10 @@ def _req(t, name, dtype=_f32):
     return t
 
 
+def moco_infonce_workspace_bytes(B, D, K, n_keys=1):
+    return int(lib.avssl_moco_infonce_workspace_bytes(B, D, K, n_keys))
+
+
 def sm_count():
     n = lib.avssl_device_sm_count()
     if n < 0:
@@ -119,7 +123,7 @@ def _workspace(device, nbytes):
     return ws
 
 
-def moco_infonce(feat_q, keys, queue, T, want_logits=True, impl=_lib.IMPL_AUTO, out=None, enqueue=None):
+def moco_infonce(feat_q, keys, queue, T, want_logits=True, impl=_lib.IMPL_AUTO, out=None, enqueue=None, workspace=None):
     """Fused l2-norm + logits + InfoNCE forward/backward (K2+K3).
 
     Returns dict(loss[1], dfeat[B,D], q[B,D], lse[n_keys*B], logits[n_keys*B,K+1] or None).
@@ -127,6 +131,8 @@ def moco_infonce(feat_q, keys, queue, T, want_logits=True, impl=_lib.IMPL_AUTO, 
     `enqueue=(ptr, status)` additionally performs K4 for keys[0] after the loss has been
     computed against the old queue: queue[ptr:ptr+B] = keys[0], ptr advanced on the device
     (same launch with the tcgen05 kernels); `status` may be None.
+    `workspace`: optional caller-owned uint8 tensor of `moco_infonce_workspace_bytes()` bytes,
+    zero-filled once (CUDA-graph capture: no allocation or memset inside the captured region).
     """
     _req(feat_q, "feat_q")
     _req(queue, "queue")
@@ -151,7 +157,12 @@ def moco_infonce(feat_q, keys, queue, T, want_logits=True, impl=_lib.IMPL_AUTO, 
     if want_logits:
         logits = out.get("logits") if "logits" in out else torch.empty(n_keys * B, K + 1, dtype=_f32, device=dev)
     nbytes = lib.avssl_moco_infonce_workspace_bytes(B, D, K, n_keys)
-    ws = _workspace(dev, nbytes)
+    if workspace is not None:
+        ws = _req(workspace, "workspace", torch.uint8)
+        if ws.numel() < nbytes:
+            raise ValueError("workspace has %d bytes, need %d" % (ws.numel(), nbytes))
+    else:
+        ws = _workspace(dev, nbytes)
     key_ptrs = (ctypes.c_void_p * n_keys)(*[k.data_ptr() for k in keys])
     if enqueue is None:
         check(lib.avssl_moco_infonce_fwd_bwd(

@@ -195,6 +195,7 @@ def gpu_arm(args):
     comm = torch.cuda.Stream(device=dev) if world > 1 else None
     impl = {"auto": _lib.IMPL_AUTO, "simt": _lib.IMPL_SIMT, "tc3x": _lib.IMPL_TC3X, "tc1x": _lib.IMPL_TC1X}[args.kernel]
     out = {}
+    head_ws = torch.zeros(ops.moco_infonce_workspace_bytes(B_PER_GPU, DIM, QUEUE_LEN, 1), dtype=torch.uint8, device=dev)
     state = {"n": 0}
     launches_per_step = 2 if args.kernel != "simt" else 4  # ema + fused head (simt: ema, split, combine, enqueue)
     ema_events = []
@@ -223,7 +224,7 @@ def gpu_arm(args):
             torch.cuda.current_stream().wait_stream(comm)
             k = gathered[rank * B_PER_GPU:(rank + 1) * B_PER_GPU]
         return ops.moco_infonce(f, [k], queue, TEMP, want_logits=not args.no_logits, impl=impl, out=out,
-                                enqueue=(ptr, status))
+                                enqueue=(ptr, status), workspace=head_ws)
 
     def step(i, f, k, time_ema=False):
         """EMA -> [gather keys] -> fused head + enqueue (reference order, :308-316, :486-503)."""
@@ -239,18 +240,49 @@ def gpu_arm(args):
     # ---- device-resident timing (value)
     for i in range(args.warmup):
         r = step(i, feats[i % POOL], keys[i % POOL])
-        out = r if not out else out
+        if not out:
+            out.update(r)  # the step's output tensors are reused from here on (static for graph capture)
     sync_all()
+
+    # One CUDA graph per input slot: [key all_gather on the comm stream ||] EMA -> fused head.  Replaying
+    # it removes the per-launch host work (which bounds the step once the NCCL enqueue is added) and
+    # the launch gaps between the kernels; the kernels and their order are the same as in eager mode.
+    graphs, graph_err = None, None
+    if not args.no_graph:
+        try:
+            graphs = []
+            for slot in range(POOL):
+                g_ = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_):
+                    step(slot, feats[slot], keys[slot])
+                graphs.append(g_)
+            for slot in range(POOL):  # one untimed replay each
+                graphs[slot].replay()
+            sync_all()
+        except Exception as e:  # capture is an optimisation: fall back to eager launches and say so
+            graphs, graph_err = None, "%s: %s" % (type(e).__name__, e)
+            torch.cuda.synchronize()
+
     sampler = ClockSampler(local)
     sampler.start()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
-    for i in range(args.steps):
-        step(i, feats[i % POOL], keys[i % POOL], time_ema=True)
+    if graphs is not None:
+        for i in range(args.steps):
+            graphs[i % POOL].replay()
+    else:
+        for i in range(args.steps):
+            step(i, feats[i % POOL], keys[i % POOL])
     t_end.record()
     sync_all()
     clocks = sampler.stop()
     ms_total = t_start.elapsed_time(t_end)
+
+    # duration of the dominant kernel (EMA) with CUDA events on its stream, same step sequence, eager
+    # launches (event records cannot be timed inside a captured graph)
+    for i in range(min(args.steps, 100)):
+        step(i, feats[i % POOL], keys[i % POOL], time_ema=True)
+    sync_all()
     ema_ms = sum(a.elapsed_time(b) for a, b in ema_events) / len(ema_events)
     loss_val = float(out["loss"].item())
     assert int(status.item()) == 0, "device status word set: %d" % int(status.item())
@@ -284,10 +316,44 @@ def gpu_arm(args):
     for i in range(min(args.warmup, 10)):
         e2e_step(i)
     sync_all()
+
+    # the same end-to-end step as one graph per input slot: H2D copies (copy stream) || EMA -> head -> loss D2H
+    e2e_graphs = None
+    if graphs is not None:
+        try:
+            e2e_graphs = []
+            for slot in range(POOL):
+                g_ = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_):
+                    cur = torch.cuda.current_stream()
+                    h2d.wait_stream(cur)  # fork: the copies depend on nothing in this step
+                    with torch.cuda.stream(h2d):
+                        k_dev.copy_(keys_h[slot], non_blocking=True)
+                        f_dev.copy_(feats_h[slot], non_blocking=True)
+                    if world > 1:
+                        comm.wait_stream(h2d)  # the key all_gather needs this step's keys
+                    ema_part(k_dev)            # runs beside the copies
+                    cur.wait_stream(h2d)
+                    r = head_part(f_dev, k_dev)
+                    loss_h.copy_(r["loss"], non_blocking=True)
+                e2e_graphs.append(g_)
+            for slot in range(POOL):
+                e2e_graphs[slot].replay()
+            sync_all()
+        except Exception as e:
+            e2e_graphs, graph_err = None, "e2e %s: %s" % (type(e).__name__, e)
+            torch.cuda.synchronize()
+
+    def e2e_graph_step(i):
+        e2e_graphs[i % POOL].replay()
+        torch.cuda.current_stream().synchronize()
+        return float(loss_h[0])
+
+    run_e2e = e2e_graph_step if e2e_graphs is not None else e2e_step
     e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e_start.record()
     for i in range(e2e_steps):
-        e2e_step(i)
+        run_e2e(i)
     e_end.record()
     sync_all()
     e2e_ms = e_start.elapsed_time(e_end)
@@ -316,7 +382,8 @@ def gpu_arm(args):
         "config": {"workload": WORKLOAD, "batch_per_gpu": B_PER_GPU, "global_batch": n_gpus * B_PER_GPU,
                    "queue_len": QUEUE_LEN, "dim": DIM, "T": TEMP, "ema_tensors": len(online),
                    "ema_params": n_params, "logits_materialised": not args.no_logits,
-                   "infonce_kernel": args.kernel,
+                   "infonce_kernel": args.kernel, "cuda_graph": graphs is not None,
+                   "e2e_cuda_graph": e2e_graphs is not None, "cuda_graph_error": graph_err,
                    "parallelism": "dp%d (queue/EMA replicated, batch sharded; key all_gather only)" % n_gpus,
                    "l2": "no explicit flush: one step streams %.0f MB (> 126 MB L2) so nothing survives between steps" % (step_bytes / 1e6)},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / e2e_steps,
@@ -355,6 +422,7 @@ def main():
     ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tc3x", "tc1x"])
     ap.add_argument("--no-logits", action="store_true", help="do not materialise the [B,K+1] logits tensor")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
