@@ -192,7 +192,8 @@ def gpu_arm(args):
     status = torch.zeros(1, dtype=torch.int32, device=dev)
     plan = ops.EmaPlan(online, hist)
     gathered = torch.empty(world * B_PER_GPU, DIM, device=dev) if world > 1 else None
-    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    # high-priority side stream: the all_gather's single CTA is scheduled ahead of the EMA's queued CTAs
+    comm = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
     impl = {"auto": _lib.IMPL_AUTO, "simt": _lib.IMPL_SIMT, "tc3x": _lib.IMPL_TC3X, "tc1x": _lib.IMPL_TC1X}[args.kernel]
     out = {}
     head_ws = torch.zeros(ops.moco_infonce_workspace_bytes(B_PER_GPU, DIM, QUEUE_LEN, 1), dtype=torch.uint8, device=dev)
@@ -407,9 +408,14 @@ def gpu_arm(args):
             "ms_per_step": dt * 1e3,
             "sample": "%d full steps of the same workload on the CPU oracle (torch CPU, all threads) after 2 warm-up" % done}
     if rank == 0:
-        print(json.dumps(result))
+        print(json.dumps(result), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without tearing NCCL down: destroy_process_group() blocks forever while captured graphs
+        # still reference the communicator (seen at N=2), and the process is finished anyway.
+        sync_all()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 
