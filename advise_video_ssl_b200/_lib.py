@@ -24,6 +24,14 @@ class EmaChunk(ctypes.Structure):
     _fields_ = [("online", c_void_p), ("hist", c_void_p), ("n", ctypes.c_uint32), ("flags", ctypes.c_uint32)]
 
 
+class PeerXchg(ctypes.Structure):
+    """Mirror of `avssl_peer_xchg` (include/avssl_b200.h)."""
+    _fields_ = [("base", c_void_p * 16), ("world", c_int), ("rank", c_int), ("rows_per_rank", c_int), ("D", c_int)]
+
+
+MAX_PEERS = 16
+IPC_HANDLE_BYTES = 64
+
 # name -> (restype, argtypes).  Every function declared in include/avssl_b200.h is
 # listed here; tests/test_abi.py checks the two stay in sync.
 SIGNATURES = {
@@ -61,6 +69,18 @@ SIGNATURES = {
                                   c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "avssl_sinkhorn_workspace_bytes": (c_size_t, [c_int, c_int]),
     "avssl_sinkhorn": (c_int, [c_void_p, c_int, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "avssl_peer_xchg_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "avssl_peer_alloc": (c_int, [c_size_t, c_void_p, c_void_p]),
+    "avssl_peer_open": (c_int, [c_void_p, c_void_p]),
+    "avssl_peer_close": (c_int, [c_void_p]),
+    "avssl_peer_free": (c_int, [c_void_p]),
+    "avssl_peer_push_rows": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "avssl_peer_wait_gather": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "avssl_ema_multi_tensor_push": (c_int, [c_void_p, c_int64, c_float, c_float, c_void_p, c_int, c_int, c_void_p,
+                                            c_void_p, c_void_p, c_void_p]),
+    "avssl_moco_infonce_fwd_bwd_enqueue_peer": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                        c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                                                        c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "avssl_swav_ce_workspace_bytes": (c_size_t, [c_int]),
     "avssl_swav_ce_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -10,6 +10,7 @@
 // ATen kernels, i.e. three separately rounded fp32 operations.  __fmul_rn/__fadd_rn
 // are never contracted into an FMA by nvcc, so every element matches bit for bit.
 #include "common.cuh"
+#include "peer.cuh"
 
 namespace avssl {
 
@@ -29,15 +30,16 @@ __device__ __forceinline__ float4 ema_blend4(const float4& o, const float4& h, f
 // the device.  kBump (only with a host-known `iter`): CTA 0 performs `self.iter += 1`
 // (models/contrastive.py:314) -- nobody reads `iter` inside the kernel then, so there is no
 // ordering to enforce.
+//
+// `chunk` is this CTA's entry of the table, `n_ctas` the number of CTAs working on the table.
 template <int kFirstMode, bool kBump>
-__global__ void __launch_bounds__(kEmaThreads)
-ema_multi_tensor_kernel(const avssl_ema_chunk* __restrict__ table, float m, float om,
-                        int64_t* iter, uint32_t* done_counter) {
-  const avssl_ema_chunk c = table[blockIdx.x];
+__device__ __forceinline__ void ema_cta(const avssl_ema_chunk* __restrict__ table, unsigned chunk, unsigned n_ctas,
+                                        float m, float om, int64_t* iter, uint32_t* done_counter) {
+  const avssl_ema_chunk c = table[chunk];
   // iter == 0: history := online first (models/contrastive.py:167-169)
   const bool first = kFirstMode == 2 ? (*reinterpret_cast<volatile int64_t*>(iter) == 0) : (kFirstMode == 1);
   const int tid = threadIdx.x;
-  if (kBump && kFirstMode != 2 && blockIdx.x == 0 && tid == 0) *iter += 1;
+  if (kBump && kFirstMode != 2 && chunk == 0 && tid == 0) *iter += 1;
 
   if ((c.flags & 1u) && c.n == (uint32_t)kEmaChunk) {
     const float4* o4 = reinterpret_cast<const float4*>(c.online) + tid;
@@ -84,13 +86,35 @@ ema_multi_tensor_kernel(const avssl_ema_chunk* __restrict__ table, float m, floa
     if (tid == 0) {
       __threadfence();
       const uint32_t prev = atomicAdd(done_counter, 1u);
-      if (prev == gridDim.x - 1) {
+      if (prev == n_ctas - 1) {
         *iter = *reinterpret_cast<volatile int64_t*>(iter) + 1;
         *done_counter = 0u;
         __threadfence();
       }
     }
   }
+}
+
+template <int kFirstMode, bool kBump>
+__global__ void __launch_bounds__(kEmaThreads)
+ema_multi_tensor_kernel(const avssl_ema_chunk* __restrict__ table, float m, float om,
+                        int64_t* iter, uint32_t* done_counter) {
+  ema_cta<kFirstMode, kBump>(table, blockIdx.x, gridDim.x, m, om, iter, done_counter);
+}
+
+// K1 + C3 push in one launch: the first `world` CTAs store this rank's key rows into every peer's
+// exchange buffer over NVLink (peer.cuh) while the others stream the parameters; the transfer
+// rides under the 70 us of EMA traffic and costs no launch of its own.
+template <int kFirstMode, bool kBump>
+__global__ void __launch_bounds__(kEmaThreads)
+ema_multi_tensor_push_kernel(const avssl_ema_chunk* __restrict__ table, float m, float om, int64_t* iter,
+                             uint32_t* done_counter, const avssl_peer_xchg x, const float* __restrict__ rows) {
+  __shared__ unsigned long long s_epoch;
+  if (blockIdx.x < (unsigned)x.world) {
+    peer_push_cta(x, rows, blockIdx.x, &s_epoch);
+    return;
+  }
+  ema_cta<kFirstMode, kBump>(table, blockIdx.x - x.world, gridDim.x - x.world, m, om, iter, done_counter);
 }
 
 __global__ void bump_iter_kernel(int64_t* iter) { *iter += 1; }
@@ -138,9 +162,11 @@ extern "C" int avssl_ema_plan_fill(const uint64_t* online_ptrs_host, const uint6
   return AVSSL_OK;
 }
 
-extern "C" int avssl_ema_multi_tensor(const avssl_ema_chunk* table_dev, int64_t n_chunks, float m,
-                                      float one_minus_m, int64_t* iter_dev, int first_iter, int bump_iter,
-                                      uint32_t* done_counter_dev, void* stream) {
+namespace {
+
+int ema_run(const avssl_ema_chunk* table_dev, int64_t n_chunks, float m, float one_minus_m, int64_t* iter_dev,
+            int first_iter, int bump_iter, uint32_t* done_counter_dev, const avssl_peer_xchg* x, const float* rows,
+            void* stream) {
   AVSSL_REQUIRE(iter_dev, AVSSL_ERR_INVALID_ARGUMENT, "ema_multi_tensor: iter_dev is null");
   AVSSL_REQUIRE(first_iter >= -1 && first_iter <= 1, AVSSL_ERR_INVALID_ARGUMENT, "ema_multi_tensor: first_iter must be -1, 0 or 1");
   AVSSL_REQUIRE(n_chunks >= 0 && n_chunks < (1ll << 31), AVSSL_ERR_INVALID_ARGUMENT,
@@ -153,12 +179,19 @@ extern "C" int avssl_ema_multi_tensor(const avssl_ema_chunk* table_dev, int64_t 
       bump_iter_kernel<<<1, 1, 0, s>>>(iter_dev);
       AVSSL_LAUNCH_OK("bump_iter_kernel");
     }
-    return AVSSL_OK;
+    return x ? avssl_peer_push_rows(x, rows, stream) : AVSSL_OK;
   }
   AVSSL_REQUIRE(table_dev, AVSSL_ERR_INVALID_ARGUMENT, "ema_multi_tensor: table_dev is null");
-  const unsigned grid = (unsigned)n_chunks;
-#define AVSSL_EMA_LAUNCH(MODE, BUMP) \
-  ema_multi_tensor_kernel<MODE, BUMP><<<grid, kEmaThreads, 0, s>>>(table_dev, m, one_minus_m, iter_dev, done_counter_dev)
+  const unsigned grid = (unsigned)n_chunks + (x ? (unsigned)x->world : 0u);
+#define AVSSL_EMA_LAUNCH(MODE, BUMP)                                                                              \
+  do {                                                                                                            \
+    if (x)                                                                                                        \
+      ema_multi_tensor_push_kernel<MODE, BUMP><<<grid, kEmaThreads, 0, s>>>(table_dev, m, one_minus_m, iter_dev, \
+                                                                             done_counter_dev, *x, rows);         \
+    else                                                                                                          \
+      ema_multi_tensor_kernel<MODE, BUMP><<<grid, kEmaThreads, 0, s>>>(table_dev, m, one_minus_m, iter_dev,      \
+                                                                        done_counter_dev);                        \
+  } while (0)
   if (first_iter < 0) {
     if (bump_iter) AVSSL_EMA_LAUNCH(2, true); else AVSSL_EMA_LAUNCH(2, false);
   } else if (first_iter == 1) {
@@ -169,4 +202,25 @@ extern "C" int avssl_ema_multi_tensor(const avssl_ema_chunk* table_dev, int64_t 
 #undef AVSSL_EMA_LAUNCH
   AVSSL_LAUNCH_OK("ema_multi_tensor_kernel");
   return AVSSL_OK;
+}
+
+}  // namespace
+
+extern "C" int avssl_ema_multi_tensor(const avssl_ema_chunk* table_dev, int64_t n_chunks, float m,
+                                      float one_minus_m, int64_t* iter_dev, int first_iter, int bump_iter,
+                                      uint32_t* done_counter_dev, void* stream) {
+  return ema_run(table_dev, n_chunks, m, one_minus_m, iter_dev, first_iter, bump_iter, done_counter_dev, nullptr,
+                 nullptr, stream);
+}
+
+extern "C" int avssl_ema_multi_tensor_push(const avssl_ema_chunk* table_dev, int64_t n_chunks, float m,
+                                           float one_minus_m, int64_t* iter_dev, int first_iter, int bump_iter,
+                                           uint32_t* done_counter_dev, const avssl_peer_xchg* x, const float* rows,
+                                           void* stream) {
+  int rc = peer_check(x, "ema_multi_tensor_push");
+  if (rc != AVSSL_OK) return rc;
+  AVSSL_REQUIRE(rows && (reinterpret_cast<uintptr_t>(rows) & 15u) == 0, AVSSL_ERR_INVALID_ARGUMENT,
+                "ema_multi_tensor_push: rows is null or not 16-byte aligned");
+  return ema_run(table_dev, n_chunks, m, one_minus_m, iter_dev, first_iter, bump_iter, done_counter_dev, x, rows,
+                 stream);
 }

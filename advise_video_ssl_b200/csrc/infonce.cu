@@ -1,4 +1,6 @@
 // K2+K3 front door: argument checks, workspace carving, implementation choice.
+#include <string.h>
+
 #include "infonce.cuh"
 
 using namespace avssl;
@@ -49,8 +51,9 @@ namespace {
 int moco_infonce_run(const float* feat_q, const float* const* keys_host, int n_keys, const float* queue,
                      float* queue_rw, int64_t* ptr_dev, uint32_t* status_dev, int B, int D, int K, float T,
                      float* q_out, float* loss_out, float* dfeat_out, float* row_lse_out, float* logits_out,
-                     void* workspace, size_t workspace_bytes, int impl, void* stream) {
-  AVSSL_REQUIRE(feat_q && keys_host && queue && q_out && loss_out && dfeat_out && workspace,
+                     void* workspace, size_t workspace_bytes, int impl, void* stream,
+                     const avssl_peer_xchg* peer = nullptr, const int64_t* peer_row_idx = nullptr) {
+  AVSSL_REQUIRE(feat_q && (keys_host || peer) && queue && q_out && loss_out && dfeat_out && workspace,
                 AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: null pointer");
   AVSSL_REQUIRE(B > 0 && D > 0 && K > 0, AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: bad sizes B=%d D=%d K=%d", B, D, K);
   AVSSL_REQUIRE(n_keys >= 1 && n_keys <= AVSSL_MAX_KEYS, AVSSL_ERR_INVALID_ARGUMENT,
@@ -65,9 +68,20 @@ int moco_infonce_run(const float* feat_q, const float* const* keys_host, int n_k
 
   InfoNceParams p;
   p.feat_q = feat_q;
-  for (int k = 0; k < AVSSL_MAX_KEYS; ++k) p.keys[k] = k < n_keys ? keys_host[k] : nullptr;
-  for (int k = 0; k < n_keys; ++k)
+  for (int k = 0; k < AVSSL_MAX_KEYS; ++k) p.keys[k] = (k < n_keys && !peer) ? keys_host[k] : nullptr;
+  for (int k = 0; k < n_keys && !peer; ++k)
     AVSSL_REQUIRE(p.keys[k], AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: keys[%d] is null", k);
+  p.use_peer = peer ? 1 : 0;
+  p.peer_row_idx = reinterpret_cast<const long long*>(peer_row_idx);
+  memset(&p.peer, 0, sizeof(p.peer));
+  if (peer) {
+    const int rc = peer_check(peer, "moco_infonce_peer");
+    if (rc != AVSSL_OK) return rc;
+    AVSSL_REQUIRE(n_keys == 1 && peer->D == D && (peer_row_idx || peer->rows_per_rank == B), AVSSL_ERR_INVALID_ARGUMENT,
+                  "moco_infonce_peer: exchange is [%d x %d] per rank, head has B=%d D=%d (one key tensor only)",
+                  peer->rows_per_rank, peer->D, B, D);
+    p.peer = *peer;
+  }
   p.n_keys = n_keys;
   p.queue = queue;
   p.B = B;
@@ -85,7 +99,7 @@ int moco_infonce_run(const float* feat_q, const float* const* keys_host, int n_k
   if (ptr_dev) {
     // models/contrastive.py:284  assert self.k % num_items == 0
     AVSSL_REQUIRE(K % B == 0, AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: K=%d is not a multiple of the key batch %d", K, B);
-    AVSSL_REQUIRE(queue_rw && (reinterpret_cast<uintptr_t>(p.keys[0]) & 15u) == 0 && D % 4 == 0,
+    AVSSL_REQUIRE(queue_rw && (peer || (reinterpret_cast<uintptr_t>(p.keys[0]) & 15u) == 0) && D % 4 == 0,
                   AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: fused enqueue needs a writable queue and 16-byte aligned keys[0]");
   }
 
@@ -93,6 +107,9 @@ int moco_infonce_run(const float* feat_q, const float* const* keys_host, int n_k
   if (use == AVSSL_IMPL_AUTO) use = infonce_tc_supported(B, D, K) ? AVSSL_IMPL_TC3X : AVSSL_IMPL_SIMT;
   AVSSL_REQUIRE(use == AVSSL_IMPL_SIMT || use == AVSSL_IMPL_TC3X || use == AVSSL_IMPL_TC1X,
                 AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: unknown impl %d", impl);
+  AVSSL_REQUIRE(!peer || use != AVSSL_IMPL_SIMT, AVSSL_ERR_UNSUPPORTED,
+                "moco_infonce_peer: the fused exchange wait needs the tcgen05 kernel (D in {32,64,96,128}); "
+                "call avssl_peer_wait_gather and the plain entry point instead");
 
   // split the queue over the SMs in whole tiles
   const int tile = (use == AVSSL_IMPL_SIMT) ? kSimtTileRows : kTcTileRows;
@@ -146,4 +163,16 @@ extern "C" int avssl_moco_infonce_fwd_bwd_enqueue(const float* feat_q, const flo
   AVSSL_REQUIRE(ptr_dev, AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce_enqueue: ptr_dev is null");
   return moco_infonce_run(feat_q, keys_host, n_keys, queue, queue, ptr_dev, status_dev, B, D, K, T, q_out, loss_out,
                           dfeat_out, row_lse_out, logits_out, workspace, workspace_bytes, impl, stream);
+}
+
+extern "C" int avssl_moco_infonce_fwd_bwd_enqueue_peer(const float* feat_q, const avssl_peer_xchg* x,
+                                                       const int64_t* row_idx, float* queue, int64_t* ptr_dev,
+                                                       uint32_t* status_dev, int B, int D, int K, float T,
+                                                       float* q_out, float* loss_out, float* dfeat_out,
+                                                       float* row_lse_out, float* logits_out, void* workspace,
+                                                       size_t workspace_bytes, int impl, void* stream) {
+  AVSSL_REQUIRE(x, AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce_peer: exchange descriptor is null");
+  return moco_infonce_run(feat_q, nullptr, 1, queue, ptr_dev ? queue : nullptr, ptr_dev, status_dev, B, D, K, T, q_out,
+                          loss_out, dfeat_out, row_lse_out, logits_out, workspace, workspace_bytes, impl, stream, x,
+                          row_idx);
 }

@@ -1,6 +1,7 @@
 // Shared declarations for the MoCo l2-norm + logits + InfoNCE kernels (K2+K3).
 #pragma once
 #include "common.cuh"
+#include "peer.cuh"
 
 namespace avssl {
 
@@ -39,6 +40,12 @@ struct InfoNceParams {
   float* queue_rw;
   long long* enq_ptr;
   uint32_t* enq_status;
+  // optional fused C3 wait (tcgen05 kernel only): key row i is row
+  // (peer_row_idx ? peer_row_idx[i] : peer.rank * B + i) of the peer exchange buffer, read after
+  // the merge CTAs have waited for every rank's push of the current epoch.  keys[0] is unused then.
+  int use_peer;
+  const long long* peer_row_idx;
+  avssl_peer_xchg peer;
 };
 
 // 1 / ||row|| computed by ONE warp with a fixed summation order, so that every

@@ -25,6 +25,7 @@ struct CombineSmem {
   float bcast[4];
   __align__(16) float acc[kThreads / 32][2 * kCombineCols];
   unsigned is_last;
+  int peer_slot;
   long long enq_ptr;
 };
 
@@ -40,6 +41,8 @@ __device__ __forceinline__ float fast_lg2(float x) {
 }
 
 // All kThreads threads of the CTA call this with the same row i.  MAXC = ceil(D / 128).
+// key0_row: row i of the first key tensor (p.keys[0] + i * D, or a row of the peer exchange
+// buffer -- read through L2, it may have been written by another GPU).
 //
 // Latency matters more than bandwidth here (the partials sit in L2, ~75 KB per row at 148
 // splits), and the code runs once per launch with a cold instruction cache, so it is kept
@@ -49,7 +52,8 @@ __device__ __forceinline__ float fast_lg2(float x) {
 // non-unrolled loops, and transcendental functions use the hardware approximations
 // (relative error ~2^-22, far inside the fp32 tolerance of the loss).
 template <int kThreads, int MAXC>
-__device__ __forceinline__ void infonce_combine_row(const InfoNceParams& p, int i, CombineSmem<kThreads>& sm) {
+__device__ __forceinline__ void infonce_combine_row(const InfoNceParams& p, int i, CombineSmem<kThreads>& sm,
+                                                    const float* __restrict__ key0_row) {
   constexpr int kGroups = kThreads / 32;
   constexpr int kWide = 11;  // split rows in flight per lane (11 x 14 warps covers 148 splits)
   constexpr int kMl = (kMaxSplits + kThreads - 1) / kThreads;
@@ -86,7 +90,7 @@ __device__ __forceinline__ void infonce_combine_row(const InfoNceParams& p, int 
   for (int u = 0; u < MAXC; ++u) {
     const int c = col + u * kCombineCols;
     fv[u] = (owner && c < D) ? f[c] : 0.f;
-    kv0[u] = (owner && c < D) ? p.keys[0][(size_t)i * D + c] : 0.f;
+    kv0[u] = (owner && c < D) ? __ldcg(key0_row + c) : 0.f;
   }
   if (warp == kGroups - 1) {  // the last warp holds the fewest partial rows
     const float nrm = warp_row_norm(f, D, lane);

@@ -166,7 +166,7 @@ constexpr int kCombineThreads = 512;
 
 __global__ void __launch_bounds__(kCombineThreads) infonce_combine_kernel(const InfoNceParams p) {
   __shared__ CombineSmem<kCombineThreads> sm;
-  infonce_combine_row<kCombineThreads, 2>(p, blockIdx.x, sm);
+  infonce_combine_row<kCombineThreads, 2>(p, blockIdx.x, sm, p.keys[0] + (size_t)blockIdx.x * p.D);
   infonce_finish<kCombineThreads>(p, gridDim.x, sm);
 }
 

@@ -603,12 +603,27 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
     enq_ptr = *reinterpret_cast<volatile long long*>(p.enq_ptr);  // advanced only after every CTA arrived below
     enq_ok = enq_ptr >= 0 && enq_ptr + p.B <= p.K;               // models/contrastive.py:285
   }
+  const float* key_base = p.keys[0];
+  if (p.use_peer && cta < p.B) {  // C3: the keys come from the peer exchange buffer (peer.cuh)
+    if (tid == 0) csm.peer_slot = peer_wait_all(p.peer);  // long since landed: the sweep took ~15 us
+    __syncthreads();
+    key_base = peer_payload(p.peer.base[p.peer.rank], csm.peer_slot, p.peer);
+  }
   for (int i = cta; i < p.B; i += (int)n_ctas) {
-    infonce_combine_row<kTcThreads, 1>(p, i, csm);
+    long long krow = i;
+    if (p.use_peer) {
+      krow = p.peer_row_idx ? p.peer_row_idx[i] : (long long)p.peer.rank * p.B + i;
+      if (krow < 0 || krow >= (long long)p.peer.world * p.peer.rows_per_rank) {  // uniform over the CTA
+        if (tid == 0 && p.enq_status) atomicOr(p.enq_status, AVSSL_DEVFLAG_BAD_INDEX);
+        krow = 0;
+      }
+    }
+    const float* key_row = key_base + (size_t)krow * D;
+    infonce_combine_row<kTcThreads, 1>(p, i, csm, key_row);
     if (enq_ok) {  // K4: queue[ptr + i] = keys[0][i]; no CTA reads the queue after the grid barrier
-      const float4* src = reinterpret_cast<const float4*>(p.keys[0] + (size_t)i * D);
+      const float4* src = reinterpret_cast<const float4*>(key_row);
       float4* dst = reinterpret_cast<float4*>(p.queue_rw + (size_t)(enq_ptr + i) * D);
-      for (int c4 = tid; c4 < D / 4; c4 += kTcThreads) dst[c4] = src[c4];
+      for (int c4 = tid; c4 < D / 4; c4 += kTcThreads) dst[c4] = __ldcg(src + c4);
     }
   }
   if (tid == 0) TC_TRACE(14, 4);

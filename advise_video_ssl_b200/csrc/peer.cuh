@@ -1,0 +1,88 @@
+// Device side of the NVLink peer-memory row exchange (C3: the cross-GPU key gather of
+// models/contrastive.py:216-230 without a collective kernel).
+//
+// Every rank owns one exchange buffer, mapped into every other rank's address space
+// (CUDA IPC, see peer.cu):
+//
+//   offset   0  u64 flags[16]   flags[src] = epoch of the last push completed by rank `src`
+//                               (written by `src` over NVLink, release at system scope)
+//   offset 128  u64 epoch       pushes issued by the OWNER so far (local)
+//   offset 136  u32 done        CTA-finish counter of the running push (local, self-resetting)
+//   offset 256  float payload[2][world * rows * D]   slot = epoch & 1
+//
+// push(e):  rank r stores its [rows, D] block into payload[e & 1][r] of EVERY rank (one CTA per
+//           destination), fences at system scope and then publishes flags[r] = e there.
+// wait(e):  the consumer spins (acquire, system scope) until all `world` local flags are >= e.
+//
+// Two slots suffice: rank A can issue push e+2 only after its own consumer of epoch e+1 has
+// finished, which waited for B's push e+1, which B issued after ITS consumer of epoch e was done
+// with slot e & 1 (same stream).  Flags are monotonic, so a peer running one step ahead is harmless.
+#pragma once
+#include "common.cuh"
+
+namespace avssl {
+
+struct PeerHdr {
+  unsigned long long flags[AVSSL_MAX_PEERS];
+  unsigned long long epoch;
+  unsigned int done;
+  unsigned int pad_[29];
+};
+static_assert(sizeof(PeerHdr) == 256, "exchange header is 256 bytes");
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ float* peer_payload(void* base, int slot, const avssl_peer_xchg& x) {
+  return reinterpret_cast<float*>(static_cast<char*>(base) + sizeof(PeerHdr)) +
+         (size_t)slot * x.world * x.rows_per_rank * x.D;
+}
+
+// All threads of one CTA: push this rank's rows to rank `dst`.  `world` CTAs (dst = 0..world-1)
+// make one push; the last of them to finish advances the local epoch.  `s_epoch` is a shared
+// scratch word.  rows * D must be a multiple of 4 and `rows` 16-byte aligned (checked by the host).
+__device__ __forceinline__ void peer_push_cta(const avssl_peer_xchg& x, const float* __restrict__ rows, int dst,
+                                              unsigned long long* s_epoch) {
+  PeerHdr* me = static_cast<PeerHdr*>(x.base[x.rank]);
+  if (threadIdx.x == 0) *s_epoch = *reinterpret_cast<volatile unsigned long long*>(&me->epoch) + 1ull;
+  __syncthreads();
+  const unsigned long long e = *s_epoch;
+  const int n4 = x.rows_per_rank * x.D / 4;
+  const float4* src = reinterpret_cast<const float4*>(rows);
+  float4* out = reinterpret_cast<float4*>(peer_payload(x.base[dst], (int)(e & 1ull), x) +
+                                          (size_t)x.rank * x.rows_per_rank * x.D);
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) out[i] = __ldg(src + i);
+  __threadfence_system();  // every thread's stores are performed at the destination before the flag
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    st_release_sys_u64(&static_cast<PeerHdr*>(x.base[dst])->flags[x.rank], e);
+    // every CTA has read `epoch` before it arrives here, so the last one may advance it
+    const unsigned prev = atomicAdd(&me->done, 1u);
+    if (prev == (unsigned)x.world - 1u) {
+      me->done = 0u;
+      *reinterpret_cast<volatile unsigned long long*>(&me->epoch) = e;
+      __threadfence();
+    }
+  }
+}
+
+// ONE thread: wait until every rank's push of the current local epoch has landed here.
+// Returns the payload slot to read.  The caller follows with __syncthreads().
+__device__ __forceinline__ int peer_wait_all(const avssl_peer_xchg& x) {
+  PeerHdr* me = static_cast<PeerHdr*>(x.base[x.rank]);
+  const unsigned long long e = *reinterpret_cast<volatile unsigned long long*>(&me->epoch);
+  for (int r = 0; r < x.world; ++r)
+    while (ld_acquire_sys_u64(&me->flags[r]) < e) __nanosleep(32);
+  return (int)(e & 1ull);
+}
+
+// Host-side validation of an exchange descriptor (peer.cu).
+int peer_check(const avssl_peer_xchg* x, const char* who);
+
+}  // namespace avssl

@@ -94,13 +94,22 @@ class EmaPlan:
     def matches(self, online, hist):
         return self.ptr_key == tuple((o.data_ptr(), h.data_ptr()) for o, h in zip(online, hist))
 
-    def run(self, m, iter_buf, bump_iter=False, first_iter=None):
+    def run(self, m, iter_buf, bump_iter=False, first_iter=None, push=None):
         """hist <- online*(1-m) + hist*m, bit-exact with the reference's fp32 ops.
         first_iter: True/False when the caller mirrors `iter` on the host, None to let the
-        kernel read it from the device."""
+        kernel read it from the device.
+        push=(PeerExchange, rows): the same launch also pushes `rows` to every peer (C3)."""
         _req(iter_buf, "iter", torch.int64)
         m = float(m)
         fi = -1 if first_iter is None else (1 if first_iter else 0)
+        if push is not None:
+            xchg, rows = push
+            xchg.check_rows(rows)
+            check(lib.avssl_ema_multi_tensor_push(self.table.data_ptr(), self.n_chunks, m, 1.0 - m,
+                                                  iter_buf.data_ptr(), fi, 1 if bump_iter else 0,
+                                                  self.done.data_ptr(), ctypes.addressof(xchg.desc),
+                                                  rows.data_ptr(), _stream()), "avssl_ema_multi_tensor_push")
+            return
         check(lib.avssl_ema_multi_tensor(self.table.data_ptr(), self.n_chunks, m, 1.0 - m,
                                          iter_buf.data_ptr(), fi, 1 if bump_iter else 0,
                                          self.done.data_ptr(), _stream()), "avssl_ema_multi_tensor")
@@ -108,6 +117,103 @@ class EmaPlan:
     @property
     def algorithmic_bytes(self):
         return 12 * self.n_params
+
+
+# ------------------------------------------------------------------------------ C3
+class PeerExchange:
+    """Cross-GPU exchange of [rows_per_rank, D] fp32 blocks over NVLink peer memory (C3).
+
+    Replaces `cat_all_gather(keys)` + row select of `_batch_unshuffle`
+    (models/contrastive.py:216-230) for the ranks of one box with plain peer stores and epoch
+    flags: no collective kernel, no side stream, CUDA-graph capturable.  Collective set-up:
+    every rank of `group` must construct it (one all_gather of the 64-byte IPC handles), and
+    every rank must then issue the same sequence of pushes.
+
+        x = PeerExchange(B, D)                 # once
+        x.push(keys)                           # or EmaPlan.run(..., push=(x, keys))
+        k = x.wait_gather(idx_restore_rank)    # or moco_infonce(..., peer=x)
+
+    world_size 1 (or no process group) works too: the exchange then targets its own buffer.
+    """
+
+    def __init__(self, rows_per_rank, D, group=None, device=None):
+        import torch.distributed as dist
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        on = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if on else 1
+        self.rank = dist.get_rank(group) if on else 0
+        self.rows_per_rank, self.D = int(rows_per_rank), int(D)
+        if self.world > _lib.MAX_PEERS:
+            raise ValueError("PeerExchange supports at most %d ranks (one NVLink domain)" % _lib.MAX_PEERS)
+        nbytes = lib.avssl_peer_xchg_bytes(self.world, self.rows_per_rank, self.D)
+        if nbytes == 0:
+            raise ValueError("bad exchange geometry world=%d rows=%d D=%d" % (self.world, rows_per_rank, D))
+        self.nbytes = int(nbytes)
+        base = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * _lib.IPC_HANDLE_BYTES)()
+        with torch.cuda.device(self.device):
+            check(lib.avssl_peer_alloc(self.nbytes, ctypes.byref(base), ctypes.addressof(handle)), "avssl_peer_alloc")
+            self._own = base.value
+            self._opened = []
+            bases = [None] * self.world
+            bases[self.rank] = self._own
+            if self.world > 1:
+                handles = [None] * self.world
+                dist.all_gather_object(handles, (self.rank, bytes(handle)), group=group)
+                for r, h in handles:
+                    if r == self.rank:
+                        continue
+                    p = ctypes.c_void_p()
+                    buf = (ctypes.c_ubyte * _lib.IPC_HANDLE_BYTES).from_buffer_copy(h)
+                    check(lib.avssl_peer_open(ctypes.addressof(buf), ctypes.byref(p)), "avssl_peer_open(rank %d)" % r)
+                    self._opened.append(p.value)
+                    bases[r] = p.value
+                dist.barrier(group=group)  # every buffer is mapped everywhere before the first push
+        self.desc = _lib.PeerXchg()
+        for r in range(self.world):
+            self.desc.base[r] = bases[r]
+        self.desc.world, self.desc.rank = self.world, self.rank
+        self.desc.rows_per_rank, self.desc.D = self.rows_per_rank, self.D
+
+    def check_rows(self, rows):
+        _req(rows, "rows")
+        if tuple(rows.shape) != (self.rows_per_rank, self.D):
+            raise ValueError("exchange block is [%d, %d], got %s" % (self.rows_per_rank, self.D, tuple(rows.shape)))
+
+    def push(self, rows):
+        """Store `rows` into every rank's buffer and publish the new epoch (one small launch)."""
+        self.check_rows(rows)
+        check(lib.avssl_peer_push_rows(ctypes.addressof(self.desc), rows.data_ptr(), _stream()), "avssl_peer_push_rows")
+
+    def wait_gather(self, row_idx=None, out=None, status=None):
+        """Wait for every rank's push of the current epoch, then return gathered[row_idx]
+        (row_idx None: this rank's own block).  gathered = cat_all_gather order."""
+        n_out = self.rows_per_rank if row_idx is None else int(row_idx.numel())
+        if row_idx is not None:
+            _req(row_idx, "row_idx", torch.int64)
+        if out is None:
+            out = torch.empty(n_out, self.D, dtype=_f32, device=self.device)
+        _req(out, "out")
+        check(lib.avssl_peer_wait_gather(ctypes.addressof(self.desc), row_idx.data_ptr() if row_idx is not None else None,
+                                         n_out, out.data_ptr(), status.data_ptr() if status is not None else None,
+                                         _stream()), "avssl_peer_wait_gather")
+        return out
+
+    def wait_gather_all(self, out=None):
+        """All world*rows_per_rank rows in rank order (what cat_all_gather returns)."""
+        idx = torch.arange(self.world * self.rows_per_rank, dtype=torch.int64, device=self.device)
+        return self.wait_gather(idx, out=out)
+
+    def close(self):
+        """Unmap the peers' buffers and free this rank's.  Collective in spirit: call it on every
+        rank once no push or wait is in flight."""
+        if getattr(self, "_own", None) is None:
+            return
+        torch.cuda.synchronize(self.device)
+        for p in self._opened:
+            lib.avssl_peer_close(p)
+        lib.avssl_peer_free(self._own)
+        self._own, self._opened = None, []
 
 
 # ---------------------------------------------------------------------------- K2+K3
@@ -123,7 +229,8 @@ def _workspace(device, nbytes):
     return ws
 
 
-def moco_infonce(feat_q, keys, queue, T, want_logits=True, impl=_lib.IMPL_AUTO, out=None, enqueue=None, workspace=None):
+def moco_infonce(feat_q, keys, queue, T, want_logits=True, impl=_lib.IMPL_AUTO, out=None, enqueue=None, workspace=None,
+                 peer=None, peer_row_idx=None):
     """Fused l2-norm + logits + InfoNCE forward/backward (K2+K3).
 
     Returns dict(loss[1], dfeat[B,D], q[B,D], lse[n_keys*B], logits[n_keys*B,K+1] or None).
@@ -133,6 +240,9 @@ def moco_infonce(feat_q, keys, queue, T, want_logits=True, impl=_lib.IMPL_AUTO, 
     (same launch with the tcgen05 kernels); `status` may be None.
     `workspace`: optional caller-owned uint8 tensor of `moco_infonce_workspace_bytes()` bytes,
     zero-filled once (CUDA-graph capture: no allocation or memset inside the captured region).
+    `peer`: a PeerExchange whose current epoch holds the keys (`keys` must be None): the launch
+    waits for the exchange itself, after its sweep over the queue, and takes key row i from
+    gathered[peer_row_idx[i]] (default: this rank's own block) -- C3 fused into K3.
     """
     _req(feat_q, "feat_q")
     _req(queue, "queue")
@@ -140,7 +250,15 @@ def moco_infonce(feat_q, keys, queue, T, want_logits=True, impl=_lib.IMPL_AUTO, 
         raise ValueError("feat_q [B,D] and queue [K,D] expected, got %s and %s" % (tuple(feat_q.shape), tuple(queue.shape)))
     B, D = feat_q.shape
     K = queue.shape[0]
-    n_keys = len(keys)
+    if peer is not None:
+        if keys is not None:
+            raise ValueError("pass either keys or peer, not both")
+        if peer_row_idx is not None:
+            _req(peer_row_idx, "peer_row_idx", torch.int64)
+            if peer_row_idx.numel() != B:
+                raise ValueError("peer_row_idx needs %d entries" % B)
+        keys = []
+    n_keys = 1 if peer is not None else len(keys)
     if not 1 <= n_keys <= _lib.MAX_KEYS:
         raise ValueError("need 1..%d key tensors, got %d" % (_lib.MAX_KEYS, n_keys))
     for k in keys:
@@ -163,6 +281,21 @@ def moco_infonce(feat_q, keys, queue, T, want_logits=True, impl=_lib.IMPL_AUTO, 
             raise ValueError("workspace has %d bytes, need %d" % (ws.numel(), nbytes))
     else:
         ws = _workspace(dev, nbytes)
+    if peer is not None:
+        ptr, status = enqueue if enqueue is not None else (None, None)
+        if ptr is not None:
+            _req(ptr, "ptr", torch.int64)
+            assert K % B == 0, "queue length %d is not a multiple of the key batch %d" % (K, B)
+        if status is not None:
+            _req(status, "status", torch.int32)
+        check(lib.avssl_moco_infonce_fwd_bwd_enqueue_peer(
+            feat_q.data_ptr(), ctypes.addressof(peer.desc), peer_row_idx.data_ptr() if peer_row_idx is not None else None,
+            queue.data_ptr(), ptr.data_ptr() if ptr is not None else None,
+            status.data_ptr() if status is not None else None, B, D, K, float(T),
+            q.data_ptr(), loss.data_ptr(), dfeat.data_ptr(), lse.data_ptr(),
+            logits.data_ptr() if logits is not None else None, ws.data_ptr(), ws.numel(), int(impl), _stream()),
+            "avssl_moco_infonce_fwd_bwd_enqueue_peer")
+        return {"loss": loss, "dfeat": dfeat, "q": q, "lse": lse, "logits": logits}
     key_ptrs = (ctypes.c_void_p * n_keys)(*[k.data_ptr() for k in keys])
     if enqueue is None:
         check(lib.avssl_moco_infonce_fwd_bwd(

@@ -171,7 +171,13 @@ def gpu_arm(args):
                          "(use --impl reference for the CPU oracle arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    json_out = sys.stdout
     if world > 1:
+        # NCCL writes its version banner to fd 1 when the communicator is created: keep the real stdout
+        # for the ONE JSON line and point fd 1 at stderr for everything else.
+        sys.stdout.flush()
+        json_out = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
     n_gpus = world
@@ -191,29 +197,44 @@ def gpu_arm(args):
     ptr = torch.zeros(1, dtype=torch.int64, device=dev)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
     plan = ops.EmaPlan(online, hist)
+    # C3, the cross-GPU key gather.  "peer" (default): the keys are stored straight into every
+    # rank's exchange buffer over NVLink by extra CTAs of the EMA launch, and the head launch waits
+    # for them after its sweep -- no collective kernel, no side stream.  "nccl": all_gather on a
+    # high-priority side stream next to the EMA (kept for comparison).
+    use_peer = world > 1 and args.exchange == "peer"
+    use_nccl = world > 1 and not use_peer
+    xchg = ops.PeerExchange(B_PER_GPU, DIM) if use_peer else None
     gathered = torch.empty(world * B_PER_GPU, DIM, device=dev) if world > 1 else None
-    # high-priority side stream: the all_gather's single CTA is scheduled ahead of the EMA's queued CTAs
-    comm = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
+    comm = torch.cuda.Stream(device=dev, priority=-1) if use_nccl else None
+    exchange_verified = None
+    if use_peer:  # one untimed round against NCCL's all_gather: bit-identical or abort
+        dist.all_gather_into_tensor(gathered, keys[0])
+        xchg.push(keys[0])
+        exchange_verified = bool(torch.equal(xchg.wait_gather_all(), gathered))
+        assert exchange_verified, "peer exchange differs from NCCL all_gather"
     impl = {"auto": _lib.IMPL_AUTO, "simt": _lib.IMPL_SIMT, "tc3x": _lib.IMPL_TC3X, "tc1x": _lib.IMPL_TC1X}[args.kernel]
     out = {}
     head_ws = torch.zeros(ops.moco_infonce_workspace_bytes(B_PER_GPU, DIM, QUEUE_LEN, 1), dtype=torch.uint8, device=dev)
     state = {"n": 0}
     launches_per_step = 2 if args.kernel != "simt" else 4  # ema + fused head (simt: ema, split, combine, enqueue)
+    if use_peer and args.kernel == "simt":
+        raise SystemExit("--exchange peer needs the tcgen05 head kernel (fused wait)")
     ema_events = []
 
-    def ema_part(k_for_gather, time_ema=False, after=None):
-        """K1 (+ the key all_gather C3 on the side stream when N > 1)."""
+    def ema_part(k_for_gather, time_ema=False, after=None, push=True):
+        """K1 (+ C3: the key push fused into the same launch, or NCCL's all_gather on the side stream)."""
         if time_ema:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        if world > 1:
+        if use_nccl:
             # C3: key all_gather on the comm stream, overlapped with the EMA kernel
             comm.wait_stream(torch.cuda.current_stream())
             if after is not None:
                 comm.wait_event(after)
             with torch.cuda.stream(comm):
                 dist.all_gather_into_tensor(gathered, k_for_gather)
-        plan.run(MOMENTUM, it, bump_iter=True, first_iter=state["n"] == 0)  # host mirror of `iter`, as the module keeps
+        plan.run(MOMENTUM, it, bump_iter=True, first_iter=state["n"] == 0,  # host mirror of `iter`, as the module keeps
+                 push=(xchg, k_for_gather) if (use_peer and push) else None)
         state["n"] += 1
         if time_ema:
             e1.record()
@@ -221,7 +242,10 @@ def gpu_arm(args):
 
     def head_part(f, k):
         """K2+K3+K4 in one cooperative launch: loss/grad against the old queue, then the ring write."""
-        if world > 1:
+        if use_peer:  # the launch itself waits for every rank's keys and reads this rank's block
+            return ops.moco_infonce(f, None, queue, TEMP, want_logits=not args.no_logits, impl=impl, out=out,
+                                    enqueue=(ptr, status), workspace=head_ws, peer=xchg)
+        if use_nccl:
             torch.cuda.current_stream().wait_stream(comm)
             k = gathered[rank * B_PER_GPU:(rank + 1) * B_PER_GPU]
         return ops.moco_infonce(f, [k], queue, TEMP, want_logits=not args.no_logits, impl=impl, out=out,
@@ -294,19 +318,21 @@ def gpu_arm(args):
     loss_h = torch.empty(1).pin_memory()
     e2e_steps = args.steps
 
-    h2d = torch.cuda.Stream(device=dev)
+    h2d = torch.cuda.Stream(device=dev, priority=-1)
     copied = torch.cuda.Event()
 
     def e2e_step(i):
         # The momentum update does not depend on this step's inputs, so the host->device copies run on
         # a copy stream underneath it; the head (and, for N > 1, the key all_gather) waits for them.
-        if world == 1:
-            ema_part(k_dev)  # launched first: the GPU starts on it while the host enqueues the copies
+        if not use_nccl:
+            ema_part(k_dev, push=False)  # launched first: the GPU starts on it while the host enqueues the copies
         with torch.cuda.stream(h2d):
             k_dev.copy_(keys_h[i % POOL], non_blocking=True)
             f_dev.copy_(feats_h[i % POOL], non_blocking=True)
+            if use_peer:
+                xchg.push(k_dev)  # C3 right behind the copy, on the copy stream, still under the EMA
             copied.record()
-        if world > 1:
+        if use_nccl:
             ema_part(k_dev, after=copied)  # the key all_gather needs this step's keys
         torch.cuda.current_stream().wait_event(copied)
         r = head_part(f_dev, k_dev)
@@ -331,9 +357,11 @@ def gpu_arm(args):
                     with torch.cuda.stream(h2d):
                         k_dev.copy_(keys_h[slot], non_blocking=True)
                         f_dev.copy_(feats_h[slot], non_blocking=True)
-                    if world > 1:
+                        if use_peer:
+                            xchg.push(k_dev)
+                    if use_nccl:
                         comm.wait_stream(h2d)  # the key all_gather needs this step's keys
-                    ema_part(k_dev)            # runs beside the copies
+                    ema_part(k_dev, push=False)  # runs beside the copies
                     cur.wait_stream(h2d)
                     r = head_part(f_dev, k_dev)
                     loss_h.copy_(r["loss"], non_blocking=True)
@@ -385,7 +413,10 @@ def gpu_arm(args):
                    "ema_params": n_params, "logits_materialised": not args.no_logits,
                    "infonce_kernel": args.kernel, "cuda_graph": graphs is not None,
                    "e2e_cuda_graph": e2e_graphs is not None, "cuda_graph_error": graph_err,
-                   "parallelism": "dp%d (queue/EMA replicated, batch sharded; key all_gather only)" % n_gpus,
+                   "key_exchange": ("nvlink peer stores fused into the EMA launch, wait fused into the head launch"
+                                    if use_peer else ("nccl all_gather on a side stream" if use_nccl else "none (1 GPU)")),
+                   "key_exchange_verified_vs_nccl": exchange_verified,
+                   "parallelism": "dp%d (queue/EMA replicated, batch sharded; key exchange only)" % n_gpus,
                    "l2": "no explicit flush: one step streams %.0f MB (> 126 MB L2) so nothing survives between steps" % (step_bytes / 1e6)},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / e2e_steps,
                 "h2d_bytes_per_step": 2 * 4 * B_PER_GPU * DIM, "d2h_bytes_per_step": 4,
@@ -408,7 +439,8 @@ def gpu_arm(args):
             "ms_per_step": dt * 1e3,
             "sample": "%d full steps of the same workload on the CPU oracle (torch CPU, all threads) after 2 warm-up" % done}
     if rank == 0:
-        print(json.dumps(result), flush=True)
+        json_out.write(json.dumps(result) + "\n")
+        json_out.flush()
     if world > 1:
         # Leave without tearing NCCL down: destroy_process_group() blocks forever while captured graphs
         # still reference the communicator (seen at N=2), and the process is finished anyway.
@@ -429,6 +461,8 @@ def main():
     ap.add_argument("--no-logits", action="store_true", help="do not materialise the [B,K+1] logits tensor")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: cross-GPU key gather over NVLink peer memory (default) or NCCL all_gather")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

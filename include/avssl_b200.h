@@ -241,6 +241,58 @@ AVSSL_API int avssl_swav_ce_fwd_bwd(const float* scores, const float* codes, int
                           int P, float T, const float* pair_w_host, float* loss_out, float* dscores_out,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------- C3: cross-GPU key exchange over NVLink peer memory
+ * Replaces the key all_gather + row select of _batch_unshuffle (models/contrastive.py:216-230;
+ * cat_all_gather, utils/distributed.py:5-13) for the ranks of ONE box, without a collective
+ * kernel: every rank stores its [rows_per_rank, D] block straight into every peer's exchange
+ * buffer over NVLink and publishes a per-source epoch flag; consumers spin on their local flags.
+ * Bit-exact (plain copies).  Two payload slots (epoch parity) make back-to-back steps safe.
+ *
+ * Set-up (once): each rank calls avssl_peer_alloc() (cudaMalloc + zero-fill + CUDA IPC export),
+ * the caller moves the AVSSL_IPC_HANDLE_BYTES-byte handles between the processes (e.g. a
+ * torch.distributed all_gather), every rank opens the others with avssl_peer_open() and fills an
+ * avssl_peer_xchg with base[r] = rank r's buffer as mapped HERE (base[rank] = its own).
+ * Every rank must issue the same sequence of pushes (one per step).
+ */
+#define AVSSL_MAX_PEERS 16
+#define AVSSL_IPC_HANDLE_BYTES 64
+typedef struct {
+  void* base[AVSSL_MAX_PEERS]; /* exchange buffers of all ranks, in this process's address space */
+  int world, rank;
+  int rows_per_rank, D;        /* every rank pushes [rows_per_rank, D] fp32 per step */
+} avssl_peer_xchg;
+
+AVSSL_API size_t avssl_peer_xchg_bytes(int world, int rows_per_rank, int D);
+AVSSL_API int avssl_peer_alloc(size_t bytes, void** dev_ptr_out, void* ipc_handle_out_host);
+AVSSL_API int avssl_peer_open(const void* ipc_handle_host, void** dev_ptr_out);
+AVSSL_API int avssl_peer_close(void* dev_ptr);
+AVSSL_API int avssl_peer_free(void* dev_ptr);
+/* push: `world` CTAs, one per destination rank (stand-alone launch). */
+AVSSL_API int avssl_peer_push_rows(const avssl_peer_xchg* x, const float* rows, void* stream);
+/* wait for the current epoch from every rank, then out[i] = gathered[row_idx[i]] (row_idx NULL:
+ * this rank's own block, n_out <= rows_per_rank).  gathered is [world * rows_per_rank, D] in rank
+ * order = what cat_all_gather returns.  Out-of-range indices set AVSSL_DEVFLAG_BAD_INDEX. */
+AVSSL_API int avssl_peer_wait_gather(const avssl_peer_xchg* x, const int64_t* row_idx, int n_out, float* out,
+                           uint32_t* status_dev, void* stream);
+/* K1 with the push fused into the same launch: `world` extra CTAs at the front of the EMA grid
+ * push `rows` while the rest stream the parameters (north_star: the key exchange overlapped with
+ * the EMA kernel).  Other arguments as avssl_ema_multi_tensor. */
+AVSSL_API int avssl_ema_multi_tensor_push(const avssl_ema_chunk* table_dev, int64_t n_chunks, float m,
+                                float one_minus_m, int64_t* iter_dev, int first_iter, int bump_iter,
+                                uint32_t* done_counter_dev, const avssl_peer_xchg* x, const float* rows,
+                                void* stream);
+/* K2+K3+K4 with the wait fused: like avssl_moco_infonce_fwd_bwd_enqueue with n_keys = 1, but the
+ * key rows are taken from the exchange buffer (row i = gathered[row_idx ? row_idx[i] : rank*B + i])
+ * after the merge CTAs have waited for the current epoch -- the sweep over the queue never waits.
+ * tcgen05 kernels only (AVSSL_ERR_UNSUPPORTED otherwise: use avssl_peer_wait_gather first).
+ * ptr_dev may be NULL (no enqueue). */
+AVSSL_API int avssl_moco_infonce_fwd_bwd_enqueue_peer(const float* feat_q, const avssl_peer_xchg* x,
+                                            const int64_t* row_idx, float* queue, int64_t* ptr_dev,
+                                            uint32_t* status_dev, int B, int D, int K, float T, float* q_out,
+                                            float* loss_out, float* dfeat_out, float* row_lse_out,
+                                            float* logits_out, void* workspace, size_t workspace_bytes,
+                                            int impl, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,7 +34,7 @@ def test_header_symbols_exported_and_bound():
 
 def test_header_compiles_as_plain_c(tmp_path):
     c = tmp_path / "t.c"
-    c.write_text('#include "avssl_b200.h"\nint main(void){ avssl_ema_chunk c; (void)c; return AVSSL_OK; }\n')
+    c.write_text('#include "avssl_b200.h"\nint main(void){ avssl_ema_chunk c; avssl_peer_xchg x; (void)c; (void)x; return AVSSL_OK; }\n')
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(c),
                            "-o", str(tmp_path / "t.o")])
 
@@ -44,6 +44,11 @@ def test_struct_layout_matches():
     assert ctypes.sizeof(_lib.EmaChunk) == 24
     assert _lib.EmaChunk.hist.offset == 8 and _lib.EmaChunk.n.offset == 16 and _lib.EmaChunk.flags.offset == 20
     assert _lib.lib.avssl_ema_chunk_elems() == 4096
+    # avssl_peer_xchg: 16 pointers + world, rank, rows_per_rank, D
+    assert ctypes.sizeof(_lib.PeerXchg) == 16 * 8 + 16
+    assert _lib.PeerXchg.world.offset == 128 and _lib.PeerXchg.D.offset == 140
+    assert _lib.lib.avssl_peer_xchg_bytes(8, 64, 128) == 256 + 2 * 8 * 64 * 128 * 4
+    assert _lib.lib.avssl_peer_xchg_bytes(17, 64, 128) == 0
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
