@@ -605,7 +605,10 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
   }
   const float* key_base = p.keys[0];
   if (p.use_peer && cta < p.B) {  // C3: the keys come from the peer exchange buffer (peer.cuh)
-    if (tid == 0) csm.peer_slot = peer_wait_all(p.peer);  // long since landed: the sweep took ~15 us
+    if (warp == 0) {  // long since landed: the sweep took ~15 us
+      const int slot = peer_wait_all_warp(p.peer);
+      if (lane == 0) csm.peer_slot = slot;
+    }
     __syncthreads();
     key_base = peer_payload(p.peer.base[p.peer.rank], csm.peer_slot, p.peer);
   }

@@ -22,7 +22,10 @@ __global__ void __launch_bounds__(256)
 peer_wait_gather_kernel(const avssl_peer_xchg x, const long long* __restrict__ row_idx, int n_out,
                         float* __restrict__ out, uint32_t* status) {
   __shared__ int s_slot;
-  if (threadIdx.x == 0) s_slot = peer_wait_all(x);
+  if (threadIdx.x < 32) {
+    const int slot = peer_wait_all_warp(x);
+    if (threadIdx.x == 0) s_slot = slot;
+  }
   __syncthreads();
   const float* g = peer_payload(x.base[x.rank], s_slot, x);
   const int D4 = x.D / 4;

@@ -82,6 +82,26 @@ __device__ __forceinline__ int peer_wait_all(const avssl_peer_xchg& x) {
   return (int)(e & 1ull);
 }
 
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// The same wait by ONE WARP (all 32 lanes call it): lane r watches rank r's flag with relaxed
+// loads, so the wait costs one flag latency whatever the world size, and a single system-scope
+// fence orders the payload reads that follow the caller's __syncthreads().
+__device__ __forceinline__ int peer_wait_all_warp(const avssl_peer_xchg& x) {
+  PeerHdr* me = static_cast<PeerHdr*>(x.base[x.rank]);
+  const int lane = threadIdx.x & 31;
+  const unsigned long long e = *reinterpret_cast<volatile unsigned long long*>(&me->epoch);
+  if (lane < x.world)
+    while (ld_relaxed_sys_u64(&me->flags[lane]) < e) __nanosleep(32);
+  __syncwarp();
+  __threadfence_system();
+  return (int)(e & 1ull);
+}
+
 // Host-side validation of an exchange descriptor (peer.cu).
 int peer_check(const avssl_peer_xchg* x, const char* who);
 

@@ -289,7 +289,8 @@ def gpu_arm(args):
             torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
-    sampler.start()
+    if os.environ.get("BENCH_NO_SAMPLER") != "1":
+        sampler.start()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
     if graphs is not None:
