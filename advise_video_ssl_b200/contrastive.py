@@ -196,6 +196,10 @@ class ContrastiveModel(nn.Module):
         self._ema_plan = None
         self._iter_mirror = None
         self._dummy_logits = None
+        # C3 over NVLink peer memory instead of NCCL (ops.PeerExchange); opt-in because it needs all
+        # ranks of the (local) group on one box: cfg.CONTRASTIVE.PEER_EXCHANGE or enable_peer_exchange().
+        self._peer_exchange_on = bool(_cfg_get(cfg.CONTRASTIVE, "PEER_EXCHANGE", False))
+        self._peer_xchgs = {}
         self.register_buffer("_status", torch.zeros(1, dtype=torch.int32), persistent=False)
 
         if self.type == "mem":
@@ -249,6 +253,25 @@ class ContrastiveModel(nn.Module):
         self._iter_mirror = None
         self._dummy_logits = None
         return super(ContrastiveModel, self)._apply(fn, *args, **kwargs)
+
+    def enable_peer_exchange(self, on=True):
+        """Route the key gather of `_batch_unshuffle` (C3) through NVLink peer stores + epoch flags
+        (ops.PeerExchange) instead of an NCCL all_gather.  Collective: call it on every rank; all
+        ranks of the shuffle group must sit on one box."""
+        self._peer_exchange_on = bool(on)
+        if not on:
+            for ex in self._peer_xchgs.values():
+                ex.close()
+            self._peer_xchgs = {}
+        return self
+
+    def _peer_xchg(self, rows, dim, local):
+        key = (rows, dim, bool(local))
+        ex = self._peer_xchgs.get(key)
+        if ex is None:
+            ex = ops.PeerExchange(rows, dim, group=du._LOCAL_PROCESS_GROUP if local else None)
+            self._peer_xchgs[key] = ex
+        return ex
 
     def check_device_status(self):
         """Host check of the device status word that replaces the reference's host
@@ -373,6 +396,15 @@ class ContrastiveModel(nn.Module):
 
     @torch.no_grad()
     def _batch_unshuffle(self, x, idx_restore):
+        if (self.num_gpus > 1 and self._peer_exchange_on and x.is_cuda and x.dim() == 2
+                and x.dtype == torch.float32 and x.shape[1] % 4 == 0):
+            # C3 without a collective kernel: push this rank's keys into every peer's buffer, then
+            # wait + select idx_restore[rank] in one small launch (bit-identical to the path below)
+            local = bool(self.cfg.CONTRASTIVE.LOCAL_SHUFFLE_BN)
+            gpu_idx = du.get_local_rank() if local else torch.distributed.get_rank()
+            ex = self._peer_xchg(x.shape[0], x.shape[1], local)
+            ex.push(x.contiguous())
+            return ex.wait_gather(idx_restore[gpu_idx, :].contiguous(), status=self._status)
         if self.num_gpus > 1:
             if self.cfg.CONTRASTIVE.LOCAL_SHUFFLE_BN:
                 x = du.cat_all_gather(x, local=True)

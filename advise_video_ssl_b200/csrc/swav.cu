@@ -125,6 +125,120 @@ __global__ void __launch_bounds__(256, 1) sinkhorn_kernel(const SinkArgs a) {
   }
 }
 
+// Single-cluster variant: when the whole Q0 matrix fits the shared memory of ONE thread-block
+// cluster (16 CTAs x ~216 KB: Btot x P <= ~800k elements, e.g. 256 x 3000), the iterations need
+// no global memory and no grid barrier at all -- row sums are combined through distributed shared
+// memory in a fixed order (deterministic) behind hardware cluster barriers.  CTA c owns `spc`
+// samples; it finishes the prototype slice [c * kslice, (c + 1) * kslice) of every row step and
+// broadcasts the new alpha values into all CTAs of the cluster.
+constexpr int kSinkClusterThreads = 1024;
+
+__global__ void __launch_bounds__(kSinkClusterThreads, 1) sinkhorn_cluster_kernel(const SinkArgs a) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) float sm[];
+  const int P = a.P;
+  const int Pp = (P + 3) & ~3;
+  float* alpha = sm;                          // [Pp]
+  float* part = alpha + Pp;                   // [Pp]  this CTA's partial row sums
+  float* beta = part + Pp;                    // [spc]
+  float* slab = beta + ((a.spc + 3) & ~3);    // [spc][P]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = kSinkClusterThreads >> 5;
+  const unsigned nc = cluster.num_blocks(), cr = cluster.block_rank();
+  const int b0 = (int)cr * a.spc;
+  const int nb = max(0, min(a.spc, a.Btot - b0));
+
+  // Q0 rows of this CTA: one contiguous block of nb * P scores.  Only 16 SMs pull the whole matrix,
+  // so every thread keeps 4 x 128-bit loads in flight.
+  if ((P & 3) == 0 && (reinterpret_cast<uintptr_t>(a.scores) & 15u) == 0) {
+    const float4* src4 = reinterpret_cast<const float4*>(a.scores + (size_t)b0 * P);
+    float4* slab4 = reinterpret_cast<float4*>(slab);
+    const int n4 = nb * (P >> 2);
+    for (int i0 = 0; i0 < n4; i0 += 4 * kSinkClusterThreads) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kSinkClusterThreads + tid;
+        v[u] = i < n4 ? ldg_stream(src4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kSinkClusterThreads + tid;
+        if (i < n4)
+          slab4[i] = make_float4(expf(v[u].x * a.inv_eps), expf(v[u].y * a.inv_eps), expf(v[u].z * a.inv_eps),
+                                 expf(v[u].w * a.inv_eps));
+      }
+    }
+  } else {
+    for (int b = 0; b < nb; ++b) {
+      const float* src = a.scores + (size_t)(b0 + b) * P;
+      for (int k = tid; k < P; k += kSinkClusterThreads) slab[b * P + k] = expf(__ldg(src + k) * a.inv_eps);
+    }
+  }
+  for (int b = tid; b < nb; b += kSinkClusterThreads) beta[b] = 1.f;
+  __syncthreads();
+
+  const float r = 1.f / (float)P, c = 1.f / (float)a.Btot;
+  const int kslice = (P + (int)nc - 1) / (int)nc;
+  const int k_lo = (int)cr * kslice, k_hi = min(P, k_lo + kslice);
+  for (int it = 0; it < a.iters; ++it) {
+    // row step, part 1: partial sums over this CTA's samples
+    for (int k = tid; k < P; k += kSinkClusterThreads) {
+      float s0 = 0.f, s1 = 0.f;
+      int b = 0;
+#pragma unroll 4
+      for (; b + 1 < nb; b += 2) {
+        s0 = fmaf(slab[b * P + k], beta[b], s0);
+        s1 = fmaf(slab[(b + 1) * P + k], beta[b + 1], s1);
+      }
+      if (b < nb) s0 = fmaf(slab[b * P + k], beta[b], s0);
+      part[k] = s0 + s1;
+    }
+    cluster.sync();
+    // row step, part 2: finish this CTA's slice over all CTAs (rank order), broadcast alpha
+    for (int k = k_lo + tid; k < k_hi; k += kSinkClusterThreads) {
+      float s = 0.f;
+      for (unsigned g = 0; g < nc; ++g) s += cluster.map_shared_rank(part, g)[k];
+      const float al = r / s;
+      for (unsigned g = 0; g < nc; ++g) cluster.map_shared_rank(alpha, g)[k] = al;
+    }
+    cluster.sync();
+    if (it < a.iters - 1) {
+      // col step (local): one warp per sample
+      // one warp per sample, two independent accumulators per lane
+      for (int b = warp; b < nb; b += nw) {
+        float s0 = 0.f, s1 = 0.f;
+        int k = lane;
+#pragma unroll 4
+        for (; k + 32 < P; k += 64) {
+          s0 = fmaf(alpha[k], slab[b * P + k], s0);
+          s1 = fmaf(alpha[k + 32], slab[b * P + k + 32], s1);
+        }
+        if (k < P) s0 = fmaf(alpha[k], slab[b * P + k], s0);
+        const float sum = warp_sum(s0 + s1);
+        if (lane == 0) beta[b] = c / sum;
+      }
+      __syncthreads();
+    }
+  }
+  if (a.iters == 0) {
+    for (int k = tid; k < P; k += kSinkClusterThreads) alpha[k] = 1.f;
+    __syncthreads();
+  }
+  // final column normalisation + output of the kept rows
+  const int first_keep = a.Btot - a.keep_last;
+  for (int b = warp; b < nb; b += nw) {
+    const int gb = b0 + b;
+    if (gb < first_keep) continue;
+    float s = 0.f;
+    for (int k = lane; k < P; k += 32) s = fmaf(alpha[k], slab[b * P + k], s);
+    s = warp_sum(s);
+    const float bb = 1.f / s;
+    float* dst = a.out + (size_t)(gb - first_keep) * P;
+    for (int k = lane; k < P; k += 32) __stcs(dst + k, alpha[k] * slab[b * P + k] * bb);
+  }
+}
+
 // ------------------------------------------------------- soft-target cross-entropy
 // One CTA per score row (crop v, sample r).  For every code set `a` with weight
 // w[a][v] != 0:   loss += w * ( lse * sum_k code - sum_k code * s/T )
@@ -211,6 +325,138 @@ __global__ void __launch_bounds__(256) swav_ce_kernel(const SwavCeArgs a) {
   }
 }
 
+// Register-resident variant (P % 4 == 0, P <= 256 * 4 * kCeVec): the score row and the code rows
+// are read from global memory exactly once as 128-bit loads, exp() is evaluated once per element
+// and reused by the gradient, and the per-code reductions share one block-wide reduction.
+// Algorithmic traffic: read scores, read codes (L2-resident: every code row serves n_crops - 1
+// score rows), write dscores.
+constexpr int kCeVec = 3;  // float4 per thread: rows up to 3072 columns
+
+template <int kN>
+__device__ __forceinline__ void block_sum_n(float (&v)[kN], float* scratch /* >= 32 * kN */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int i = 0; i < kN; ++i) v[i] = warp_sum(v[i]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < kN; ++i) scratch[i * 32 + warp] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kN; ++i) {
+    float r = lane < nw ? scratch[i * 32 + lane] : 0.f;
+    v[i] = warp_sum(r);
+  }
+}
+
+template <int kA>  // code sets held in registers (n_assign <= kA)
+__global__ void __launch_bounds__(256) swav_ce_reg_kernel(const SwavCeArgs a) {
+  __shared__ float s_red[32 * (1 + 2 * kA)];
+  __shared__ unsigned s_last;
+  const int row = blockIdx.x;
+  const int v = row / a.bs, r = row % a.bs;
+  const int P4 = a.P >> 2, tid = threadIdx.x;
+  const float4* s4 = reinterpret_cast<const float4*>(a.scores + (size_t)row * a.P);
+
+  float4 x[kCeVec];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < kCeVec; ++j) {
+    const int c = tid + j * 256;
+    if (c < P4) {
+      x[j] = ldg_stream(s4 + c);
+      x[j].x *= a.inv_T; x[j].y *= a.inv_T; x[j].z *= a.inv_T; x[j].w *= a.inv_T;
+      mx = fmaxf(mx, fmaxf(fmaxf(x[j].x, x[j].y), fmaxf(x[j].z, x[j].w)));
+    } else {
+      x[j] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+  }
+  // code rows in flight while the max is reduced
+  float wa[kA];
+  float4 cd[kA][kCeVec];
+#pragma unroll
+  for (int as = 0; as < kA; ++as) {
+    wa[as] = as < a.n_assign ? a.w[as * a.n_crops + v] : 0.f;
+    const float4* c4 = reinterpret_cast<const float4*>(a.codes + ((size_t)as * a.bs + r) * a.P);
+#pragma unroll
+    for (int j = 0; j < kCeVec; ++j) {
+      const int c = tid + j * 256;
+      cd[as][j] = (wa[as] != 0.f && c < P4) ? __ldg(c4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  mx = warp_max(mx);
+  if ((tid & 31) == 0) s_red[tid >> 5] = mx;
+  __syncthreads();
+  mx = s_red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, s_red[w]);
+
+  // one reduction for: sum exp, and per code set (dot with s/T, sum of the code)
+  float red[1 + 2 * kA];
+#pragma unroll
+  for (int i = 0; i < 1 + 2 * kA; ++i) red[i] = 0.f;
+  float4 e[kCeVec];
+#pragma unroll
+  for (int j = 0; j < kCeVec; ++j) {
+    e[j] = make_float4(__expf(x[j].x - mx), __expf(x[j].y - mx), __expf(x[j].z - mx), __expf(x[j].w - mx));
+    red[0] += (e[j].x + e[j].y) + (e[j].z + e[j].w);
+    const bool in = tid + j * 256 < P4;
+#pragma unroll
+    for (int as = 0; as < kA; ++as) {
+      const float4 c = cd[as][j];
+      if (in) {
+        red[1 + 2 * as] = fmaf(c.x, x[j].x, fmaf(c.y, x[j].y, fmaf(c.z, x[j].z, fmaf(c.w, x[j].w, red[1 + 2 * as]))));
+        red[2 + 2 * as] += (c.x + c.y) + (c.z + c.w);
+      }
+    }
+  }
+  block_sum_n<1 + 2 * kA>(red, s_red);
+  const float lse = mx + logf(red[0]);
+  float loss = 0.f, wsum = 0.f;  // wsum = sum_a w * sum_k code
+#pragma unroll
+  for (int as = 0; as < kA; ++as) {
+    loss += wa[as] * (lse * red[2 + 2 * as] - red[1 + 2 * as]);
+    wsum += wa[as] * red[2 + 2 * as];
+  }
+  if (a.dscores) {
+    float4* d4 = reinterpret_cast<float4*>(a.dscores + (size_t)row * a.P);
+    const float pscale = wsum / red[0];  // softmax_k * wsum = e_k * wsum / sum(e)
+#pragma unroll
+    for (int j = 0; j < kCeVec; ++j) {
+      const int c = tid + j * 256;
+      if (c < P4) {
+        float4 g = make_float4(e[j].x * pscale, e[j].y * pscale, e[j].z * pscale, e[j].w * pscale);
+#pragma unroll
+        for (int as = 0; as < kA; ++as) {
+          g.x = fmaf(-wa[as], cd[as][j].x, g.x);
+          g.y = fmaf(-wa[as], cd[as][j].y, g.y);
+          g.z = fmaf(-wa[as], cd[as][j].z, g.z);
+          g.w = fmaf(-wa[as], cd[as][j].w, g.w);
+        }
+        st_stream(d4 + c, make_float4(g.x * a.inv_T, g.y * a.inv_T, g.z * a.inv_T, g.w * a.inv_T));
+      }
+    }
+  }
+  if (tid == 0) {
+    a.row_loss[row] = loss;
+    __threadfence();
+    s_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    float tot = 0.f;
+    const int n = a.n_crops * a.bs;
+    for (int i = tid; i < n; i += blockDim.x) tot += __ldcg(a.row_loss + i);
+    tot = block_sum(tot, s_red);
+    if (tid == 0) {
+      *a.loss_out = tot;
+      *a.counter = 0u;
+    }
+  }
+}
+
 }  // namespace avssl
 
 using namespace avssl;
@@ -219,6 +465,60 @@ static int sink_grid(int Btot) {
   int sms = sm_count();
   if (sms <= 0) return -1;
   return Btot < sms ? Btot : sms;
+}
+
+// Launches the single-cluster kernel when the problem fits one cluster of 16 (or 8) CTAs and the
+// device can schedule such a cluster; returns false to fall back to the cooperative grid kernel.
+static bool sinkhorn_try_cluster(SinkArgs& a, cudaStream_t s) {
+  static int max_cluster = -1;  // largest schedulable cluster size with the full shared-memory carve-out
+  constexpr size_t kSmemMax = 227 * 1024;
+  if (max_cluster < 0) {
+    max_cluster = 0;
+    if (cudaFuncSetAttribute(sinkhorn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax) == cudaSuccess &&
+        cudaFuncSetAttribute(sinkhorn_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+      for (int cs = 16; cs >= 8 && !max_cluster; cs >>= 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(cs);
+        cfg.blockDim = dim3(kSinkClusterThreads);
+        cfg.dynamicSmemBytes = kSmemMax;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cs;
+        at[0].val.clusterDim.y = at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, sinkhorn_cluster_kernel, &cfg) == cudaSuccess && n >= 1) max_cluster = cs;
+      }
+    }
+    cudaGetLastError();
+  }
+  if (max_cluster == 0) return false;
+  const int cs = max_cluster;
+  const int spc = (a.Btot + cs - 1) / cs;
+  const size_t Pp = ((size_t)a.P + 3) & ~(size_t)3;
+  const size_t smem = sizeof(float) * (2 * Pp + ((spc + 3) & ~3) + (size_t)spc * a.P);
+  if (smem > kSmemMax) return false;
+  a.spc = spc;
+  a.slab_in_smem = 1;
+  a.g_part = a.g_alpha = nullptr;
+  a.bar = nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cs);
+  cfg.blockDim = dim3(kSinkClusterThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cs;
+  at[0].val.clusterDim.y = at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, sinkhorn_cluster_kernel, a) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return true;
 }
 
 extern "C" size_t avssl_sinkhorn_workspace_bytes(int Btot, int P) {
@@ -247,6 +547,7 @@ extern "C" int avssl_sinkhorn(const float* scores, int Btot, int P, float eps, i
   a.iters = iters;
   a.keep_last = keep_last;
   a.out = codes_out;
+  if (sinkhorn_try_cluster(a, static_cast<cudaStream_t>(stream))) return AVSSL_OK;
   char* w = static_cast<char*>(workspace);
   a.bar = reinterpret_cast<unsigned*>(w);
   a.g_alpha = reinterpret_cast<float*>(w + 256);
@@ -287,7 +588,15 @@ extern "C" int avssl_swav_ce_fwd_bwd(const float* scores, const float* codes, in
   a.dscores = dscores_out;
   a.counter = static_cast<unsigned*>(workspace);
   a.row_loss = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
-  swav_ce_kernel<<<n_crops * bs, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  const bool reg_path = P % 4 == 0 && P <= 256 * 4 * kCeVec &&
+                        ((reinterpret_cast<uintptr_t>(scores) | reinterpret_cast<uintptr_t>(codes) |
+                          reinterpret_cast<uintptr_t>(dscores_out)) & 15u) == 0;
+  if (reg_path && n_assign <= 2)
+    swav_ce_reg_kernel<2><<<n_crops * bs, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  else if (reg_path)
+    swav_ce_reg_kernel<kMaxAssign><<<n_crops * bs, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  else
+    swav_ce_kernel<<<n_crops * bs, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   AVSSL_LAUNCH_OK("swav_ce_kernel");
   return AVSSL_OK;
 }

@@ -50,6 +50,22 @@ for step in range(6):
     bad += int(not torch.equal(queue_a, queue_b)) + int(not torch.equal(ptr_a, ptr_b))
     bad += sum(int(not torch.equal(p, q)) for p, q in zip(hist_a, hist_b))
 
+# the module's _batch_unshuffle: peer path against the NCCL path (models/contrastive.py:216-230)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from helpers import make_cfg, register_backbones
+C = register_backbones()
+cfg = make_cfg(CONTRASTIVE__TYPE="moco", CONTRASTIVE__DIM=D, CONTRASTIVE__QUEUE_LEN=1024, NUM_GPUS=world)
+model = C.ContrastiveModel(cfg).to(dev).train()
+for step in range(4):
+    y = F.normalize(torch.randn(B, D, generator=g)).to(dev)
+    restore = torch.argsort(torch.randperm(world * B, generator=gp)).view(world, B).to(dev)
+    model.enable_peer_exchange(False)
+    ref = model._batch_unshuffle(y, restore)
+    model.enable_peer_exchange(True)
+    got = model._batch_unshuffle(y, restore)
+    bad += int(not torch.equal(ref, got))
+bad += int(model.check_device_status() != 0)
+
 # the same step as a replayed graph (static inputs): results must keep matching the eager ones
 f = torch.randn(B, D, generator=g).to(dev); rows = F.normalize(torch.randn(B, D, generator=g)).to(dev)
 out = {}
