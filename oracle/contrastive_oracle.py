@@ -137,6 +137,33 @@ def enqueue(queue, ptr, keys, K, multi_view=False, extra_keys=None):
     return ptr
 
 
+# ------------------------------------------------ TemporalModel path
+def temporal_ema_update(online, hist, m, first):
+    """TemporalModel._update_history, models/temporal_modeling.py:217-238.
+
+    online / hist: name-matched parameter lists of temporal_encoder + head_projector and their
+    *_hist twins.  On the first call (`init_flag` absent, :226-232) the history is overwritten
+    with the online weights and THEN blended (:234-237), exactly like ContrastiveModel at iter 0.
+    """
+    if first:
+        hist = [o.clone() for o in online]
+    return [o * (1.0 - m) + h * m for o, h in zip(online, hist)]
+
+
+def temporal_contrast_loss(qs_raw, ks_raw, T):
+    """TemporalModel.contrast_forward, models/temporal_modeling.py:354-375, after the heads:
+    qs_raw[i] = head_predictor(head_projector(feat_i)), ks_raw[i] = head_projector_hist(key_i)
+    with the keys already reversed (:356).  loss = mean_i( -mean_n(l2(q).l2(k)) / T ) + 1/T."""
+    loss = 0.0
+    for q, k in zip(qs_raw, ks_raw):
+        q = l2_normalize(q)
+        k = l2_normalize(k)
+        sim = torch.einsum("nc,nc->n", [q, k])
+        sim = sim / T
+        loss = loss + (-sim.mean())
+    return loss / len(qs_raw) + 1.0 / T
+
+
 # ----------------------------------------------------------------------------- K7
 def byol_sim_loss(p, k, T):
     """sim_loss, models/contrastive.py:243-249: -mean_n(sum_c p k) / T."""

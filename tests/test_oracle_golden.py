@@ -295,3 +295,40 @@ def test_distributed_sinkhorn_matches_local_when_one_rank():
     a = O.sinkhorn(Q, 3)
     (b,) = O.distributed_sinkhorn_emulated([Q.t().clone()], 3)
     assert torch.allclose(a, b, rtol=1e-5, atol=1e-8)
+
+
+# ------------------------------------------- TemporalModel path
+def _temporal_names(g):
+    return [k[len("hist_init/"):] for k in g.keys() if k.startswith("hist_init/")]
+
+
+def test_temporal_ema(golden):
+    """temporal.npz comes from the reference's own TemporalModel._update_history
+    (tests/golden/make_golden_temporal.py): three steps, the first one initialising."""
+    g = golden("temporal")
+    names = _temporal_names(g)
+    hist = [g["hist_init/" + n] for n in names]
+    for s in range(int(g.scalar("n_steps"))):
+        online = [g["online%d/%s" % (s, n)] for n in names]
+        hist = O.temporal_ema_update(online, hist, g.scalar("m"), s == 0)
+        for h, n in zip(hist, names):
+            assert torch.equal(h, g["hist%d/%s" % (s, n)]), (s, n)
+
+
+def test_temporal_contrast_loss(golden):
+    g = golden("temporal")
+    T = g.scalar("T")
+    s = int(g.scalar("n_steps")) - 1
+    lin = torch.nn.functional.linear
+    feats = [g["feat%d" % i].clone().requires_grad_(True) for i in range(2)]
+    keys = [g["key1"], g["key0"]]  # keys[::-1], :356
+    Wp, bp = g["online%d/proj/weight" % s], g["online%d/proj/bias" % s]
+    Wq, bq = g["online0/pred/weight"], g["online0/pred/bias"]
+    Wh, bh = g["hist%d/proj/weight" % s], g["hist%d/proj/bias" % s]
+    qs = [lin(lin(f, Wp, bp), Wq, bq) for f in feats]
+    ks = [lin(k, Wh, bh) for k in keys]
+    loss = O.temporal_contrast_loss(qs, ks, T)
+    loss.backward()
+    assert torch.equal(loss.detach(), g["loss"])
+    for i in range(2):
+        assert torch.equal(feats[i].grad, g["dfeat%d" % i])
