@@ -1,0 +1,103 @@
+// Multi-tensor L2 norm: replaces get_grad_norm_
+// (models/optimizer.py:375-397, called every step from utils/solver.py:109-111) and the
+// per-parameter torch.norm pairs of LARS.step (models/optimizer.py:351-352).
+//
+// Same flat chunk table as the momentum update (K1): one 256-thread CTA per 4096-element chunk,
+// four independent 128-bit streaming loads per thread, fp32 sum of squares per chunk written to a
+// partial array; a second one-CTA launch folds the partials per tensor (chunk order) and the
+// per-tensor norms into the total, all in a fixed order (deterministic, no fp atomics).
+// HBM-bound: 4 bytes per element, read once.
+#include "common.cuh"
+
+namespace avssl {
+
+constexpr int kNormThreads = 256;
+constexpr int kNormChunk = 4096;  // == avssl_ema_chunk_elems()
+
+__global__ void __launch_bounds__(kNormThreads)
+multi_l2norm_kernel(const avssl_ema_chunk* __restrict__ table, float* __restrict__ partial) {
+  __shared__ float s_red[32];
+  const avssl_ema_chunk c = table[blockIdx.x];
+  const int tid = threadIdx.x;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if ((c.flags & 1u) && c.n == (uint32_t)kNormChunk) {
+    const float4* x4 = reinterpret_cast<const float4*>(c.online) + tid;
+    const float4 a = ldg_stream(x4), b = ldg_stream(x4 + kNormThreads), d = ldg_stream(x4 + 2 * kNormThreads),
+                 e = ldg_stream(x4 + 3 * kNormThreads);
+    s0 = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+    s1 = b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+    s2 = d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
+    s3 = e.x * e.x + e.y * e.y + e.z * e.z + e.w * e.w;
+  } else {
+    for (uint32_t i = tid; i < c.n; i += kNormThreads) {
+      const float v = c.online[i];
+      s0 = fmaf(v, v, s0);
+    }
+  }
+  const float ss = block_sum((s0 + s1) + (s2 + s3), s_red);
+  if (tid == 0) partial[blockIdx.x] = ss;
+}
+
+// Second, single-CTA launch: 32 warps, one warp per tensor (lanes stride over its chunks in a
+// fixed order), then the total over the tensors in tensor order.
+constexpr int kFoldThreads = 1024;
+__global__ void __launch_bounds__(kFoldThreads)
+multi_l2norm_fold_kernel(const int* __restrict__ first_chunk, int n_tensors, const float* __restrict__ partial,
+                         float* __restrict__ per_tensor, float* __restrict__ total) {
+  __shared__ float s_tot[kFoldThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float tot = 0.f;  // lane 0 of each warp accumulates norm_t^2 over its tensors
+  for (int t = warp; t < n_tensors; t += kFoldThreads / 32) {
+    const int k0 = __ldg(first_chunk + t), k1 = __ldg(first_chunk + t + 1);
+    float s = 0.f;
+    for (int k = k0 + lane; k < k1; k += 32) s += __ldcg(partial + k);
+    s = warp_sum(s);
+    if (lane == 0) {
+      if (per_tensor) per_tensor[t] = sqrtf(s);
+      tot += s;
+    }
+  }
+  if (lane == 0) s_tot[warp] = tot;
+  __syncthreads();
+  if (tid == 0) {
+    float a = 0.f;
+    for (int w = 0; w < kFoldThreads / 32; ++w) a += s_tot[w];
+    *total = sqrtf(a);  // norm(stack(norm_t)) = sqrt(sum_t norm_t^2)
+  }
+}
+
+__global__ void multi_l2norm_empty_kernel(float* total) { *total = 0.f; }
+
+}  // namespace avssl
+
+using namespace avssl;
+
+extern "C" size_t avssl_multi_l2norm_workspace_bytes(int64_t n_chunks) {
+  if (n_chunks < 0) return 0;
+  return 256 + 4 * (size_t)n_chunks;
+}
+
+extern "C" int avssl_multi_l2norm(const avssl_ema_chunk* table_dev, int64_t n_chunks, const int32_t* first_chunk_dev,
+                                  int n_tensors, float* per_tensor_norm_out, float* total_norm_out, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  AVSSL_REQUIRE(total_norm_out && workspace, AVSSL_ERR_INVALID_ARGUMENT, "multi_l2norm: null pointer");
+  AVSSL_REQUIRE(n_chunks >= 0 && n_chunks < (1ll << 31) && n_tensors >= 0, AVSSL_ERR_INVALID_ARGUMENT,
+                "multi_l2norm: bad sizes n_chunks=%lld n_tensors=%d", (long long)n_chunks, n_tensors);
+  AVSSL_REQUIRE(workspace_bytes >= avssl_multi_l2norm_workspace_bytes(n_chunks), AVSSL_ERR_WORKSPACE,
+                "multi_l2norm: workspace too small");
+  AVSSL_REQUIRE(sm_count() > 0, AVSSL_ERR_CUDA, "multi_l2norm: no CUDA device (there is no CPU fallback)");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (n_chunks == 0) {  // get_grad_norm_ returns 0.0 for an empty list (models/optimizer.py:380-381)
+    multi_l2norm_empty_kernel<<<1, 1, 0, s>>>(total_norm_out);
+    AVSSL_LAUNCH_OK("multi_l2norm_empty_kernel");
+    return AVSSL_OK;
+  }
+  AVSSL_REQUIRE(table_dev && first_chunk_dev && n_tensors > 0, AVSSL_ERR_INVALID_ARGUMENT, "multi_l2norm: null table");
+  float* partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
+  multi_l2norm_kernel<<<(unsigned)n_chunks, kNormThreads, 0, s>>>(table_dev, partial);
+  AVSSL_LAUNCH_OK("multi_l2norm_kernel");
+  multi_l2norm_fold_kernel<<<1, kFoldThreads, 0, s>>>(first_chunk_dev, n_tensors, partial, per_tensor_norm_out,
+                                                      total_norm_out);
+  AVSSL_LAUNCH_OK("multi_l2norm_fold_kernel");
+  return AVSSL_OK;
+}

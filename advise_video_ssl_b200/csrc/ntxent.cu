@@ -136,89 +136,109 @@ __global__ void ntxent_sum_z_kernel(const float* __restrict__ part_z, int n_spli
   z_loc[i] = z;
 }
 
-// One warp per local row: merge the gradient partials (one pass, all loads of a split row
-// in flight together), subtract the positive term, apply 1/(2N T) and the world-size factor,
-// then chain through the l2-normalisation.  D <= 256: each lane owns up to 8 columns c = lane + 32 u.
-__global__ void __launch_bounds__(256)
-ntxent_combine_kernel(const NtxArgs a, const float* __restrict__ norm_loc, float gscale, float* __restrict__ dfeat) {
-  constexpr int kU = 8;
-  const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (i >= a.n_loc) return;
-  const int r = a.rows[i];
-  const int half = a.N2 / 2;
-  const int rp = r < half ? r + half : r - half;
-  const float* o = a.out + (size_t)r * a.D;
-  const float* op = a.out + (size_t)rp * a.D;
-  float g[kU], ov[kU], pv[kU];
-#pragma unroll
-  for (int u = 0; u < kU; ++u) {
-    const int c = lane + 32 * u;
-    g[u] = 0.f;
-    ov[u] = c < a.D ? __ldg(o + c) : 0.f;
-    pv[u] = c < a.D ? __ldg(op + c) : 0.f;
-  }
-  const float* pg = a.part_g + (size_t)i * a.D + lane;
-  const size_t sstride = (size_t)a.n_loc * a.D;
-  for (int s = 0; s < a.n_splits; ++s) {  // fixed order: deterministic
-#pragma unroll
-    for (int u = 0; u < kU; ++u)
-      if (lane + 32 * u < a.D) g[u] += __ldcg(pg + (size_t)s * sstride + 32 * u);
-  }
-  float dot = 0.f;
-#pragma unroll
-  for (int u = 0; u < kU; ++u) {
-    g[u] = (g[u] - 2.f * pv[u]) * gscale;
-    dot = fmaf(g[u], ov[u], dot);
-  }
-  dot = warp_sum(dot);
-  const float rn = 1.f / norm_loc[i];
-#pragma unroll
-  for (int u = 0; u < kU; ++u) {
-    const int c = lane + 32 * u;
-    if (c < a.D) dfeat[(size_t)i * a.D + c] = (g[u] - dot * ov[u]) * rn;
-  }
-}
+// Finalisation of pass 2 in ONE launch (4 warps per CTA, one warp per unit of work):
+//   CTAs [0, comb_blocks):  one warp per local row -- merge the gradient partials in split order
+//     (deterministic; 128-bit loads, 8 split rows in flight per lane), subtract the positive term,
+//     apply 1/(2N T) and the world-size factor, then chain through the l2-normalisation.
+//     D <= 256: lane l owns columns 4l..4l+3 and 128+4l..128+4l+3.
+//   CTAs [comb_blocks, ...): one warp per PAIR (r, r+) of all 2N rows -- both rows share the same
+//     dot product: loss = mean_r( log Z_r + 1/T - out_r . out_{r+} / T ); the last of these CTAs
+//     to finish takes the mean in row order.
+constexpr int kFinWarps = 4;
 
-// loss = mean_r( log Z_r + 1/T - out_r . out_{r+} / T ) over all 2N rows.  One warp per PAIR
-// (r, r+): both rows share the same dot product.
-__global__ void __launch_bounds__(256)
-ntxent_loss_kernel(const float* __restrict__ out, const float* __restrict__ z_all, int N2, int D, float inv_T,
-                   float* loss_out, float* row_term, unsigned* counter) {
+__global__ void __launch_bounds__(kFinWarps * 32)
+ntxent_finish_kernel(const NtxArgs a, const float* __restrict__ norm_loc, float gscale, float* __restrict__ dfeat,
+                     int comb_blocks, float* loss_out, float* row_term, unsigned* counter) {
   __shared__ float s_red[32];
   __shared__ unsigned s_last;
-  const int lane = threadIdx.x & 31;
-  const int half = N2 / 2;
-  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // pair index
-  if (r < half) {
-    const float* x = out + (size_t)r * D;
-    const float* y = out + (size_t)(r + half) * D;
-    float d0 = 0.f, d1 = 0.f;
-    int c = lane;
-    for (; c + 32 < D; c += 64) {
-      d0 = fmaf(__ldg(x + c), __ldg(y + c), d0);
-      d1 = fmaf(__ldg(x + c + 32), __ldg(y + c + 32), d1);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int D = a.D, half = a.N2 / 2;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  if ((int)blockIdx.x < comb_blocks) {
+    const int i = blockIdx.x * kFinWarps + warp;
+    if (i >= a.n_loc) return;
+    const int r = a.rows[i];
+    const int rp = r < half ? r + half : r - half;
+    const int c0 = 4 * lane, c1 = 128 + 4 * lane;
+    const bool in0 = c0 < D, in1 = c1 < D;
+    const float4* o4 = reinterpret_cast<const float4*>(a.out + (size_t)r * D);
+    const float4* p4 = reinterpret_cast<const float4*>(a.out + (size_t)rp * D);
+    const float4 ov0 = in0 ? __ldg(o4 + lane) : zero4, ov1 = in1 ? __ldg(o4 + 32 + lane) : zero4;
+    const float4 pv0 = in0 ? __ldg(p4 + lane) : zero4, pv1 = in1 ? __ldg(p4 + 32 + lane) : zero4;
+    const float rn = 1.f / norm_loc[i];
+    float4 g0 = zero4, g1 = zero4;
+    const float4* pg = reinterpret_cast<const float4*>(a.part_g + (size_t)i * D);
+    const size_t sstride4 = (size_t)a.n_loc * D / 4;
+    constexpr int kS = 8;
+    for (int s0 = 0; s0 < a.n_splits; s0 += kS) {  // fixed order: deterministic
+      float4 v0[kS], v1[kS];
+#pragma unroll
+      for (int u = 0; u < kS; ++u) {
+        const bool live = s0 + u < a.n_splits;
+        v0[u] = (live && in0) ? __ldcg(pg + (size_t)(s0 + u) * sstride4 + lane) : zero4;
+        v1[u] = (live && in1) ? __ldcg(pg + (size_t)(s0 + u) * sstride4 + 32 + lane) : zero4;
+      }
+#pragma unroll
+      for (int u = 0; u < kS; ++u) {
+        g0.x += v0[u].x; g0.y += v0[u].y; g0.z += v0[u].z; g0.w += v0[u].w;
+        g1.x += v1[u].x; g1.y += v1[u].y; g1.z += v1[u].z; g1.w += v1[u].w;
+      }
     }
-    if (c < D) d0 = fmaf(__ldg(x + c), __ldg(y + c), d0);
-    const float dot = warp_sum(d0 + d1);
+    g0 = make_float4((g0.x - 2.f * pv0.x) * gscale, (g0.y - 2.f * pv0.y) * gscale, (g0.z - 2.f * pv0.z) * gscale,
+                     (g0.w - 2.f * pv0.w) * gscale);
+    g1 = make_float4((g1.x - 2.f * pv1.x) * gscale, (g1.y - 2.f * pv1.y) * gscale, (g1.z - 2.f * pv1.z) * gscale,
+                     (g1.w - 2.f * pv1.w) * gscale);
+    float dot = g0.x * ov0.x + g0.y * ov0.y + g0.z * ov0.z + g0.w * ov0.w + g1.x * ov1.x + g1.y * ov1.y + g1.z * ov1.z +
+                g1.w * ov1.w;
+    dot = warp_sum(dot);
+    float4* d4 = reinterpret_cast<float4*>(dfeat + (size_t)i * D);
+    if (in0)
+      d4[lane] = make_float4((g0.x - dot * ov0.x) * rn, (g0.y - dot * ov0.y) * rn, (g0.z - dot * ov0.z) * rn,
+                             (g0.w - dot * ov0.w) * rn);
+    if (in1)
+      d4[32 + lane] = make_float4((g1.x - dot * ov1.x) * rn, (g1.y - dot * ov1.y) * rn, (g1.z - dot * ov1.z) * rn,
+                                  (g1.w - dot * ov1.w) * rn);
+    return;
+  }
+
+  const int n_loss_blocks = gridDim.x - comb_blocks;
+  const int r = ((int)blockIdx.x - comb_blocks) * kFinWarps + warp;  // pair index
+  if (r < half) {
+    const float4* x4 = reinterpret_cast<const float4*>(a.out + (size_t)r * D);
+    const float4* y4 = reinterpret_cast<const float4*>(a.out + (size_t)(r + half) * D);
+    const bool in0 = 4 * lane < D, in1 = 128 + 4 * lane < D;
+    const float4 x0 = in0 ? __ldg(x4 + lane) : zero4, y0 = in0 ? __ldg(y4 + lane) : zero4;
+    const float4 x1 = in1 ? __ldg(x4 + 32 + lane) : zero4, y1 = in1 ? __ldg(y4 + 32 + lane) : zero4;
+    const float za = a.z_all[r], zb = a.z_all[r + half];
+    float dot = (x0.x * y0.x + x0.y * y0.y) + (x0.z * y0.z + x0.w * y0.w) + (x1.x * y1.x + x1.y * y1.y) +
+                (x1.z * y1.z + x1.w * y1.w);
+    dot = warp_sum(dot);
     if (lane == 0) {
-      row_term[r] = logf(z_all[r]) + inv_T - dot * inv_T;
-      row_term[r + half] = logf(z_all[r + half]) + inv_T - dot * inv_T;
+      row_term[r] = logf(za) + a.inv_T - dot * a.inv_T;
+      row_term[r + half] = logf(zb) + a.inv_T - dot * a.inv_T;
     }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    s_last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+    s_last = (atomicAdd(counter, 1u) == (unsigned)n_loss_blocks - 1u) ? 1u : 0u;
   }
   __syncthreads();
   if (s_last) {
     __threadfence();
-    float tot = 0.f;
-    for (int i = threadIdx.x; i < N2; i += blockDim.x) tot += __ldcg(row_term + i);
-    tot = block_sum(tot, s_red);
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+    int k = threadIdx.x;
+    for (; k + 3 * (int)blockDim.x < a.N2; k += 4 * blockDim.x) {
+      t0 += __ldcg(row_term + k);
+      t1 += __ldcg(row_term + k + blockDim.x);
+      t2 += __ldcg(row_term + k + 2 * blockDim.x);
+      t3 += __ldcg(row_term + k + 3 * blockDim.x);
+    }
+    for (; k < a.N2; k += blockDim.x) t0 += __ldcg(row_term + k);
+    const float tot = block_sum((t0 + t1) + (t2 + t3), s_red);
     if (threadIdx.x == 0) {
-      *loss_out = tot / (float)N2;
+      *loss_out = tot / (float)a.N2;
       *counter = 0u;
     }
   }
@@ -326,15 +346,18 @@ extern "C" int avssl_ntxent_grad(const float* out, const int* rows, const float*
   int rc = ntx_setup(a, out, rows, z_all, N2, D, n_loc, T, workspace, workspace_bytes, impl, &use_tc, "ntxent_grad");
   if (rc) return rc;
   AVSSL_REQUIRE(z_all && norm_loc && loss_out && dfeat_out, AVSSL_ERR_INVALID_ARGUMENT, "ntxent_grad: null pointer");
+  AVSSL_REQUIRE(((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(dfeat_out)) & 15u) == 0,
+                AVSSL_ERR_INVALID_ARGUMENT, "ntxent_grad: out and dfeat_out must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   rc = use_tc ? launch_ntxent_tc(a, true, s) : launch_pass_d<true>(a, s);
   if (rc) return rc;
   const float gscale = grad_scale * a.inv_T / (float)N2;
-  ntxent_combine_kernel<<<(n_loc + 7) / 8, 256, 0, s>>>(a, norm_loc, gscale, dfeat_out);
-  AVSSL_LAUNCH_OK("ntxent_combine_kernel");
   unsigned* counter = static_cast<unsigned*>(workspace);
   float* row_term = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
-  ntxent_loss_kernel<<<(N2 / 2 + 7) / 8, 256, 0, s>>>(out, z_all, N2, D, a.inv_T, loss_out, row_term, counter);
-  AVSSL_LAUNCH_OK("ntxent_loss_kernel");
+  const int comb_blocks = (n_loc + kFinWarps - 1) / kFinWarps;
+  const int loss_blocks = (N2 / 2 + kFinWarps - 1) / kFinWarps;
+  ntxent_finish_kernel<<<comb_blocks + loss_blocks, kFinWarps * 32, 0, s>>>(a, norm_loc, gscale, dfeat_out, comb_blocks,
+                                                                           loss_out, row_term, counter);
+  AVSSL_LAUNCH_OK("ntxent_finish_kernel");
   return AVSSL_OK;
 }

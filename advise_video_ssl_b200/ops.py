@@ -119,6 +119,57 @@ class EmaPlan:
         return 12 * self.n_params
 
 
+class MultiTensorNorm:
+    """Device plan for the multi-tensor L2 norm (get_grad_norm_, models/optimizer.py:375-397;
+    LARS.step's per-parameter norms, :351-352): one launch over all tensors, no host sync.
+
+        plan = MultiTensorNorm(grads)      # rebuilt only when a tensor's storage moves
+        total, per_tensor = plan.run()     # device tensors [1], [n]
+    """
+
+    def __init__(self, tensors):
+        dev = None
+        for t in tensors:
+            _req(t, "tensor")
+            dev = t.device if dev is None else dev
+            if t.device != dev:
+                raise ValueError("all tensors must live on one device")
+        if dev is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError("MultiTensorNorm needs a CUDA device: the contrastive hot path has no CPU fallback")
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        self.n_tensors = len(tensors)
+        self.n_elems = int(sum(t.numel() for t in tensors))
+        self.ptr_key = tuple(t.data_ptr() for t in tensors)
+        ptrs = [t.data_ptr() for t in tensors]
+        numels = [t.numel() for t in tensors]
+        table = ema_plan_table(ptrs, ptrs, numels)
+        self.n_chunks = int(table.shape[0])
+        chunk = int(lib.avssl_ema_chunk_elems())
+        first = np.zeros(self.n_tensors + 1, dtype=np.int32)
+        first[1:] = np.cumsum([(n + chunk - 1) // chunk for n in numels], dtype=np.int64)
+        host = torch.from_numpy(table.view(np.uint8).reshape(-1).copy()) if self.n_chunks else torch.zeros(24, dtype=torch.uint8)
+        self.table = host.to(dev)
+        self.first = torch.from_numpy(first).to(dev)
+        self.ws = torch.zeros(int(lib.avssl_multi_l2norm_workspace_bytes(self.n_chunks)), dtype=torch.uint8, device=dev)
+        self.per_tensor = torch.zeros(max(self.n_tensors, 1), dtype=_f32, device=dev)
+        self.total = torch.zeros(1, dtype=_f32, device=dev)
+
+    def matches(self, tensors):
+        return self.ptr_key == tuple(t.data_ptr() for t in tensors)
+
+    def run(self):
+        check(lib.avssl_multi_l2norm(self.table.data_ptr(), self.n_chunks, self.first.data_ptr(), self.n_tensors,
+                                     self.per_tensor.data_ptr(), self.total.data_ptr(), self.ws.data_ptr(),
+                                     self.ws.numel(), _stream()), "avssl_multi_l2norm")
+        return self.total, self.per_tensor[:self.n_tensors]
+
+    @property
+    def algorithmic_bytes(self):
+        return 4 * self.n_elems
+
+
 # ------------------------------------------------------------------------------ C3
 class PeerExchange:
     """Cross-GPU exchange of [rows_per_rank, D] fp32 blocks over NVLink peer memory (C3).
@@ -151,24 +202,45 @@ class PeerExchange:
         self.nbytes = int(nbytes)
         base = ctypes.c_void_p()
         handle = (ctypes.c_ubyte * _lib.IPC_HANDLE_BYTES)()
+        self._own, self._opened = None, []
+        err = None
         with torch.cuda.device(self.device):
-            check(lib.avssl_peer_alloc(self.nbytes, ctypes.byref(base), ctypes.addressof(handle)), "avssl_peer_alloc")
-            self._own = base.value
-            self._opened = []
+            # Every rank reaches every collective below whatever happens locally, and all ranks raise
+            # together if any of them failed: a half-built exchange would hang the first push.
+            try:
+                check(lib.avssl_peer_alloc(self.nbytes, ctypes.byref(base), ctypes.addressof(handle)), "avssl_peer_alloc")
+                self._own = base.value
+            except Exception as e:  # noqa: BLE001
+                err = "rank %d: %s" % (self.rank, e)
             bases = [None] * self.world
             bases[self.rank] = self._own
             if self.world > 1:
                 handles = [None] * self.world
-                dist.all_gather_object(handles, (self.rank, bytes(handle)), group=group)
-                for r, h in handles:
-                    if r == self.rank:
-                        continue
-                    p = ctypes.c_void_p()
-                    buf = (ctypes.c_ubyte * _lib.IPC_HANDLE_BYTES).from_buffer_copy(h)
-                    check(lib.avssl_peer_open(ctypes.addressof(buf), ctypes.byref(p)), "avssl_peer_open(rank %d)" % r)
-                    self._opened.append(p.value)
-                    bases[r] = p.value
-                dist.barrier(group=group)  # every buffer is mapped everywhere before the first push
+                dist.all_gather_object(handles, (self.rank, bytes(handle) if err is None else None, err), group=group)
+                errs = [h[2] for h in handles if h[2]]
+                if not errs:
+                    for r, h, _ in handles:
+                        if r == self.rank:
+                            continue
+                        p = ctypes.c_void_p()
+                        buf = (ctypes.c_ubyte * _lib.IPC_HANDLE_BYTES).from_buffer_copy(h)
+                        try:
+                            check(lib.avssl_peer_open(ctypes.addressof(buf), ctypes.byref(p)), "avssl_peer_open(rank %d)" % r)
+                        except Exception as e:  # noqa: BLE001
+                            err = "rank %d: %s" % (self.rank, e)
+                            break
+                        self._opened.append(p.value)
+                        bases[r] = p.value
+                    # doubles as the barrier: every buffer is mapped everywhere before the first push
+                    flags = [None] * self.world
+                    dist.all_gather_object(flags, err, group=group)
+                    errs = [f for f in flags if f]
+                if errs:
+                    self.close()
+                    raise _lib.AvsslError("PeerExchange set-up failed (CUDA IPC between the ranks of one box is "
+                                          "required): " + "; ".join(errs))
+            elif err is not None:
+                raise _lib.AvsslError(err)
         self.desc = _lib.PeerXchg()
         for r in range(self.world):
             self.desc.base[r] = bases[r]
@@ -207,12 +279,13 @@ class PeerExchange:
     def close(self):
         """Unmap the peers' buffers and free this rank's.  Collective in spirit: call it on every
         rank once no push or wait is in flight."""
-        if getattr(self, "_own", None) is None:
+        if getattr(self, "_own", None) is None and not getattr(self, "_opened", None):
             return
         torch.cuda.synchronize(self.device)
         for p in self._opened:
             lib.avssl_peer_close(p)
-        lib.avssl_peer_free(self._own)
+        if self._own is not None:
+            lib.avssl_peer_free(self._own)
         self._own, self._opened = None, []
 
 

@@ -293,6 +293,22 @@ AVSSL_API int avssl_moco_infonce_fwd_bwd_enqueue_peer(const float* feat_q, const
                                             float* logits_out, void* workspace, size_t workspace_bytes,
                                             int impl, void* stream);
 
+/* ------------------------------------------- multi-tensor L2 norm
+ * Replaces get_grad_norm_ (models/optimizer.py:375-397; one torch.norm per parameter, a stack and a
+ * .cpu() sync every step from utils/solver.py:109-111) and the torch.norm pairs of LARS.step
+ * (models/optimizer.py:351-352):
+ *     per_tensor[t] = ||x_t||_2 ,   total = || (per_tensor) ||_2 = sqrt(sum_t ||x_t||^2)
+ * table_dev: the chunk table of avssl_ema_plan_fill() built with the tensors as `online`
+ *   (`hist` is not read; pass the same pointers); first_chunk_dev: int32[n_tensors + 1], the first
+ *   chunk of every tensor (prefix sum of ceil(numel / avssl_ema_chunk_elems())).
+ * per_tensor_norm_out may be NULL.  An empty list gives total = 0 (:380-381).
+ * workspace: avssl_multi_l2norm_workspace_bytes(), zero-filled once, reusable.
+ */
+AVSSL_API size_t avssl_multi_l2norm_workspace_bytes(int64_t n_chunks);
+AVSSL_API int avssl_multi_l2norm(const avssl_ema_chunk* table_dev, int64_t n_chunks, const int32_t* first_chunk_dev,
+                       int n_tensors, float* per_tensor_norm_out, float* total_norm_out, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -164,6 +164,14 @@ def temporal_contrast_loss(qs_raw, ks_raw, T):
     return loss / len(qs_raw) + 1.0 / T
 
 
+def grad_norm(grads, norm_type=2.0):
+    """get_grad_norm_, models/optimizer.py:375-397 (p-norm branch): norm of the stacked
+    per-tensor norms.  An empty list gives tensor(0.0) (:380-381)."""
+    if len(grads) == 0:
+        return torch.tensor(0.0)
+    return torch.norm(torch.stack([torch.norm(g.detach(), norm_type) for g in grads]), norm_type)
+
+
 # ----------------------------------------------------------------------------- K7
 def byol_sim_loss(p, k, T):
     """sim_loss, models/contrastive.py:243-249: -mean_n(sum_c p k) / T."""

@@ -332,3 +332,11 @@ def test_temporal_contrast_loss(golden):
     assert torch.equal(loss.detach(), g["loss"])
     for i in range(2):
         assert torch.equal(feats[i].grad, g["dfeat%d" % i])
+
+
+def test_grad_norm(golden):
+    """gradnorm.npz comes from the reference's own get_grad_norm_ (make_golden_gradnorm.py)."""
+    g = golden("gradnorm")
+    grads = [g["grad%d" % i] for i in range(int(g.scalar("n")))]
+    assert torch.equal(O.grad_norm(grads), g["total"])
+    assert O.grad_norm([]).item() == g["empty"].item() == 0.0

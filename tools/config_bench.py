@@ -61,6 +61,13 @@ for tag in shapes:
     report("K1 EMA %s (%d tensors, %d params)" % (tag, len(shp), plan.n_params),
            lambda: plan.run(0.996, it, True, first_iter=False), nbytes=plan.algorithmic_bytes)
     del online, hist, plan
+# ---------------------------------------------- get_grad_norm_ over the Slow-R50 gradient list (8f rank 4)
+shp = [tuple(s) for _, s in shapes["slow_r50_moco_dim128"]["shapes"]]
+grads = [torch.randn(s, device=dev) for s in shp]
+nplan = ops.MultiTensorNorm(grads)
+report("multi-tensor L2 norm (get_grad_norm_) slow_r50_moco_dim128 (%d tensors, %d elements)" % (len(shp), nplan.n_elems),
+       lambda: nplan.run(), nbytes=nplan.algorithmic_bytes)
+del grads, nplan
 pred = torch.randn(64, 256, device=dev)
 key = torch.nn.functional.normalize(torch.randn(64, 256, device=dev))
 report("K7 BYOL sim_loss fwd+bwd B=64 D=256 (one pair)", lambda: ops.byol_simloss(pred, key, 1.0), nbytes=3 * 4 * 64 * 256,
