@@ -2,8 +2,8 @@
 // (models/optimizer.py:375-397, called every step from utils/solver.py:109-111) and the
 // per-parameter torch.norm pairs of LARS.step (models/optimizer.py:351-352).
 //
-// Same flat chunk table as the momentum update (K1): one 256-thread CTA per 4096-element chunk,
-// four independent 128-bit streaming loads per thread, fp32 sum of squares per chunk written to a
+// Same flat chunk table as the momentum update (K1): one 256-thread CTA per four 4096-element
+// chunks, sixteen independent 128-bit streaming loads per thread, fp32 sum of squares per chunk written to a
 // partial array; a second one-CTA launch folds the partials per tensor (chunk order) and the
 // per-tensor norms into the total, all in a fixed order (deterministic, no fp atomics).
 // HBM-bound: 4 bytes per element, read once.
@@ -14,28 +14,77 @@ namespace avssl {
 constexpr int kNormThreads = 256;
 constexpr int kNormChunk = 4096;  // == avssl_ema_chunk_elems()
 
+constexpr int kNormChunksPerCta = 4;  // 64 KiB per CTA: amortises the CTA turn-over and the block reduction
+
+template <int kN>
+__device__ __forceinline__ void norm_block_sum_n(float (&v)[kN], float* scratch /* >= 8 * kN */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < kN; ++i) v[i] = warp_sum(v[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < kN; ++i) scratch[i * 8 + warp] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kN; ++i) {
+    float r = lane < kNormThreads / 32 ? scratch[i * 8 + lane] : 0.f;
+    v[i] = warp_sum(r);
+  }
+}
+
 __global__ void __launch_bounds__(kNormThreads)
-multi_l2norm_kernel(const avssl_ema_chunk* __restrict__ table, float* __restrict__ partial) {
-  __shared__ float s_red[32];
-  const avssl_ema_chunk c = table[blockIdx.x];
+multi_l2norm_kernel(const avssl_ema_chunk* __restrict__ table, int n_chunks, float* __restrict__ partial) {
+  __shared__ float s_red[8 * kNormChunksPerCta];
   const int tid = threadIdx.x;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  if ((c.flags & 1u) && c.n == (uint32_t)kNormChunk) {
-    const float4* x4 = reinterpret_cast<const float4*>(c.online) + tid;
-    const float4 a = ldg_stream(x4), b = ldg_stream(x4 + kNormThreads), d = ldg_stream(x4 + 2 * kNormThreads),
-                 e = ldg_stream(x4 + 3 * kNormThreads);
-    s0 = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
-    s1 = b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
-    s2 = d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
-    s3 = e.x * e.x + e.y * e.y + e.z * e.z + e.w * e.w;
+  const int c0 = blockIdx.x * kNormChunksPerCta;
+  avssl_ema_chunk c[kNormChunksPerCta];
+  bool fast = true;
+#pragma unroll
+  for (int u = 0; u < kNormChunksPerCta; ++u) {
+    if (c0 + u < n_chunks) {
+      c[u] = table[c0 + u];
+    } else {
+      c[u].online = nullptr;
+      c[u].n = 0;
+      c[u].flags = 1u;
+    }
+    fast = fast && (c[u].flags & 1u) && c[u].n == (uint32_t)kNormChunk;
+  }
+  float ss[kNormChunksPerCta];
+  if (fast) {  // all loads of the CTA's chunks in flight before the first use
+    float4 v[kNormChunksPerCta][4];
+#pragma unroll
+    for (int u = 0; u < kNormChunksPerCta; ++u) {
+      const float4* x4 = reinterpret_cast<const float4*>(c[u].online) + tid;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[u][k] = ldg_stream(x4 + k * kNormThreads);
+    }
+#pragma unroll
+    for (int u = 0; u < kNormChunksPerCta; ++u) {
+      float a[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) a[k] = v[u][k].x * v[u][k].x + v[u][k].y * v[u][k].y + v[u][k].z * v[u][k].z + v[u][k].w * v[u][k].w;
+      ss[u] = (a[0] + a[1]) + (a[2] + a[3]);
+    }
   } else {
-    for (uint32_t i = tid; i < c.n; i += kNormThreads) {
-      const float v = c.online[i];
-      s0 = fmaf(v, v, s0);
+#pragma unroll
+    for (int u = 0; u < kNormChunksPerCta; ++u) {
+      float a = 0.f;
+      for (uint32_t i = tid; i < c[u].n; i += kNormThreads) {
+        const float x = c[u].online[i];
+        a = fmaf(x, x, a);
+      }
+      ss[u] = a;
     }
   }
-  const float ss = block_sum((s0 + s1) + (s2 + s3), s_red);
-  if (tid == 0) partial[blockIdx.x] = ss;
+  norm_block_sum_n<kNormChunksPerCta>(ss, s_red);
+  if (tid < kNormChunksPerCta && c0 + tid < n_chunks) {
+    float out = ss[0];
+#pragma unroll
+    for (int u = 1; u < kNormChunksPerCta; ++u) out = tid == u ? ss[u] : out;
+    partial[c0 + tid] = out;
+  }
 }
 
 // Second, single-CTA launch: 32 warps, one warp per tensor (lanes stride over its chunks in a
@@ -94,7 +143,8 @@ extern "C" int avssl_multi_l2norm(const avssl_ema_chunk* table_dev, int64_t n_ch
   }
   AVSSL_REQUIRE(table_dev && first_chunk_dev && n_tensors > 0, AVSSL_ERR_INVALID_ARGUMENT, "multi_l2norm: null table");
   float* partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
-  multi_l2norm_kernel<<<(unsigned)n_chunks, kNormThreads, 0, s>>>(table_dev, partial);
+  const unsigned grid = (unsigned)((n_chunks + kNormChunksPerCta - 1) / kNormChunksPerCta);
+  multi_l2norm_kernel<<<grid, kNormThreads, 0, s>>>(table_dev, (int)n_chunks, partial);
   AVSSL_LAUNCH_OK("multi_l2norm_kernel");
   multi_l2norm_fold_kernel<<<1, kFoldThreads, 0, s>>>(first_chunk_dev, n_tensors, partial, per_tensor_norm_out,
                                                       total_norm_out);

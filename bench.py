@@ -277,7 +277,7 @@ def gpu_arm(args):
     # One CUDA graph per input slot: [key all_gather on the comm stream ||] EMA -> fused head.  Replaying
     # it removes the per-launch host work (which bounds the step once the NCCL enqueue is added) and
     # the launch gaps between the kernels; the kernels and their order are the same as in eager mode.
-    graphs, graph_err = None, None
+    graphs, pool_graph, graph_err = None, None, None
     if not args.no_graph:
         try:
             graphs = []
@@ -286,21 +286,43 @@ def gpu_arm(args):
                 with torch.cuda.graph(g_):
                     step(slot, feats[slot], keys[slot])
                 graphs.append(g_)
+            # ... and one graph holding all POOL steps back to back: relaunching one graph is cheaper on the
+            # host than alternating between POOL of them, which matters once 8 ranks submit work at the same
+            # time (N=8: 107 us/step with alternating single-step graphs, same kernels).
+            pool_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(pool_graph):
+                for slot in range(POOL):
+                    step(slot, feats[slot], keys[slot])
             for slot in range(POOL):  # one untimed replay each
                 graphs[slot].replay()
+            pool_graph.replay()
             sync_all()
         except Exception as e:  # capture is an optimisation: fall back to eager launches and say so
-            graphs, graph_err = None, "%s: %s" % (type(e).__name__, e)
+            graphs, pool_graph, graph_err = None, None, "%s: %s" % (type(e).__name__, e)
             torch.cuda.synchronize()
 
+    # NVML is set up before the barrier (nvmlInit takes milliseconds and a different time on every rank)
+    # and polled by rank 0 only (its calls take a driver-wide lock).
     sampler = ClockSampler(local)
-    if os.environ.get("BENCH_NO_SAMPLER") != "1":
+    sync_all()
+    if rank == 0 and os.environ.get("BENCH_NO_SAMPLER") != "1":
         sampler.start()
+
+    def align_ranks(i=0):
+        """One UNTIMED step after the barrier, N > 1 only: the ranks leave the host barrier up to milliseconds
+        apart, and the first exchange would charge that skew to the timed region of the early ranks (seen as
+        +15 us/step over 200 steps at N=8).  After one coupled step the streams are within microseconds."""
+        if world > 1:
+            step(i, feats[i % POOL], keys[i % POOL])
+
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    align_ranks()
     t_start.record()
     if graphs is not None:
-        for i in range(args.steps):
-            graphs[i % POOL].replay()
+        for _ in range(args.steps // POOL):  # POOL steps per launch ...
+            pool_graph.replay()
+        for i in range(args.steps % POOL):   # ... and the remainder one step at a time: exactly K steps
+            graphs[i].replay()
     else:
         for i in range(args.steps):
             step(i, feats[i % POOL], keys[i % POOL])
@@ -387,6 +409,8 @@ def gpu_arm(args):
     # (a) strict: the host waits for the loss of step i before it enqueues step i+1
     run_e2e = e2e_graph_step if e2e_graphs is not None else e2e_step
     e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        run_e2e(0)  # untimed: aligns the ranks after the host barrier (see align_ranks)
     e_start.record()
     for i in range(e2e_steps):
         run_e2e(i)
@@ -402,6 +426,8 @@ def gpu_arm(args):
         done = [torch.cuda.Event(), torch.cuda.Event()]
         acc = 0.0
         sync_all()
+        if world > 1:
+            e2e_graph_step(0)  # untimed: aligns the ranks after the host barrier
         e_start.record()
         for i in range(e2e_steps):
             e2e_graphs[i % POOL].replay()
@@ -441,7 +467,8 @@ def gpu_arm(args):
         "config": {"workload": WORKLOAD, "batch_per_gpu": B_PER_GPU, "global_batch": n_gpus * B_PER_GPU,
                    "queue_len": QUEUE_LEN, "dim": DIM, "T": TEMP, "ema_tensors": len(online),
                    "ema_params": n_params, "logits_materialised": not args.no_logits,
-                   "infonce_kernel": args.kernel, "cuda_graph": graphs is not None,
+                   "infonce_kernel": args.kernel, "cuda_graph": graphs is not None, "steps_per_graph_launch": POOL if graphs is not None else None,
+                   "rank_alignment": "one untimed step between the barrier and the first timed event (N>1)" if world > 1 else None,
                    "e2e_cuda_graph": e2e_graphs is not None, "cuda_graph_error": graph_err,
                    "key_exchange": ("nvlink peer stores fused into the EMA launch, wait fused into the head launch"
                                     if use_peer else ("nccl all_gather on a side stream" if use_nccl else "none (1 GPU)")),
