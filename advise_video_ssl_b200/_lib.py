@@ -81,7 +81,7 @@ SIGNATURES = {
     "avssl_moco_infonce_fwd_bwd_enqueue_peer": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                                         c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
                                                         c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
-    "avssl_multi_l2norm_workspace_bytes": (c_size_t, [c_int64]),
+    "avssl_multi_l2norm_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "avssl_multi_l2norm": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "avssl_swav_ce_workspace_bytes": (c_size_t, [c_int]),
     "avssl_swav_ce_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,

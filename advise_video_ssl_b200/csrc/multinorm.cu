@@ -87,31 +87,41 @@ multi_l2norm_kernel(const avssl_ema_chunk* __restrict__ table, int n_chunks, flo
   }
 }
 
-// Second, single-CTA launch: 32 warps, one warp per tensor (lanes stride over its chunks in a
-// fixed order), then the total over the tensors in tensor order.
-constexpr int kFoldThreads = 1024;
+// Second launch: one warp per tensor (lanes stride over its chunks in a fixed order) across
+// ceil(n_tensors / 8) CTAs; the last CTA to finish adds the squared norms in tensor order.
+constexpr int kFoldThreads = 256;
 __global__ void __launch_bounds__(kFoldThreads)
 multi_l2norm_fold_kernel(const int* __restrict__ first_chunk, int n_tensors, const float* __restrict__ partial,
-                         float* __restrict__ per_tensor, float* __restrict__ total) {
-  __shared__ float s_tot[kFoldThreads / 32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float tot = 0.f;  // lane 0 of each warp accumulates norm_t^2 over its tensors
-  for (int t = warp; t < n_tensors; t += kFoldThreads / 32) {
+                         float* __restrict__ sq, float* __restrict__ per_tensor, float* __restrict__ total,
+                         unsigned* counter) {
+  __shared__ float s_red[32];
+  __shared__ unsigned s_last;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int t = blockIdx.x * (kFoldThreads / 32) + (tid >> 5);
+  if (t < n_tensors) {
     const int k0 = __ldg(first_chunk + t), k1 = __ldg(first_chunk + t + 1);
     float s = 0.f;
     for (int k = k0 + lane; k < k1; k += 32) s += __ldcg(partial + k);
     s = warp_sum(s);
     if (lane == 0) {
+      sq[t] = s;
       if (per_tensor) per_tensor[t] = sqrtf(s);
-      tot += s;
     }
   }
-  if (lane == 0) s_tot[warp] = tot;
   __syncthreads();
   if (tid == 0) {
-    float a = 0.f;
-    for (int w = 0; w < kFoldThreads / 32; ++w) a += s_tot[w];
+    __threadfence();
+    s_last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float a = 0.f;
+  for (int k = tid; k < n_tensors; k += kFoldThreads) a += __ldcg(sq + k);
+  a = block_sum(a, s_red);
+  if (tid == 0) {
     *total = sqrtf(a);  // norm(stack(norm_t)) = sqrt(sum_t norm_t^2)
+    *counter = 0u;
   }
 }
 
@@ -121,9 +131,9 @@ __global__ void multi_l2norm_empty_kernel(float* total) { *total = 0.f; }
 
 using namespace avssl;
 
-extern "C" size_t avssl_multi_l2norm_workspace_bytes(int64_t n_chunks) {
-  if (n_chunks < 0) return 0;
-  return 256 + 4 * (size_t)n_chunks;
+extern "C" size_t avssl_multi_l2norm_workspace_bytes(int64_t n_chunks, int n_tensors) {
+  if (n_chunks < 0 || n_tensors < 0) return 0;
+  return 256 + 4 * (size_t)n_chunks + 4 * (size_t)n_tensors + 256;  // counter | partial[n_chunks] | sq[n_tensors]
 }
 
 extern "C" int avssl_multi_l2norm(const avssl_ema_chunk* table_dev, int64_t n_chunks, const int32_t* first_chunk_dev,
@@ -132,7 +142,7 @@ extern "C" int avssl_multi_l2norm(const avssl_ema_chunk* table_dev, int64_t n_ch
   AVSSL_REQUIRE(total_norm_out && workspace, AVSSL_ERR_INVALID_ARGUMENT, "multi_l2norm: null pointer");
   AVSSL_REQUIRE(n_chunks >= 0 && n_chunks < (1ll << 31) && n_tensors >= 0, AVSSL_ERR_INVALID_ARGUMENT,
                 "multi_l2norm: bad sizes n_chunks=%lld n_tensors=%d", (long long)n_chunks, n_tensors);
-  AVSSL_REQUIRE(workspace_bytes >= avssl_multi_l2norm_workspace_bytes(n_chunks), AVSSL_ERR_WORKSPACE,
+  AVSSL_REQUIRE(workspace_bytes >= avssl_multi_l2norm_workspace_bytes(n_chunks, n_tensors), AVSSL_ERR_WORKSPACE,
                 "multi_l2norm: workspace too small");
   AVSSL_REQUIRE(sm_count() > 0, AVSSL_ERR_CUDA, "multi_l2norm: no CUDA device (there is no CPU fallback)");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -146,8 +156,10 @@ extern "C" int avssl_multi_l2norm(const avssl_ema_chunk* table_dev, int64_t n_ch
   const unsigned grid = (unsigned)((n_chunks + kNormChunksPerCta - 1) / kNormChunksPerCta);
   multi_l2norm_kernel<<<grid, kNormThreads, 0, s>>>(table_dev, (int)n_chunks, partial);
   AVSSL_LAUNCH_OK("multi_l2norm_kernel");
-  multi_l2norm_fold_kernel<<<1, kFoldThreads, 0, s>>>(first_chunk_dev, n_tensors, partial, per_tensor_norm_out,
-                                                      total_norm_out);
+  float* sq = partial + n_chunks;
+  unsigned* counter = static_cast<unsigned*>(workspace);
+  multi_l2norm_fold_kernel<<<(n_tensors + kFoldThreads / 32 - 1) / (kFoldThreads / 32), kFoldThreads, 0, s>>>(
+      first_chunk_dev, n_tensors, partial, sq, per_tensor_norm_out, total_norm_out, counter);
   AVSSL_LAUNCH_OK("multi_l2norm_fold_kernel");
   return AVSSL_OK;
 }

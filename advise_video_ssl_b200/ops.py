@@ -152,7 +152,7 @@ class MultiTensorNorm:
         host = torch.from_numpy(table.view(np.uint8).reshape(-1).copy()) if self.n_chunks else torch.zeros(24, dtype=torch.uint8)
         self.table = host.to(dev)
         self.first = torch.from_numpy(first).to(dev)
-        self.ws = torch.zeros(int(lib.avssl_multi_l2norm_workspace_bytes(self.n_chunks)), dtype=torch.uint8, device=dev)
+        self.ws = torch.zeros(int(lib.avssl_multi_l2norm_workspace_bytes(self.n_chunks, self.n_tensors)), dtype=torch.uint8, device=dev)
         self.per_tensor = torch.zeros(max(self.n_tensors, 1), dtype=_f32, device=dev)
         self.total = torch.zeros(1, dtype=_f32, device=dev)
 

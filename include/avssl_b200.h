@@ -304,7 +304,7 @@ AVSSL_API int avssl_moco_infonce_fwd_bwd_enqueue_peer(const float* feat_q, const
  * per_tensor_norm_out may be NULL.  An empty list gives total = 0 (:380-381).
  * workspace: avssl_multi_l2norm_workspace_bytes(), zero-filled once, reusable.
  */
-AVSSL_API size_t avssl_multi_l2norm_workspace_bytes(int64_t n_chunks);
+AVSSL_API size_t avssl_multi_l2norm_workspace_bytes(int64_t n_chunks, int n_tensors);
 AVSSL_API int avssl_multi_l2norm(const avssl_ema_chunk* table_dev, int64_t n_chunks, const int32_t* first_chunk_dev,
                        int n_tensors, float* per_tensor_norm_out, float* total_norm_out, void* workspace,
                        size_t workspace_bytes, void* stream);

@@ -37,7 +37,7 @@ def test_multi_norm_unaligned_ragged_and_full_size():
     from advise_video_ssl_b200 import ops
     torch.manual_seed(4)
     base = torch.randn(3 * 4096 + 77, device="cuda")
-    views = [base[1:4098], base[4099:4100], base[4100:]]  # misaligned starts, 1-element tensor, ragged tail
+    views = [base[1:4098], base[4099:4100], base[4100:4100], base[4100:]]  # misaligned, 1-element, EMPTY, ragged tail
     plan = ops.MultiTensorNorm(views)
     total, per = plan.run()
     ref = [torch.norm(v.cpu().double()) for v in views]
