@@ -39,6 +39,18 @@ void set_error(const char* fmt, ...);
 
 int sm_count();  // cached per process; <0 on error
 
+// cudaFuncSetAttribute() applies to the CURRENT device only: kernels that opt in to large dynamic
+// shared memory keep a bitmask of the device ordinals already configured (per kernel instantiation).
+// Returns true the first time it is called for the current device.
+inline bool first_use_on_device(unsigned long long& mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return true;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -173,10 +173,9 @@ __global__ void __launch_bounds__(kCombineThreads) infonce_combine_kernel(const 
 template <int DP>
 static int launch_simt_dp(const InfoNceParams& p, cudaStream_t s) {
   const size_t smem = sizeof(float) * ((size_t)kTileI * (DP + 4) + 2 * kTileJ * (DP + 4) + kTileI * kPsStride);
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0ull;  // device ordinals already set up
+  if (first_use_on_device(configured)) {
     AVSSL_CUDA_OK(cudaFuncSetAttribute(infonce_simt_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   dim3 grid(p.n_splits, (p.B + kTileI - 1) / kTileI);
   infonce_simt_kernel<DP><<<grid, kSimtThreads, smem, s>>>(p);

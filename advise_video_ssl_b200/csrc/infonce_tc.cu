@@ -695,11 +695,10 @@ int launch_tc(const InfoNceParams& p, cudaStream_t s) {
     cache.K = p.K;
     cache.D = D;
   }
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0ull;  // device ordinals already set up
+  if (first_use_on_device(configured)) {
     AVSSL_CUDA_OK(cudaFuncSetAttribute(infonce_tc_kernel<D, kThreeTerm>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)C::kSmemBytes));
-    configured = true;
   }
   dim3 grid(p.n_splits, (p.B + kM - 1) / kM);
   AVSSL_REQUIRE((int)(grid.x * grid.y) <= sm_count(), AVSSL_ERR_INVALID_ARGUMENT,

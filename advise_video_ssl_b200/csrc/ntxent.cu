@@ -247,10 +247,9 @@ ntxent_finish_kernel(const NtxArgs a, const float* __restrict__ norm_loc, float 
 template <int DP, bool kGrad>
 static int launch_pass(const NtxArgs& a, cudaStream_t s) {
   const size_t smem = simt_smem_bytes(DP, kGrad);
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0ull;  // device ordinals already set up
+  if (first_use_on_device(configured)) {
     AVSSL_CUDA_OK(cudaFuncSetAttribute(ntxent_pass_kernel<DP, kGrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   dim3 grid(a.n_splits, (a.n_loc + kTileI - 1) / kTileI);
   ntxent_pass_kernel<DP, kGrad><<<grid, kSimtThreads, smem, s>>>(a);

@@ -359,10 +359,9 @@ int launch_nt(const NtxArgs& a, cudaStream_t st) {
     cache.N2 = a.N2;
     cache.D = D;
   }
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0ull;  // device ordinals already set up
+  if (first_use_on_device(configured)) {
     AVSSL_CUDA_OK(cudaFuncSetAttribute(ntxent_tc_kernel<D, kGrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes));
-    configured = true;
   }
   dim3 grid(a.n_splits, (a.n_loc + kMt - 1) / kMt);
   ntxent_tc_kernel<D, kGrad><<<grid, kNtThreads, C::kSmemBytes, st>>>(a, cache.s, cache.v);

@@ -470,9 +470,10 @@ static int sink_grid(int Btot) {
 // Launches the single-cluster kernel when the problem fits one cluster of 16 (or 8) CTAs and the
 // device can schedule such a cluster; returns false to fall back to the cooperative grid kernel.
 static bool sinkhorn_try_cluster(SinkArgs& a, cudaStream_t s) {
-  static int max_cluster = -1;  // largest schedulable cluster size with the full shared-memory carve-out
+  static int max_cluster = 0;  // largest schedulable cluster size with the full shared-memory carve-out
+  static unsigned long long configured = 0ull;  // device ordinals whose function attributes are set
   constexpr size_t kSmemMax = 227 * 1024;
-  if (max_cluster < 0) {
+  if (first_use_on_device(configured)) {
     max_cluster = 0;
     if (cudaFuncSetAttribute(sinkhorn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax) == cudaSuccess &&
         cudaFuncSetAttribute(sinkhorn_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
