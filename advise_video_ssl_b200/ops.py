@@ -276,6 +276,12 @@ class PeerExchange:
         idx = torch.arange(self.world * self.rows_per_rank, dtype=torch.int64, device=self.device)
         return self.wait_gather(idx, out=out)
 
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001  (interpreter shutdown, lost context)
+            pass
+
     def close(self):
         """Unmap the peers' buffers and free this rank's.  Collective in spirit: call it on every
         rank once no push or wait is in flight."""
