@@ -12,7 +12,7 @@
 //
 // push(e):  rank r stores its [rows, D] block into payload[e & 1][r] of EVERY rank (one CTA per
 //           destination), fences at system scope and then publishes flags[r] = e there.
-// wait(e):  the consumer spins (acquire, system scope) until all `world` local flags are >= e.
+// wait(e):  one consumer warp polls all `world` local flags until they are >= e, then fences (system scope).
 //
 // Two slots suffice: rank A can issue push e+2 only after its own consumer of epoch e+1 has
 // finished, which waited for B's push e+1, which B issued after ITS consumer of epoch e was done
@@ -30,11 +30,6 @@ struct PeerHdr {
 };
 static_assert(sizeof(PeerHdr) == 256, "exchange header is 256 bytes");
 
-__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -72,25 +67,17 @@ __device__ __forceinline__ void peer_push_cta(const avssl_peer_xchg& x, const fl
   }
 }
 
-// ONE thread: wait until every rank's push of the current local epoch has landed here.
-// Returns the payload slot to read.  The caller follows with __syncthreads().
-__device__ __forceinline__ int peer_wait_all(const avssl_peer_xchg& x) {
-  PeerHdr* me = static_cast<PeerHdr*>(x.base[x.rank]);
-  const unsigned long long e = *reinterpret_cast<volatile unsigned long long*>(&me->epoch);
-  for (int r = 0; r < x.world; ++r)
-    while (ld_acquire_sys_u64(&me->flags[r]) < e) __nanosleep(32);
-  return (int)(e & 1ull);
-}
-
 __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 
-// The same wait by ONE WARP (all 32 lanes call it): lane r watches rank r's flag with relaxed
-// loads, so the wait costs one flag latency whatever the world size, and a single system-scope
-// fence orders the payload reads that follow the caller's __syncthreads().
+// wait, by ONE WARP (all 32 lanes call it): until every rank's push of the current local epoch has
+// landed here.  Lane r watches rank r's flag with relaxed loads, so the wait costs one flag latency
+// whatever the world size (W sequential ld.acquire.sys cost +14 us per step at W = 4), and a single
+// system-scope fence orders the payload reads that follow the caller's __syncthreads().
+// Returns the payload slot to read.
 __device__ __forceinline__ int peer_wait_all_warp(const avssl_peer_xchg& x) {
   PeerHdr* me = static_cast<PeerHdr*>(x.base[x.rank]);
   const int lane = threadIdx.x & 31;
