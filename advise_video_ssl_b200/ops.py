@@ -189,6 +189,8 @@ class PeerExchange:
 
     def __init__(self, rows_per_rank, D, group=None, device=None):
         import torch.distributed as dist
+        if not torch.cuda.is_available():
+            raise RuntimeError("PeerExchange needs a CUDA device: the contrastive hot path has no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         on = dist.is_available() and dist.is_initialized()
         self.world = dist.get_world_size(group) if on else 1

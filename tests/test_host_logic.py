@@ -97,3 +97,54 @@ def test_queue_divisibility_assert():
     m = C.ContrastiveModel(cfg)
     with pytest.raises(AssertionError):
         m._dequeue_and_enqueue([torch.randn(5, 16)])
+
+
+# ------------------------------------------------- round-1 additions: no silent CPU paths
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_new_entry_points_have_no_cpu_fallback():
+    from advise_video_ssl_b200 import ops, optimizer, temporal
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.PeerExchange(8, 32)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.MultiTensorNorm([torch.randn(16)])
+    p = torch.nn.Parameter(torch.zeros(16))
+    p.grad = torch.randn(16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        optimizer.get_grad_norm_([p])                       # the 2-norm is the CUDA path, never a torch fallback
+    assert optimizer.get_grad_norm_([torch.nn.Parameter(torch.zeros(3))]).item() == 0.0   # no grads: 0.0 (:380-381)
+
+    class Holder(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.temporal_encoder = torch.nn.Linear(4, 4)
+            self.temporal_encoder_hist = torch.nn.Linear(4, 4)
+            self.head_projector = torch.nn.Linear(4, 2)
+            self.head_projector_hist = torch.nn.Linear(4, 2)
+            self.mmt, self.T = 0.99, 0.1
+
+    h = Holder()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        temporal.update_history(h)
+
+
+def test_momentum_pairs_follow_reference_order():
+    """temporal._pairs walks temporal_encoder_hist then head_projector_hist by NAME
+    (models/temporal_modeling.py:220-237), whatever the registration order of the online modules."""
+    from advise_video_ssl_b200 import temporal
+
+    class Holder(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.head_projector = torch.nn.Linear(4, 2)
+            self.temporal_encoder = torch.nn.Sequential(torch.nn.Linear(4, 4), torch.nn.LayerNorm(4))
+            self.temporal_encoder_hist = torch.nn.Sequential(torch.nn.Linear(4, 4), torch.nn.LayerNorm(4))
+            self.head_projector_hist = torch.nn.Linear(4, 2)
+
+    h = Holder()
+    online, hist = temporal._pairs(h)
+    names = [n for n, _ in h.temporal_encoder_hist.named_parameters()] + [n for n, _ in h.head_projector_hist.named_parameters()]
+    assert len(online) == len(hist) == len(names) == 6
+    enc, proj = dict(h.temporal_encoder.named_parameters()), dict(h.head_projector.named_parameters())
+    for i, n in enumerate(names):
+        src = enc[n] if i < 4 else proj[n]
+        assert online[i].data_ptr() == src.data_ptr() and online[i].shape == hist[i].shape
