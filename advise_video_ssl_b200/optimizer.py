@@ -12,15 +12,18 @@ import torch
 
 from . import ops
 
-_plans = {}
+_plans = {}        # storage-pointer tuple -> ops.MultiTensorNorm (insertion-ordered: oldest first)
+_MAX_PLANS = 8     # gradients, parameters (LARS) and a few sub-lists; storages are stable across steps
 
 
 def _plan_for(tensors):
-    key = tuple(t.data_ptr() for t in tensors)
-    plan = _plans.get(len(tensors))
-    if plan is None or plan.ptr_key != key:
+    key = tuple((t.data_ptr(), t.numel()) for t in tensors)  # a recycled address with another size is a new list
+    plan = _plans.pop(key, None)
+    if plan is None:
         plan = ops.MultiTensorNorm(tensors)
-        _plans[len(tensors)] = plan  # one cached plan per list length: gradient storages are stable across steps
+        while len(_plans) >= _MAX_PLANS:
+            _plans.pop(next(iter(_plans)))  # drop the least recently used plan
+    _plans[key] = plan                      # (re)insert as most recently used
     return plan
 
 
