@@ -13,7 +13,10 @@
  *   - every call is asynchronous on `stream` and never synchronises unless stated.
  *   - return value: 0 = AVSSL_OK, otherwise an avssl_status code; the message for
  *     the calling thread's last failure is available from avssl_last_error().
- *   - the caller owns all memory; the library keeps no global device state.
+ *   - the caller owns all memory; the library keeps no global device state.  The one exception
+ *     is the peer-exchange buffer of avssl_peer_alloc(): it must be a whole cudaMalloc allocation
+ *     to be exportable over CUDA IPC, so the library allocates it and the caller frees it with
+ *     avssl_peer_free().
  *   - there is NO CPU fallback: without a CUDA device every compute call fails.
  *   - fp32 tensors are row-major and contiguous; indices / pointers are int64.
  */
