@@ -34,7 +34,7 @@ import torch  # noqa: E402
 
 B_PER_GPU, DIM, QUEUE_LEN, TEMP, MOMENTUM = 64, 128, 65536, 0.1, 0.999
 POOL = 8  # distinct synthetic batches rotated through the steps
-EMA_DRAM_TRAFFIC = 385_177_600  # bytes per launch of the EMA kernel measured by ncu (289.0 MB read + 96.2 MB written)
+EMA_DRAM_TRAFFIC = 383_585_280  # bytes per launch of the EMA kernel measured by ncu (289.0 MB read + 94.6 MB written, profiles/r1_ema_ncu.md)
 WORKLOAD = ("configs[1] head: Slow-R50 MoCo, 2 views/clip, queue 65536, dim 128, batch 64/GPU; "
             "EMA(164 tensors, 36.1M fp32) + l2norm + logits + InfoNCE fwd/bwd + enqueue; backbone excluded")
 METRIC, UNIT = "contrastive_head_clips_per_sec", "clips/s"
