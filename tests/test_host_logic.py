@@ -148,3 +148,24 @@ def test_momentum_pairs_follow_reference_order():
     for i, n in enumerate(names):
         src = enc[n] if i < 4 else proj[n]
         assert online[i].data_ptr() == src.data_ptr() and online[i].shape == hist[i].shape
+
+
+def test_state_dict_contract_matches_reference():
+    """Checkpoint contract (utils/misc.py:118-137,300-339): names, shapes, dtypes of every state_dict
+    entry and the frozen-parameter set, in every mode, against the unmodified reference
+    (tests/golden/state_dict_contract.json, generated by make_golden_statedict.py)."""
+    import json
+    import os
+    C = register_backbones()
+    path = os.path.join(os.path.dirname(__file__), "golden", "state_dict_contract.json")
+    ref = json.load(open(path))
+    assert set(ref) == {"moco", "moco_knn", "byol", "swav", "swav_queue", "simclr", "mem_1d", "mem_2d"}
+    for name, case in ref.items():
+        cfg = make_cfg(**case["cfg"])
+        torch.manual_seed(0)
+        m = C.ContrastiveModel(cfg)
+        mine = sorted([k, list(v.shape), str(v.dtype)] for k, v in m.state_dict().items())
+        assert mine == case["state_dict"], (name, [x for x in mine if x not in case["state_dict"]],
+                                            [x for x in case["state_dict"] if x not in mine])
+        frozen = sorted(n for n, p in m.named_parameters() if not p.requires_grad)
+        assert frozen == case["frozen"], name
