@@ -21,10 +21,23 @@ HBM = float(peaks.get("hbm_gbs", 6650.0))
 TF = float(peaks.get("bf16_tflops", 1590.0))
 
 
+# L2 flush before every timed call.  "zero" (what profiles/r1_config_bench.jsonl was measured with) leaves
+# up to 126 MB of dirty lines that are written back DURING the timed kernel; "read" streams the buffer
+# through L2 instead, so the timed kernel starts with a clean cache (fairer to read-only kernels).
+FLUSH = os.environ.get("AVSSL_FLUSH", "zero")
+
+
+def flush_l2():
+    if FLUSH == "read":
+        flush.sum(dtype=torch.int64)
+    else:
+        flush.zero_()
+
+
 def timed(fn, n=30):
     ts = []
     for _ in range(n):
-        flush.zero_()
+        flush_l2()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn()
