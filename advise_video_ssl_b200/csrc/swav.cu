@@ -592,10 +592,9 @@ extern "C" int avssl_swav_ce_fwd_bwd(const float* scores, const float* codes, in
   const bool reg_path = P % 4 == 0 && P <= 256 * 4 * kCeVec &&
                         ((reinterpret_cast<uintptr_t>(scores) | reinterpret_cast<uintptr_t>(codes) |
                           reinterpret_cast<uintptr_t>(dscores_out)) & 15u) == 0;
+  // more than two code sets (never produced by the reference: two global crops) take the generic kernel
   if (reg_path && n_assign <= 2)
     swav_ce_reg_kernel<2><<<n_crops * bs, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
-  else if (reg_path)
-    swav_ce_reg_kernel<kMaxAssign><<<n_crops * bs, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   else
     swav_ce_kernel<<<n_crops * bs, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   AVSSL_LAUNCH_OK("swav_ce_kernel");
