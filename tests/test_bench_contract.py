@@ -42,3 +42,31 @@ def test_gpu_arm_has_no_cpu_fallback():
     r = _run("--steps", "3", "--warmup", "3")
     assert r.returncode != 0
     assert "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_committed_bench_lines_carry_every_contract_key():
+    """The bench lines kept under profiles/ (produced by bench.py on the B200 box) have every key the
+    driver and the judge read; a key dropped from bench.py would show up here on the next refresh."""
+    prof = os.path.join(ROOT, "profiles")
+    top = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+           "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline"}
+    for name, n in (("r1_bench_graph.json", 1), ("r1_bench_n2.json", 2), ("r1_bench_n4.json", 4), ("r1_bench_n8.json", 8)):
+        d = json.loads(open(os.path.join(prof, name)).read().strip().splitlines()[-1])
+        assert top <= set(d), (name, top - set(d))
+        assert d["n_gpus"] == n and d["metric"] == "contrastive_head_clips_per_sec" and d["dtype"] == "f32"
+        assert d["scaling"] == "weak" and d["vs_baseline"] is None and d["data"] == "synthetic"
+        assert "workload" in d["config"] and "model" not in d["config"]
+        assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
+        assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+        assert d["e2e"]["value"] < d["value"]  # the end-to-end number is measured, not a copy of `value`
+        assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        r = d["roofline"]
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["bound"] == "hbm"
+        assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0.5 < r["frac"] < 1.0
+        assert d["gpu_launches"] == 2 * d["steps"]
+        assert abs(d["value"] - n * 64 / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
+        if n == 1:
+            assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
+        else:
+            assert d["config"]["key_exchange_verified_vs_nccl"] is True
