@@ -1,10 +1,11 @@
 """Developer probe (GPU box): run the tcgen05 InfoNCE kernels on a few shapes and print
-their errors against the CPU oracle, plus a quick timing.  Not part of the test suite."""
+their errors against the CPU oracle, plus a quick timing.  Lives under tests/ because it imports the
+oracle (test infrastructure); it is not collected by pytest."""
 import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 from advise_video_ssl_b200 import ops  # noqa: E402

@@ -71,3 +71,18 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt, os.path.join(dirpath, f)
+
+
+def test_only_test_infrastructure_imports_the_oracle():
+    """oracle/ is a checker: besides tests/, only __graft_entry__.smoke() and bench.py's CPU legs may use it."""
+    allowed = {os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")}
+    for dirpath, dirs, files in os.walk(ROOT):
+        dirs[:] = [d for d in dirs if d not in (".git", "gpurun_out", "tests", "oracle", "__pycache__", "build", "baseline")]
+        for f in files:
+            if not f.endswith(".py"):
+                continue
+            path = os.path.join(dirpath, f)
+            if path in allowed:
+                continue
+            txt = open(path).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), path
