@@ -26,7 +26,8 @@ class EmaChunk(ctypes.Structure):
 
 class PeerXchg(ctypes.Structure):
     """Mirror of `avssl_peer_xchg` (include/avssl_b200.h)."""
-    _fields_ = [("base", c_void_p * 16), ("world", c_int), ("rank", c_int), ("rows_per_rank", c_int), ("D", c_int)]
+    _fields_ = [("base", c_void_p * 16), ("world", c_int), ("rank", c_int), ("rows_per_rank", c_int), ("D", c_int),
+                ("timeout_ms", ctypes.c_uint32), ("reserved_", ctypes.c_uint32)]
 
 
 MAX_PEERS = 16
@@ -75,11 +76,12 @@ SIGNATURES = {
     "avssl_peer_close": (c_int, [c_void_p]),
     "avssl_peer_free": (c_int, [c_void_p]),
     "avssl_peer_push_rows": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "avssl_l2norm_push_rows": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
     "avssl_peer_wait_gather": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "avssl_ema_multi_tensor_push": (c_int, [c_void_p, c_int64, c_float, c_float, c_void_p, c_int, c_int, c_void_p,
                                             c_void_p, c_void_p, c_void_p]),
-    "avssl_moco_infonce_fwd_bwd_enqueue_peer": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                                        c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
+    "avssl_moco_infonce_fwd_bwd_enqueue_peer": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                                        c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
                                                         c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "avssl_multi_l2norm_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "avssl_multi_l2norm": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -92,6 +94,8 @@ IMPL_AUTO, IMPL_SIMT, IMPL_TC3X, IMPL_TC1X = 0, 1, 2, 3
 MAX_KEYS = 8
 DEVFLAG_QUEUE_OVERRUN = 1
 DEVFLAG_BAD_INDEX = 2
+DEVFLAG_PEER_TIMEOUT = 4
+ABI_VERSION = 2
 
 
 def _load():
@@ -106,6 +110,9 @@ def _load():
         fn = getattr(lib, name)  # AttributeError if the .so is stale: fail loudly
         fn.restype = res
         fn.argtypes = args
+    if lib.avssl_abi_version() != ABI_VERSION:
+        raise ImportError("advise_video_ssl_b200: %s has ABI version %d, this package needs %d: rebuild it "
+                          "(python advise_video_ssl_b200/build.py)" % (LIB_PATH, lib.avssl_abi_version(), ABI_VERSION))
     return lib
 
 

@@ -1,32 +1,32 @@
-"""B200-native `ContrastiveModel` — drop-in for the reference's
-`models/contrastive.py` (same class / function names, arguments, return values,
-buffer names and error behaviour), with every hot op routed to the hand-written
-sm_100a kernels behind `include/avssl_b200.h`.
+"""B200-native `ContrastiveModel`: the drop-in for the reference's `models/contrastive.py`
+(same class / function names, arguments, return values, buffer names, error behaviour).
+All arithmetic on the path runs in the hand-written sm_100a kernels behind
+`include/avssl_b200.h`; this file is host orchestration written against the behavioural
+contract of the reference (file:line below are in /root/reference), not a translation of it.
 
-Reference map (file:line are in /root/reference):
-  ContrastiveModel.__init__            models/contrastive.py:37-129
-  _update_history (K1)                 :158-172   -> ops.EmaPlan (one launch, device `iter`)
-  _batch_shuffle/_batch_unshuffle      :174-230   -> all-to-all exchange (C1) / single all_gather (C3)
-  _dequeue_and_enqueue (K4)            :263-292   -> ops.queue_enqueue (device `ptr`, no .item())
-  compute_key_feat                     :308-371
-  forward: mem / moco / byol / swav / simclr   :373-804
-  sinkhorn / distributed_sinkhorn      :872-910   -> ops.sinkhorn (single cooperative kernel)
-  Normalize / Memory / Memory1D        :923-1080
-  contrastive_parameter_surgery        :1083-1116
-  contrastive_forward                  :1119-1171
+Step anatomy in MoCo mode (A2-A6; the step `bench.py` times through `contrastive_forward`):
 
-Differences that are deliberate and documented in DESIGN.md:
-  * no host synchronisation on the step path (`iter`, `ptr` stay on the device; the
-    reference's asserts on them become a device status word, `check_device_status()`);
+    launch 1  EMA of the key encoder + `iter += 1`                         (K1,  :158-172, :313-314)
+    [hist encoder forward - the host application's backbone]
+    launch 2  Normalize(key features) [+ store into every rank's exchange  (K2 + C3 push, :350, :216-230)
+              buffer over NVLink, W > 1]
+    launch 3  Normalize(f) + logits + InfoNCE fwd/bwd [+ wait for the      (K2 + K3 + C3 wait + K4 + C9,
+              exchange, un-shuffle by index] + queue ring write            :462-503, :263-292)
+
+What deliberately differs from the reference:
+  * no host synchronisation on the step path: `iter` / `ptr` stay on the device, the shuffle
+    permutation travels between hosts, and the reference's asserts on `ptr` / bank indices become
+    bits of a device status word (`check_device_status()`);
   * history parameters are updated in place (the reference rebinds `.data`);
-  * `logits` is returned detached (the loss carries the gradient), and can be skipped
-    with `materialize_logits = False`;
-  * the dummy logits of byol/swav/simclr are a cached device constant (K8);
-  * SwAV prototype count is `cfg.CONTRASTIVE.SWAV_NUM_PROTOTYPES` if present, else the
-    reference's hard-coded 1000.
-The backbones are not part of this package: `_MODEL_TYPES` is filled from the host
-application's `models.video_model_builder` when it is importable (i.e. inside the
-reference tree), or by the caller.
+  * `logits` is returned detached (the loss carries the gradient) and can be skipped with
+    `materialize_logits = False`; the dummy logits of byol / swav / simclr are a cached constant;
+  * multi-GPU queue consistency (C9) is explicit: `queue_mode` "reference" (default) makes every
+    rank enqueue rank 0's keys - what the reference's DDP buffer broadcast (models/build.py:76-83)
+    leaves in every queue - without broadcasting 33.5 MB per step; "canonical" enqueues all W*B keys;
+    "local" is the reference's raw per-rank behaviour (correct only under that DDP broadcast);
+  * the SwAV prototype count is `cfg.CONTRASTIVE.SWAV_NUM_PROTOTYPES` when present (reference: 1000).
+Backbones are not part of this package: `_MODEL_TYPES` is filled from the host application's
+`models.video_model_builder` when importable (inside the reference tree), or by the caller.
 """
 import logging
 import math
@@ -38,261 +38,199 @@ import torch.nn as nn
 from . import _lib, ops
 from . import distributed as du
 from . import losses
+from .autograd import (BankDot, ByolSimilarity, MocoInfoNce, NtXentRows, SwavSwappedCe, l2norm_lastdim)
+from .banks import Memory, Memory1D, Normalize, _bank_init
+from .shuffle import ShufflePlan, broadcast_from_rank0
 
 logger = logging.getLogger(__name__)
 
-# Supported model types (models/contrastive.py:20-28); filled lazily, see module doc.
+# models/contrastive.py:20-28 - architecture name -> backbone class
 _MODEL_TYPES = {}
-try:  # inside the reference tree the video backbones are used unchanged
+try:
     from models.video_model_builder import X3D, MViT, ResNet, SlowFast  # type: ignore
 
-    _MODEL_TYPES.update({"slowfast": SlowFast, "slow": ResNet, "c2d": ResNet, "i3d": ResNet,
-                         "slow_c2d": ResNet, "x3d": X3D, "mvit": MViT})
-except Exception:  # pragma: no cover - standalone use: the caller registers backbones
+    for _name, _cls in (("slowfast", SlowFast), ("slow", ResNet), ("c2d", ResNet), ("i3d", ResNet),
+                        ("slow_c2d", ResNet), ("x3d", X3D), ("mvit", MViT)):
+        _MODEL_TYPES[_name] = _cls
+except Exception:  # pragma: no cover - outside the reference tree the caller registers backbones
     pass
 
 try:
     from models.build import MODEL_REGISTRY  # type: ignore
 except Exception:  # pragma: no cover
     class _Registry(dict):
+        """Just enough of fvcore's Registry for `MODEL_REGISTRY.get("ContrastiveModel")(cfg)`."""
+
         def register(self, obj=None):
-            def deco(o):
-                self[o.__name__] = o
-                return o
-            return deco(obj) if obj is not None else deco
+            if obj is None:
+                return self.register
+            self[obj.__name__] = obj
+            return obj
 
         def get(self, name):
             return self[name]
 
     MODEL_REGISTRY = _Registry()
 
+QUEUE_MODES = ("reference", "canonical", "local")
 
-def _cfg_get(node, name, default):
+
+def _opt(node, name, default):
+    """cfg keys this package adds are optional: the host's yaml need not know them."""
     try:
         return getattr(node, name)
     except (AttributeError, KeyError):
         return default
 
 
-# ------------------------------------------------------------------ autograd bridges
-class _L2NormFn(torch.autograd.Function):
-    """y = x / max(||x||, eps) per row (K2 forward / backward kernels)."""
-
-    @staticmethod
-    def forward(ctx, x, eps):
-        y, nrm = ops.l2norm_fwd(x.contiguous(), eps)
-        ctx.save_for_backward(y, nrm)
-        ctx.eps = eps
-        return y
-
-    @staticmethod
-    def backward(ctx, dy):
-        y, nrm = ctx.saved_tensors
-        return ops.l2norm_bwd(y, nrm, dy, ctx.eps), None
+def _first_if_list(x):
+    return (x[0], list(x[1:])) if isinstance(x, (list, tuple)) else (x, [])
 
 
-def _l2norm_rows(x, eps=0.0):
-    """Row-normalise the last dim of a >=2-D tensor through the CUDA kernel."""
-    shp = x.shape
-    y = _L2NormFn.apply(x.reshape(-1, shp[-1]), eps)
-    return y.reshape(shp)
+class _KeyBatch:
+    """The key features of one encoder pass, possibly still in flight between the GPUs.
+
+    `local` (when set) holds this rank's normalised keys in the original row order.  When the
+    keys went through the NVLink exchange instead, `xchg` holds every rank's rows in SHUFFLED
+    rank-major order and `restore` ([W, B] device int64, None without shuffle) maps original rows
+    to it; consumers index the buffer rather than materialising an un-shuffled copy.
+    """
+
+    __slots__ = ("local", "xchg", "restore", "rank", "rows")
+
+    def __init__(self, local=None, xchg=None, restore=None, rank=0, rows=0):
+        self.local, self.xchg, self.restore, self.rank, self.rows = local, xchg, restore, rank, rows
 
 
-class _MocoInfoNceFn(torch.autograd.Function):
-    """Fused l2-norm + logits + InfoNCE, forward and backward in one pass (K2+K3)."""
-
-    @staticmethod
-    def forward(ctx, feat_q, queue, T, want_logits, impl, enqueue, *keys):
-        # enqueue = (ptr, status) folds K4 for keys[0] into the same launch (after the loss
-        # has been computed against the old queue, models/contrastive.py:486-503)
-        out = ops.moco_infonce(feat_q.detach().contiguous(), [k.detach().contiguous() for k in keys],
-                               queue, T, want_logits=want_logits, impl=impl, enqueue=enqueue)
-        ctx.save_for_backward(out["dfeat"])
-        logits = out["logits"] if want_logits else feat_q.new_empty(0)
-        ctx.mark_non_differentiable(logits, out["q"])
-        return out["loss"].reshape(()), logits, out["q"]
-
-    @staticmethod
-    def backward(ctx, g_loss, g_logits, g_q):
-        (dfeat,) = ctx.saved_tensors
-        return (dfeat * g_loss,) + (None,) * (len(ctx.needs_input_grad) - 1)
-
-
-class _ByolSimFn(torch.autograd.Function):
-    """-mean(p.k)/T with the predictor l2-norm fused in (K7)."""
-
-    @staticmethod
-    def forward(ctx, pred, key, T, normalize):
-        loss, dpred = ops.byol_simloss(pred.detach().contiguous(), key.detach().contiguous(), T,
-                                       normalize=normalize, want_grad=True)
-        ctx.save_for_backward(dpred)
-        return loss.reshape(())
-
-    @staticmethod
-    def backward(ctx, g):
-        (dpred,) = ctx.saved_tensors
-        return dpred * g, None, None, None
-
-
-class _NtXentFn(torch.autograd.Function):
-    """SimCLR NT-Xent over this rank's rows against all gathered columns (K6 + C4/C5)."""
-
-    @staticmethod
-    def forward(ctx, feat1, feat2, T, impl):
-        loss, d1, d2 = ops.ntxent(feat1.detach().contiguous(), feat2.detach().contiguous(), T, impl=impl)
-        ctx.save_for_backward(d1, d2)
-        return loss.reshape(())
-
-    @staticmethod
-    def backward(ctx, g):
-        d1, d2 = ctx.saved_tensors
-        return d1 * g, d2 * g, None, None
-
-
-class _SwavCeFn(torch.autograd.Function):
-    """SwAV soft-target cross-entropy over all (assign crop, other crop) pairs (K11)."""
-
-    @staticmethod
-    def forward(ctx, output, codes, n_crops, bs, T):
-        loss, dout = ops.swav_ce(output.detach().contiguous(), codes, n_crops, bs, T)
-        ctx.save_for_backward(dout)
-        return loss.reshape(())
-
-    @staticmethod
-    def backward(ctx, g):
-        (dout,) = ctx.saved_tensors
-        return dout * g, None, None, None, None
-
-
-# ------------------------------------------------------------------------ the model
 class ContrastiveModel(nn.Module):
-    """Contrastive head in its mem / moco / byol / swav / simclr modes."""
+    """Contrastive head in its mem / moco / byol / swav / simclr modes (models/contrastive.py:31-916)."""
 
     def __init__(self, cfg):
         super(ContrastiveModel, self).__init__()
-        self.backbone = _MODEL_TYPES[cfg.MODEL.ARCH](cfg)
-        self.type = cfg.CONTRASTIVE.TYPE
-        self.T = cfg.CONTRASTIVE.T
-        self.dim = cfg.CONTRASTIVE.DIM
-        self.length = cfg.CONTRASTIVE.LENGTH
-        self.k = cfg.CONTRASTIVE.QUEUE_LEN
-        self.mmt = cfg.CONTRASTIVE.MOMENTUM
-        self.momentum_annealing = cfg.CONTRASTIVE.MOMENTUM_ANNEALING
-        self.duration = 1
+        ct = cfg.CONTRASTIVE
         self.cfg = cfg
+        self.backbone = _MODEL_TYPES[cfg.MODEL.ARCH](cfg)
+        self.type, self.T, self.dim = ct.TYPE, ct.T, ct.DIM
+        self.length, self.k = ct.LENGTH, ct.QUEUE_LEN
+        self.mmt, self.momentum_annealing = ct.MOMENTUM, ct.MOMENTUM_ANNEALING
+        self.duration = 1
         self.num_gpus = cfg.NUM_GPUS
         self.l2_norm = Normalize()
         self.knn_num_imgs = 0
-        self.knn_on = cfg.CONTRASTIVE.KNN_ON
+        self.knn_on = ct.KNN_ON
         self.train_labels = np.zeros((0,), dtype=np.int32)
         self.num_pos = 2
-        self.num_crops = self.cfg.DATA.TRAIN_CROP_NUM_TEMPORAL * self.cfg.DATA.TRAIN_CROP_NUM_SPATIAL
+        self.num_crops = cfg.DATA.TRAIN_CROP_NUM_TEMPORAL * cfg.DATA.TRAIN_CROP_NUM_SPATIAL
         self.nce_loss_fun = losses.get_loss_func("contrastive_loss")(reduction="mean")
         self.softmax = nn.Softmax(dim=1)
-        # B200-path knobs (not in the reference)
+
+        # ---- knobs of the B200 path (absent from the reference)
         self.materialize_logits = True
         self.infonce_impl = _lib.IMPL_AUTO
-        self.ntxent_impl = _lib.IMPL_AUTO  # tcgen05 (tf32, both operands rounded to nearest) when D allows; IMPL_SIMT = exact fp32
-        self._ema_plan = None
-        self._iter_mirror = None
-        self._dummy_logits = None
-        # C3 over NVLink peer memory instead of NCCL (ops.PeerExchange); opt-in because it needs all
-        # ranks of the (local) group on one box: cfg.CONTRASTIVE.PEER_EXCHANGE or enable_peer_exchange().
-        self._peer_exchange_on = bool(_cfg_get(cfg.CONTRASTIVE, "PEER_EXCHANGE", False))
+        self.ntxent_impl = _lib.IMPL_AUTO  # tcgen05 tf32 when D allows it; IMPL_SIMT = exact fp32
+        self.queue_mode = str(_opt(ct, "QUEUE_MODE", "reference"))
+        assert self.queue_mode in QUEUE_MODES, "CONTRASTIVE.QUEUE_MODE must be one of %s" % (QUEUE_MODES,)
+        # C3 over NVLink peer memory: None = decide at the first multi-GPU step (on when all ranks of
+        # the shuffle group share one box and CUDA IPC works), True / False = forced
+        self._peer_exchange_on = _opt(ct, "PEER_EXCHANGE", None)
         self._peer_xchgs = {}
-        self.register_buffer("_status", torch.zeros(1, dtype=torch.int32), persistent=False)
+        self._ema = None          # (online params, history params, ops.EmaPlan)
+        self._iter_seen = None    # host mirror of `iter`: [(data_ptr, version), value]
+        self._const = {}          # small cached device constants (dummy logits, row index ranges)
+        self._status = torch.zeros(1, dtype=torch.int32)  # device status word; plain attribute, moved by _apply
 
-        if self.type == "mem":
-            self.mem_type = cfg.CONTRASTIVE.MEM_TYPE
-            if self.mem_type == "1d":
-                self.memory = Memory1D(self.length, self.duration, self.dim, cfg)
-            else:
-                self.memory = Memory(self.length, self.duration, self.dim, cfg)
-            self.examplar_type = "video"
-            self.interp = cfg.CONTRASTIVE.INTERP_MEMORY
-        elif self.type == "self":
-            pass
-        elif self.type == "moco" or self.type == "byol":
-            self.backbone_hist = _MODEL_TYPES[cfg.MODEL.ARCH](cfg)
-            for p in self.backbone_hist.parameters():
-                p.requires_grad = False
-            self.register_buffer("ptr", torch.tensor([0]))
-            self.ptr.requires_grad = False
-            stdv = 1.0 / math.sqrt(self.dim / 3)
-            self.register_buffer("queue_x", torch.rand(self.k, self.dim).mul_(2 * stdv).add_(-stdv))
-            self.register_buffer("iter", torch.zeros([1], dtype=torch.long))
-            self._batch_shuffle_on = (
-                False
-                if ("sync" in cfg.BN.NORM_TYPE and cfg.BN.NUM_SYNC_DEVICES == cfg.NUM_GPUS)
-                or self.type == "byol"
-                else True
-            )
-        elif self.type == "swav":
-            self.swav_use_public_code = True
-            n_proto = int(_cfg_get(cfg.CONTRASTIVE, "SWAV_NUM_PROTOTYPES", 1000))
-            self.swav_prototypes = nn.Linear(self.dim, n_proto, bias=False)
-            self.swav_eps_sinkhorn = 0.05
-            self.swav_use_the_queue = False
-            if self.cfg.CONTRASTIVE.SWAV_QEUE_LEN > 0:
-                self.register_buffer(
-                    "queue_swav",
-                    torch.zeros(2, self.cfg.CONTRASTIVE.SWAV_QEUE_LEN // du.get_world_size(), self.dim))
-        elif self.type == "simclr":
-            # the reference precomputes float64 pos/neg masks here (:806-846) that its
-            # live loss never reads (distributed_loss=False, :748; SURVEY §9 Q8).
-            self.pos_mask, self.neg_mask = [], None
-        self.simclr_dist_on = cfg.CONTRASTIVE.SIMCLR_DIST_ON
-
+        build = getattr(self, "_build_" + self.type, None)
+        if build is not None:
+            build(cfg)
+        self.simclr_dist_on = ct.SIMCLR_DIST_ON
         if self.knn_on:
             self.knn_mem = Memory(self.length, 1, self.dim, cfg)
 
-    # -------------------------------------------------------------- housekeeping
+    # ---- per-mode state (buffer names / shapes / dtypes / draw order = the checkpoint contract, :72-129)
+    def _build_mem(self, cfg):
+        self.mem_type = cfg.CONTRASTIVE.MEM_TYPE
+        bank = Memory1D if self.mem_type == "1d" else Memory
+        self.memory = bank(self.length, self.duration, self.dim, cfg)
+        self.examplar_type = "video"
+        self.interp = cfg.CONTRASTIVE.INTERP_MEMORY
+
+    def _build_momentum_pair(self, cfg):
+        self.backbone_hist = _MODEL_TYPES[cfg.MODEL.ARCH](cfg)
+        for p in self.backbone_hist.parameters():
+            p.requires_grad = False
+        self.register_buffer("ptr", torch.tensor([0]))
+        self.ptr.requires_grad = False
+        self.register_buffer("queue_x", _bank_init(self.k, self.dim))
+        self.register_buffer("iter", torch.zeros([1], dtype=torch.long))
+        # shuffle BN is pointless when sync-BN already spans every GPU, and BYOL never shuffles (:91-99)
+        bn = cfg.BN
+        spans_all = "sync" in bn.NORM_TYPE and bn.NUM_SYNC_DEVICES == cfg.NUM_GPUS
+        self._batch_shuffle_on = not (spans_all or self.type == "byol")
+
+    _build_moco = _build_momentum_pair
+    _build_byol = _build_momentum_pair
+
+    def _build_swav(self, cfg):
+        self.swav_use_public_code = True
+        n_proto = int(_opt(cfg.CONTRASTIVE, "SWAV_NUM_PROTOTYPES", 1000))
+        self.swav_prototypes = nn.Linear(self.dim, n_proto, bias=False)
+        self.swav_eps_sinkhorn = 0.05
+        self.swav_use_the_queue = False
+        rows = cfg.CONTRASTIVE.SWAV_QEUE_LEN
+        if rows > 0:
+            self.register_buffer("queue_swav", torch.zeros(2, rows // du.get_world_size(), self.dim))
+
+    def _build_simclr(self, cfg):
+        self._simclr_precompute_pos_neg_mask_multi()
+
+    def _simclr_precompute_pos_neg_mask_multi(self):
+        """The reference builds float64 masks here (:806-846) that only its dead `distributed_loss`
+        branch (:748-768) reads; the attributes exist, empty."""
+        self.pos_mask, self.neg_mask = [], None
+
+    # ------------------------------------------------------------------ housekeeping
     def _apply(self, fn, *args, **kwargs):
-        # .cuda()/.to()/.float() move parameter storage: drop cached pointer tables
-        self._ema_plan = None
-        self._iter_mirror = None
-        self._dummy_logits = None
-        return super(ContrastiveModel, self)._apply(fn, *args, **kwargs)
+        # .cuda() / .to() / .float() move storages: every cached device pointer or constant is stale
+        self._ema = None
+        self._iter_seen = None
+        self._const = {}
+        out = super(ContrastiveModel, self)._apply(fn, *args, **kwargs)
+        self._status = fn(self._status)
+        return out
 
-    def enable_peer_exchange(self, on=True):
-        """Route the key gather of `_batch_unshuffle` (C3) through NVLink peer stores + epoch flags
-        (ops.PeerExchange) instead of an NCCL all_gather.  Collective: call it on every rank; all
-        ranks of the shuffle group must sit on one box."""
-        self._peer_exchange_on = bool(on)
-        if not on:
-            for ex in self._peer_xchgs.values():
-                ex.close()
-            self._peer_xchgs = {}
-        return self
-
-    def _peer_xchg(self, rows, dim, local):
-        key = (rows, dim, bool(local))
-        ex = self._peer_xchgs.get(key)
-        if ex is None:
-            ex = ops.PeerExchange(rows, dim, group=du._LOCAL_PROCESS_GROUP if local else None)
-            self._peer_xchgs[key] = ex
-        return ex
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._iter_seen = None  # `iter` may change under us
+        return super(ContrastiveModel, self)._load_from_state_dict(*args, **kwargs)
 
     def check_device_status(self):
-        """Host check of the device status word that replaces the reference's host
-        asserts on `ptr` / bank indices (synchronises; call it off the step path)."""
+        """Raise what the reference's host asserts on `ptr` / bank indices would have raised, from the
+        device status word (one synchronisation: call it at logging / epoch boundaries)."""
         flags = int(self._status.item())
         assert not (flags & _lib.DEVFLAG_QUEUE_OVERRUN), "queue overrun: ptr + n > K (models/contrastive.py:285)"
         if flags & _lib.DEVFLAG_BAD_INDEX:
-            raise IndexError("memory-bank index out of range")
+            raise IndexError("memory-bank / exchange index out of range")
+        if flags & _lib.DEVFLAG_PEER_TIMEOUT:
+            raise RuntimeError("a peer rank's keys did not arrive within the exchange timeout (dead or stalled rank)")
         return flags
 
-    def _cached_dummy_logits(self, n, device):
-        """K8: [n, K+1] zeros with column 0 = 9999 (models/contrastive.py:585-592),
-        built once on the device instead of on the CPU every step."""
-        d = self._dummy_logits
-        if d is None or d.shape[0] != n or d.device != device:
-            d = torch.zeros(n, self.k + 1, dtype=torch.float, device=device)
-            d[:, 0] = 9999.0
-            self._dummy_logits = d
-        return d
+    def _cached(self, key, make):
+        t = self._const.get(key)
+        if t is None:
+            t = self._const[key] = make()
+        return t
 
-    # --------------------------------------------------------------------- kNN bank
+    def _cached_dummy_logits(self, n, device):
+        """K8: zeros [n, K+1] with column 0 = 9999 (:585-592), built once on the device."""
+        def make():
+            t = torch.zeros(n, self.k + 1, dtype=torch.float, device=device)
+            t[:, 0] = 9999.0
+            return t
+        return self._cached(("dummy", n, device), make)
+
+    def _row_range(self, lo, hi, device):
+        return self._cached(("rows", lo, hi, device), lambda: torch.arange(lo, hi, dtype=torch.int64, device=device))
+
+    # ---------------------------------------------------------------------- kNN bank
     @torch.no_grad()
     def knn_mem_update(self, q_knn, index):
         if self.knn_on:
@@ -301,12 +239,11 @@ class ContrastiveModel(nn.Module):
 
     @torch.no_grad()
     def init_knn_labels(self, train_loader):
+        """Labels of the whole training set next to the kNN bank (:142-156)."""
         logger.info("initializing knn labels")
-        self.num_imgs = len(train_loader.dataset._labels)
-        self.train_labels = np.zeros((self.num_imgs,), dtype=np.int32)
-        for i in range(self.num_imgs):
-            self.train_labels[i] = train_loader.dataset._labels[i]
-        self.train_labels = torch.LongTensor(self.train_labels).to(self.knn_mem.memory.device)
+        labels = np.asarray(train_loader.dataset._labels, dtype=np.int32)
+        self.num_imgs = int(labels.shape[0])
+        self.train_labels = torch.from_numpy(labels).long().to(self.knn_mem.memory.device)
         if self.length != self.num_imgs:
             logger.error("Kinetics dataloader size: {} differs from memorybank length {}".format(
                 self.num_imgs, self.length))
@@ -314,224 +251,291 @@ class ContrastiveModel(nn.Module):
 
     @torch.no_grad()
     def eval_knn(self, q_knn, knn_k=200):
-        # eval-only: stock cuBLAS + topk
-        dist = torch.einsum("nc,mc->nm", q_knn.view(q_knn.size(0), -1),
-                            self.knn_mem.memory.view(self.knn_mem.memory.size(0), -1))
-        yd, yi = dist.topk(knn_k, dim=1, largest=True, sorted=True)
-        return yd, yi
+        """Similarity of the queries to every bank row and its top-k (:232-241); eval only."""
+        bank = self.knn_mem.memory
+        sims = q_knn.reshape(q_knn.size(0), -1) @ bank.reshape(bank.size(0), -1).t()
+        return sims.topk(knn_k, dim=1, largest=True, sorted=True)
 
-    # ------------------------------------------------------------------- K1: EMA
-    def _ema_lists(self):
+    # ------------------------------------------------------------------- K1: momentum update
+    def _ema_state(self):
+        """Parameter pairs in `backbone_hist.named_parameters()` order (:164-172) and the device
+        pointer table over them.  The table caches raw addresses, so it is re-validated on every
+        call: anything that re-seats a parameter's storage without `_apply` (`p.data = ...` as the
+        reference itself does, `load_state_dict(assign=True)`, flattening) rebuilds it."""
+        st = self._ema
+        if st is not None:
+            on, hi, plan = st
+            if plan.matches([p.data for p in on], [p.data for p in hi]):
+                return st
         online = dict(self.backbone.named_parameters())
-        o_list, h_list = [], []
-        for name, p in self.backbone_hist.named_parameters():
-            o_list.append(online[name].data)
-            h_list.append(p.data)
-        return o_list, h_list
+        pairs = [(online[name], p) for name, p in self.backbone_hist.named_parameters()]
+        on, hi = [a for a, _ in pairs], [b for _, b in pairs]
+        self._ema = st = (on, hi, ops.EmaPlan([p.data for p in on], [p.data for p in hi]))
+        return st
+
+    def _ema_lists(self):
+        on, hi, _ = self._ema_state()
+        return [p.data for p in on], [p.data for p in hi]
 
     @torch.no_grad()
     def _update_history(self, _bump_iter=False):
-        """Momentum update of the key encoder (models/contrastive.py:158-172) as one
-        multi-tensor launch; `iter` is read on the device (no int(self.iter) sync)."""
-        if self._ema_plan is None:
-            o_list, h_list = self._ema_lists()
-            self._ema_plan = ops.EmaPlan(o_list, h_list)
-        # host mirror of `iter`: our kernels bump the buffer through its raw pointer, which leaves
-        # the tensor's version counter alone; any torch-side write (load_state_dict, zero_(), ...)
-        # changes it and forces one re-read.  Steady state: no D2H sync at all.
-        key = (self.iter.data_ptr(), self.iter._version)
-        if self._iter_mirror is None or self._iter_mirror[0] != key:
-            self._iter_mirror = [key, int(self.iter.item())]
-        self._ema_plan.run(self.mmt, self.iter, bump_iter=_bump_iter, first_iter=self._iter_mirror[1] == 0)
+        """hist <- online*(1-m) + hist*m over every parameter in ONE launch (:158-172).  Whether this is
+        step 0 (copy first, then blend) comes from a host mirror of `iter`: the kernels bump the
+        buffer through its raw pointer (tensor version untouched), any torch-side write bumps the
+        version and costs one re-read.  Steady state: no device->host traffic."""
+        _, _, plan = self._ema_state()
+        tag = (self.iter.data_ptr(), self.iter._version)
+        if self._iter_seen is None or self._iter_seen[0] != tag:
+            self._iter_seen = [tag, int(self.iter.item())]
+        plan.run(self.mmt, self.iter, bump_iter=_bump_iter, first_iter=self._iter_seen[1] == 0)
         if _bump_iter:
-            self._iter_mirror[1] += 1
-
-    # ------------------------------------------------------ shuffle BN (A6, C1-C3)
-    @torch.no_grad()
-    def _batch_shuffle(self, x):
-        if len(x) == 2:
-            another_crop = True
-        else:
-            another_crop = False
-        if another_crop:
-            x, x_crop = x[0], x[1]
-        else:
-            x = x[0]
-
-        world_size = self.cfg.NUM_GPUS * self.cfg.NUM_SHARDS
-        bsz = x.shape[0]
-        if self.num_gpus > 1:
-            if self.cfg.CONTRASTIVE.LOCAL_SHUFFLE_BN:
-                world_size = du.get_local_size()
-                gpu_idx = du.get_local_rank()
-            else:
-                gpu_idx = torch.distributed.get_rank()
-            n_total = bsz * world_size
-        else:
-            n_total = bsz
-
-        idx_randperm = torch.randperm(n_total).to(x.device)  # rank 0's CPU RNG, as the reference
-        if self.num_gpus > 1:
-            torch.distributed.broadcast(idx_randperm, src=0)
-        else:
-            gpu_idx = 0
-        idx_randperm = idx_randperm.view(world_size, -1)
-        if self.num_gpus > 1:
-            # C1 as an all-to-all: only the rows this rank keeps cross the fabric
-            # (the reference all_gathers the whole batch and discards (W-1)/W of it).
-            x = _exchange_rows(x, idx_randperm, gpu_idx, world_size)
-            if another_crop:
-                x_crop = _exchange_rows(x_crop, idx_randperm, gpu_idx, world_size)
-        else:
-            x = x[idx_randperm[gpu_idx, :]]
-            if another_crop:
-                x_crop = x_crop[idx_randperm[gpu_idx, :]]
-
-        idx_restore = torch.argsort(idx_randperm.view(-1))
-        idx_restore = idx_restore.view(world_size, -1)
-        if another_crop:
-            return [x, x_crop], idx_restore
-        else:
-            return [x], idx_restore
-
-    @torch.no_grad()
-    def _batch_unshuffle(self, x, idx_restore):
-        if (self.num_gpus > 1 and self._peer_exchange_on and x.is_cuda and x.dim() == 2
-                and x.dtype == torch.float32 and x.shape[1] % 4 == 0):
-            # C3 without a collective kernel: push this rank's keys into every peer's buffer, then
-            # wait + select idx_restore[rank] in one small launch (bit-identical to the path below)
-            local = bool(self.cfg.CONTRASTIVE.LOCAL_SHUFFLE_BN)
-            gpu_idx = du.get_local_rank() if local else torch.distributed.get_rank()
-            ex = self._peer_xchg(x.shape[0], x.shape[1], local)
-            ex.push(x.contiguous())
-            return ex.wait_gather(idx_restore[gpu_idx, :].contiguous(), status=self._status)
-        if self.num_gpus > 1:
-            if self.cfg.CONTRASTIVE.LOCAL_SHUFFLE_BN:
-                x = du.cat_all_gather(x, local=True)
-                gpu_idx = du.get_local_rank()
-            else:
-                x = du.cat_all_gather(x)
-                gpu_idx = torch.distributed.get_rank()
-        else:
-            gpu_idx = 0
-        idx = idx_restore[gpu_idx, :]
-        x = x[idx]
-        return x
-
-    # ---------------------------------------------------------------------- BYOL
-    def sim_loss(self, q, k):
-        """models/contrastive.py:243-249 (q already normalised)."""
-        return _ByolSimFn.apply(q, k, self.T, False)
+            self._iter_seen[1] += 1
 
     @torch.no_grad()
     def momentum_anneal_cosine(self, epoch_exact):
-        self.mmt = (1 - (1 - self.cfg.CONTRASTIVE.MOMENTUM)
-                    * (math.cos(math.pi * epoch_exact / self.cfg.SOLVER.MAX_EPOCH) + 1.0) * 0.5)
+        """m = 1 - (1 - m0) (cos(pi e / E) + 1) / 2 in host fp64 (:251-261)."""
+        base = self.cfg.CONTRASTIVE.MOMENTUM
+        phase = math.cos(math.pi * epoch_exact / self.cfg.SOLVER.MAX_EPOCH) + 1.0
+        self.mmt = 1 - (1 - base) * phase * 0.5
 
-    # ----------------------------------------------------------------- K4: queue
+    # --------------------------------------------------------- shuffle BN (A6; C1, C2, C3)
+    def _shuffle_scope(self):
+        """(group, size, rank) the shuffle runs over: the local process group under LOCAL_SHUFFLE_BN
+        (:185-197), else WORLD."""
+        if self.num_gpus <= 1:
+            return None, 1, 0
+        if self.cfg.CONTRASTIVE.LOCAL_SHUFFLE_BN:
+            return du._LOCAL_PROCESS_GROUP, du.get_local_size(), du.get_local_rank()
+        return None, self.cfg.NUM_GPUS * self.cfg.NUM_SHARDS, torch.distributed.get_rank()
+
+    @torch.no_grad()
+    def _batch_shuffle(self, x):
+        """x: [clip] or [clip, crop].  Returns ([shuffled...], idx_restore) like the reference; the rows
+        this rank ends up with are those of `cat_all_gather(x)[perm.view(W, -1)[rank]]`."""
+        assert len(x) in (1, 2)
+        group, size, rank = self._shuffle_scope()
+        bsz = x[0].shape[0]
+        # every rank consumes its CPU generator exactly like the reference (:198); rank 0's draw wins (C2)
+        perm = torch.randperm(bsz * size)
+        if self.num_gpus > 1:
+            perm = broadcast_from_rank0(perm, x[0].device)
+        plan = ShufflePlan(perm.numpy(), size, rank, bsz, x[0].device)
+        if x[0].is_cuda and torch.cuda.is_current_stream_capturing():
+            # the captured upload nodes read the plan's pinned host buffers on every replay
+            self._const.setdefault("captured_plans", []).append(plan)
+        return [plan.shuffled(t, group) for t in x], plan.restore
+
+    def _use_peer_exchange(self, x):
+        """Can the key gather for `x` go over NVLink peer memory?  Decided (collectively) once."""
+        if not (x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and x.shape[1] % 4 == 0):
+            return False
+        if self._peer_exchange_on is None:
+            group, size, _ = self._shuffle_scope()
+            one_box = int(_opt(self.cfg, "NUM_SHARDS", 1)) == 1 or (self.cfg.CONTRASTIVE.LOCAL_SHUFFLE_BN and group is not None)
+            on = bool(one_box) and size <= _lib.MAX_PEERS
+            if on:
+                try:  # PeerExchange raises on every rank together or on none
+                    self._peer_xchg(x.shape[0], x.shape[1])
+                except _lib.AvsslError as e:
+                    logger.warning("NVLink peer exchange unavailable, using NCCL all_gather: %s", e)
+                    on = False
+            self._peer_exchange_on = on
+        return bool(self._peer_exchange_on)
+
+    def enable_peer_exchange(self, on=True):
+        """Force the key exchange (C3) onto NVLink peer memory (`ops.PeerExchange`) or back onto NCCL.
+        Collective: call it on every rank."""
+        self._peer_exchange_on = bool(on)
+        if not on:
+            for ex in self._peer_xchgs.values():
+                ex.close()
+            self._peer_xchgs = {}
+        return self
+
+    def _peer_xchg(self, rows, dim):
+        key = (rows, dim)
+        ex = self._peer_xchgs.get(key)
+        if ex is None:
+            group, _, _ = self._shuffle_scope()
+            ex = self._peer_xchgs[key] = ops.PeerExchange(rows, dim, group=group)
+        return ex
+
+    @torch.no_grad()
+    def _batch_unshuffle(self, x, idx_restore):
+        """Rows of this rank's ORIGINAL batch out of the per-rank results `x` computed on the shuffled
+        batch: cat_all_gather(x)[idx_restore[rank]] (:216-230)."""
+        group, size, rank = self._shuffle_scope()
+        mine = idx_restore[rank, :]
+        if size == 1:
+            return x[mine]
+        if self._use_peer_exchange(x):
+            ex = self._peer_xchg(x.shape[0], x.shape[1])
+            ex.push(x.contiguous())
+            return ex.wait_gather(mine.contiguous(), status=self._status)
+        everyone = du.cat_all_gather(x, local=bool(self.cfg.CONTRASTIVE.LOCAL_SHUFFLE_BN))
+        return everyone[mine]
+
+    # ---------------------------------------------------------------------- BYOL
+    def sim_loss(self, q, k):
+        """-mean(sum_c q k) / T for already-normalised q (:243-249)."""
+        return ByolSimilarity.apply(q, k, self.T, False)
+
+    # ------------------------------------------------------------------- K4 (+ C9): queue
+    def _queue_rows_across_ranks(self, key):
+        """C9.  The reference enqueues each rank's own keys and relies on DDP re-broadcasting rank 0's
+        buffers before every forward (models/build.py:76-83), so what survives in every queue is rank
+        0's keys.  "reference": take rank 0's rows directly (32 KB broadcast instead of 33.5 MB);
+        "canonical": all ranks' rows in rank order; "local": this rank's rows."""
+        if self.num_gpus <= 1 or self.queue_mode == "local":
+            return key
+        if self.queue_mode == "canonical":
+            return du.cat_all_gather(key.contiguous())
+        shared = key.contiguous().clone()
+        torch.distributed.broadcast(shared, src=0)
+        return shared
+
     @torch.no_grad()
     def _dequeue_and_enqueue(self, keys, extra_keys=None):
-        if not self.cfg.CONTRASTIVE.MOCO_MULTI_VIEW_QUEUE:
-            keys_queue_update = [keys[0]]
-        else:
+        """queue_x[ptr:ptr+n] = rows; ptr = (ptr + n) wrapping exactly at K (:263-292), `ptr` never
+        leaving the device.  keys[0] only, unless MOCO_MULTI_VIEW_QUEUE adds the other views and
+        `extra_keys`."""
+        batch = [keys[0]]
+        if self.cfg.CONTRASTIVE.MOCO_MULTI_VIEW_QUEUE:
             assert len(keys) > 0, "need to have multiple views for adding them to queue"
-            keys_queue_update = []
-            keys_queue_update += keys
-            if extra_keys:
-                keys_queue_update += [item for sublist in extra_keys for item in sublist]
-        for key in keys_queue_update:
-            num_items = int(key.size(0))
-            assert self.k % num_items == 0
-            # `assert ptr + num_items <= self.k` (:285) is evaluated on the device
-            ops.queue_enqueue(self.queue_x, self.ptr, key.detach().contiguous(), self._status)
+            batch = list(keys)
+            for group in (extra_keys or []):
+                batch.extend(group)
+        for key in batch:
+            rows = self._queue_rows_across_ranks(key.detach())
+            assert self.k % int(rows.size(0)) == 0  # :284; `ptr + n <= K` (:285) is checked on the device
+            ops.queue_enqueue(self.queue_x, self.ptr, rows.contiguous(), self._status)
 
+    # ---------------------------------------------------------------- key features (A5)
     @torch.no_grad()
     def batch_clips(self, clips):
-        clips_batched = [None] * len(clips[0])
-        for i, clip in enumerate(clips):
-            for j, view in enumerate(clip):
-                if i == 0:
-                    clips_batched[j] = view
-                else:
-                    clips_batched[j] = torch.cat([clips_batched[j], view], dim=0)
-                del view
-        return clips_batched
+        """[[pathway tensors] per clip] -> [per pathway: all clips stacked along the batch] (:294-306)."""
+        if len(clips) == 1:
+            return list(clips[0])
+        return [torch.cat([clip[j] for clip in clips], dim=0) for j in range(len(clips[0]))]
+
+    def _normalised_keys(self, feats, restore, defer):
+        """Normalize + un-shuffle of one [rows, D] output of the key encoder.  With `defer` and a usable
+        NVLink exchange both happen in ONE launch (normalise and store into every rank's buffer) and the
+        rows stay in the buffer for the head kernel to index; otherwise this rank's rows come back."""
+        shuffled = restore is not None
+        _, size, rank = self._shuffle_scope()
+        # through the exchange buffer when rows must cross ranks (un-shuffle, or the queue rows of C9), and
+        # also on one GPU when the head launch can do the un-shuffle gather by index (defer)
+        via_buffer = (shuffled and (defer or size > 1)) or (size > 1 and defer and self.queue_mode != "local")
+        if via_buffer and self._use_peer_exchange(feats):
+            ex = self._peer_xchg(feats.shape[0], feats.shape[1])
+            ex.push_normalized(feats.contiguous(), 0.0)
+            pending = _KeyBatch(xchg=ex, restore=restore, rank=rank, rows=feats.shape[0])
+            if defer:
+                return pending
+            return _KeyBatch(local=ex.wait_gather(self._local_rows(pending), status=self._status))
+        keys = self.l2_norm(feats)
+        if shuffled:
+            keys = self._batch_unshuffle(keys, restore).detach()
+        return _KeyBatch(local=keys)
+
+    def _local_rows(self, kb):
+        """Index of this rank's original rows in the exchange buffer (None = its own block, in order)."""
+        return None if kb.restore is None else kb.restore[kb.rank, :].contiguous()
+
+    def _queue_rows(self, kb, device):
+        """Rows of the exchange buffer that go into the queue under `queue_mode` (C9), None = own block."""
+        n, world = kb.rows, kb.xchg.world
+        if self.queue_mode == "local":
+            return self._local_rows(kb)
+        if self.queue_mode == "reference":
+            return kb.restore[0, :].contiguous() if kb.restore is not None else self._row_range(0, n, device)
+        return kb.restore.reshape(-1).contiguous() if kb.restore is not None else self._row_range(0, world * n, device)
+
+    def _shuffle_ahead(self, groups):
+        """Shuffle every key clip NOW, on a side stream, so that the index uploads, the row gathers and
+        (W > 1) the all-to-all of the clip rows (C1) run underneath the momentum update that the caller
+        launches next on the main stream (north_star: the exchange overlaps the EMA kernel)."""
+        dev_t = groups[0][0]
+        if not dev_t.is_cuda:
+            return [self._batch_shuffle(clip) for clip in groups], None
+        main = torch.cuda.current_stream(dev_t.device)
+        side = self._cached(("side_stream", dev_t.device), lambda: torch.cuda.Stream(device=dev_t.device, priority=-1))
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            done = [self._batch_shuffle(clip) for clip in groups]
+        for views, restore in done:
+            for t in list(views) + [restore]:
+                t.record_stream(main)
+        return done, side
+
+    def _encode_keys(self, clip, restore, want_pred, defer=False):
+        """One pass of the key encoder over one (possibly batched, already shuffled) clip: forward,
+        Normalize, un-shuffle (:335-357).  Returns (_KeyBatch, [predictor keys])."""
+        feats, heads = _first_if_list(self.backbone_hist(clip))
+        pred = []
+        if want_pred:
+            pred = [self._normalised_keys(h, restore, False).local for h in heads]
+        return self._normalised_keys(feats, restore, defer), pred
 
     @torch.no_grad()
     def compute_key_feat(self, clips_k, compute_predictor_keys=False, batched_inference=True):
+        """Momentum-update the key encoder, count the iteration, and run it over the key clips (:308-371).
+        Returns the list of [B, D] keys (and the list of predictor-key lists when asked)."""
+        out = self._key_batches(clips_k, compute_predictor_keys, batched_inference, defer=False)
+        keys = [kb.local for kb in out[0]]
+        return (keys, out[1]) if compute_predictor_keys else keys
+
+    @torch.no_grad()
+    def _key_batches(self, clips_k, want_pred, batched_inference, defer):
         assert self.training
-        # momentum update key encoder + `self.iter += 1` (:313-314), one launch
-        self._update_history(_bump_iter=True)
         n_clips = len(clips_k)
-        bsz = clips_k[0][0].shape[0]
-        if n_clips * bsz * clips_k[0][0].numel() > 4 * 64 * 3 * 8 * 224 * 224:
-            batched_inference = False  # hack to avoid oom on large inputs
         assert n_clips > 0
-        if batched_inference and all(
-            [clips_k[i][j].shape[1:] == clips_k[0][j].shape[1:]
-             for i in range(len(clips_k)) for j in range(len(clips_k[i]))]):
-            clips_k = [self.batch_clips(clips_k)]
-            batched = True
-        else:
-            batched = False
+        bsz = clips_k[0][0].shape[0]
+        # the reference's size test (:318-319; numel() already includes the batch, SURVEY §9 Q14)
+        if n_clips * bsz * clips_k[0][0].numel() > 4 * 64 * 3 * 8 * 224 * 224:
+            batched_inference = False
+        same_shape = all(view.shape[1:] == ref.shape[1:] for clip in clips_k for view, ref in zip(clip, clips_k[0]))
+        batched = bool(batched_inference and same_shape)
+        # all key clips through the encoder as one batch, split back per clip afterwards (:321-331, :359-369)
+        groups = [self.batch_clips(clips_k)] if batched else list(clips_k)
+        restores, side = [None] * len(groups), None
+        if self._batch_shuffle_on:
+            done, side = self._shuffle_ahead(groups)
+            groups, restores = [g for g, _ in done], [r for _, r in done]
+        self._update_history(_bump_iter=True)  # :313-314, one launch; the shuffles above run beside it
+        if side is not None:
+            torch.cuda.current_stream(side.device).wait_stream(side)
+        defer = defer and n_clips == 1
+        encoded = [self._encode_keys(g, r, want_pred, defer) for g, r in zip(groups, restores)]
+        if not batched:
+            return [kb for kb, _ in encoded], [pk for _, pk in encoded if pk]
+        kb, pred = encoded[0]
+        if n_clips == 1:
+            return [kb], [pred]
+        keys = [_KeyBatch(local=kb.local[i * bsz:(i + 1) * bsz]) for i in range(n_clips)]
+        # (the reference slices the LIST of predictor keys here, :367 - an empty or one-element list per clip)
+        return keys, [pred[i * bsz:(i + 1) * bsz] for i in range(n_clips)]
 
-        keys, pred_keys = [], []
-        for k in range(0, len(clips_k)):
-            clip_k = clips_k[k]
-            if self._batch_shuffle_on:
-                clip_k, idx_restore = self._batch_shuffle(clip_k)
-            hist_feat = self.backbone_hist(clip_k)
-            if isinstance(hist_feat, list):
-                hist_time = hist_feat[1:]
-                hist_feat = hist_feat[0]
-                if compute_predictor_keys:
-                    tks = []
-                    for tk in hist_time:
-                        tk = self.l2_norm(tk)
-                        if self._batch_shuffle_on:
-                            tk = self._batch_unshuffle(tk, idx_restore).detach()
-                        tks.append(tk)
-                    pred_keys.append(tks)
-            x_hist = self.l2_norm(hist_feat)
-            if self._batch_shuffle_on:
-                x_hist = self._batch_unshuffle(x_hist, idx_restore).detach()
-            keys.append(x_hist)
-        if batched:
-            assert len(keys) == 1, "batched input uses single clip"
-            batched_key = keys[0]
-            if compute_predictor_keys:
-                batched_pred_key = pred_keys[0]
-            keys, pred_keys = [], []
-            for k in range(0, n_clips):
-                keys.append(batched_key[k * bsz:(k + 1) * bsz])
-                if compute_predictor_keys:
-                    pred_keys.append(batched_pred_key[k * bsz:(k + 1) * bsz])
-        if compute_predictor_keys:
-            return keys, pred_keys
-        else:
-            return keys
-
-    # -------------------------------------------------------------------- forward
+    # ------------------------------------------------------------------------ forward
     def forward(self, clips, index=None, time=None, epoch_exact=None, keys=None):
         if epoch_exact is not None and self.momentum_annealing:
             self.momentum_anneal_cosine(epoch_exact)
-
         if self.type == "mem":
             return self._forward_mem(clips, index, time)
-        elif self.type == "moco":
+        if self.type == "moco":
             return self._forward_moco(clips, index, time, keys)
-        elif self.type == "byol":
+        if self.type == "byol":
             return self._forward_byol(clips, index, keys)
-        elif self.type == "swav":
+        if self.type == "swav":
             return self._forward_swav(clips, index, epoch_exact)
-        elif self.type == "simclr":
+        if self.type == "simclr":
             return self._forward_simclr(clips, index)
-        else:
-            raise NotImplementedError()
+        raise NotImplementedError()
 
-    # models/contrastive.py:379-442
+    # ---- mem (:379-442): loss computed and dropped, returns (prod, 0.0, True) like the reference
     def _forward_mem(self, clips, index, time):
-        batch_size = clips[0].size(0)
+        n = clips[0].size(0)
         q = self.backbone(clips)
         if index is None:
             return q
@@ -540,465 +544,284 @@ class ContrastiveModel(nn.Module):
             assert self.knn_mem.duration == 1
             return self.eval_knn(q)
         time *= self.duration - 1
-        # negatives come from the CPU generator exactly as in the reference (:390-397),
-        # so a seeded run draws the same indices (RNG parity).
-        clip_ind = torch.randint(0, self.length, size=(batch_size, self.k + 1)).to(q.device)
-        clip_ind.select(1, 0).copy_(index.data)
-        if self.mem_type == "2d":
-            if self.interp:
-                time_ind = torch.empty(batch_size, self.k + 1).uniform_(0, self.duration - 1).to(q.device)
-            else:
-                time_ind = torch.randint(0, self.duration - 1, size=(batch_size, self.k + 1)).to(q.device)
+        # negatives from the CPU generator, as the reference draws them (:390-397): a seeded run sees the
+        # same indices.  Column 0 is the positive.
+        cols = self.k + 1
+        clip_ind = torch.randint(0, self.length, size=(n, cols)).to(q.device)
+        clip_ind[:, 0] = index.data
+        if self.mem_type != "2d":
+            time_ind = torch.zeros(size=(n, cols), dtype=int).to(q.device)
+        elif self.interp:
+            time_ind = torch.empty(n, cols).uniform_(0, self.duration - 1).to(q.device)
         else:
-            time_ind = torch.zeros(size=(batch_size, self.k + 1), dtype=int).to(q.device)
+            time_ind = torch.randint(0, self.duration - 1, size=(n, cols)).to(q.device)
         if self.examplar_type == "clip":
-            time_ind.select(1, 0).copy_(time.data)
-        elif self.examplar_type == "video":
-            pass
-        else:
+            time_ind[:, 0] = time.data
+        elif self.examplar_type != "video":
             raise NotImplementedError("unsupported examplar_type {}".format(self.examplar_type))
-        # K14: q . bank[ind] / T without the [B, K+1, D] gather
-        prod = _MemDotFn.apply(q, self.memory.memory, clip_ind, time_ind, self.T,
-                               bool(self.interp) and self.mem_type == "2d", self._status)
-        loss = self.nce_loss_fun(prod)  # computed and dropped, as in the reference (:436,442)
-        del loss
+        interp = bool(self.interp) and self.mem_type == "2d"
+        prod = BankDot.apply(q, self.memory.memory, clip_ind, time_ind, self.T, interp, self._status)
+        self.nce_loss_fun(prod)  # evaluated and discarded (:436, :442)
         self.memory.update(q, momentum=self.mmt, ind=index, time=time, interp=self.interp, status=self._status)
         self.knn_mem_update(q, index)
         return prod, 0.0, True
 
-    # models/contrastive.py:443-506
+    # ---- moco (:443-506)
     def _forward_moco(self, clips, index, time, keys):
+        clips_k = None
         if isinstance(clips[0], list):
-            n_clips = len(clips)
-            ind_clips = np.arange(n_clips)
-            clip_q = clips[ind_clips[0]]
-            clips_k = [clips[i] for i in ind_clips[1:]]
-            time_q = time[:, ind_clips[0], :]  # noqa: F841 (kept: raises like the reference when time is None)
-            time_k = (time[:, ind_clips[1:], :] if keys is None else time[:, ind_clips[0] + 1:, :])  # noqa: F841
+            clip_q, clips_k = clips[0], list(clips[1:])
+            time[:, 0, :], time[:, 1:, :]  # the reference slices `time` here: None raises TypeError as it does there
         else:
             clip_q = clips
-
-        feat_q = self.backbone(clip_q)
-        extra_projs = []
-        if isinstance(feat_q, list):
-            extra_projs = feat_q[1:]
-            feat_q = feat_q[0]
-            extra_projs = [self.l2_norm(feat) for feat in extra_projs]  # noqa: F841
-
+        feat_q, _extra = _first_if_list(self.backbone(clip_q))
         if index is None:
             return feat_q
         if not self.training:
             return self.eval_knn(self.l2_norm(feat_q))
 
-        if keys is None:
-            keys = self.compute_key_feat(clips_k, compute_predictor_keys=False)
-            auto_enqueue_keys = True
+        own_keys = keys is None
+        head_kw = dict(want_logits=self.materialize_logits, impl=self.infonce_impl)
+        B, D = feat_q.shape
+        # the fused ring write rides in the head launch when exactly keys[0] is enqueued (the default) and
+        # the kernel's vector path applies; anything else goes through _dequeue_and_enqueue afterwards
+        can_fuse = (own_keys and not self.cfg.CONTRASTIVE.MOCO_MULTI_VIEW_QUEUE and D % 4 == 0)
+        deferred = None
+        if own_keys:
+            defer = can_fuse and len(clips_k) == 1 and self._tc_head_ok(B, D)
+            batches, _ = self._key_batches(clips_k, False, True, defer)
+            if batches[0].xchg is not None and batches[0].local is None:
+                deferred = batches[0]
+            else:
+                keys = [kb.local for kb in batches]
+        if deferred is not None:
+            # keys still sit in the exchange buffers: the head launch waits for them, un-shuffles by index
+            # and writes the queue rows `queue_mode` asks for
+            n_enq = self._enqueue_count(deferred)
+            assert self.k % n_enq == 0  # :284
+            head_kw.update(peer=deferred.xchg, peer_row_idx=self._local_rows(deferred),
+                           enq_row_idx=self._queue_rows(deferred, feat_q.device), enqueue=(self.ptr, self._status))
+            plan = {"keys": None, "kw": head_kw}
+            fused = True
         else:
-            auto_enqueue_keys = False
-
-        # K2+K3: q = l2norm(feat_q); logits = [q.k, q.queue^T]/T; InfoNCE fwd + bwd
-        # K4 rides in the same launch when exactly keys[0] is enqueued (the default,
-        # CONTRASTIVE.MOCO_MULTI_VIEW_QUEUE off): the ring write happens behind a grid-wide
-        # barrier after the last read of the queue.
-        enqueue_here = self.training and auto_enqueue_keys
-        fused = (enqueue_here and not self.cfg.CONTRASTIVE.MOCO_MULTI_VIEW_QUEUE
-                 and keys[0].shape == feat_q.shape and self.k % int(keys[0].size(0)) == 0)
-        loss, logits, q = _MocoInfoNceFn.apply(feat_q, self.queue_x, self.T, self.materialize_logits,
-                                               self.infonce_impl, (self.ptr, self._status) if fused else None,
-                                               *keys)
-        if not self.materialize_logits:
-            logits = None
-        if enqueue_here and not fused:
+            fused = (can_fuse and tuple(keys[0].shape) == (B, D) and self.k % B == 0
+                     and (self.num_gpus <= 1 or self.queue_mode == "local"))
+            if fused:
+                head_kw["enqueue"] = (self.ptr, self._status)
+            plan = {"keys": [k.detach().contiguous() for k in keys], "kw": head_kw}
+        loss, logits, q = MocoInfoNce.apply(feat_q, self.queue_x, self.T, plan)
+        if own_keys and not fused:
             self._dequeue_and_enqueue(keys)
         self.knn_mem_update(q, index)
-        return logits, loss
+        return (logits if self.materialize_logits else None), loss
 
-    # models/contrastive.py:508-596
+    def _tc_head_ok(self, B, D):
+        return self.infonce_impl != _lib.IMPL_SIMT and D in (32, 64, 96, 128)
+
+    def _enqueue_count(self, kb):
+        return kb.rows * (kb.xchg.world if self.queue_mode == "canonical" else 1)
+
+    # ---- byol (:508-596)
     def _forward_byol(self, clips, index, keys):
-        clips_key = [None] * len(clips)
-        for i, clip in enumerate(clips):
-            p = []
-            for path in clip:
-                p.append(path)
-            clips_key[i] = p
-        if isinstance(clips[0], list):
-            n_clips = len(clips)
-            clip_q = clips[0]
-        else:
-            clip_q = clips
-
-        feat_q = self.backbone(clip_q)
-        if isinstance(feat_q, list):
-            predictors = feat_q[1:]
-            feat_q = feat_q[0]
-        else:
+        clip_q = clips[0] if isinstance(clips[0], list) else clips
+        out = self.backbone(clip_q)
+        if not isinstance(out, list):
             raise NotImplementedError("BYOL: predictor is missing")
-        assert len(predictors) == 1
+        feat_q, preds = out[0], out[1:]
+        assert len(preds) == 1
         if index is None:
             return feat_q
         if not self.training:
             return self.eval_knn(self.l2_norm(feat_q))
-
         if keys is None:
-            keys = self.compute_key_feat(clips_key, compute_predictor_keys=False)
+            keys = self.compute_key_feat([list(c) for c in clips], compute_predictor_keys=False)
 
-        # sim_loss(l2_norm(pred), key) with the normalisation fused into the kernel (K7)
+        def sim(pred, key):  # sim_loss(l2_norm(pred), key) in one kernel (K7)
+            return ByolSimilarity.apply(pred, key, self.T, True)
+
         if self.cfg.CONTRASTIVE.SEQUENTIAL:
-            loss_reg = _ByolSimFn.apply(predictors[0], keys[0], self.T, True)
-            for i in range(1, len(keys)):
-                loss_reg = loss_reg + _ByolSimFn.apply(predictors[0], keys[i], self.T, True)
-            loss_reg = loss_reg / len(keys)
+            # this view's prediction against every other view's key, averaged (:558-562)
+            loss = sim(preds[0], keys[0])
+            for key in keys[1:]:
+                loss = loss + sim(preds[0], key)
+            loss = loss / len(keys)
         else:
-            loss_q1 = _ByolSimFn.apply(predictors[0], keys[1], self.T, True)
+            # symmetric pair: view 1 predicts key 2, view 2 predicts key 1 (:572-582)
             assert len(clips) == 2
-            clip_q2 = clips[1]
-            feat_q2 = self.backbone(clip_q2)
-            predictors2 = feat_q2[1:]
-            assert len(predictors2) == 1
-            loss_q2 = _ByolSimFn.apply(predictors2[0], keys[0], self.T, True)
-            loss_reg = loss_q1 + loss_q2
+            preds2 = self.backbone(clips[1])[1:]
+            assert len(preds2) == 1
+            loss = sim(preds[0], keys[1]) + sim(preds2[0], keys[0])
+        return self._cached_dummy_logits(len(index), feat_q.device), loss
 
-        dummy_logits = self._cached_dummy_logits(len(index), feat_q.device)
-        return dummy_logits, loss_reg
-
-    # models/contrastive.py:598-731 (public-code branch, the only live one)
+    # ---- swav (:598-731; the public-code branch is the only live one)
     def _forward_swav(self, clips, index, epoch_exact):
         if not isinstance(clips[0], list):
-            proj_1, _ = self.run_swav_orig_encoder_q(clips)
+            emb, _ = self.run_swav_orig_encoder_q(clips)
             if index is None:
-                return proj_1
+                return emb
             if not self.training:
-                return self.eval_knn(proj_1)
-        n_clips = len(clips)
-
-        # K9: prototype rows to unit l2, in place (:617-621)
-        with torch.no_grad():
-            m = getattr(self, "module", self)
-            w, _ = ops.l2norm_fwd(m.swav_prototypes.weight.data.contiguous(), 1e-12)
-            m.swav_prototypes.weight.copy_(w)
+                return self.eval_knn(emb)
+        n_crops = len(clips)
+        head = getattr(self, "module", self).swav_prototypes
+        with torch.no_grad():  # K9: prototype rows back onto the unit sphere, in place (:617-621)
+            unit, _ = ops.l2norm_fwd(head.weight.data.contiguous(), 1e-12)
+            head.weight.copy_(unit)
 
         bs = clips[0][0].size(0)
-        output, embedding = [], []
-        for i, clip_q in enumerate(clips):
-            x = self.run_swav_orig_encoder_q(clip_q)
-            embedding.append(x[0])
-            output.append(x[1])
-        q_knn = embedding[0]
-        embedding = torch.cat(embedding, dim=0)
-        output = torch.cat(output, dim=0)
+        encoded = [self.run_swav_orig_encoder_q(c) for c in clips]
+        q_knn = encoded[0][0]
+        embedding = torch.cat([e for e, _ in encoded], dim=0)
+        scores = torch.cat([s for _, s in encoded], dim=0)
 
-        swav_extra_crops = n_clips - 2
-        self.swav_crops_for_assign = np.arange(n_clips - swav_extra_crops)
+        # the first two crops (the large ones) get codes; every crop is scored against them (:633-679)
+        self.swav_crops_for_assign = np.arange(min(2, n_crops))
+        queue_live = self.cfg.CONTRASTIVE.SWAV_QEUE_LEN > 0 and epoch_exact >= 15.0
         codes = []
-        for i, crop_id in enumerate(self.swav_crops_for_assign):
-            with torch.no_grad():
-                out = output[bs * crop_id:bs * (crop_id + 1)].detach()
-                if self.cfg.CONTRASTIVE.SWAV_QEUE_LEN > 0 and epoch_exact >= 15.0:
-                    # (:651-653) one host sync, only while the queue is still filling
-                    if self.swav_use_the_queue or not torch.all(self.queue_swav[i, -1, :] == 0):
-                        self.swav_use_the_queue = True
-                        out = torch.cat((torch.mm(self.queue_swav[i], m.swav_prototypes.weight.t()), out))
-                    # K12: FIFO shift by bs, newest first (:659-664)
-                    self.queue_swav[i] = torch.cat(
-                        (embedding[crop_id * bs:(crop_id + 1) * bs].detach(), self.queue_swav[i, :-bs]))
-                # K10: Q = exp(out/eps)^T, 3 Sinkhorn-Knopp iterations, last bs rows
+        with torch.no_grad():
+            for slot, crop in enumerate(self.swav_crops_for_assign):
+                rows = slice(bs * crop, bs * (crop + 1))
+                out = scores[rows].detach()
+                if queue_live:
+                    out = self._swav_queue_step(slot, embedding[rows].detach(), out, head.weight)
                 if self.cfg.NUM_SHARDS > 1:
                     q = self.distributed_sinkhorn(torch.exp(out / self.swav_eps_sinkhorn).t(), 3)[-bs:]
-                else:
+                else:  # K10
                     q = ops.sinkhorn(out.contiguous(), self.swav_eps_sinkhorn, 3, keep_last=bs)
-            codes.append(q)
-        # K11: all (assign crop, other crop) soft-target cross-entropies, fwd + bwd
-        loss_swav = _SwavCeFn.apply(output, torch.stack(codes, 0), n_clips, bs, self.T)
+                codes.append(q)
+        loss = SwavSwappedCe.apply(scores, torch.stack(codes, 0), n_crops, bs, self.T)  # K11
         self.knn_mem_update(q_knn, index)
-        dummy_logits = self._cached_dummy_logits(len(index), output.device)
-        return dummy_logits, loss_swav
+        return self._cached_dummy_logits(len(index), scores.device), loss
 
-    # models/contrastive.py:733-802 (live branch: distributed_loss=False, gather with gradient)
+    def _swav_queue_step(self, slot, emb, out, proto_w):
+        """K12 (:642-664): once the feature queue of this crop is full its scores are prepended to the
+        batch's, then the batch's embeddings enter the queue, newest first."""
+        queue = self.queue_swav[slot]
+        bs = emb.shape[0]
+        if not self.swav_use_the_queue:
+            # the queue starts as zeros and fills from the front: full <=> its last row is non-zero.  One
+            # host read per step until that happens, as in the reference (:651)
+            self.swav_use_the_queue = bool(torch.any(queue[-1] != 0).item())
+        if self.swav_use_the_queue:
+            out = torch.cat((queue @ proto_w.t(), out))
+        self.queue_swav[slot] = torch.cat((emb, queue[:-bs]))
+        return out
+
+    # ---- simclr (:733-802; `distributed_loss` is False in the reference, so: gather with gradient)
     def _forward_simclr(self, clips, index):
-        if isinstance(clips[0], list):
-            clip_q = clips[0]
-        else:
-            clip_q = clips
+        clip_q = clips[0] if isinstance(clips[0], list) else clips
         feat_q = self.backbone(clip_q)
         if index is None:
             return self.l2_norm(feat_q)
         if not self.training:
             return self.eval_knn(self.l2_norm(feat_q))
         feat_q2 = self.backbone(clips[1])
-        # K6 (+C4/C5): l2-norm, all_gather, NT-Xent rows of this rank, gradient incl. the
-        # reference's world-size factor (utils/distributed.py:142-155)
-        loss = _NtXentFn.apply(feat_q, feat_q2, self.T, self.ntxent_impl)
+        # K6 + C4/C5: normalise, gather, NT-Xent over this rank's rows, gradient with the reference's
+        # world-size factor (utils/distributed.py:142-155)
+        loss = NtXentRows.apply(feat_q, feat_q2, self.T, self.ntxent_impl)
         with torch.no_grad():
-            q_knn = self.l2_norm(feat_q.detach())
-        self.knn_mem_update(q_knn, index)
-        dummy_logits = self._cached_dummy_logits(len(index), feat_q.device)
-        return dummy_logits, loss
-
-    def _simclr_precompute_pos_neg_mask_multi(self):
-        """models/contrastive.py:806-846 builds masks only the dead branch (:749-768) reads."""
-        self.pos_mask, self.neg_mask = [], None
+            self.knn_mem_update(self.l2_norm(feat_q.detach()), index)
+        return self._cached_dummy_logits(len(index), feat_q.device), loss
 
     # ------------------------------------------------------------------ SwAV helpers
+    def run_swav_orig_encoder_q(self, x):
+        """F.normalize(backbone(x)) and its prototype scores (:865-870); the score GEMM is a plain
+        library Linear."""
+        emb = l2norm_lastdim(self.backbone(x), 1e-12)
+        if self.swav_prototypes is None:
+            return emb
+        return emb, self.swav_prototypes(emb)
+
     def run_swav_encoder_q(self, im):
-        """models/contrastive.py:848-853 (non-public-code variant; prototypes as a matrix)."""
-        proj = self.backbone(im)
-        proj = _l2norm_rows(proj, 1e-12)
-        w = self.swav_prototypes.weight.t() if isinstance(self.swav_prototypes, nn.Linear) else self.swav_prototypes
-        protos = _l2norm_rows(w.t().contiguous(), 1e-12).t()
-        out = proj @ protos
-        return proj, out
+        """The non-public-code variant (:848-853): prototypes normalised on the fly."""
+        emb = l2norm_lastdim(self.backbone(im), 1e-12)
+        w = self.swav_prototypes.weight if isinstance(self.swav_prototypes, nn.Linear) else self.swav_prototypes.t()
+        return emb, emb @ l2norm_lastdim(w.contiguous(), 1e-12).t()
 
     @torch.no_grad()
     def get_code(self, out):
-        """models/contrastive.py:855-863."""
+        """Sinkhorn codes of a score matrix (:855-863)."""
         if self.cfg.NUM_SHARDS > 1:
             return self.distributed_sinkhorn(torch.exp(out / self.swav_eps_sinkhorn).t(), 3)
         return ops.sinkhorn(out.contiguous(), self.swav_eps_sinkhorn, 3)
 
-    def run_swav_orig_encoder_q(self, x):
-        """models/contrastive.py:865-870: F.normalize (eps 1e-12) + bias-free prototype Linear."""
-        x = self.backbone(x)
-        x = _l2norm_rows(x, 1e-12)
-        if self.swav_prototypes is not None:
-            return x, self.swav_prototypes(x)  # plain library GEMM (cuBLAS), autograd as usual
-        return x
-
     @torch.no_grad()
     def sinkhorn(self, Q, iters):
-        """models/contrastive.py:872-887.  Q: [B, P] = exp(scores / eps), as the reference
-        passes it; the kernel works on log Q so the exp is undone here (API parity only —
-        the forward path hands raw scores to ops.sinkhorn directly)."""
+        """:872-887.  Takes Q = exp(scores / eps) [B, P] as the reference passes it; the kernel works from
+        log Q (API parity only - `forward` hands raw scores to `ops.sinkhorn`)."""
         return ops.sinkhorn(torch.log(Q).contiguous(), 1.0, iters)
 
     def distributed_sinkhorn(self, Q, nmb_iters):
-        """models/contrastive.py:889-910 (multi-node only, NUM_SHARDS > 1).  Q: [P, B_local].
-        Same kernel; the row sums are all-reduced between the two halves of an iteration."""
+        """:889-910, multi-node only (NUM_SHARDS > 1): Q is [P, B_local]; row sums are all-reduced."""
         return ops.sinkhorn_distributed(Q, nmb_iters)
 
     def KLDivLoss(self, out, code):
-        """models/contrastive.py:912-916."""
-        return _SwavCeFn.apply(out, code.unsqueeze(0), 1, out.shape[0], self.T)
+        """:912-916: -mean_n sum_p code * log softmax(out / T)."""
+        return SwavSwappedCe.apply(out, code.unsqueeze(0), 1, out.shape[0], self.T)
 
 
 def l2_loss(x, y):
+    """:919-920."""
     return 2 - 2 * (x * y).sum(dim=-1)
 
 
-class _MemDotFn(torch.autograd.Function):
-    """prod = q . bank[ind, time] / T (K14).  Backward recomputes the gather."""
-
-    @staticmethod
-    def forward(ctx, q, bank, ind, time, T, interp, status):
-        prod = ops.membank_gather_dot(bank, q.detach().contiguous(), ind, time, T, interp=interp, status=status)
-        ctx.save_for_backward(bank, ind, time)
-        ctx.T, ctx.interp = T, interp
-        return prod
-
-    @staticmethod
-    def backward(ctx, g):
-        # rarely used (the reference drops the mem-mode loss): plain torch gather-matmul
-        bank, ind, time = ctx.saved_tensors
-        B = ind.shape[0]
-        b3 = bank if bank.dim() == 3 else bank.unsqueeze(1)
-        if ctx.interp:
-            t0 = time.floor().long().clamp(0, b3.shape[1] - 1)
-            t1 = (t0 + 1).clamp(0, b3.shape[1] - 1)
-            w1 = 1 - (time - t0).reshape(-1, 1).float()
-            sel = b3[ind.reshape(-1), t0.reshape(-1)] * (1 - w1) + b3[ind.reshape(-1), t1.reshape(-1)] * w1
-        else:
-            sel = b3[ind.reshape(-1), time.long().reshape(-1)]
-        sel = sel.view(B, -1, b3.shape[-1])
-        dq = torch.einsum("nk,nkc->nc", g, sel) / ctx.T
-        return dq, None, None, None, None, None, None
-
-
-class Normalize(nn.Module):
-    """models/contrastive.py:923-934: x / (sum x^2)^(1/2) along `dim`, no eps."""
-
-    def __init__(self, power=2, dim=1):
-        super(Normalize, self).__init__()
-        self.dim = dim
-        self.power = power
-
-    def forward(self, x):
-        if self.power != 2:
-            raise NotImplementedError("Normalize: only power=2 has a CUDA kernel")
-        d = self.dim if self.dim >= 0 else x.dim() + self.dim
-        if d == x.dim() - 1:
-            return _l2norm_rows(x, 0.0)
-        xt = x.transpose(d, -1).contiguous()
-        return _l2norm_rows(xt, 0.0).transpose(d, -1)
-
-
-class Memory(nn.Module):
-    """models/contrastive.py:937-1039: [length, duration, dim] bank."""
-
-    def __init__(self, length, duration, dim, cfg):
-        super(Memory, self).__init__()
-        self.length = length
-        self.duration = duration
-        self.dim = dim
-        stdv = 1.0 / math.sqrt(dim / 3)
-        self.register_buffer("memory", torch.rand(length, duration, dim).mul_(2 * stdv).add_(-stdv))
-        self.device = self.memory.device
-        self.l2_norm = Normalize(dim=1)
-        self.l2_norm2d = Normalize(dim=2)
-        self.num_gpus = cfg.NUM_GPUS
-
-    def resize(self, length, duration, dim):
-        self.length = length
-        self.duration = duration
-        self.dim = dim
-        stdv = 1.0 / math.sqrt(dim / 3)
-        dev = self.memory.device
-        del self.memory
-        self.memory = torch.rand(length, duration, dim).mul_(2 * stdv).add_(-stdv).to(dev)
-
-    def get(self, ind, time, interp=False):
-        """Row gather (optionally time-interpolated), models/contrastive.py:966-987."""
-        batch_size = ind.size(0)
-        with torch.no_grad():
-            if interp:
-                t0 = time.floor().long()
-                t0 = torch.clamp(t0, 0, self.memory.shape[1] - 1)
-                t1 = torch.clamp(t0 + 1, 0, self.memory.shape[1] - 1)
-                mem_t0 = self.memory[ind.view(-1), t0.view(-1), :]
-                mem_t1 = self.memory[ind.view(-1), t1.view(-1), :]
-                w_t1 = 1 - (time - t0).view(-1, 1).float()
-                selected_mem = mem_t0 * (1 - w_t1) + mem_t1 * w_t1
-            else:
-                selected_mem = self.memory[ind.view(-1), time.long().view(-1), :]
-        return selected_mem.view(batch_size, -1, self.dim)
-
-    def update(self, mem, momentum, ind, time, interp=False, status=None):
-        """models/contrastive.py:989-1036: all_gather (C8) then the fused
-        gather-lerp-normalise-scatter kernel (K5)."""
-        if self.num_gpus > 1:
-            mem, ind, time = du.all_gather([mem, ind, time])
-        with torch.no_grad():
-            ops.membank_update(self.memory, mem.detach().reshape(mem.size(0), -1).contiguous(), ind, time,
-                               momentum, interp=interp, status=status)
-
-    def forward(self, inputs):
-        pass
-
-
-class Memory1D(nn.Module):
-    """models/contrastive.py:1042-1080: [length, dim] bank."""
-
-    def __init__(self, length, duration, dim, cfg):
-        super(Memory1D, self).__init__()
-        assert duration == 1
-        self.length = length
-        self.duration = duration
-        self.dim = dim
-        stdv = 1.0 / math.sqrt(dim / 3)
-        self.register_buffer("memory", torch.rand(length, dim).mul_(2 * stdv).add_(-stdv))
-        self.l2_norm = Normalize(dim=1)
-        self.num_gpus = cfg.NUM_GPUS
-
-    @torch.no_grad()
-    def get(self, ind, time, interp=False):
-        batch_size = ind.size(0)
-        if len(ind.shape) == 1:
-            return torch.index_select(self.memory, 0, ind.view(-1)).view(batch_size, self.dim)
-        else:
-            return torch.index_select(self.memory, 0, ind.view(-1)).view(batch_size, -1, self.dim)
-
-    @torch.no_grad()
-    def update(self, mem, momentum, ind, time, interp=False, status=None):
-        if self.num_gpus > 1:
-            mem, ind, time = du.all_gather([mem, ind, time])
-        mem = mem.view(mem.size(0), -1)
-        ops.membank_update(self.memory, mem.detach().contiguous(), ind.long(), None, momentum, interp=False,
-                           status=status)
-
-
-def _exchange_rows(x, idx_randperm, gpu_idx, world_size):
-    """C1 as an all-to-all: rank r needs rows idx_randperm[r] of the
-    rank-major concatenation; row g lives on rank g // B at local offset g % B.
-    Every rank knows the whole permutation, so all split sizes are computed locally.
-    Bit-identical to `cat_all_gather(x)[idx_randperm[r]]`."""
-    import torch.distributed as dist
-    B = x.shape[0]
-    perm = idx_randperm.cpu()  # [W, B]; 8 bytes per clip, needed on the host for the split sizes
-    owner = perm // B
-    send_rows, send_sizes = [], []
-    me = gpu_idx
-    for dst in range(world_size):
-        sel = perm[dst][owner[dst] == me] % B  # my rows that dst wants, in dst's order
-        send_rows.append(sel)
-        send_sizes.append(int(sel.numel()))
-    recv_sizes = [int((owner[me] == src).sum()) for src in range(world_size)]
-    send_idx = torch.cat(send_rows).to(x.device)
-    send_buf = x.index_select(0, send_idx).contiguous()
-    recv_buf = torch.empty((B,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
-    dist.all_to_all_single(recv_buf, send_buf, output_split_sizes=recv_sizes, input_split_sizes=send_sizes)
-    # recv_buf is grouped by source rank; put the rows into this rank's take order
-    pos = torch.argsort(owner[me], stable=True)  # positions in take order, grouped by source
-    inv = torch.empty_like(pos)
-    inv[pos] = torch.arange(B)
-    return recv_buf.index_select(0, inv.to(x.device))
-
-
 def contrastive_parameter_surgery(model, cfg, epoch_exact, cur_iter):
-    """models/contrastive.py:1083-1116."""
-    if cfg.MODEL.MODEL_NAME == "ContrastiveModel" and cfg.CONTRASTIVE.TYPE == "swav" and epoch_exact <= 1.0:
+    """:1083-1116.  SwAV: prototype gradients are dropped during the first epoch.  MoCo: no parameter
+    update while the queue still holds its random initialisation (one queue length of samples)."""
+    is_head = cfg.MODEL.MODEL_NAME == "ContrastiveModel"
+    kind = cfg.CONTRASTIVE.TYPE
+    if is_head and kind == "swav" and epoch_exact <= 1.0:
         for name, p in model.named_parameters():
             if "swav_prototypes" in name:
                 p.grad = None
-
-    iters_noupdate = 0
-    if cfg.MODEL.MODEL_NAME == "ContrastiveModel" and cfg.CONTRASTIVE.TYPE == "moco":
-        assert cfg.CONTRASTIVE.QUEUE_LEN % (cfg.TRAIN.BATCH_SIZE * cfg.NUM_SHARDS) == 0
-        iters_noupdate = cfg.CONTRASTIVE.QUEUE_LEN // cfg.TRAIN.BATCH_SIZE // cfg.NUM_SHARDS
-
-    if cur_iter < iters_noupdate and epoch_exact < 1:
-        logger.info("Not updating parameters {}/{}".format(cur_iter, iters_noupdate))
-        update_param = False
-    else:
-        update_param = True
+    warm_iters = 0
+    if is_head and kind == "moco":
+        per_iter = cfg.TRAIN.BATCH_SIZE * cfg.NUM_SHARDS
+        assert cfg.CONTRASTIVE.QUEUE_LEN % per_iter == 0
+        warm_iters = cfg.CONTRASTIVE.QUEUE_LEN // cfg.TRAIN.BATCH_SIZE // cfg.NUM_SHARDS
+    update_param = not (cur_iter < warm_iters and epoch_exact < 1)
+    if not update_param:
+        logger.info("Not updating parameters {}/{}".format(cur_iter, warm_iters))
     return model, update_param
 
 
 def contrastive_forward(model, cfg, inputs, index, time, epoch_exact, scaler=None):
-    """models/contrastive.py:1119-1171."""
-    if cfg.CONTRASTIVE.SEQUENTIAL:
-        perform_backward = False
-        mdl = getattr(model, "module", model)
-        keys = (
-            mdl.compute_key_feat(inputs, compute_predictor_keys=False,
-                                 batched_inference=True if len(inputs) < 2 else False)
-            if cfg.CONTRASTIVE.TYPE == "moco" or cfg.CONTRASTIVE.TYPE == "byol"
-            else [None] * len(inputs)
-        )
-        for k, vid in enumerate(inputs):
-            other_keys = keys[:k] + keys[k + 1:]
-            time_cur = None if time is None else torch.cat(
-                [time[:, k:k + 1, :], time[:, :k, :], time[:, k + 1:, :]], 1)  # q, kpre, kpost
-            vids = [vid]
-            if cfg.CONTRASTIVE.TYPE == "swav" or cfg.CONTRASTIVE.TYPE == "simclr":
-                if k < len(inputs) - 1:
-                    vids = inputs[k:k + 2]
-                else:
-                    break
-            lgt_k, loss_k = model(vids, index, time_cur, epoch_exact, keys=other_keys)
-            if scaler is not None:
-                scaler.scale(loss_k).backward()
-            else:
-                loss_k.backward()
-            if k == 0:
-                preds, partial_loss = lgt_k, loss_k.detach()
-            else:
-                preds = torch.cat([preds, lgt_k], dim=0)
-                partial_loss += loss_k.detach()
-        partial_loss /= len(inputs) * 2.0  # to have same loss as symm model
-        if cfg.CONTRASTIVE.TYPE == "moco":
-            mdl._dequeue_and_enqueue(keys)
-    else:
-        perform_backward = True
+    """The training loop's entry point (:1119-1171; called from tools/train.py:63-77).
+
+    SEQUENTIAL: every view takes a turn as the query against the keys of the others (moco / byol) or is
+    paired with its successor (swav / simclr); each turn back-propagates at once, the summed loss is
+    divided by 2 * len(inputs) (so that it matches the symmetric formulation), and MoCo enqueues all
+    keys at the end.  Otherwise one forward; the caller back-propagates (`perform_backward`).
+    """
+    if not cfg.CONTRASTIVE.SEQUENTIAL:
         preds, partial_loss = model(inputs, index, time, epoch_exact, keys=None)
-    return model, preds, partial_loss, perform_backward
+        return model, preds, partial_loss, True
+
+    kind = cfg.CONTRASTIVE.TYPE
+    core = getattr(model, "module", model)
+    n_views = len(inputs)
+    if kind in ("moco", "byol"):
+        keys = core.compute_key_feat(inputs, compute_predictor_keys=False, batched_inference=n_views < 2)
+    else:
+        keys = [None] * n_views
+    pairwise = kind in ("swav", "simclr")
+    preds, partial_loss = None, None
+    for turn in range(n_views - 1 if pairwise else n_views):
+        vids = inputs[turn:turn + 2] if pairwise else [inputs[turn]]
+        others = keys[:turn] + keys[turn + 1:]
+        t_turn = None
+        if time is not None:  # this view's time first, then the earlier and the later ones
+            t_turn = torch.cat([time[:, turn:turn + 1, :], time[:, :turn, :], time[:, turn + 1:, :]], 1)
+        lgt, loss = model(vids, index, t_turn, epoch_exact, keys=others)
+        (scaler.scale(loss) if scaler is not None else loss).backward()
+        if preds is None:
+            preds, partial_loss = lgt, loss.detach()
+        else:
+            preds = torch.cat([preds, lgt], dim=0)
+            partial_loss += loss.detach()
+    partial_loss /= n_views * 2.0
+    if kind == "moco":
+        core._dequeue_and_enqueue(keys)
+    return model, preds, partial_loss, False
 
 
 try:

@@ -62,6 +62,17 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Sum of squares of one row by ONE warp, fixed order (lane l takes columns l, l+32, ...): every kernel
+// that normalises the same row obtains the same bits.
+__device__ __forceinline__ float row_sumsq(const float* __restrict__ x, int D, int lane) {
+  float ss = 0.f;
+  for (int c = lane; c < D; c += 32) {
+    const float v = x[c];
+    ss = fmaf(v, v, ss);
+  }
+  return warp_sum(ss);
+}
+
 // Block-wide sum for blockDim.x <= 1024 (multiple of 32). `scratch` >= 32 floats.
 __device__ __forceinline__ float block_sum(float v, float* scratch) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

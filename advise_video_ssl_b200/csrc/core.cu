@@ -31,7 +31,7 @@ int sm_count() {
 
 }  // namespace avssl
 
-extern "C" int avssl_abi_version(void) { return 1; }
+extern "C" int avssl_abi_version(void) { return 2; }
 
 extern "C" const char* avssl_last_error(void) { return avssl::g_err; }
 

@@ -111,7 +111,7 @@ ema_multi_tensor_push_kernel(const avssl_ema_chunk* __restrict__ table, float m,
                              uint32_t* done_counter, const avssl_peer_xchg x, const float* __restrict__ rows) {
   __shared__ unsigned long long s_epoch;
   if (blockIdx.x < (unsigned)x.world) {
-    peer_push_cta(x, rows, blockIdx.x, &s_epoch);
+    peer_push_cta<false>(x, rows, blockIdx.x, &s_epoch);
     return;
   }
   ema_cta<kFirstMode, kBump>(table, blockIdx.x - x.world, gridDim.x - x.world, m, om, iter, done_counter);

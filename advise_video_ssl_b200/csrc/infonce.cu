@@ -52,7 +52,8 @@ int moco_infonce_run(const float* feat_q, const float* const* keys_host, int n_k
                      float* queue_rw, int64_t* ptr_dev, uint32_t* status_dev, int B, int D, int K, float T,
                      float* q_out, float* loss_out, float* dfeat_out, float* row_lse_out, float* logits_out,
                      void* workspace, size_t workspace_bytes, int impl, void* stream,
-                     const avssl_peer_xchg* peer = nullptr, const int64_t* peer_row_idx = nullptr) {
+                     const avssl_peer_xchg* peer = nullptr, const int64_t* peer_row_idx = nullptr,
+                     const int64_t* enq_row_idx = nullptr, int n_enq = 0) {
   AVSSL_REQUIRE(feat_q && (keys_host || peer) && queue && q_out && loss_out && dfeat_out && workspace,
                 AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: null pointer");
   AVSSL_REQUIRE(B > 0 && D > 0 && K > 0, AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: bad sizes B=%d D=%d K=%d", B, D, K);
@@ -73,6 +74,8 @@ int moco_infonce_run(const float* feat_q, const float* const* keys_host, int n_k
     AVSSL_REQUIRE(p.keys[k], AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: keys[%d] is null", k);
   p.use_peer = peer ? 1 : 0;
   p.peer_row_idx = reinterpret_cast<const long long*>(peer_row_idx);
+  p.enq_row_idx = reinterpret_cast<const long long*>(enq_row_idx);
+  p.n_enq = (ptr_dev && n_enq > 0) ? n_enq : B;
   memset(&p.peer, 0, sizeof(p.peer));
   if (peer) {
     const int rc = peer_check(peer, "moco_infonce_peer");
@@ -98,7 +101,10 @@ int moco_infonce_run(const float* feat_q, const float* const* keys_host, int n_k
   p.enq_status = status_dev;
   if (ptr_dev) {
     // models/contrastive.py:284  assert self.k % num_items == 0
-    AVSSL_REQUIRE(K % B == 0, AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: K=%d is not a multiple of the key batch %d", K, B);
+    AVSSL_REQUIRE(K % p.n_enq == 0, AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: K=%d is not a multiple of the %d enqueued rows", K,
+                  p.n_enq);
+    AVSSL_REQUIRE(peer ? (enq_row_idx != nullptr || p.n_enq == peer->rows_per_rank) : (enq_row_idx == nullptr && p.n_enq == B),
+                  AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: n_enq=%d needs a row list into the exchange buffer", p.n_enq);
     AVSSL_REQUIRE(queue_rw && (peer || (reinterpret_cast<uintptr_t>(p.keys[0]) & 15u) == 0) && D % 4 == 0,
                   AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: fused enqueue needs a writable queue and 16-byte aligned keys[0]");
   }
@@ -166,7 +172,8 @@ extern "C" int avssl_moco_infonce_fwd_bwd_enqueue(const float* feat_q, const flo
 }
 
 extern "C" int avssl_moco_infonce_fwd_bwd_enqueue_peer(const float* feat_q, const avssl_peer_xchg* x,
-                                                       const int64_t* row_idx, float* queue, int64_t* ptr_dev,
+                                                       const int64_t* row_idx, const int64_t* enq_row_idx, int n_enq,
+                                                       float* queue, int64_t* ptr_dev,
                                                        uint32_t* status_dev, int B, int D, int K, float T,
                                                        float* q_out, float* loss_out, float* dfeat_out,
                                                        float* row_lse_out, float* logits_out, void* workspace,
@@ -174,5 +181,5 @@ extern "C" int avssl_moco_infonce_fwd_bwd_enqueue_peer(const float* feat_q, cons
   AVSSL_REQUIRE(x, AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce_peer: exchange descriptor is null");
   return moco_infonce_run(feat_q, nullptr, 1, queue, ptr_dev ? queue : nullptr, ptr_dev, status_dev, B, D, K, T, q_out,
                           loss_out, dfeat_out, row_lse_out, logits_out, workspace, workspace_bytes, impl, stream, x,
-                          row_idx);
+                          row_idx, enq_row_idx, n_enq);
 }

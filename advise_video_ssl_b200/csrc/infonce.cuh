@@ -45,19 +45,16 @@ struct InfoNceParams {
   // the merge CTAs have waited for every rank's push of the current epoch.  keys[0] is unused then.
   int use_peer;
   const long long* peer_row_idx;
+  // rows written by the fused enqueue: gathered[enq_row_idx[e]] (peer) or keys[0][e], e < n_enq
+  const long long* enq_row_idx;
+  int n_enq;
   avssl_peer_xchg peer;
 };
 
 // 1 / ||row|| computed by ONE warp with a fixed summation order, so that every
 // kernel that normalises the same row obtains the same bits.
 __device__ __forceinline__ float warp_row_norm(const float* __restrict__ row, int D, int lane) {
-  float ss = 0.f;
-  for (int c = lane; c < D; c += 32) {
-    const float v = row[c];
-    ss = fmaf(v, v, ss);
-  }
-  ss = warp_sum(ss);
-  return sqrtf(ss);  // Normalize: x / sum(x^2)^(1/2), no eps (models/contrastive.py:929-934)
+  return sqrtf(row_sumsq(row, D, lane));  // Normalize: x / sum(x^2)^(1/2), no eps (models/contrastive.py:929-934)
 }
 
 int launch_infonce_simt(const InfoNceParams& p, cudaStream_t s);

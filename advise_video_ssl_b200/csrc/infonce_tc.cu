@@ -601,12 +601,13 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
   bool enq_ok = false;
   if (p.enq_ptr) {
     enq_ptr = *reinterpret_cast<volatile long long*>(p.enq_ptr);  // advanced only after every CTA arrived below
-    enq_ok = enq_ptr >= 0 && enq_ptr + p.B <= p.K;               // models/contrastive.py:285
+    enq_ok = enq_ptr >= 0 && enq_ptr + p.n_enq <= p.K;           // models/contrastive.py:285
   }
   const float* key_base = p.keys[0];
-  if (p.use_peer && cta < p.B) {  // C3: the keys come from the peer exchange buffer (peer.cuh)
+  const long long n_peer_rows = (long long)p.peer.world * p.peer.rows_per_rank;
+  if (p.use_peer && (cta < p.B || (enq_ok && cta < p.n_enq))) {  // C3: the keys come from the peer exchange buffer (peer.cuh)
     if (warp == 0) {  // long since landed: the sweep took ~15 us
-      const int slot = peer_wait_all_warp(p.peer);
+      const int slot = peer_wait_all_warp(p.peer, p.enq_status);
       if (lane == 0) csm.peer_slot = slot;
     }
     __syncthreads();
@@ -616,16 +617,28 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
     long long krow = i;
     if (p.use_peer) {
       krow = p.peer_row_idx ? p.peer_row_idx[i] : (long long)p.peer.rank * p.B + i;
-      if (krow < 0 || krow >= (long long)p.peer.world * p.peer.rows_per_rank) {  // uniform over the CTA
+      if (krow < 0 || krow >= n_peer_rows) {  // uniform over the CTA
         if (tid == 0 && p.enq_status) atomicOr(p.enq_status, AVSSL_DEVFLAG_BAD_INDEX);
         krow = 0;
       }
     }
-    const float* key_row = key_base + (size_t)krow * D;
-    infonce_combine_row<kTcThreads, 1>(p, i, csm, key_row);
-    if (enq_ok) {  // K4: queue[ptr + i] = keys[0][i]; no CTA reads the queue after the grid barrier
-      const float4* src = reinterpret_cast<const float4*>(key_row);
-      float4* dst = reinterpret_cast<float4*>(p.queue_rw + (size_t)(enq_ptr + i) * D);
+    infonce_combine_row<kTcThreads, 1>(p, i, csm, key_base + (size_t)krow * D);
+  }
+  if (enq_ok) {
+    // K4 (+ C9): queue[ptr + e] = the e-th row of the enqueue list -- keys[0][e], or gathered[enq_row_idx[e]]
+    // (rank 0's block on every rank keeps the queues of all ranks identical, as the reference's DDP buffer
+    // broadcast does; all world*B rows = canonical MoCo).  No CTA reads the queue after the grid barrier.
+    for (int e = cta; e < p.n_enq; e += (int)n_ctas) {
+      long long krow = e;
+      if (p.use_peer) {
+        krow = p.enq_row_idx ? p.enq_row_idx[e] : (long long)p.peer.rank * p.peer.rows_per_rank + e;
+        if (krow < 0 || krow >= n_peer_rows) {
+          if (tid == 0 && p.enq_status) atomicOr(p.enq_status, AVSSL_DEVFLAG_BAD_INDEX);
+          continue;
+        }
+      }
+      const float4* src = reinterpret_cast<const float4*>(key_base + (size_t)krow * D);
+      float4* dst = reinterpret_cast<float4*>(p.queue_rw + (size_t)(enq_ptr + e) * D);
       for (int c4 = tid; c4 < D / 4; c4 += kTcThreads) dst[c4] = __ldcg(src + c4);
     }
   }
@@ -637,7 +650,7 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
       p.counter[1] = 0u;  // every CTA is past the barrier: it incremented counter[0] afterwards
       if (p.enq_ptr) {
         if (enq_ok) {
-          long long np = enq_ptr + p.B;
+          long long np = enq_ptr + p.n_enq;
           if (np == p.K) np = 0;  // wrap only when landing exactly on K (:290-291)
           *p.enq_ptr = np;
         } else if (p.enq_status) {

@@ -14,7 +14,15 @@ namespace avssl {
 
 __global__ void __launch_bounds__(256) peer_push_kernel(const avssl_peer_xchg x, const float* __restrict__ rows) {
   __shared__ unsigned long long s_epoch;
-  peer_push_cta(x, rows, blockIdx.x, &s_epoch);
+  peer_push_cta<false>(x, rows, blockIdx.x, &s_epoch);
+}
+
+// K2 + push in one launch: what travels is l2norm(feat) (Normalize of the key features,
+// models/contrastive.py:350 + :216-230); CTA `rank` also keeps a local copy when y_local != null.
+__global__ void __launch_bounds__(256)
+l2norm_push_kernel(const avssl_peer_xchg x, const float* __restrict__ feat, float eps, float* __restrict__ y_local) {
+  __shared__ unsigned long long s_epoch;
+  peer_push_cta<true>(x, feat, blockIdx.x, &s_epoch, eps, y_local);
 }
 
 // out[i] = gathered[row_idx ? row_idx[i] : rank * rows_per_rank + i]; bit-exact copy.
@@ -23,7 +31,7 @@ peer_wait_gather_kernel(const avssl_peer_xchg x, const long long* __restrict__ r
                         float* __restrict__ out, uint32_t* status) {
   __shared__ int s_slot;
   if (threadIdx.x < 32) {
-    const int slot = peer_wait_all_warp(x);
+    const int slot = peer_wait_all_warp(x, status);
     if (threadIdx.x == 0) s_slot = slot;
   }
   __syncthreads();
@@ -109,6 +117,16 @@ extern "C" int avssl_peer_push_rows(const avssl_peer_xchg* x, const float* rows,
                 "peer_push_rows: rows is null or not 16-byte aligned");
   peer_push_kernel<<<x->world, 256, 0, static_cast<cudaStream_t>(stream)>>>(*x, rows);
   AVSSL_LAUNCH_OK("peer_push_kernel");
+  return AVSSL_OK;
+}
+
+extern "C" int avssl_l2norm_push_rows(const avssl_peer_xchg* x, const float* feat, float eps, float* y_local_out,
+                                      void* stream) {
+  int rc = peer_check(x, "l2norm_push_rows");
+  if (rc != AVSSL_OK) return rc;
+  AVSSL_REQUIRE(feat && eps >= 0.f, AVSSL_ERR_INVALID_ARGUMENT, "l2norm_push_rows: feat is null or eps < 0");
+  l2norm_push_kernel<<<x->world, 256, 0, static_cast<cudaStream_t>(stream)>>>(*x, feat, eps, y_local_out);
+  AVSSL_LAUNCH_OK("l2norm_push_kernel");
   return AVSSL_OK;
 }
 

@@ -42,17 +42,37 @@ __device__ __forceinline__ float* peer_payload(void* base, int slot, const avssl
 // All threads of one CTA: push this rank's rows to rank `dst`.  `world` CTAs (dst = 0..world-1)
 // make one push; the last of them to finish advances the local epoch.  `s_epoch` is a shared
 // scratch word.  rows * D must be a multiple of 4 and `rows` 16-byte aligned (checked by the host).
+// kNormalize: the rows are raw features and what travels is x / max(||x||, eps), computed with the
+// arithmetic of l2norm_fwd_kernel (same summation order, true division), so the receivers hold the
+// bits a separate Normalize launch would have produced; the CTA whose destination is this rank
+// also stores them to y_local (may be null).
+template <bool kNormalize>
 __device__ __forceinline__ void peer_push_cta(const avssl_peer_xchg& x, const float* __restrict__ rows, int dst,
-                                              unsigned long long* s_epoch) {
+                                              unsigned long long* s_epoch, float eps = 0.f,
+                                              float* __restrict__ y_local = nullptr) {
   PeerHdr* me = static_cast<PeerHdr*>(x.base[x.rank]);
   if (threadIdx.x == 0) *s_epoch = *reinterpret_cast<volatile unsigned long long*>(&me->epoch) + 1ull;
   __syncthreads();
   const unsigned long long e = *s_epoch;
-  const int n4 = x.rows_per_rank * x.D / 4;
-  const float4* src = reinterpret_cast<const float4*>(rows);
-  float4* out = reinterpret_cast<float4*>(peer_payload(x.base[dst], (int)(e & 1ull), x) +
-                                          (size_t)x.rank * x.rows_per_rank * x.D);
-  for (int i = threadIdx.x; i < n4; i += blockDim.x) out[i] = __ldg(src + i);
+  float* out_f = peer_payload(x.base[dst], (int)(e & 1ull), x) + (size_t)x.rank * x.rows_per_rank * x.D;
+  if (kNormalize) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const bool keep = y_local != nullptr && dst == x.rank;
+    for (int r = warp; r < x.rows_per_rank; r += n_warps) {
+      const float* xr = rows + (size_t)r * x.D;
+      const float den = fmaxf(sqrtf(row_sumsq(xr, x.D, lane)), eps);
+      for (int c = lane; c < x.D; c += 32) {
+        const float y = xr[c] / den;
+        out_f[(size_t)r * x.D + c] = y;
+        if (keep) y_local[(size_t)r * x.D + c] = y;
+      }
+    }
+  } else {
+    const int n4 = x.rows_per_rank * x.D / 4;
+    const float4* src = reinterpret_cast<const float4*>(rows);
+    float4* out = reinterpret_cast<float4*>(out_f);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) out[i] = __ldg(src + i);
+  }
   __threadfence_system();  // every thread's stores are performed at the destination before the flag
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -73,17 +93,39 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned 
   return v;
 }
 
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // wait, by ONE WARP (all 32 lanes call it): until every rank's push of the current local epoch has
 // landed here.  Lane r watches rank r's flag with relaxed loads, so the wait costs one flag latency
 // whatever the world size (W sequential ld.acquire.sys cost +14 us per step at W = 4), and a single
 // system-scope fence orders the payload reads that follow the caller's __syncthreads().
-// Returns the payload slot to read.
-__device__ __forceinline__ int peer_wait_all_warp(const avssl_peer_xchg& x) {
+// The spin is bounded: after x.timeout_ms (0 = never) without the flag the lane gives up, ors
+// AVSSL_DEVFLAG_PEER_TIMEOUT into *status (may be null) and the kernel carries on with whatever the
+// slot holds -- a dead peer then costs one garbage step that the host sees in the status word
+// instead of a hung cooperative kernel.  Returns the payload slot to read.
+__device__ __forceinline__ int peer_wait_all_warp(const avssl_peer_xchg& x, uint32_t* status) {
   PeerHdr* me = static_cast<PeerHdr*>(x.base[x.rank]);
   const int lane = threadIdx.x & 31;
   const unsigned long long e = *reinterpret_cast<volatile unsigned long long*>(&me->epoch);
-  if (lane < x.world)
-    while (ld_relaxed_sys_u64(&me->flags[lane]) < e) __nanosleep(32);
+  if (lane < x.world) {
+    unsigned spins = 0;
+    unsigned long long t0 = 0ull;
+    while (ld_relaxed_sys_u64(&me->flags[lane]) < e) {
+      __nanosleep(32);
+      if (x.timeout_ms != 0u && (++spins & 1023u) == 0u) {  // look at the clock every ~1000 polls
+        const unsigned long long now = global_timer_ns();
+        if (t0 == 0ull) t0 = now;
+        else if (now - t0 > (unsigned long long)x.timeout_ms * 1000000ull) {
+          if (status) atomicOr(status, AVSSL_DEVFLAG_PEER_TIMEOUT);
+          break;
+        }
+      }
+    }
+  }
   __syncwarp();
   __threadfence_system();
   return (int)(e & 1ull);

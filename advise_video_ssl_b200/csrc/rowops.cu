@@ -7,15 +7,6 @@
 
 namespace avssl {
 
-__device__ __forceinline__ float row_sumsq(const float* __restrict__ x, int D, int lane) {
-  float ss = 0.f;
-  for (int c = lane; c < D; c += 32) {
-    const float v = x[c];
-    ss = fmaf(v, v, ss);
-  }
-  return warp_sum(ss);
-}
-
 __global__ void __launch_bounds__(256)
 l2norm_fwd_kernel(const float* __restrict__ x, int n, int D, float eps, float* __restrict__ y, float* __restrict__ norm_out) {
   const int lane = threadIdx.x & 31;

@@ -187,7 +187,8 @@ class PeerExchange:
     world_size 1 (or no process group) works too: the exchange then targets its own buffer.
     """
 
-    def __init__(self, rows_per_rank, D, group=None, device=None):
+    def __init__(self, rows_per_rank, D, group=None, device=None, timeout_ms=None):
+        import os
         import torch.distributed as dist
         if not torch.cuda.is_available():
             raise RuntimeError("PeerExchange needs a CUDA device: the contrastive hot path has no CPU fallback")
@@ -248,6 +249,11 @@ class PeerExchange:
             self.desc.base[r] = bases[r]
         self.desc.world, self.desc.rank = self.world, self.rank
         self.desc.rows_per_rank, self.desc.D = self.rows_per_rank, self.D
+        # bound of the consumer's spin on a peer's flag (0 = forever); on expiry the kernel sets
+        # DEVFLAG_PEER_TIMEOUT in the status word it was given and carries on instead of hanging
+        if timeout_ms is None:
+            timeout_ms = int(os.environ.get("AVSSL_PEER_TIMEOUT_MS", "30000"))
+        self.desc.timeout_ms = max(0, int(timeout_ms))
 
     def check_rows(self, rows):
         _req(rows, "rows")
@@ -258,6 +264,17 @@ class PeerExchange:
         """Store `rows` into every rank's buffer and publish the new epoch (one small launch)."""
         self.check_rows(rows)
         check(lib.avssl_peer_push_rows(ctypes.addressof(self.desc), rows.data_ptr(), _stream()), "avssl_peer_push_rows")
+
+    def push_normalized(self, feat, eps=0.0, keep=None):
+        """Normalize + push in one launch: every rank receives feat / max(||feat||, eps), the
+        bits `l2norm_fwd` then `push` would have moved.  `keep` ([rows, D], optional) receives
+        this rank's normalised rows."""
+        self.check_rows(feat)
+        if keep is not None:
+            self.check_rows(keep)
+        check(lib.avssl_l2norm_push_rows(ctypes.addressof(self.desc), feat.data_ptr(), float(eps),
+                                         keep.data_ptr() if keep is not None else None, _stream()),
+              "avssl_l2norm_push_rows")
 
     def wait_gather(self, row_idx=None, out=None, status=None):
         """Wait for every rank's push of the current epoch, then return gathered[row_idx]
@@ -301,8 +318,12 @@ class PeerExchange:
 _workspaces = {}
 
 
-def _workspace(device, nbytes):
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+def _workspace(device, nbytes, op):
+    """Zero-once scratch per (op, device, stream).  Every op keeps its own: the kernels leave
+    their barrier / counter words in an op-specific state between launches (the cooperative
+    Sinkhorn's generation word never returns to zero, the InfoNCE grid barrier expects zero),
+    so two ops must never see each other's words."""
+    key = (op, device.index, torch.cuda.current_stream(device).cuda_stream)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
@@ -311,7 +332,7 @@ def _workspace(device, nbytes):
 
 
 def moco_infonce(feat_q, keys, queue, T, want_logits=True, impl=_lib.IMPL_AUTO, out=None, enqueue=None, workspace=None,
-                 peer=None, peer_row_idx=None):
+                 peer=None, peer_row_idx=None, enq_row_idx=None):
     """Fused l2-norm + logits + InfoNCE forward/backward (K2+K3).
 
     Returns dict(loss[1], dfeat[B,D], q[B,D], lse[n_keys*B], logits[n_keys*B,K+1] or None).
@@ -324,6 +345,9 @@ def moco_infonce(feat_q, keys, queue, T, want_logits=True, impl=_lib.IMPL_AUTO, 
     `peer`: a PeerExchange whose current epoch holds the keys (`keys` must be None): the launch
     waits for the exchange itself, after its sweep over the queue, and takes key row i from
     gathered[peer_row_idx[i]] (default: this rank's own block) -- C3 fused into K3.
+    `enq_row_idx` (peer only, int64): the rows of the gathered buffer that the fused enqueue writes,
+    ptr advancing by their count (C9: rank 0's rows on every rank = the reference's effective
+    semantics under DDP's buffer broadcast; all rows = canonical MoCo).  Default: this rank's block.
     """
     _req(feat_q, "feat_q")
     _req(queue, "queue")
@@ -361,16 +385,21 @@ def moco_infonce(feat_q, keys, queue, T, want_logits=True, impl=_lib.IMPL_AUTO, 
         if ws.numel() < nbytes:
             raise ValueError("workspace has %d bytes, need %d" % (ws.numel(), nbytes))
     else:
-        ws = _workspace(dev, nbytes)
+        ws = _workspace(dev, nbytes, "moco_infonce")
     if peer is not None:
         ptr, status = enqueue if enqueue is not None else (None, None)
+        n_enq = B
+        if enq_row_idx is not None:
+            _req(enq_row_idx, "enq_row_idx", torch.int64)
+            n_enq = int(enq_row_idx.numel())
         if ptr is not None:
             _req(ptr, "ptr", torch.int64)
-            assert K % B == 0, "queue length %d is not a multiple of the key batch %d" % (K, B)
+            assert K % n_enq == 0, "queue length %d is not a multiple of the key batch %d" % (K, n_enq)
         if status is not None:
             _req(status, "status", torch.int32)
         check(lib.avssl_moco_infonce_fwd_bwd_enqueue_peer(
             feat_q.data_ptr(), ctypes.addressof(peer.desc), peer_row_idx.data_ptr() if peer_row_idx is not None else None,
+            enq_row_idx.data_ptr() if enq_row_idx is not None else None, n_enq,
             queue.data_ptr(), ptr.data_ptr() if ptr is not None else None,
             status.data_ptr() if status is not None else None, B, D, K, float(T),
             q.data_ptr(), loss.data_ptr(), dfeat.data_ptr(), lse.data_ptr(),
@@ -508,7 +537,7 @@ def byol_simloss(pred, key, T, normalize=True, want_grad=True):
     n, D = pred.shape
     loss = torch.empty(1, dtype=_f32, device=pred.device)
     dpred = torch.empty_like(pred) if want_grad else None
-    ws = _workspace(pred.device, lib.avssl_byol_simloss_workspace_bytes(n))
+    ws = _workspace(pred.device, lib.avssl_byol_simloss_workspace_bytes(n), "byol_simloss")
     check(lib.avssl_byol_simloss_fwd_bwd(pred.data_ptr(), key.data_ptr(), n, D, float(T), 1 if normalize else 0,
                                          loss.data_ptr(), dpred.data_ptr() if want_grad else None,
                                          ws.data_ptr(), ws.numel(), _stream()), "avssl_byol_simloss_fwd_bwd")
@@ -521,7 +550,7 @@ def ce_target0_fwd(logits):
     n, C = logits.shape
     loss = torch.empty(1, dtype=_f32, device=logits.device)
     lse = torch.empty(n, dtype=_f32, device=logits.device)
-    ws = _workspace(logits.device, lib.avssl_ce_target0_workspace_bytes(n))
+    ws = _workspace(logits.device, lib.avssl_ce_target0_workspace_bytes(n), "ce_target0")
     check(lib.avssl_ce_target0_fwd(logits.data_ptr(), n, C, loss.data_ptr(), lse.data_ptr(), ws.data_ptr(),
                                    ws.numel(), _stream()), "avssl_ce_target0_fwd")
     return loss, lse
@@ -568,7 +597,7 @@ def ntxent(feat1, feat2, T, gather=None, impl=_lib.IMPL_AUTO):
     rows = torch.cat([torch.arange(rank * B, (rank + 1) * B, dtype=torch.int32, device=dev),
                       torch.arange(N + rank * B, N + (rank + 1) * B, dtype=torch.int32, device=dev)])
     n_loc = 2 * B
-    ws = _workspace(dev, lib.avssl_ntxent_workspace_bytes(2 * N, D, n_loc))
+    ws = _workspace(dev, lib.avssl_ntxent_workspace_bytes(2 * N, D, n_loc), "ntxent")
     z_loc = torch.empty(n_loc, dtype=_f32, device=dev)
     check(lib.avssl_ntxent_rowsum(out.data_ptr(), rows.data_ptr(), 2 * N, D, n_loc, float(T), z_loc.data_ptr(),
                                   ws.data_ptr(), ws.numel(), int(impl), _stream()), "avssl_ntxent_rowsum")
@@ -594,7 +623,7 @@ def sinkhorn(scores, eps, iters, keep_last=None):
     Btot, P = scores.shape
     keep = Btot if keep_last is None else int(keep_last)
     out = torch.empty(keep, P, dtype=_f32, device=scores.device)
-    ws = _workspace(scores.device, lib.avssl_sinkhorn_workspace_bytes(Btot, P))
+    ws = _workspace(scores.device, lib.avssl_sinkhorn_workspace_bytes(Btot, P), "sinkhorn")
     check(lib.avssl_sinkhorn(scores.data_ptr(), Btot, P, float(eps), int(iters), keep, out.data_ptr(),
                              ws.data_ptr(), ws.numel(), _stream()), "avssl_sinkhorn")
     return out
@@ -651,7 +680,7 @@ def swav_ce(scores, codes, n_crops, bs, T, pair_w=None, want_grad=True):
     pair_w = np.ascontiguousarray(pair_w, dtype=np.float32)
     loss = torch.empty(1, dtype=_f32, device=scores.device)
     d = torch.empty_like(scores) if want_grad else None
-    ws = _workspace(scores.device, lib.avssl_swav_ce_workspace_bytes(n_crops * bs))
+    ws = _workspace(scores.device, lib.avssl_swav_ce_workspace_bytes(n_crops * bs), "swav_ce")
     check(lib.avssl_swav_ce_fwd_bwd(scores.data_ptr(), codes.data_ptr(), n_crops, n_assign, bs, P, float(T),
                                     pair_w.ctypes.data, loss.data_ptr(), d.data_ptr() if want_grad else None,
                                     ws.data_ptr(), ws.numel(), _stream()), "avssl_swav_ce_fwd_bwd")

@@ -20,7 +20,7 @@ import logging
 import torch
 
 from . import ops
-from .contrastive import _ByolSimFn
+from .autograd import ByolSimilarity
 
 logger = logging.getLogger(__name__)
 
@@ -70,7 +70,7 @@ def contrast_forward(self, feats, keys):
         with torch.no_grad():
             k = self.head_projector_hist(key)
             k, _ = ops.l2norm_fwd(k.float().contiguous(), eps=0.0)       # Normalize(dim=1), no eps
-        loss = loss + _ByolSimFn.apply(q.float(), k, self.T, True)      # -mean(l2(q).k)/T, q normalised inside
+        loss = loss + ByolSimilarity.apply(q.float(), k, self.T, True)  # -mean(l2(q).k)/T, q normalised inside
     return loss / len(feats) + 1.0 / self.T
 
 

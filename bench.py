@@ -11,10 +11,18 @@ Workload (configs[1] of BASELINE.json, head only — SURVEY.md §8(d) cfg2):
   forward/backward are out of scope and excluded.  Synthetic embeddings, random
   weights.
 
-`value`  : clips/s = N * 64 / step time, inputs already resident in HBM.
-`e2e`    : same metric through the public module API with pinned HOST embeddings:
-           H2D of the step's inputs and D2H of the loss inside the timed region,
-           one host synchronisation per step.
+Both numbers go through the reference-facing API, the call tools/train.py:63-77 makes:
+    contrastive_forward(model, cfg, inputs, index, time, epoch_exact) ; loss.backward()
+on a `ContrastiveModel` whose two backbones are a stub registered in `_MODEL_TYPES`: it
+OWNS the 164 Slow-R50 parameter tensors (so the EMA streams the real 36.1 M parameters)
+and forwards the synthetic [B, D] embedding it is given (backbone compute is excluded).
+`value`  : clips/s = N * 64 / step time, inputs already resident in HBM (CUDA-graph replay
+           of the captured module step).
+`e2e`    : the same call with pinned HOST embeddings: H2D of the step's inputs and D2H of
+           the loss inside the timed region.  `e2e.strict_sync` (also at the top level as
+           `e2e_strict`) waits for step i's loss before enqueuing step i+1.
+`ops_level`: the kernel-only step (EMA[+push] -> head launch) driven through ops.* as in
+           round 1, kept beside the module number.
 `roofline`: the dominant kernel (the EMA, 93 % of the step's bytes): algorithmic
            bytes 12 B/param per launch / CUDA-event duration of that launch.
 `cpu_baseline` / `--impl reference`: the CPU oracle port of the same step
@@ -138,6 +146,10 @@ def run_cpu(steps, warmup, budget_s=None):
 
 
 def reference_arm(args):
+    """CPU arm: the oracle port of the step (torch CPU ops in the reference's own order).  The unmodified
+    reference module cannot travel to the GPU box (it is never copied into this repo, and its imports
+    need fvcore / pytorchvideo, absent from the image), so `kind` is "port": the port is pinned bit for
+    bit to the unmodified reference by tests/golden (see oracle/contrastive_oracle.py)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -151,7 +163,9 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": done, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU oracle port (torch CPU ops = the reference's own op sequence), rank 0 only"},
+        "config": {"workload": WORKLOAD, "note": "CPU oracle port (torch CPU ops = the reference's own op sequence, pinned to the "
+                                                 "unmodified reference by tests/golden; the reference itself cannot travel to "
+                                                 "the GPU box), rank 0 only"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -159,6 +173,57 @@ def reference_arm(args):
 
 
 # ------------------------------------------------------------------------ GPU arm
+class _Node:
+    """Attribute tree standing in for the host application's fvcore CfgNode."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def head_cfg(world):
+    """The cfg keys the contrastive path reads (configs/defaults.py:87-158), at the BASELINE configs[1] values."""
+    return _Node(
+        NUM_GPUS=world, NUM_SHARDS=1, SHARD_ID=0,
+        MODEL=_Node(MODEL_NAME="ContrastiveModel", ARCH="stub_slow_r50"),
+        BN=_Node(NORM_TYPE="batchnorm", NUM_SYNC_DEVICES=1),  # no cross-GPU sync BN -> shuffle BN is ON (the reference default)
+        DATA=_Node(TRAIN_CROP_NUM_TEMPORAL=2, TRAIN_CROP_NUM_SPATIAL=1),
+        SOLVER=_Node(MAX_EPOCH=200),
+        TRAIN=_Node(BATCH_SIZE=B_PER_GPU * world),
+        CONTRASTIVE=_Node(T=TEMP, DIM=DIM, LENGTH=239975, QUEUE_LEN=QUEUE_LEN, MOMENTUM=MOMENTUM, MOMENTUM_ANNEALING=False,
+                          TYPE="moco", INTERP_MEMORY=False, MEM_TYPE="1d", LOCAL_SHUFFLE_BN=True,
+                          MOCO_MULTI_VIEW_QUEUE=False, PREDICTOR_DEPTHS=[], SEQUENTIAL=False, SIMCLR_DIST_ON=True,
+                          SWAV_QEUE_LEN=0, KNN_ON=False))
+
+
+def register_stub_backbone():
+    import torch.nn as nn
+    from advise_video_ssl_b200 import contrastive as C
+
+    class SlowR50Stub(nn.Module):
+        """Owns the reference's Slow-R50 + MLP-head parameter list (164 tensors, 36,095,168 fp32) so that the
+        momentum update streams the real thing; its forward hands the synthetic [B, D] embedding through
+        (backbone forward/backward are out of scope and excluded)."""
+
+        def __init__(self, cfg):
+            super().__init__()
+            g = torch.Generator().manual_seed(1234)
+            self.weights = nn.ParameterList([nn.Parameter(torch.randn(s, generator=g) * 0.02) for s in param_shapes()])
+
+        def forward(self, x):
+            return x[0] if isinstance(x, (list, tuple)) else x
+
+    C._MODEL_TYPES["stub_slow_r50"] = SlowR50Stub
+    return C
+
+
+class Timer:
+    def __init__(self):
+        self.a, self.b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def ms(self):
+        return self.a.elapsed_time(self.b)
+
+
 def gpu_arm(args):
     import torch.distributed as dist
     from advise_video_ssl_b200 import ops, _lib
@@ -181,85 +246,7 @@ def gpu_arm(args):
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
     n_gpus = world
-
-    g = torch.Generator().manual_seed(1000 + rank)
-    online = [(torch.randn(s, generator=g) * 0.02).to(dev) for s in param_shapes()]
-    hist = [torch.zeros_like(o) for o in online]
-    n_params = sum(o.numel() for o in online)
-    stdv = 1.0 / (DIM / 3) ** 0.5
-    gq = torch.Generator().manual_seed(7)
-    queue = torch.rand(QUEUE_LEN, DIM, generator=gq).mul_(2 * stdv).add_(-stdv).to(dev)
-    feats_h = [torch.randn(B_PER_GPU, DIM, generator=g).pin_memory() for _ in range(POOL)]
-    keys_h = [torch.nn.functional.normalize(torch.randn(B_PER_GPU, DIM, generator=g)).pin_memory() for _ in range(POOL)]
-    feats = [t.to(dev) for t in feats_h]
-    keys = [t.to(dev) for t in keys_h]
-    it = torch.zeros(1, dtype=torch.int64, device=dev)
-    ptr = torch.zeros(1, dtype=torch.int64, device=dev)
-    status = torch.zeros(1, dtype=torch.int32, device=dev)
-    plan = ops.EmaPlan(online, hist)
-    # C3, the cross-GPU key gather.  "peer" (default): the keys are stored straight into every
-    # rank's exchange buffer over NVLink by extra CTAs of the EMA launch, and the head launch waits
-    # for them after its sweep -- no collective kernel, no side stream.  "nccl": all_gather on a
-    # high-priority side stream next to the EMA (kept for comparison).
-    use_peer = world > 1 and args.exchange == "peer"
-    xchg, exchange_note = None, None
-    if use_peer:
-        try:
-            xchg = ops.PeerExchange(B_PER_GPU, DIM)  # raises on every rank together if any rank cannot map its peers
-        except Exception as e:  # noqa: BLE001  (e.g. CUDA IPC not permitted in this container): NCCL path, and say so
-            use_peer, exchange_note = False, "peer exchange unavailable, NCCL all_gather used: %s" % e
-    use_nccl = world > 1 and not use_peer
-    gathered = torch.empty(world * B_PER_GPU, DIM, device=dev) if world > 1 else None
-    comm = torch.cuda.Stream(device=dev, priority=-1) if use_nccl else None
-    exchange_verified = None
-    if use_peer:  # one untimed round against NCCL's all_gather: bit-identical or abort
-        dist.all_gather_into_tensor(gathered, keys[0])
-        xchg.push(keys[0])
-        exchange_verified = bool(torch.equal(xchg.wait_gather_all(), gathered))
-        assert exchange_verified, "peer exchange differs from NCCL all_gather"
     impl = {"auto": _lib.IMPL_AUTO, "simt": _lib.IMPL_SIMT, "tc3x": _lib.IMPL_TC3X, "tc1x": _lib.IMPL_TC1X}[args.kernel]
-    out = {}
-    head_ws = torch.zeros(ops.moco_infonce_workspace_bytes(B_PER_GPU, DIM, QUEUE_LEN, 1), dtype=torch.uint8, device=dev)
-    state = {"n": 0}
-    launches_per_step = 2 if args.kernel != "simt" else 4  # ema + fused head (simt: ema, split, combine, enqueue)
-    if use_peer and args.kernel == "simt":
-        raise SystemExit("--exchange peer needs the tcgen05 head kernel (fused wait)")
-    ema_events = []
-
-    def ema_part(k_for_gather, time_ema=False, after=None, push=True):
-        """K1 (+ C3: the key push fused into the same launch, or NCCL's all_gather on the side stream)."""
-        if time_ema:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        if use_nccl:
-            # C3: key all_gather on the comm stream, overlapped with the EMA kernel
-            comm.wait_stream(torch.cuda.current_stream())
-            if after is not None:
-                comm.wait_event(after)
-            with torch.cuda.stream(comm):
-                dist.all_gather_into_tensor(gathered, k_for_gather)
-        plan.run(MOMENTUM, it, bump_iter=True, first_iter=state["n"] == 0,  # host mirror of `iter`, as the module keeps
-                 push=(xchg, k_for_gather) if (use_peer and push) else None)
-        state["n"] += 1
-        if time_ema:
-            e1.record()
-            ema_events.append((e0, e1))
-
-    def head_part(f, k):
-        """K2+K3+K4 in one cooperative launch: loss/grad against the old queue, then the ring write."""
-        if use_peer:  # the launch itself waits for every rank's keys and reads this rank's block
-            return ops.moco_infonce(f, None, queue, TEMP, want_logits=not args.no_logits, impl=impl, out=out,
-                                    enqueue=(ptr, status), workspace=head_ws, peer=xchg)
-        if use_nccl:
-            torch.cuda.current_stream().wait_stream(comm)
-            k = gathered[rank * B_PER_GPU:(rank + 1) * B_PER_GPU]
-        return ops.moco_infonce(f, [k], queue, TEMP, want_logits=not args.no_logits, impl=impl, out=out,
-                                enqueue=(ptr, status), workspace=head_ws)
-
-    def step(i, f, k, time_ema=False):
-        """EMA -> [gather keys] -> fused head + enqueue (reference order, :308-316, :486-503)."""
-        ema_part(k, time_ema)
-        return head_part(f, k)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -267,39 +254,82 @@ def gpu_arm(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- device-resident timing (value)
-    for i in range(args.warmup):
-        r = step(i, feats[i % POOL], keys[i % POOL])
-        if not out:
-            out.update(r)  # the step's output tensors are reused from here on (static for graph capture)
-    sync_all()
+    # ---- synthetic data (seeded per rank), shared by the module path and the ops-level path
+    g = torch.Generator().manual_seed(1000 + rank)
+    stdv = 1.0 / (DIM / 3) ** 0.5
+    gq = torch.Generator().manual_seed(7)
+    queue0 = torch.rand(QUEUE_LEN, DIM, generator=gq).mul_(2 * stdv).add_(-stdv)
+    feats_h = [torch.randn(B_PER_GPU, DIM, generator=g).pin_memory() for _ in range(POOL)]
+    kfeat_h = [torch.randn(B_PER_GPU, DIM, generator=g).pin_memory() for _ in range(POOL)]  # raw key-encoder outputs
 
-    # One CUDA graph per input slot: [key all_gather on the comm stream ||] EMA -> fused head.  Replaying
-    # it removes the per-launch host work (which bounds the step once the NCCL enqueue is added) and
-    # the launch gaps between the kernels; the kernels and their order are the same as in eager mode.
+    # =========================================================== the module path (value, e2e)
+    C = register_stub_backbone()
+    cfg = head_cfg(world)
+    torch.manual_seed(99)
+    model = C.ContrastiveModel(cfg).to(dev).train()
+    model.infonce_impl = impl
+    model.materialize_logits = not args.no_logits
+    if args.exchange == "nccl":
+        model.enable_peer_exchange(False)
+    with torch.no_grad():
+        model.queue_x.copy_(queue0)
+    n_params = sum(p.numel() for p in model.backbone_hist.parameters())
+    n_tensors = len(list(model.backbone_hist.parameters()))
+    index = torch.arange(B_PER_GPU, device=dev)
+    time_in = torch.zeros(B_PER_GPU, 2, 1, device=dev)
+    xq = [t.to(dev).requires_grad_(True) for t in feats_h]  # static leaves: one pair per input slot
+    xk = [t.to(dev) for t in kfeat_h]
+    last = {}
+
+    def module_step(slot):
+        """What tools/train.py does per iteration with the head (:63-77, :202-205): forward through the
+        public entry point, then backward of the returned loss."""
+        xq[slot].grad = None
+        _, preds, loss, do_backward = C.contrastive_forward(model, cfg, [[xq[slot]], [xk[slot]]], index, time_in, 0.0)
+        if do_backward:
+            loss.backward()
+        last["loss"], last["grad"], last["preds"] = loss, xq[slot].grad, preds
+        return loss
+
+    for i in range(args.warmup):
+        module_step(i % POOL)
+    sync_all()
+    deferred_path = any(ex is not None for ex in model._peer_xchgs.values())
+    torch.manual_seed(4242)  # every rank captures with its own CPU generator state; rank 0's draws decide (C2)
+
     graphs, pool_graph, graph_err = None, None, None
+    losses_static = [None] * POOL
     if not args.no_graph:
         try:
             graphs = []
             for slot in range(POOL):
                 g_ = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g_):
-                    step(slot, feats[slot], keys[slot])
+                    losses_static[slot] = module_step(slot)
                 graphs.append(g_)
-            # ... and one graph holding all POOL steps back to back: relaunching one graph is cheaper on the
-            # host than alternating between POOL of them, which matters once 8 ranks submit work at the same
-            # time (N=8: 107 us/step with alternating single-step graphs, same kernels).
+            # ... and one graph holding all POOL steps back to back: relaunching one graph is cheaper on the host
+            # than alternating between POOL of them, which matters once 8 ranks submit work at the same time
             pool_graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(pool_graph):
                 for slot in range(POOL):
-                    step(slot, feats[slot], keys[slot])
-            for slot in range(POOL):  # one untimed replay each
+                    module_step(slot)
+            for slot in range(POOL):
                 graphs[slot].replay()
             pool_graph.replay()
             sync_all()
         except Exception as e:  # capture is an optimisation: fall back to eager launches and say so
             graphs, pool_graph, graph_err = None, None, "%s: %s" % (type(e).__name__, e)
             torch.cuda.synchronize()
+
+    def run_steps(n, one_step, many=None):
+        if many is not None:
+            for _ in range(n // POOL):
+                many()
+            for i in range(n % POOL):
+                one_step(i)
+        else:
+            for i in range(n):
+                one_step(i % POOL)
 
     # NVML is set up before the barrier (nvmlInit takes milliseconds and a different time on every rank)
     # and polled by rank 0 only (its calls take a driver-wide lock).
@@ -308,71 +338,64 @@ def gpu_arm(args):
     if rank == 0 and os.environ.get("BENCH_NO_SAMPLER") != "1":
         sampler.start()
 
-    def align_ranks(i=0):
-        """One UNTIMED step after the barrier, N > 1 only: the ranks leave the host barrier up to milliseconds
-        apart, and the first exchange would charge that skew to the timed region of the early ranks (seen as
-        +15 us/step over 200 steps at N=8).  After one coupled step the streams are within microseconds."""
-        if world > 1:
-            step(i, feats[i % POOL], keys[i % POOL])
-
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    align_ranks()
-    t_start.record()
-    if graphs is not None:
-        for _ in range(args.steps // POOL):  # POOL steps per launch ...
-            pool_graph.replay()
-        for i in range(args.steps % POOL):   # ... and the remainder one step at a time: exactly K steps
-            graphs[i].replay()
-    else:
-        for i in range(args.steps):
-            step(i, feats[i % POOL], keys[i % POOL])
-    t_end.record()
+    replay_one = (lambda i: graphs[i].replay()) if graphs is not None else module_step
+    replay_pool = pool_graph.replay if pool_graph is not None else None
+    t_mod = Timer()
+    if world > 1:
+        # one UNTIMED coupled step after the barrier: the ranks leave the host barrier up to milliseconds apart
+        # and the first exchange would charge that skew to the timed region of the early ranks
+        replay_one(0)
+    t_mod.a.record()
+    run_steps(args.steps, replay_one, replay_pool)
+    t_mod.b.record()
     sync_all()
     clocks = sampler.stop()
-    ms_total = t_start.elapsed_time(t_end)
+    ms_total = t_mod.ms()
+    loss_val = float(last["loss"].item()) if graphs is None else float(losses_static[(args.steps - 1) % POOL].item())
+    model.check_device_status()
 
-    # duration of the dominant kernel (EMA) with CUDA events on its stream, same step sequence, eager
-    # launches (event records cannot be timed inside a captured graph)
+    # ---- duration of the dominant kernel (the EMA) with CUDA events on its stream, inside the same step
+    # sequence, eager launches (event records cannot be timed inside a captured graph)
+    ema_events = []
+    plain_update = model._update_history
+
+    def timed_update(*a, **k):
+        t = Timer()
+        t.a.record()
+        plain_update(*a, **k)
+        t.b.record()
+        ema_events.append(t)
+
+    model._update_history = timed_update
     for i in range(min(args.steps, 100)):
-        step(i, feats[i % POOL], keys[i % POOL], time_ema=True)
+        module_step(i % POOL)
     sync_all()
-    ema_ms = sum(a.elapsed_time(b) for a, b in ema_events) / len(ema_events)
-    loss_val = float(out["loss"].item())
-    assert int(status.item()) == 0, "device status word set: %d" % int(status.item())
+    del model._update_history
+    ema_ms = sum(t.ms() for t in ema_events) / len(ema_events)
 
-    # ---- end-to-end timing: pinned host inputs, loss read back, one sync per step
-    f_dev = torch.empty(B_PER_GPU, DIM, device=dev)
-    k_dev = torch.empty(B_PER_GPU, DIM, device=dev)
+    # ---- end-to-end through the same API: pinned host inputs in, loss out, every step
     loss_h = torch.empty(2).pin_memory()  # two slots: step i's loss is read while step i+1 runs
-    e2e_steps = args.steps
+    xq_in = torch.empty(B_PER_GPU, DIM, device=dev).requires_grad_(True)
+    xk_in = torch.empty(B_PER_GPU, DIM, device=dev)
 
-    h2d = torch.cuda.Stream(device=dev, priority=-1)
-    copied = torch.cuda.Event()
+    def e2e_step(slot, out_slot=0):
+        with torch.no_grad():
+            xq_in.copy_(feats_h[slot], non_blocking=True)
+            xk_in.copy_(kfeat_h[slot], non_blocking=True)
+        xq_in.grad = None
+        _, _, loss, do_backward = C.contrastive_forward(model, cfg, [[xq_in], [xk_in]], index, time_in, 0.0)
+        if do_backward:
+            loss.backward()
+        loss_h[out_slot:out_slot + 1].copy_(loss.detach().reshape(1), non_blocking=True)
 
-    def e2e_step(i):
-        # The momentum update does not depend on this step's inputs, so the host->device copies run on
-        # a copy stream underneath it; the head (and, for N > 1, the key all_gather) waits for them.
-        if not use_nccl:
-            ema_part(k_dev, push=False)  # launched first: the GPU starts on it while the host enqueues the copies
-        with torch.cuda.stream(h2d):
-            k_dev.copy_(keys_h[i % POOL], non_blocking=True)
-            f_dev.copy_(feats_h[i % POOL], non_blocking=True)
-            if use_peer:
-                xchg.push(k_dev)  # C3 right behind the copy, on the copy stream, still under the EMA
-            copied.record()
-        if use_nccl:
-            ema_part(k_dev, after=copied)  # the key all_gather needs this step's keys
-        torch.cuda.current_stream().wait_event(copied)
-        r = head_part(f_dev, k_dev)
-        loss_h[0:1].copy_(r["loss"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # also orders the next step's copies after this step's reads
+    def e2e_eager(i):
+        e2e_step(i % POOL)
+        torch.cuda.current_stream().synchronize()
         return float(loss_h[0])
 
     for i in range(min(args.warmup, 10)):
-        e2e_step(i)
+        e2e_eager(i)
     sync_all()
-
-    # the same end-to-end step as one graph per input slot: H2D copies (copy stream) || EMA -> head -> loss D2H
     e2e_graphs = None
     if graphs is not None:
         try:
@@ -380,19 +403,7 @@ def gpu_arm(args):
             for slot in range(POOL):
                 g_ = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g_):
-                    cur = torch.cuda.current_stream()
-                    h2d.wait_stream(cur)  # fork: the copies depend on nothing in this step
-                    with torch.cuda.stream(h2d):
-                        k_dev.copy_(keys_h[slot], non_blocking=True)
-                        f_dev.copy_(feats_h[slot], non_blocking=True)
-                        if use_peer:
-                            xchg.push(k_dev)
-                    if use_nccl:
-                        comm.wait_stream(h2d)  # the key all_gather needs this step's keys
-                    ema_part(k_dev, push=False)  # runs beside the copies
-                    cur.wait_stream(h2d)
-                    r = head_part(f_dev, k_dev)
-                    loss_h[slot & 1:(slot & 1) + 1].copy_(r["loss"], non_blocking=True)
+                    e2e_step(slot, slot & 1)
                 e2e_graphs.append(g_)
             for slot in range(POOL):
                 e2e_graphs[slot].replay()
@@ -407,97 +418,123 @@ def gpu_arm(args):
         return float(loss_h[i & 1])
 
     # (a) strict: the host waits for the loss of step i before it enqueues step i+1
-    run_e2e = e2e_graph_step if e2e_graphs is not None else e2e_step
-    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    run_e2e = e2e_graph_step if e2e_graphs is not None else e2e_eager
+    t_e2e = Timer()
     if world > 1:
-        run_e2e(0)  # untimed: aligns the ranks after the host barrier (see align_ranks)
-    e_start.record()
-    for i in range(e2e_steps):
+        run_e2e(0)  # untimed: aligns the ranks after the host barrier
+    t_e2e.a.record()
+    for i in range(args.steps):
         run_e2e(i)
-    e_end.record()
+    t_e2e.b.record()
     sync_all()
-    e2e_strict_ms = e_start.elapsed_time(e_end)
+    e2e_strict_ms = t_e2e.ms()
     e2e_ms, e2e_mode = e2e_strict_ms, "strict: host waits for step i's loss before enqueuing step i+1"
 
-    # (b) one step in flight: the host enqueues step i+1 (its H2D copies included), then waits for and
-    # reads the loss of step i -- every step still copies its inputs from pinned host memory and has
-    # its loss read on the host, one host wait per step; the launch latency hides behind the GPU work.
+    # (b) one step in flight: the host enqueues step i+1 (its H2D copies included), then waits for and reads the
+    # loss of step i -- every step still copies its inputs from pinned host memory and has its loss read on the
+    # host, one host wait per step; the launch latency hides behind the GPU work.
     if e2e_graphs is not None and POOL % 2 == 0:
         done = [torch.cuda.Event(), torch.cuda.Event()]
         acc = 0.0
         sync_all()
         if world > 1:
-            e2e_graph_step(0)  # untimed: aligns the ranks after the host barrier
-        e_start.record()
-        for i in range(e2e_steps):
+            e2e_graph_step(0)
+        t_e2e.a.record()
+        for i in range(args.steps):
             e2e_graphs[i % POOL].replay()
             done[i & 1].record()
             if i > 0:
                 done[(i - 1) & 1].synchronize()
                 acc += float(loss_h[(i - 1) & 1])
-        done[(e2e_steps - 1) & 1].synchronize()
-        acc += float(loss_h[(e2e_steps - 1) & 1])
-        e_end.record()
+        done[(args.steps - 1) & 1].synchronize()
+        acc += float(loss_h[(args.steps - 1) & 1])
+        t_e2e.b.record()
         sync_all()
         assert acc == acc, "non-finite loss in the end-to-end run"
-        e2e_ms = e_start.elapsed_time(e_end)
+        e2e_ms = t_e2e.ms()
         e2e_mode = "one step in flight: step i+1 is enqueued before the host waits for and reads the loss of step i"
+    model.check_device_status()
+
+    # ================================================ the ops-level step (kernel-only, as in round 1)
+    ops_ms = None
+    ops_note = None
+    if not args.no_ops_level:
+        try:
+            ops_ms = ops_level(args, ops, dist, dev, world, rank, impl, queue0, feats_h, kfeat_h, model, sync_all)
+        except Exception as e:  # noqa: BLE001 - secondary number: report, do not fail the line
+            ops_note = "%s: %s" % (type(e).__name__, e)
 
     # max over ranks
     if world > 1:
-        t = torch.tensor([ms_total, e2e_ms, ema_ms, e2e_strict_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms_total, e2e_ms, ema_ms, e2e_strict_ms, ops_ms if ops_ms is not None else -1.0], device=dev,
+                         dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_ms, ema_ms, e2e_strict_ms = (float(x) for x in t.tolist())
+        ms_total, e2e_ms, ema_ms, e2e_strict_ms, om = (float(x) for x in t.tolist())
+        ops_ms = om if om >= 0 else None
 
     ms_per_step = ms_total / args.steps
-    value = n_gpus * B_PER_GPU / (ms_per_step * 1e-3)
-    e2e_value = n_gpus * B_PER_GPU / (e2e_ms / e2e_steps * 1e-3)
+    clips = n_gpus * B_PER_GPU
+    value = clips / (ms_per_step * 1e-3)
     peak, peak_src = measured_peaks()
     ema_bytes = 12 * n_params
     achieved = ema_bytes / (ema_ms * 1e-3) / 1e9
     step_bytes = ema_bytes + 4 * QUEUE_LEN * DIM + 4 * B_PER_GPU * DIM * 3 + 8 * B_PER_GPU * DIM
     if not args.no_logits:
         step_bytes += 4 * B_PER_GPU * (QUEUE_LEN + 1)
+    floor_us = step_bytes / (peak * 1e9) * 1e6
+    own_launches = 3 if (deferred_path or world == 1) else 4  # EMA, Normalize(+push), head(+wait+enqueue) [, wait_gather]
+
+    def per_step(ms):
+        return {"value": clips / (ms / args.steps * 1e-3), "unit": UNIT, "ms_per_step": ms / args.steps}
 
     result = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "step_us": ms_per_step * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": B_PER_GPU, "global_batch": n_gpus * B_PER_GPU,
-                   "queue_len": QUEUE_LEN, "dim": DIM, "T": TEMP, "ema_tensors": len(online),
-                   "ema_params": n_params, "logits_materialised": not args.no_logits,
-                   "infonce_kernel": args.kernel, "cuda_graph": graphs is not None, "steps_per_graph_launch": POOL if graphs is not None else None,
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B_PER_GPU, "global_batch": clips,
+                   "queue_len": QUEUE_LEN, "dim": DIM, "T": TEMP, "ema_tensors": n_tensors, "ema_params": n_params,
+                   "api": "contrastive_forward(model, cfg, inputs, index, time, epoch) + loss.backward() on ContrastiveModel "
+                          "(moco, SEQUENTIAL off, shuffle BN on, KNN_ON off, queue_mode=%s); stub backbone forwards the "
+                          "synthetic embedding" % model.queue_mode,
+                   "logits_materialised": not args.no_logits, "infonce_kernel": args.kernel,
+                   "cuda_graph": graphs is not None, "steps_per_graph_launch": POOL if graphs is not None else None,
+                   "shuffle_perm": "drawn per captured step (frozen in its graph); %d input slots" % POOL,
                    "rank_alignment": "one untimed step between the barrier and the first timed event (N>1)" if world > 1 else None,
                    "e2e_cuda_graph": e2e_graphs is not None, "cuda_graph_error": graph_err,
-                   "key_exchange": ("nvlink peer stores fused into the EMA launch, wait fused into the head launch"
-                                    if use_peer else ("nccl all_gather on a side stream" if use_nccl else "none (1 GPU)")),
-                   "key_exchange_verified_vs_nccl": exchange_verified, "key_exchange_note": exchange_note,
-                   "parallelism": "dp%d (queue/EMA replicated, batch sharded; key exchange only)" % n_gpus,
+                   "key_exchange": ("Normalize + NVLink peer stores in one launch; the head launch waits, un-shuffles by index "
+                                    "and enqueues rank 0's rows" if deferred_path and world > 1 else
+                                    ("exchange buffer on one GPU (un-shuffle by index inside the head launch)" if deferred_path
+                                     else ("nccl all_gather + broadcast" if world > 1 else "none"))),
+                   "clip_shuffle": "all-to-all of the key-encoder input rows on a side stream under the EMA" if world > 1
+                                   else "local row gather on a side stream under the EMA",
+                   "parallelism": "dp%d (queue/EMA replicated, batch sharded; exchanges: shuffle all-to-all, keys)" % n_gpus,
                    "l2": "no explicit flush: one step streams %.0f MB (> 126 MB L2) so nothing survives between steps" % (step_bytes / 1e6)},
-        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / e2e_steps,
-                "h2d_bytes_per_step": 2 * 4 * B_PER_GPU * DIM, "d2h_bytes_per_step": 4,
-                "mode": e2e_mode,
-                "strict_sync": {"value": n_gpus * B_PER_GPU / (e2e_strict_ms / e2e_steps * 1e-3), "unit": UNIT,
-                                "ms_per_step": e2e_strict_ms / e2e_steps},
-                "note": "pinned host embeddings -> H2D on a copy stream (under the EMA) -> head+enqueue -> loss D2H to pinned memory, one host wait per step"},
-        "gpu_launches": launches_per_step * args.steps,
+        "e2e": dict(per_step(e2e_ms), h2d_bytes_per_step=2 * 4 * B_PER_GPU * DIM, d2h_bytes_per_step=4, mode=e2e_mode,
+                    strict_sync=per_step(e2e_strict_ms),
+                    note="pinned host embeddings -> H2D -> contrastive_forward + backward -> loss D2H to pinned memory, one host wait per step"),
+        "e2e_strict": per_step(e2e_strict_ms),
+        "ops_level": ({"ms_per_step": ops_ms / args.steps, "step_us": ops_ms / args.steps * 1e3,
+                       "what": "EMA[+push] launch -> head launch driven through ops.* (no module, no autograd), CUDA-graph replay"}
+                      if ops_ms is not None else {"skipped": ops_note or "--no-ops-level"}),
+        "gpu_launches": own_launches * args.steps,
+        "gpu_launches_note": "own kernels per step: EMA, Normalize(+push), head(+wait+enqueue); plus torch's row gather of the "
+                             "shuffle and one elementwise multiply in backward",
         "clocks": clocks,
         "roofline": {"kernel": "ema_multi_tensor_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": EMA_DRAM_TRAFFIC,
                      "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch "
                                        "(profiles/r1_ema_ncu.md)",
                      "bytes_per_launch": ema_bytes, "us_per_launch": ema_ms * 1e3, "peak_source": peak_src},
-        "step_roofline": {"bytes_per_step": step_bytes, "floor_us": step_bytes / (peak * 1e9) * 1e6,
-                          "frac": (step_bytes / (peak * 1e9) * 1e3) / ms_per_step},
+        "step_roofline": {"bytes_per_step": step_bytes, "floor_us": floor_us, "frac": floor_us / (ms_per_step * 1e3)},
         "loss": loss_val,
     }
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
-        dt, done = run_cpu(50, 2, budget_s=15.0)
+        dt, done_n = run_cpu(50, 2, budget_s=15.0)
         result["cpu_baseline"] = {
             "value": B_PER_GPU / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
             "ms_per_step": dt * 1e3,
-            "sample": "%d full steps of the same workload on the CPU oracle (torch CPU, all threads) after 2 warm-up" % done}
+            "sample": "%d full steps of the same workload on the CPU oracle (torch CPU, all threads) after 2 warm-up" % done_n}
     if rank == 0:
         json_out.write(json.dumps(result) + "\n")
         json_out.flush()
@@ -511,6 +548,83 @@ def gpu_arm(args):
     return 0
 
 
+def ops_level(args, ops, dist, dev, world, rank, impl, queue0, feats_h, kfeat_h, model, sync_all):
+    """The two-launch kernel-only step of round 1, for comparison: EMA (+ the key push riding in the same
+    launch) -> head (+ wait + enqueue).  Keys are pre-normalised device tensors, no autograd, no shuffle."""
+    online, hist = model._ema_lists()
+    plan = ops.EmaPlan(online, hist)
+    queue = queue0.to(dev)
+    feats = [t.to(dev) for t in feats_h]
+    keys = [torch.nn.functional.normalize(t).to(dev) for t in kfeat_h]
+    it = torch.ones(1, dtype=torch.int64, device=dev)
+    ptr = torch.zeros(1, dtype=torch.int64, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    xchg = None
+    if world > 1 and args.exchange == "peer" and args.kernel != "simt":
+        xchg = ops.PeerExchange(B_PER_GPU, DIM)
+    gathered = torch.empty(world * B_PER_GPU, DIM, device=dev) if (world > 1 and xchg is None) else None
+    comm = torch.cuda.Stream(device=dev, priority=-1) if gathered is not None else None
+    gperm = torch.Generator().manual_seed(31337)  # the same un-shuffle table on every rank
+    restore = torch.argsort(torch.randperm(world * B_PER_GPU, generator=gperm)).view(world, B_PER_GPU).to(dev)
+    out = {}
+    ws = torch.zeros(ops.moco_infonce_workspace_bytes(B_PER_GPU, DIM, QUEUE_LEN, 1), dtype=torch.uint8, device=dev)
+
+    def step(slot):
+        f, k = feats[slot], keys[slot]
+        if gathered is not None:
+            comm.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(comm):
+                dist.all_gather_into_tensor(gathered, k)
+        plan.run(MOMENTUM, it, bump_iter=True, first_iter=False, push=(xchg, k) if xchg is not None else None)
+        if xchg is not None:
+            r = ops.moco_infonce(f, None, queue, TEMP, want_logits=not args.no_logits, impl=impl, out=out,
+                                 enqueue=(ptr, status), workspace=ws, peer=xchg, peer_row_idx=restore[rank].contiguous(),
+                                 enq_row_idx=restore[0].contiguous())
+        else:
+            if gathered is not None:
+                torch.cuda.current_stream().wait_stream(comm)
+                k = gathered[rank * B_PER_GPU:(rank + 1) * B_PER_GPU]
+            r = ops.moco_infonce(f, [k], queue, TEMP, want_logits=not args.no_logits, impl=impl, out=out,
+                                 enqueue=(ptr, status), workspace=ws)
+        if not out:
+            out.update(r)
+
+    for i in range(max(3, min(args.warmup, 10))):
+        step(i % POOL)
+    sync_all()
+    one, many = step, None
+    if not args.no_graph:
+        pool_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(pool_graph):
+            for slot in range(POOL):
+                step(slot)
+        singles = []
+        for slot in range(POOL):
+            g_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_):
+                step(slot)
+            singles.append(g_)
+        pool_graph.replay()
+        sync_all()
+        one, many = (lambda i: singles[i].replay()), pool_graph.replay
+    t = Timer()
+    if world > 1:
+        one(0)
+    t.a.record()
+    if many is not None:
+        for _ in range(args.steps // POOL):
+            many()
+        for i in range(args.steps % POOL):
+            one(i)
+    else:
+        for i in range(args.steps):
+            one(i % POOL)
+    t.b.record()
+    sync_all()
+    assert int(status.item()) == 0, "device status word set in the ops-level run: %d" % int(status.item())
+    return t.ms()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -520,6 +634,7 @@ def main():
     ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tc3x", "tc1x"])
     ap.add_argument("--no-logits", action="store_true", help="do not materialise the [B,K+1] logits tensor")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ops-level", action="store_true", help="skip the secondary kernel-only (ops.*) measurement")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: cross-GPU key gather over NVLink peer memory (default) or NCCL all_gather")

@@ -47,6 +47,7 @@ typedef enum {
 /* Bits of the device-side status word written by kernels that replace host asserts. */
 #define AVSSL_DEVFLAG_QUEUE_OVERRUN 1u /* ptr + n > K   (models/contrastive.py:285) */
 #define AVSSL_DEVFLAG_BAD_INDEX 2u     /* bank index out of range                   */
+#define AVSSL_DEVFLAG_PEER_TIMEOUT 4u  /* a peer's push did not arrive within avssl_peer_xchg.timeout_ms */
 
 AVSSL_API int avssl_abi_version(void);
 AVSSL_API const char* avssl_last_error(void);
@@ -263,6 +264,10 @@ typedef struct {
   void* base[AVSSL_MAX_PEERS]; /* exchange buffers of all ranks, in this process's address space */
   int world, rank;
   int rows_per_rank, D;        /* every rank pushes [rows_per_rank, D] fp32 per step */
+  uint32_t timeout_ms;         /* bound of the consumer's spin on a peer's flag; 0 = wait forever.  On expiry
+                                  AVSSL_DEVFLAG_PEER_TIMEOUT is or-ed into the status word and the kernel
+                                  carries on (that step's keys are garbage; the host must stop). */
+  uint32_t reserved_;
 } avssl_peer_xchg;
 
 AVSSL_API size_t avssl_peer_xchg_bytes(int world, int rows_per_rank, int D);
@@ -272,6 +277,11 @@ AVSSL_API int avssl_peer_close(void* dev_ptr);
 AVSSL_API int avssl_peer_free(void* dev_ptr);
 /* push: `world` CTAs, one per destination rank (stand-alone launch). */
 AVSSL_API int avssl_peer_push_rows(const avssl_peer_xchg* x, const float* rows, void* stream);
+/* push with Normalize fused in (models/contrastive.py:923-934 applied to the key features, :350):
+ * what travels is feat / max(||feat||, eps), bit-identical to avssl_l2norm_fwd followed by
+ * avssl_peer_push_rows.  y_local_out (optional, [rows_per_rank, D]) receives this rank's rows. */
+AVSSL_API int avssl_l2norm_push_rows(const avssl_peer_xchg* x, const float* feat, float eps, float* y_local_out,
+                           void* stream);
 /* wait for the current epoch from every rank, then out[i] = gathered[row_idx[i]] (row_idx NULL:
  * this rank's own block, n_out <= rows_per_rank).  gathered is [world * rows_per_rank, D] in rank
  * order = what cat_all_gather returns.  Out-of-range indices set AVSSL_DEVFLAG_BAD_INDEX. */
@@ -288,9 +298,16 @@ AVSSL_API int avssl_ema_multi_tensor_push(const avssl_ema_chunk* table_dev, int6
  * key rows are taken from the exchange buffer (row i = gathered[row_idx ? row_idx[i] : rank*B + i])
  * after the merge CTAs have waited for the current epoch -- the sweep over the queue never waits.
  * tcgen05 kernels only (AVSSL_ERR_UNSUPPORTED otherwise: use avssl_peer_wait_gather first).
- * ptr_dev may be NULL (no enqueue). */
+ * ptr_dev may be NULL (no enqueue).
+ * Queue consistency across ranks (C9: the reference enqueues local keys and lets DDP's buffer
+ * broadcast, models/build.py:76-83, overwrite every queue with rank 0's): the rows written to the
+ * queue are gathered[enq_row_idx[e]], e < n_enq, and ptr advances by n_enq (K % n_enq == 0).
+ * enq_row_idx NULL: this rank's own block (n_enq must be B).  With enq_row_idx = rank 0's rows on
+ * every rank the queues stay bit-identical without any broadcast; with all world*B rows it is
+ * canonical MoCo. */
 AVSSL_API int avssl_moco_infonce_fwd_bwd_enqueue_peer(const float* feat_q, const avssl_peer_xchg* x,
-                                            const int64_t* row_idx, float* queue, int64_t* ptr_dev,
+                                            const int64_t* row_idx, const int64_t* enq_row_idx, int n_enq,
+                                            float* queue, int64_t* ptr_dev,
                                             uint32_t* status_dev, int B, int D, int K, float T, float* q_out,
                                             float* loss_out, float* dfeat_out, float* row_lse_out,
                                             float* logits_out, void* workspace, size_t workspace_bytes,

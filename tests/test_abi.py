@@ -29,7 +29,7 @@ def test_header_symbols_exported_and_bound():
     # nothing but the C-ABI leaks out of the shared object
     leaked = [l for l in out.splitlines() if " T " in l and "avssl_" not in l]
     assert not leaked, leaked
-    assert _lib.lib.avssl_abi_version() == 1
+    assert _lib.lib.avssl_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_header_compiles_as_plain_c(tmp_path):
@@ -44,9 +44,9 @@ def test_struct_layout_matches():
     assert ctypes.sizeof(_lib.EmaChunk) == 24
     assert _lib.EmaChunk.hist.offset == 8 and _lib.EmaChunk.n.offset == 16 and _lib.EmaChunk.flags.offset == 20
     assert _lib.lib.avssl_ema_chunk_elems() == 4096
-    # avssl_peer_xchg: 16 pointers + world, rank, rows_per_rank, D
-    assert ctypes.sizeof(_lib.PeerXchg) == 16 * 8 + 16
-    assert _lib.PeerXchg.world.offset == 128 and _lib.PeerXchg.D.offset == 140
+    # avssl_peer_xchg: 16 pointers + world, rank, rows_per_rank, D + timeout_ms, reserved
+    assert ctypes.sizeof(_lib.PeerXchg) == 16 * 8 + 24
+    assert _lib.PeerXchg.world.offset == 128 and _lib.PeerXchg.D.offset == 140 and _lib.PeerXchg.timeout_ms.offset == 144
     assert _lib.lib.avssl_peer_xchg_bytes(8, 64, 128) == 256 + 2 * 8 * 64 * 128 * 4
     assert _lib.lib.avssl_peer_xchg_bytes(17, 64, 128) == 0
 

@@ -113,6 +113,38 @@ def _body_shuffle(rank, world):
     assert torch.equal(back, parts[rank].flatten(1).sum(1, keepdim=True))
 
 
+def _body_shuffle_local_group(rank, world):
+    """LOCAL_SHUFFLE_BN with a real per-node group smaller than WORLD (the reference's SLURM path):
+    the permutation comes from GLOBAL rank 0 (broadcast over WORLD, :199-201) but rows are exchanged
+    inside each node's group only; shuffle and un-shuffle must use the same group."""
+    from helpers import make_cfg, register_backbones
+    from advise_video_ssl_b200 import distributed as du
+    from oracle import contrastive_oracle as O
+    C = register_backbones()
+    local = 2
+    groups = [dist.new_group(list(range(n * local, (n + 1) * local))) for n in range(world // local)]
+    du._LOCAL_PROCESS_GROUP = groups[rank // local]
+    try:
+        cfg = make_cfg(CONTRASTIVE__TYPE="moco", CONTRASTIVE__DIM=8, CONTRASTIVE__QUEUE_LEN=32, NUM_GPUS=local,
+                       NUM_SHARDS=world // local)
+        model = C.ContrastiveModel(cfg).train()
+        assert du.get_local_size() == local and du.get_local_rank() == rank % local
+        B = 6
+        gen = torch.Generator().manual_seed(321)
+        parts = [torch.randn(B, 4, generator=gen) for _ in range(world)]
+        torch.manual_seed(5 + rank)
+        (x,), restore = model._batch_shuffle([parts[rank]])
+        torch.manual_seed(5)  # global rank 0's draw
+        perm = torch.randperm(local * B)
+        node = rank // local
+        ref_x, ref_restore = O.shuffle_emulated(parts[node * local:(node + 1) * local], perm)
+        assert torch.equal(x, ref_x[rank % local]) and torch.equal(restore, ref_restore)
+        y = x * 2 + 1
+        assert torch.equal(model._batch_unshuffle(y, restore), parts[rank] * 2 + 1)
+    finally:
+        du._LOCAL_PROCESS_GROUP = None
+
+
 def _body_dist_sinkhorn(rank, world):
     """ops.sinkhorn_distributed is the multi-node cold path; it needs CUDA tensors, so on
     gloo/CPU only the oracle's rank emulation is checked for consistency with the
@@ -128,3 +160,7 @@ def _body_dist_sinkhorn(rank, world):
 @pytest.mark.parametrize("fn", ["_body_helpers", "_body_allgather_grad", "_body_shuffle", "_body_dist_sinkhorn"])
 def test_world2(fn):
     _run(fn)
+
+
+def test_world4_local_groups_of_2():
+    _run("_body_shuffle_local_group", world=4)

@@ -442,9 +442,82 @@ def test_state_dict_contract():
     # EMA pointer table survives load_state_dict (in-place copy) and is rebuilt after .to()
     x = torch.randn(4, 16).cuda()
     model([[x], [x]], torch.arange(4).cuda(), torch.zeros(4, 2, 1).cuda(), 0.0)
-    plan = model._ema_plan
+    plan = model._ema[2]
     model.load_state_dict(sd)
-    assert model._ema_plan is plan and int(model.iter.item()) == 0
+    model._update_history()
+    assert model._ema[2] is plan and int(model.iter.item()) == 0
     model.cuda()
-    assert model._ema_plan is None
+    assert model._ema is None
     np.testing.assert_equal(int(model.ptr.item()), 0)
+    # the status word is a plain attribute that follows the module between devices
+    assert model._status.is_cuda and "_status" not in dict(model.named_buffers())
+
+
+def test_ema_plan_follows_rebound_parameter_storage():
+    """The reference itself re-seats `p.data` every step (models/contrastive.py:172); a pointer table that
+    survived such a rebind would read and write freed memory.  The table is re-validated on every call."""
+    cfg = make_cfg(CONTRASTIVE__TYPE="moco", CONTRASTIVE__DIM=16, CONTRASTIVE__QUEUE_LEN=64, CONTRASTIVE__MOMENTUM=0.75)
+    C, model = _model(cfg)
+    model._update_history()           # iter == 0: copy, then blend
+    plan = model._ema[2]
+    w_on = model.backbone.proj.weight
+    w_hi = model.backbone_hist.proj.weight
+    keep_alive = w_hi.data            # noqa: F841  (the old storage stays allocated: a stale table would hit it)
+    w_hi.data = w_hi.data.clone() * 0 + 3.0
+    w_on.data = w_on.data.clone()
+    with torch.no_grad():
+        model.iter += 1
+    model._update_history()
+    assert model._ema[2] is not plan
+    ref = w_on.detach().cpu() * (1.0 - 0.75) + torch.full_like(w_on.detach().cpu(), 3.0) * 0.75
+    assert torch.equal(w_hi.detach().cpu(), ref)
+
+
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_module_step_captures_into_a_cuda_graph(shuffle):
+    """contrastive_forward + backward (the call tools/train.py makes) is capturable: no host synchronisation,
+    allocation-stable, and replays reproduce the eager step (same kernels, same order)."""
+    B, D, K, T = 32, 128, 1024, 0.1
+    cfg = make_cfg(CONTRASTIVE__TYPE="moco", CONTRASTIVE__T=T, CONTRASTIVE__DIM=D, CONTRASTIVE__QUEUE_LEN=K,
+                   CONTRASTIVE__MOMENTUM=0.99, MODEL__ARCH="identity")
+    cfg.EMA_SHAPES = [(257, 33), (4096,), (128,)]
+    C = register_backbones()
+    torch.manual_seed(11)
+    model = C.ContrastiveModel(cfg).cuda().train()
+    model._batch_shuffle_on = shuffle
+    ref = C.ContrastiveModel(cfg).cuda().train()
+    ref._batch_shuffle_on = shuffle
+    ref.load_state_dict(model.state_dict())
+    xq = torch.randn(B, D).cuda().requires_grad_(True)
+    xk = torch.randn(B, D).cuda()
+    index, time = torch.arange(B).cuda(), torch.zeros(B, 2, 1).cuda()
+
+    def step(m, q):
+        q.grad = None
+        _, preds, loss, bwd = C.contrastive_forward(m, cfg, [[q], [xk]], index, time, 0.0)
+        assert bwd is True
+        loss.backward()
+        return preds, loss
+
+    for _ in range(3):  # warm-up: workspaces, exchange buffer, host mirror of `iter`
+        step(model, xq)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        preds, loss = step(model, xq)
+    n_replays = 4
+    for _ in range(n_replays):
+        graph.replay()
+    torch.cuda.synchronize()
+    # the same 3 + 1 + n_replays steps, eagerly, on the twin
+    xr = xq.detach().clone().requires_grad_(True)
+    for _ in range(3 + 1 + n_replays):
+        rp, rl = step(ref, xr)
+    torch.cuda.synchronize()
+    assert int(model.iter.item()) == int(ref.iter.item()) == 3 + 1 + n_replays
+    assert torch.equal(model.ptr, ref.ptr)
+    assert torch.equal(model.queue_x, ref.queue_x)   # keys are a row permutation away from the perm, not its values
+    for a, b in zip(model.backbone_hist.parameters(), ref.backbone_hist.parameters()):
+        assert torch.equal(a, b)
+    assert torch.equal(loss, rl) and torch.equal(xq.grad, xr.grad) and torch.equal(preds, rp)
+    assert model.check_device_status() == 0

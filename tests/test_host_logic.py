@@ -169,3 +169,33 @@ def test_state_dict_contract_matches_reference():
                                             [x for x in case["state_dict"] if x not in mine])
         frozen = sorted(n for n, p in m.named_parameters() if not p.requires_grad)
         assert frozen == case["frozen"], name
+
+
+# ------------------------------------------------------------------ shuffle plan (A6, host side)
+@pytest.mark.parametrize("world,bsz", [(1, 7), (2, 5), (4, 3), (8, 64)])
+def test_shuffle_plan_matches_gather_then_select(world, bsz):
+    """The all-to-all lists of every rank, replayed in-process, reproduce the reference's
+    cat_all_gather(x)[perm.view(W, -1)[rank]] (models/contrastive.py:186-207) and its idx_restore."""
+    import numpy as np
+    from advise_video_ssl_b200.shuffle import ShufflePlan
+    from oracle import contrastive_oracle as O
+    g = torch.Generator().manual_seed(world * 100 + bsz)
+    parts = [torch.randn(bsz, 3, generator=g) for _ in range(world)]
+    perm = torch.randperm(world * bsz, generator=g)
+    ref_x, ref_restore = O.shuffle_emulated(parts, perm)
+    cpu = torch.device("cpu")
+    plans = [ShufflePlan(perm.numpy(), world, r, bsz, cpu) for r in range(world)]
+    for r, plan in enumerate(plans):
+        assert torch.equal(plan.restore, ref_restore) and plan.restore.dtype == torch.int64
+        if world == 1:
+            assert torch.equal(plan.shuffled(parts[0]), ref_x[0])
+            continue
+        assert sum(plan.send_counts) == bsz == sum(plan.recv_counts)
+        # what rank r receives: from every source s, s's block destined to r
+        recv = []
+        for s_rank, sp in enumerate(plans):
+            off = int(np.sum(sp.send_counts[:r]))
+            assert sp.send_counts[r] == plan.recv_counts[s_rank]
+            recv.append(parts[s_rank].index_select(0, sp.send_rows)[off:off + sp.send_counts[r]])
+        got = torch.cat(recv).index_select(0, plan.place)
+        assert torch.equal(got, ref_x[r])
