@@ -64,9 +64,10 @@ SIGNATURES = {
     "avssl_ce_target0_fwd": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "avssl_ce_target0_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "avssl_ntxent_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
-    "avssl_ntxent_rowsum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_size_t,
+    "avssl_ntxent_prepare": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "avssl_ntxent_rowsum": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_size_t,
                                     c_int, c_void_p]),
-    "avssl_ntxent_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float,
+    "avssl_ntxent_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float,
                                   c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "avssl_sinkhorn_workspace_bytes": (c_size_t, [c_int, c_int]),
     "avssl_sinkhorn": (c_int, [c_void_p, c_int, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -83,6 +84,10 @@ SIGNATURES = {
     "avssl_moco_infonce_fwd_bwd_enqueue_peer": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                                         c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
                                                         c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "avssl_moco_infonce_fwd_bwd_enqueue_indexed": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int,
+                                                           c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
+                                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                           c_size_t, c_int, c_void_p]),
     "avssl_multi_l2norm_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "avssl_multi_l2norm": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "avssl_swav_ce_workspace_bytes": (c_size_t, [c_int]),

@@ -52,6 +52,7 @@ class MocoInfoNce(torch.autograd.Function):
     def forward(ctx, feat_q, queue, T, plan):
         res = ops.moco_infonce(feat_q.detach().contiguous(), plan.get("keys"), queue, T, **plan["kw"])
         ctx.save_for_backward(res["dfeat"])
+        ctx.set_materialize_grads(False)  # no zero-filled [n_keys*B, K+1] gradient for the detached logits
         logits = res["logits"] if res["logits"] is not None else feat_q.new_empty(0)
         ctx.mark_non_differentiable(logits, res["q"])
         return res["loss"].reshape(()), logits, res["q"]
@@ -59,7 +60,7 @@ class MocoInfoNce(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss, _g_logits, _g_q):
         (dfeat,) = ctx.saved_tensors
-        return _scaled(dfeat, g_loss), None, None, None
+        return (None if g_loss is None else _scaled(dfeat, g_loss)), None, None, None
 
 
 class ByolSimilarity(torch.autograd.Function):

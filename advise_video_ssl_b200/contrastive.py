@@ -88,18 +88,21 @@ def _first_if_list(x):
 
 
 class _KeyBatch:
-    """The key features of one encoder pass, possibly still in flight between the GPUs.
+    """The key features of one encoder pass, possibly not yet in this rank's original row order.
 
-    `local` (when set) holds this rank's normalised keys in the original row order.  When the
-    keys went through the NVLink exchange instead, `xchg` holds every rank's rows in SHUFFLED
-    rank-major order and `restore` ([W, B] device int64, None without shuffle) maps original rows
-    to it; consumers index the buffer rather than materialising an un-shuffled copy.
+    `local` (when set) holds this rank's normalised keys in the original row order.  Otherwise the rows
+    are still where the encoder / the exchange left them and consumers index them instead of
+    materialising an un-shuffled copy:
+      xchg   every rank's normalised rows in the NVLink exchange buffers (encoder order, rank-major), or
+      table  a [world * rows, D] tensor on this device in the same order (`raw`: still un-normalised);
+      restore ([W, B] device int64, None without shuffle) maps original rows to that order.
     """
 
-    __slots__ = ("local", "xchg", "restore", "rank", "rows")
+    __slots__ = ("local", "xchg", "table", "raw", "restore", "rank", "rows", "world")
 
-    def __init__(self, local=None, xchg=None, restore=None, rank=0, rows=0):
-        self.local, self.xchg, self.restore, self.rank, self.rows = local, xchg, restore, rank, rows
+    def __init__(self, local=None, xchg=None, table=None, raw=False, restore=None, rank=0, rows=0, world=1):
+        self.local, self.xchg, self.table, self.raw = local, xchg, table, raw
+        self.restore, self.rank, self.rows, self.world = restore, rank, rows, world
 
 
 class ContrastiveModel(nn.Module):
@@ -419,38 +422,52 @@ class ContrastiveModel(nn.Module):
         return [torch.cat([clip[j] for clip in clips], dim=0) for j in range(len(clips[0]))]
 
     def _normalised_keys(self, feats, restore, defer):
-        """Normalize + un-shuffle of one [rows, D] output of the key encoder.  With `defer` and a usable
-        NVLink exchange both happen in ONE launch (normalise and store into every rank's buffer) and the
-        rows stay in the buffer for the head kernel to index; otherwise this rank's rows come back."""
+        """Normalize + un-shuffle of one [rows, D] output of the key encoder.  With `defer` the rows stay
+        where they are and the head launch picks them up by index: on one GPU even un-normalised (Normalize
+        happens inside the head launch, no launch of its own); across GPUs Normalize and the store into
+        every rank's NVLink exchange buffer are ONE launch.  Without `defer` this rank's rows come back."""
         shuffled = restore is not None
         _, size, rank = self._shuffle_scope()
-        # through the exchange buffer when rows must cross ranks (un-shuffle, or the queue rows of C9), and
-        # also on one GPU when the head launch can do the un-shuffle gather by index (defer)
-        via_buffer = (shuffled and (defer or size > 1)) or (size > 1 and defer and self.queue_mode != "local")
-        if via_buffer and self._use_peer_exchange(feats):
-            ex = self._peer_xchg(feats.shape[0], feats.shape[1])
+        n = feats.shape[0]
+        if size == 1:
+            if defer:
+                return _KeyBatch(table=feats.contiguous(), raw=True, restore=restore, rows=n)
+            keys = self.l2_norm(feats)
+            return _KeyBatch(local=keys[restore[0, :]] if shuffled else keys)
+        # rows must cross ranks for the un-shuffle, and for the queue rows of C9 when the head takes them by index
+        crosses = shuffled or (defer and self.queue_mode != "local")
+        if crosses and self._use_peer_exchange(feats):
+            ex = self._peer_xchg(n, feats.shape[1])
             ex.push_normalized(feats.contiguous(), 0.0)
-            pending = _KeyBatch(xchg=ex, restore=restore, rank=rank, rows=feats.shape[0])
+            pending = _KeyBatch(xchg=ex, restore=restore, rank=rank, rows=n, world=size)
             if defer:
                 return pending
-            return _KeyBatch(local=ex.wait_gather(self._local_rows(pending), status=self._status))
+            return _KeyBatch(local=ex.wait_gather(self._local_rows(pending, feats.device), status=self._status))
         keys = self.l2_norm(feats)
-        if shuffled:
-            keys = self._batch_unshuffle(keys, restore).detach()
-        return _KeyBatch(local=keys)
+        if not crosses:
+            return _KeyBatch(local=keys)
+        everyone = du.cat_all_gather(keys.contiguous(), local=bool(self.cfg.CONTRASTIVE.LOCAL_SHUFFLE_BN))
+        if defer:
+            return _KeyBatch(table=everyone, restore=restore, rank=rank, rows=n, world=size)
+        return _KeyBatch(local=everyone[restore[rank, :]].detach())
 
-    def _local_rows(self, kb):
-        """Index of this rank's original rows in the exchange buffer (None = its own block, in order)."""
-        return None if kb.restore is None else kb.restore[kb.rank, :].contiguous()
+    def _local_rows(self, kb, device):
+        """Where this rank's original rows sit in the key rows (None = the kernel's default: its own block)."""
+        if kb.restore is not None:
+            return kb.restore[kb.rank, :].contiguous()
+        if kb.xchg is not None or kb.world == 1:
+            return None
+        return self._row_range(kb.rank * kb.rows, (kb.rank + 1) * kb.rows, device)
 
     def _queue_rows(self, kb, device):
-        """Rows of the exchange buffer that go into the queue under `queue_mode` (C9), None = own block."""
-        n, world = kb.rows, kb.xchg.world
-        if self.queue_mode == "local":
-            return self._local_rows(kb)
-        if self.queue_mode == "reference":
-            return kb.restore[0, :].contiguous() if kb.restore is not None else self._row_range(0, n, device)
-        return kb.restore.reshape(-1).contiguous() if kb.restore is not None else self._row_range(0, world * n, device)
+        """The key rows that go into the queue under `queue_mode` (C9), None = this rank's own block in order."""
+        if self.queue_mode == "local" or kb.world == 1:
+            return self._local_rows(kb, device)
+        if self.queue_mode == "reference":  # rank 0's original rows, on every rank
+            return kb.restore[0, :].contiguous() if kb.restore is not None else self._row_range(0, kb.rows, device)
+        if kb.restore is not None:          # canonical: every rank's original rows, rank-major
+            return kb.restore.reshape(-1).contiguous()
+        return self._row_range(0, kb.world * kb.rows, device)
 
     def _shuffle_ahead(self, groups):
         """Shuffle every key clip NOW, on a side stream, so that the index uploads, the row gathers and
@@ -581,8 +598,10 @@ class ContrastiveModel(nn.Module):
             return self.eval_knn(self.l2_norm(feat_q))
 
         own_keys = keys is None
-        head_kw = dict(want_logits=self.materialize_logits, impl=self.infonce_impl)
         B, D = feat_q.shape
+        n_k = 1 if own_keys and len(clips_k) == 1 else (len(clips_k) if own_keys else len(keys))
+        head_kw = dict(want_logits=self.materialize_logits, impl=self.infonce_impl,
+                       workspace=self._head_workspace(B, D, n_k, feat_q.device))
         # the fused ring write rides in the head launch when exactly keys[0] is enqueued (the default) and
         # the kernel's vector path applies; anything else goes through _dequeue_and_enqueue afterwards
         can_fuse = (own_keys and not self.cfg.CONTRASTIVE.MOCO_MULTI_VIEW_QUEUE and D % 4 == 0)
@@ -590,17 +609,21 @@ class ContrastiveModel(nn.Module):
         if own_keys:
             defer = can_fuse and len(clips_k) == 1 and self._tc_head_ok(B, D)
             batches, _ = self._key_batches(clips_k, False, True, defer)
-            if batches[0].xchg is not None and batches[0].local is None:
+            if batches[0].local is None:
                 deferred = batches[0]
             else:
                 keys = [kb.local for kb in batches]
         if deferred is not None:
-            # keys still sit in the exchange buffers: the head launch waits for them, un-shuffles by index
-            # and writes the queue rows `queue_mode` asks for
-            n_enq = self._enqueue_count(deferred)
+            # the key rows are still in encoder order (exchange buffers, gathered table, or the raw encoder output):
+            # the head launch [waits for them,] un-shuffles by index and writes the queue rows `queue_mode` asks for
+            n_enq = deferred.rows * (deferred.world if self.queue_mode == "canonical" else 1)
             assert self.k % n_enq == 0  # :284
-            head_kw.update(peer=deferred.xchg, peer_row_idx=self._local_rows(deferred),
+            head_kw.update(peer_row_idx=self._local_rows(deferred, feat_q.device),
                            enq_row_idx=self._queue_rows(deferred, feat_q.device), enqueue=(self.ptr, self._status))
+            if deferred.xchg is not None:
+                head_kw["peer"] = deferred.xchg
+            else:
+                head_kw.update(key_rows=deferred.table, keys_raw=deferred.raw)
             plan = {"keys": None, "kw": head_kw}
             fused = True
         else:
@@ -615,11 +638,15 @@ class ContrastiveModel(nn.Module):
         self.knn_mem_update(q, index)
         return (logits if self.materialize_logits else None), loss
 
+    def _head_workspace(self, B, D, n_keys, device):
+        """Scratch of the head launch (split partials + barrier words), owned by the module and zero-filled once:
+        the step is stream-ordered, and a CUDA-graph capture must not allocate or clear it on every replay."""
+        nbytes = ops.moco_infonce_workspace_bytes(B, D, self.k, n_keys)
+        return self._cached(("head_ws", B, D, n_keys, device),
+                            lambda: torch.zeros(nbytes, dtype=torch.uint8, device=device))
+
     def _tc_head_ok(self, B, D):
         return self.infonce_impl != _lib.IMPL_SIMT and D in (32, 64, 96, 128)
-
-    def _enqueue_count(self, kb):
-        return kb.rows * (kb.xchg.world if self.queue_mode == "canonical" else 1)
 
     # ---- byol (:508-596)
     def _forward_byol(self, clips, index, keys):

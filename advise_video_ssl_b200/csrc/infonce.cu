@@ -53,7 +53,7 @@ int moco_infonce_run(const float* feat_q, const float* const* keys_host, int n_k
                      float* q_out, float* loss_out, float* dfeat_out, float* row_lse_out, float* logits_out,
                      void* workspace, size_t workspace_bytes, int impl, void* stream,
                      const avssl_peer_xchg* peer = nullptr, const int64_t* peer_row_idx = nullptr,
-                     const int64_t* enq_row_idx = nullptr, int n_enq = 0) {
+                     const int64_t* enq_row_idx = nullptr, int n_enq = 0, int n_key_rows = 0, int keys_raw = 0) {
   AVSSL_REQUIRE(feat_q && (keys_host || peer) && queue && q_out && loss_out && dfeat_out && workspace,
                 AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: null pointer");
   AVSSL_REQUIRE(B > 0 && D > 0 && K > 0, AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: bad sizes B=%d D=%d K=%d", B, D, K);
@@ -76,6 +76,11 @@ int moco_infonce_run(const float* feat_q, const float* const* keys_host, int n_k
   p.peer_row_idx = reinterpret_cast<const long long*>(peer_row_idx);
   p.enq_row_idx = reinterpret_cast<const long long*>(enq_row_idx);
   p.n_enq = (ptr_dev && n_enq > 0) ? n_enq : B;
+  p.n_key_rows = n_key_rows > 0 ? n_key_rows : B;
+  p.keys_raw = keys_raw ? 1 : 0;
+  const bool indexed = !peer && (peer_row_idx || enq_row_idx || keys_raw || p.n_key_rows != B);
+  AVSSL_REQUIRE(!indexed || n_keys == 1, AVSSL_ERR_INVALID_ARGUMENT,
+                "moco_infonce_indexed: one key tensor only (got %d)", n_keys);
   memset(&p.peer, 0, sizeof(p.peer));
   if (peer) {
     const int rc = peer_check(peer, "moco_infonce_peer");
@@ -103,8 +108,8 @@ int moco_infonce_run(const float* feat_q, const float* const* keys_host, int n_k
     // models/contrastive.py:284  assert self.k % num_items == 0
     AVSSL_REQUIRE(K % p.n_enq == 0, AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: K=%d is not a multiple of the %d enqueued rows", K,
                   p.n_enq);
-    AVSSL_REQUIRE(peer ? (enq_row_idx != nullptr || p.n_enq == peer->rows_per_rank) : (enq_row_idx == nullptr && p.n_enq == B),
-                  AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: n_enq=%d needs a row list into the exchange buffer", p.n_enq);
+    AVSSL_REQUIRE(enq_row_idx != nullptr || p.n_enq == (peer ? peer->rows_per_rank : B), AVSSL_ERR_INVALID_ARGUMENT,
+                  "moco_infonce: n_enq=%d needs a row list into the key buffer", p.n_enq);
     AVSSL_REQUIRE(queue_rw && (peer || (reinterpret_cast<uintptr_t>(p.keys[0]) & 15u) == 0) && D % 4 == 0,
                   AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: fused enqueue needs a writable queue and 16-byte aligned keys[0]");
   }
@@ -113,6 +118,9 @@ int moco_infonce_run(const float* feat_q, const float* const* keys_host, int n_k
   if (use == AVSSL_IMPL_AUTO) use = infonce_tc_supported(B, D, K) ? AVSSL_IMPL_TC3X : AVSSL_IMPL_SIMT;
   AVSSL_REQUIRE(use == AVSSL_IMPL_SIMT || use == AVSSL_IMPL_TC3X || use == AVSSL_IMPL_TC1X,
                 AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: unknown impl %d", impl);
+  AVSSL_REQUIRE(!indexed || use != AVSSL_IMPL_SIMT, AVSSL_ERR_UNSUPPORTED,
+                "moco_infonce_indexed: row indices / raw keys need the tcgen05 kernel (D in {32,64,96,128}); normalise and "
+                "gather the keys first and call the plain entry point instead");
   AVSSL_REQUIRE(!peer || use != AVSSL_IMPL_SIMT, AVSSL_ERR_UNSUPPORTED,
                 "moco_infonce_peer: the fused exchange wait needs the tcgen05 kernel (D in {32,64,96,128}); "
                 "call avssl_peer_wait_gather and the plain entry point instead");
@@ -182,4 +190,20 @@ extern "C" int avssl_moco_infonce_fwd_bwd_enqueue_peer(const float* feat_q, cons
   return moco_infonce_run(feat_q, nullptr, 1, queue, ptr_dev ? queue : nullptr, ptr_dev, status_dev, B, D, K, T, q_out,
                           loss_out, dfeat_out, row_lse_out, logits_out, workspace, workspace_bytes, impl, stream, x,
                           row_idx, enq_row_idx, n_enq);
+}
+
+extern "C" int avssl_moco_infonce_fwd_bwd_enqueue_indexed(const float* feat_q, const float* key_rows, int n_key_rows,
+                                                          int keys_raw, const int64_t* row_idx,
+                                                          const int64_t* enq_row_idx, int n_enq, float* queue,
+                                                          int64_t* ptr_dev, uint32_t* status_dev, int B, int D, int K,
+                                                          float T, float* q_out, float* loss_out, float* dfeat_out,
+                                                          float* row_lse_out, float* logits_out, void* workspace,
+                                                          size_t workspace_bytes, int impl, void* stream) {
+  AVSSL_REQUIRE(key_rows && n_key_rows > 0, AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce_indexed: key_rows is null or empty");
+  AVSSL_REQUIRE(row_idx || n_key_rows >= B, AVSSL_ERR_INVALID_ARGUMENT,
+                "moco_infonce_indexed: %d key rows for B=%d without a row index", n_key_rows, B);
+  const float* keys_host[1] = {key_rows};
+  return moco_infonce_run(feat_q, keys_host, 1, queue, ptr_dev ? queue : nullptr, ptr_dev, status_dev, B, D, K, T, q_out,
+                          loss_out, dfeat_out, row_lse_out, logits_out, workspace, workspace_bytes, impl, stream, nullptr,
+                          row_idx, enq_row_idx, n_enq, n_key_rows, keys_raw);
 }

@@ -45,9 +45,15 @@ struct InfoNceParams {
   // the merge CTAs have waited for every rank's push of the current epoch.  keys[0] is unused then.
   int use_peer;
   const long long* peer_row_idx;
-  // rows written by the fused enqueue: gathered[enq_row_idx[e]] (peer) or keys[0][e], e < n_enq
+  // rows written by the fused enqueue: gathered[enq_row_idx[e]] (peer) or keys[0][enq_row_idx ? enq_row_idx[e] : e], e < n_enq
   const long long* enq_row_idx;
   int n_enq;
+  // indexed plain keys (tcgen05 kernel, n_keys == 1): keys[0] is [n_key_rows, D] and key row i is
+  // keys[0][peer_row_idx[i]] -- the un-shuffle of models/contrastive.py:216-230 folded into the head launch.
+  // keys_raw: keys[0] holds the key encoder's RAW output; Normalize (:350) is applied where the rows are read
+  // (positive logit and enqueue), with the arithmetic of l2norm_fwd_kernel.
+  int n_key_rows;
+  int keys_raw;
   avssl_peer_xchg peer;
 };
 

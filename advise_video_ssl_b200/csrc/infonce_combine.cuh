@@ -95,6 +95,9 @@ __device__ __forceinline__ void infonce_combine_row(const InfoNceParams& p, int 
   if (warp == kGroups - 1) {  // the last warp holds the fewest partial rows
     const float nrm = warp_row_norm(f, D, lane);
     if (lane == 0) sm.bcast[0] = nrm;
+  } else if (warp == kGroups - 2 && p.keys_raw) {  // Normalize of the raw key row, same arithmetic as l2norm_fwd_kernel
+    const float knrm = warp_row_norm(key0_row, D, lane);
+    if (lane == 0) sm.bcast[1] = knrm;
   }
 
   // ---- global max over the splits, weights, L
@@ -110,6 +113,11 @@ __device__ __forceinline__ void infonce_combine_row(const InfoNceParams& p, int 
 #pragma unroll
   for (int w = 1; w < kGroups; ++w) M = fmaxf(M, sm.red[w]);
   const float nrm = sm.bcast[0];
+  if (p.keys_raw) {
+    const float knrm = sm.bcast[1];
+#pragma unroll
+    for (int u = 0; u < MAXC; ++u) kv0[u] = kv0[u] / knrm;
+  }
   float lloc = 0.f;
 #pragma unroll
   for (int k = 0; k < kMl; ++k) {

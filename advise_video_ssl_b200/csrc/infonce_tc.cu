@@ -604,7 +604,8 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
     enq_ok = enq_ptr >= 0 && enq_ptr + p.n_enq <= p.K;           // models/contrastive.py:285
   }
   const float* key_base = p.keys[0];
-  const long long n_peer_rows = (long long)p.peer.world * p.peer.rows_per_rank;
+  const long long n_key_rows = p.use_peer ? (long long)p.peer.world * p.peer.rows_per_rank : (long long)p.n_key_rows;
+  const long long own_base = p.use_peer ? (long long)p.peer.rank * p.peer.rows_per_rank : 0ll;
   if (p.use_peer && (cta < p.B || (enq_ok && cta < p.n_enq))) {  // C3: the keys come from the peer exchange buffer (peer.cuh)
     if (warp == 0) {  // long since landed: the sweep took ~15 us
       const int slot = peer_wait_all_warp(p.peer, p.enq_status);
@@ -614,32 +615,41 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
     key_base = peer_payload(p.peer.base[p.peer.rank], csm.peer_slot, p.peer);
   }
   for (int i = cta; i < p.B; i += (int)n_ctas) {
-    long long krow = i;
-    if (p.use_peer) {
-      krow = p.peer_row_idx ? p.peer_row_idx[i] : (long long)p.peer.rank * p.B + i;
-      if (krow < 0 || krow >= n_peer_rows) {  // uniform over the CTA
-        if (tid == 0 && p.enq_status) atomicOr(p.enq_status, AVSSL_DEVFLAG_BAD_INDEX);
-        krow = 0;
-      }
+    long long krow = p.peer_row_idx ? p.peer_row_idx[i] : own_base + i;  // un-shuffle by index (:216-230)
+    if (krow < 0 || krow >= n_key_rows) {  // uniform over the CTA
+      if (tid == 0 && p.enq_status) atomicOr(p.enq_status, AVSSL_DEVFLAG_BAD_INDEX);
+      krow = 0;
     }
     infonce_combine_row<kTcThreads, 1>(p, i, csm, key_base + (size_t)krow * D);
   }
   if (enq_ok) {
-    // K4 (+ C9): queue[ptr + e] = the e-th row of the enqueue list -- keys[0][e], or gathered[enq_row_idx[e]]
-    // (rank 0's block on every rank keeps the queues of all ranks identical, as the reference's DDP buffer
-    // broadcast does; all world*B rows = canonical MoCo).  No CTA reads the queue after the grid barrier.
+    // K4 (+ C9): queue[ptr + e] = the e-th row of the enqueue list -- keys[0][e], or key rows picked by enq_row_idx
+    // (rank 0's block of the gathered buffer on every rank keeps the queues of all ranks identical, as the
+    // reference's DDP buffer broadcast does; all world*B rows = canonical MoCo).  No CTA reads the queue after
+    // the grid barrier.
     for (int e = cta; e < p.n_enq; e += (int)n_ctas) {
-      long long krow = e;
-      if (p.use_peer) {
-        krow = p.enq_row_idx ? p.enq_row_idx[e] : (long long)p.peer.rank * p.peer.rows_per_rank + e;
-        if (krow < 0 || krow >= n_peer_rows) {
-          if (tid == 0 && p.enq_status) atomicOr(p.enq_status, AVSSL_DEVFLAG_BAD_INDEX);
-          continue;
-        }
+      const long long krow = p.enq_row_idx ? p.enq_row_idx[e] : own_base + e;
+      if (krow < 0 || krow >= n_key_rows) {
+        if (tid == 0 && p.enq_status) atomicOr(p.enq_status, AVSSL_DEVFLAG_BAD_INDEX);
+        continue;
       }
-      const float4* src = reinterpret_cast<const float4*>(key_base + (size_t)krow * D);
+      const float* src_row = key_base + (size_t)krow * D;
       float4* dst = reinterpret_cast<float4*>(p.queue_rw + (size_t)(enq_ptr + e) * D);
-      for (int c4 = tid; c4 < D / 4; c4 += kTcThreads) dst[c4] = __ldcg(src + c4);
+      if (p.keys_raw) {  // Normalize on the way in: x / ||x||, the bits l2norm_fwd_kernel writes
+        __syncthreads();
+        if (warp == 0) {
+          const float knrm = warp_row_norm(src_row, D, lane);
+          if (lane == 0) csm.bcast[1] = knrm;
+        }
+        __syncthreads();
+        const float knrm = csm.bcast[1];
+        for (int c4 = tid; c4 < D / 4; c4 += kTcThreads) {
+          const float4 v = __ldcg(reinterpret_cast<const float4*>(src_row) + c4);
+          dst[c4] = make_float4(v.x / knrm, v.y / knrm, v.z / knrm, v.w / knrm);
+        }
+      } else {
+        for (int c4 = tid; c4 < D / 4; c4 += kTcThreads) dst[c4] = __ldcg(reinterpret_cast<const float4*>(src_row) + c4);
+      }
     }
   }
   if (tid == 0) TC_TRACE(14, 4);

@@ -11,13 +11,17 @@
 // double-buffered S/P tile (128), so pass 2 sweeps the columns once per 128-wide half of D and
 // recomputes S for the second half (tensor time is cheap here: 28 k cycles per CTA at cfg3).
 //
-// Precision: single-pass tf32 with BOTH operands rounded to nearest (Q when it is written to
-// TMEM, the tiles in place in shared memory by eight helper warps), so there is no truncation
+// Precision: single-pass tf32 with BOTH operands rounded to nearest, so there is no truncation
 // bias; measured errors are ~1e-5 (loss) and ~3e-4 (gradient), inside the 1e-3 fp32 tolerance.
-// The CUDA-core kernels (AVSSL_IMPL_SIMT) remain the exact-fp32 reference.
+// The rounding happens ONCE, when `out` is assembled from the gathered rows (avssl_ntxent_prepare
+// writes the exact rows and a tf32-rounded copy): the tiles go from TMA straight to the tensor core.
+// (Round 1 re-rounded every tile in shared memory with eight helper warps: 128 KB of extra
+// shared-memory traffic per 64 KB tile and one more hop in the role chain; ncu showed the tensor
+// pipe 22-32 % active.)  The CUDA-core kernels (AVSSL_IMPL_SIMT) remain the exact-fp32 reference.
 //
-// Warp roles (448 threads, 1 CTA / SM): 0 TMA producer | 1 MMA issuer + TMEM allocator |
-// 2-9 helper warps (round tiles to tf32, stage 1/Z_c) | 10-13 softmax + epilogue (thread = row).
+// Warp roles (320 threads, 1 CTA / SM): 0 TMA producer | 1 MMA issuer + TMEM allocator |
+// 2-9 softmax + epilogue: thread = row, and the two warps that share a TMEM sub-partition (w, w+4)
+// split every tile's 64 columns (and the accumulator read-out) between them.
 #include "ntxent.cuh"
 #include "sm100_ptx.cuh"
 
@@ -27,9 +31,10 @@ namespace {
 
 constexpr int kBJ = 64;    // columns of `out` per tile
 constexpr int kMt = 128;   // local rows per CTA
-constexpr int kNtThreads = 448;
-constexpr int kSoftmax = 128, kHelpers = 256;
-constexpr int kSlots = 2;
+constexpr int kNtThreads = 320;
+constexpr int kSoftmax = 256;
+constexpr int kMaxSlots = 4;
+constexpr int kHalfCols = kBJ / 2;  // columns of a tile per softmax warp
 constexpr float kLog2eT = 1.4426950408889634f;
 
 template <int D, bool kGrad>
@@ -44,12 +49,15 @@ struct NtCfg {
   static constexpr int kColsNeeded = D + 2 * kBJ + (kGrad ? kAcc : 0);
   static constexpr int kTmemCols = kColsNeeded <= 128 ? 128 : (kColsNeeded <= 256 ? 256 : 512);
   static_assert(kColsNeeded <= 512, "TMEM budget");
-  static constexpr size_t kSmemBytes = 1024 + (size_t)kSlots * (kTileBytes + kVBytes) + 4 * kBJ * 4 + 512;
+  static constexpr int kSlotBytes = kTileBytes + kVBytes;
+  static constexpr int kSlots = (200 * 1024 / kSlotBytes) < kMaxSlots ? (200 * 1024 / kSlotBytes) : kMaxSlots;
+  static_assert(kSlots >= 2, "at least a double buffer");
+  static constexpr size_t kSmemBytes = 1024 + (size_t)kSlots * kSlotBytes + 8 * kHalfCols * 4 + 512;
 };
 
 struct NtBarriers {
-  uint64_t s_full[kSlots], s_op[kSlots], s_free[kSlots];
-  uint64_t v_full[kSlots], v_op[kSlots], v_free[kSlots];
+  uint64_t s_full[kMaxSlots], s_free[kMaxSlots];
+  uint64_t v_full[kMaxSlots], v_free[kMaxSlots];
   uint64_t s_ready[2], p_ready[2];
   uint64_t q_ready, acc_done;
   uint32_t tmem_base;
@@ -59,12 +67,13 @@ template <int D, bool kGrad>
 __global__ void __launch_bounds__(kNtThreads, 1)
 ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_v) {
   using C = NtCfg<D, kGrad>;
+  constexpr int kSlots = C::kSlots;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   uint8_t* s_ring = smem;
   uint8_t* v_ring = smem + kSlots * C::kTileBytes;
-  float* invz_c = reinterpret_cast<float*>(smem + kSlots * (C::kTileBytes + C::kVBytes));  // [4][64]
-  NtBarriers* bar = reinterpret_cast<NtBarriers*>(smem + kSlots * (C::kTileBytes + C::kVBytes) + 4 * kBJ * 4);
+  float* invz_c = reinterpret_cast<float*>(smem + kSlots * C::kSlotBytes);  // [8 softmax warps][32]: 1/Z of the warp's columns
+  NtBarriers* bar = reinterpret_cast<NtBarriers*>(smem + kSlots * C::kSlotBytes + 8 * kHalfCols * 4);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int split = blockIdx.x;
@@ -79,10 +88,8 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
     if (kGrad) ptx::tma_prefetch_desc(&tmap_v);
     for (int s = 0; s < kSlots; ++s) {
       ptx::mbar_init(&bar->s_full[s], 1);
-      ptx::mbar_init(&bar->s_op[s], kHelpers);
       ptx::mbar_init(&bar->s_free[s], 1);
       ptx::mbar_init(&bar->v_full[s], 1);
-      ptx::mbar_init(&bar->v_op[s], kHelpers);
       ptx::mbar_init(&bar->v_free[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -131,7 +138,7 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
     ptx::tc_fence_after();
     auto issue_pv = [&](int u) {
       const int sl = u % kSlots, b = u & 1, t = u % n_tiles;
-      ptx::mbar_wait(&bar->v_op[sl], (u / kSlots) & 1);
+      ptx::mbar_wait(&bar->v_full[sl], (u / kSlots) & 1);
       ptx::mbar_wait(&bar->p_ready[b], (u >> 1) & 1);
       ptx::tc_fence_after();
       // MN-major, 32B-atom swizzle: 8 rows per k-step (1024 B) = two 4-row atoms 512 B apart (SBO);
@@ -149,7 +156,7 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
     };
     for (int u = 0; u < n_steps; ++u) {
       const int sl = u % kSlots, b = u & 1;
-      ptx::mbar_wait(&bar->s_op[sl], (u / kSlots) & 1);
+      ptx::mbar_wait(&bar->s_full[sl], (u / kSlots) & 1);
       // S(u) overwrites the TMEM buffer of step u-2: its exponentials must have been read (pass 2 gets
       // this ordering for free from PV(u-2), which waited for the same barrier)
       if (!kGrad && u >= 2) ptx::mbar_wait(&bar->p_ready[b], ((u - 2) >> 1) & 1);
@@ -168,79 +175,37 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
       if (kGrad && u > 0) issue_pv(u - 1);
     }
     if (kGrad && n_steps > 0) issue_pv(n_steps - 1);
-  } else if (warp < 10) {
-    // ============================ helper warps: round the tiles to tf32 in place (unbiased), stage 1/Z_c
-    const int ht = tid - 64;  // 0..255
-    for (int u = 0; u < n_steps; ++u) {
-      const int t = u % n_tiles, sl = u % kSlots;
-      ptx::mbar_wait_relaxed(&bar->s_full[sl], (u / kSlots) & 1);
-      float4* st = reinterpret_cast<float4*>(s_ring + (size_t)sl * C::kTileBytes);
-#pragma unroll 4
-      for (int e = ht; e < C::kTileBytes / 16; e += kHelpers) {
-        float4 x = st[e];
-        x.x = ptx::round_tf32(x.x);
-        x.y = ptx::round_tf32(x.y);
-        x.z = ptx::round_tf32(x.z);
-        x.w = ptx::round_tf32(x.w);
-        st[e] = x;
-      }
-      if (kGrad && ht < kBJ) {
-        const int j = j_begin + t * kBJ + ht;
-        invz_c[(u & 3) * kBJ + ht] = j < j_end ? 1.f / __ldg(a.z_all + j) : 0.f;
-      }
-      ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(&bar->s_op[sl]);
-      if (kGrad) {
-        ptx::mbar_wait_relaxed(&bar->v_full[sl], (u / kSlots) & 1);
-        float4* vt = reinterpret_cast<float4*>(v_ring + (size_t)sl * C::kVBytes);
-#pragma unroll 4
-        for (int e = ht; e < C::kVBytes / 16; e += kHelpers) {
-          float4 x = vt[e];
-          x.x = ptx::round_tf32(x.x);
-          x.y = ptx::round_tf32(x.y);
-          x.z = ptx::round_tf32(x.z);
-          x.w = ptx::round_tf32(x.w);
-          vt[e] = x;
-        }
-        ptx::fence_proxy_async_smem();
-        ptx::mbar_arrive(&bar->v_op[sl]);
-      }
-    }
   } else {
-    // ==================================================== softmax + epilogue (thread = local row)
-    const int sub = warp & 3;
+    // ================= softmax + epilogue: thread = local row; warp pair (w, w+4) shares a sub-partition
+    const int sw = warp - 2;                    // 0..7
+    const int sub = warp & 3;                   // TMEM sub-partition this warp may access
+    const int hc = sw >> 2;                     // which 32 columns of every tile this warp handles
     const int r = sub * 32 + lane;
     const int i = i_base + r;
     const bool row_valid = i < a.n_loc;
     const uint32_t lane_base = tmem + ((uint32_t)(sub * 32) << 16);
     const int rid = row_valid ? __ldg(a.rows + i) : -1;  // global row id: the diagonal column of this row
     const float invz_r = (kGrad && row_valid) ? 1.f / __ldg(a.z_all + rid) : 0.f;
+    float* iz = invz_c + sw * kHalfCols;        // this warp's staging of 1/Z_c (private: __syncwarp suffices)
 
-    // ---- A operand: this row of `out` (already unit length), rounded to tf32, into TMEM
+    // ---- A operand: this row of `out` (unit length, already rounded to tf32) into TMEM; the pair splits
+    // the D / 32 column blocks
     {
-      const float4* src = reinterpret_cast<const float4*>(a.out + (size_t)(row_valid ? rid : 0) * D);
-      float4 cur[8], nxt[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) cur[k] = __ldg(src + k);
+      const float4* src = reinterpret_cast<const float4*>(a.out_tf32 + (size_t)(row_valid ? rid : 0) * D);
+      constexpr int kCb = D / 32;
 #pragma unroll 1
-      for (int cb = 0; cb < D / 32; ++cb) {
-        if (cb + 1 < D / 32) {  // next 32 columns in flight while this chunk goes to TMEM
-#pragma unroll
-          for (int k = 0; k < 8; ++k) nxt[k] = __ldg(src + (cb + 1) * 8 + k);
-        }
+      for (int cb = hc; cb < kCb; cb += 2) {
         uint32_t v[32];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row_valid) x = cur[k];
-          v[4 * k + 0] = __float_as_uint(ptx::round_tf32(x.x));
-          v[4 * k + 1] = __float_as_uint(ptx::round_tf32(x.y));
-          v[4 * k + 2] = __float_as_uint(ptx::round_tf32(x.z));
-          v[4 * k + 3] = __float_as_uint(ptx::round_tf32(x.w));
+          if (row_valid) x = __ldg(src + cb * 8 + k);
+          v[4 * k + 0] = __float_as_uint(x.x);
+          v[4 * k + 1] = __float_as_uint(x.y);
+          v[4 * k + 2] = __float_as_uint(x.z);
+          v[4 * k + 3] = __float_as_uint(x.w);
         }
         ptx::tmem_st32(lane_base + C::kColQ + cb * 32, v);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) cur[k] = nxt[k];
       }
       ptx::tc_wait_st();
       ptx::tc_fence_before();
@@ -251,19 +216,22 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
 
     for (int u = 0; u < n_steps; ++u) {
       const int t = u % n_tiles, h = u / n_tiles, b = u & 1;
-      const int j0 = j_begin + t * kBJ;
+      const int j0 = j_begin + t * kBJ + hc * kHalfCols;  // first column of this warp's half tile
+      if (kGrad) {  // 1/Z of this warp's 32 columns, staged while S(u) is still being computed
+        __syncwarp();
+        iz[lane] = (j0 + lane < j_end) ? 1.f / __ldg(a.z_all + j0 + lane) : 0.f;
+        __syncwarp();
+      }
       ptx::mbar_wait(&bar->s_ready[b], (u >> 1) & 1);
       ptx::tc_fence_after();
-      const uint32_t s_col = lane_base + C::kColS + b * kBJ;
-      uint32_t sv[kBJ];
-      ptx::tmem_ld32(s_col, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
-      ptx::tmem_ld32(s_col + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+      const uint32_t s_col = lane_base + C::kColS + b * kBJ + hc * kHalfCols;
+      uint32_t sv[kHalfCols];
+      ptx::tmem_ld32(s_col, sv);
       ptx::tc_wait_ld();
-      const int diag = rid - j0;            // column of this tile that is the row itself (masked), if in [0, 64)
-      const int valid = row_valid ? min(kBJ, j_end - j0) : 0;
-      const float* iz = invz_c + (u & 3) * kBJ;
+      const int diag = rid - j0;            // column of this half tile that is the row itself (masked), if in [0, 32)
+      const int valid = row_valid ? min(kHalfCols, j_end - j0) : 0;
 #pragma unroll
-      for (int c = 0; c < kBJ; ++c) {
+      for (int c = 0; c < kHalfCols; ++c) {
         // e^{(s - 1)/T}: unit rows give s <= 1, so the exponent is <= 0
         float e;
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((__uint_as_float(sv[c]) - 1.f) * scale2));
@@ -275,8 +243,7 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
         }
       }
       if (kGrad) {
-        ptx::tmem_st32(s_col, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
-        ptx::tmem_st32(s_col + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+        ptx::tmem_st32(s_col, sv);
         ptx::tc_wait_st();
       }
       ptx::tc_fence_before();
@@ -287,7 +254,7 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
         ptx::mbar_wait(&bar->acc_done, h & 1);
         ptx::tc_fence_after();
 #pragma unroll 1
-        for (int cb = 0; cb < C::kAcc / 32; ++cb) {
+        for (int cb = hc; cb < C::kAcc / 32; cb += 2) {
           uint32_t av[32];
           ptx::tmem_ld32(lane_base + C::kColAcc + cb * 32, av);
           ptx::tc_wait_ld();
@@ -302,7 +269,14 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
         ptx::tc_fence_before();
       }
     }
-    if (!kGrad && row_valid) a.part_z[(size_t)split * a.n_loc + i] = (zs[0] + zs[1]) + (zs[2] + zs[3]);
+    if (!kGrad) {
+      // the pair's two partial row sums meet in shared memory (the 1/Z staging area is unused in this pass)
+      const float z = (zs[0] + zs[1]) + (zs[2] + zs[3]);
+      float* zx = invz_c;  // [128] floats: one per row
+      if (hc == 1) zx[r] = z;
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight softmax warps
+      if (hc == 0 && row_valid) a.part_z[(size_t)split * a.n_loc + i] = z + zx[r];
+    }
   }
 
   ptx::tc_fence_before();
@@ -340,22 +314,22 @@ template <int D, bool kGrad>
 int launch_nt(const NtxArgs& a, cudaStream_t st) {
   using C = NtCfg<D, kGrad>;
   static thread_local NtTmapCache cache;
-  if (cache.out != a.out || cache.N2 != a.N2 || cache.D != D) {
+  if (cache.out != a.out_tf32 || cache.N2 != a.N2 || cache.D != D) {
     EncodeTiledFn enc = nt_encode_fn();
     AVSSL_REQUIRE(enc, AVSSL_ERR_CUDA, "ntxent: cuTensorMapEncodeTiled is not available from the driver");
     const cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)a.N2};
     const cuuint64_t gstride[1] = {(cuuint64_t)D * sizeof(float)};
     const cuuint32_t box[2] = {32u, (cuuint32_t)kBJ};
     const cuuint32_t estride[2] = {1u, 1u};
-    CUresult r = enc(&cache.s, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a.out), gdim, gstride, box, estride,
+    CUresult r = enc(&cache.s, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a.out_tf32), gdim, gstride, box, estride,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     AVSSL_REQUIRE(r == CUDA_SUCCESS, AVSSL_ERR_CUDA, "ntxent: cuTensorMapEncodeTiled failed (%d)", (int)r);
-    r = enc(&cache.v, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a.out), gdim, gstride, box, estride,
+    r = enc(&cache.v, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a.out_tf32), gdim, gstride, box, estride,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     AVSSL_REQUIRE(r == CUDA_SUCCESS, AVSSL_ERR_CUDA, "ntxent: cuTensorMapEncodeTiled (32B atoms) failed (%d)", (int)r);
-    cache.out = a.out;
+    cache.out = a.out_tf32;
     cache.N2 = a.N2;
     cache.D = D;
   }

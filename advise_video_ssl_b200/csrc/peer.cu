@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(256) peer_push_kernel(const avssl_peer_xchg x,
 
 // K2 + push in one launch: what travels is l2norm(feat) (Normalize of the key features,
 // models/contrastive.py:350 + :216-230); CTA `rank` also keeps a local copy when y_local != null.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 l2norm_push_kernel(const avssl_peer_xchg x, const float* __restrict__ feat, float eps, float* __restrict__ y_local) {
   __shared__ unsigned long long s_epoch;
   peer_push_cta<true>(x, feat, blockIdx.x, &s_epoch, eps, y_local);
@@ -125,7 +125,9 @@ extern "C" int avssl_l2norm_push_rows(const avssl_peer_xchg* x, const float* fea
   int rc = peer_check(x, "l2norm_push_rows");
   if (rc != AVSSL_OK) return rc;
   AVSSL_REQUIRE(feat && eps >= 0.f, AVSSL_ERR_INVALID_ARGUMENT, "l2norm_push_rows: feat is null or eps < 0");
-  l2norm_push_kernel<<<x->world, 256, 0, static_cast<cudaStream_t>(stream)>>>(*x, feat, eps, y_local_out);
+  // one warp per row where possible: the launch is latency-bound (each warp: load row, reduce, divide, store)
+  const int threads = x->rows_per_rank >= 32 ? 1024 : (x->rows_per_rank >= 16 ? 512 : 256);
+  l2norm_push_kernel<<<x->world, threads, 0, static_cast<cudaStream_t>(stream)>>>(*x, feat, eps, y_local_out);
   AVSSL_LAUNCH_OK("l2norm_push_kernel");
   return AVSSL_OK;
 }

@@ -325,6 +325,12 @@ def _workspace(device, nbytes, op):
     so two ops must never see each other's words."""
     key = (op, device.index, torch.cuda.current_stream(device).cuda_stream)
     ws = _workspaces.get(key)
+    if (ws is None or ws.numel() < nbytes) and torch.cuda.is_current_stream_capturing():
+        # a CUDA-graph capture runs on its own stream: reuse the scratch of the (stream-ordered) warm-up
+        # rather than allocating and zero-filling a new one inside the graph on every replay
+        for (o, d, _), cand in _workspaces.items():
+            if o == op and d == device.index and cand.numel() >= nbytes:
+                return cand
     if ws is None or ws.numel() < nbytes:
         ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
         _workspaces[key] = ws
@@ -332,7 +338,7 @@ def _workspace(device, nbytes, op):
 
 
 def moco_infonce(feat_q, keys, queue, T, want_logits=True, impl=_lib.IMPL_AUTO, out=None, enqueue=None, workspace=None,
-                 peer=None, peer_row_idx=None, enq_row_idx=None):
+                 peer=None, peer_row_idx=None, enq_row_idx=None, key_rows=None, keys_raw=False):
     """Fused l2-norm + logits + InfoNCE forward/backward (K2+K3).
 
     Returns dict(loss[1], dfeat[B,D], q[B,D], lse[n_keys*B], logits[n_keys*B,K+1] or None).
@@ -348,6 +354,10 @@ def moco_infonce(feat_q, keys, queue, T, want_logits=True, impl=_lib.IMPL_AUTO, 
     `enq_row_idx` (peer only, int64): the rows of the gathered buffer that the fused enqueue writes,
     ptr advancing by their count (C9: rank 0's rows on every rank = the reference's effective
     semantics under DDP's buffer broadcast; all rows = canonical MoCo).  Default: this rank's block.
+    `key_rows` ([n, D], `keys` must be None): keys that live on this device but are still in the key
+    encoder's row order -- query row i meets key_rows[peer_row_idx[i]] and the queue receives
+    key_rows[enq_row_idx[e]] (the un-shuffle folded into the launch); with `keys_raw` they are the
+    encoder's raw output and Normalize is applied inside the kernel as well.
     """
     _req(feat_q, "feat_q")
     _req(queue, "queue")
@@ -355,15 +365,19 @@ def moco_infonce(feat_q, keys, queue, T, want_logits=True, impl=_lib.IMPL_AUTO, 
         raise ValueError("feat_q [B,D] and queue [K,D] expected, got %s and %s" % (tuple(feat_q.shape), tuple(queue.shape)))
     B, D = feat_q.shape
     K = queue.shape[0]
-    if peer is not None:
-        if keys is not None:
-            raise ValueError("pass either keys or peer, not both")
+    if peer is not None or key_rows is not None:
+        if keys is not None or (peer is not None and key_rows is not None):
+            raise ValueError("pass exactly one of keys, peer and key_rows")
         if peer_row_idx is not None:
             _req(peer_row_idx, "peer_row_idx", torch.int64)
             if peer_row_idx.numel() != B:
                 raise ValueError("peer_row_idx needs %d entries" % B)
+        if key_rows is not None:
+            _req(key_rows, "key_rows")
+            if key_rows.dim() != 2 or key_rows.shape[1] != D:
+                raise ValueError("key_rows must be [n, %d], got %s" % (D, tuple(key_rows.shape)))
         keys = []
-    n_keys = 1 if peer is not None else len(keys)
+    n_keys = 1 if (peer is not None or key_rows is not None) else len(keys)
     if not 1 <= n_keys <= _lib.MAX_KEYS:
         raise ValueError("need 1..%d key tensors, got %d" % (_lib.MAX_KEYS, n_keys))
     for k in keys:
@@ -386,7 +400,7 @@ def moco_infonce(feat_q, keys, queue, T, want_logits=True, impl=_lib.IMPL_AUTO, 
             raise ValueError("workspace has %d bytes, need %d" % (ws.numel(), nbytes))
     else:
         ws = _workspace(dev, nbytes, "moco_infonce")
-    if peer is not None:
+    if peer is not None or key_rows is not None:
         ptr, status = enqueue if enqueue is not None else (None, None)
         n_enq = B
         if enq_row_idx is not None:
@@ -397,6 +411,18 @@ def moco_infonce(feat_q, keys, queue, T, want_logits=True, impl=_lib.IMPL_AUTO, 
             assert K % n_enq == 0, "queue length %d is not a multiple of the key batch %d" % (K, n_enq)
         if status is not None:
             _req(status, "status", torch.int32)
+    if key_rows is not None:
+        check(lib.avssl_moco_infonce_fwd_bwd_enqueue_indexed(
+            feat_q.data_ptr(), key_rows.data_ptr(), int(key_rows.shape[0]), 1 if keys_raw else 0,
+            peer_row_idx.data_ptr() if peer_row_idx is not None else None,
+            enq_row_idx.data_ptr() if enq_row_idx is not None else None, n_enq,
+            queue.data_ptr(), ptr.data_ptr() if ptr is not None else None,
+            status.data_ptr() if status is not None else None, B, D, K, float(T),
+            q.data_ptr(), loss.data_ptr(), dfeat.data_ptr(), lse.data_ptr(),
+            logits.data_ptr() if logits is not None else None, ws.data_ptr(), ws.numel(), int(impl), _stream()),
+            "avssl_moco_infonce_fwd_bwd_enqueue_indexed")
+        return {"loss": loss, "dfeat": dfeat, "q": q, "lse": lse, "logits": logits}
+    if peer is not None:
         check(lib.avssl_moco_infonce_fwd_bwd_enqueue_peer(
             feat_q.data_ptr(), ctypes.addressof(peer.desc), peer_row_idx.data_ptr() if peer_row_idx is not None else None,
             enq_row_idx.data_ptr() if enq_row_idx is not None else None, n_enq,
@@ -590,17 +616,21 @@ def ntxent(feat1, feat2, T, gather=None, impl=_lib.IMPL_AUTO):
     if world > 1:
         allq = torch.empty(world, 2, B, D, dtype=_f32, device=dev)
         dist.all_gather_into_tensor(allq.view(world * 2 * B, D), y)
-        out = allq.permute(1, 0, 2, 3).reshape(2 * world * B, D).contiguous()  # [q_all ; q2_all]
     else:
-        out = y
+        allq = y
+    # [q_all ; q2_all] and its tf32-rounded copy (the tensor cores' operand) in one pass over the gathered rows
     N = world * B
+    out = torch.empty(2 * N, D, dtype=_f32, device=dev)
+    out_r = torch.empty(2 * N, D, dtype=_f32, device=dev)
+    check(lib.avssl_ntxent_prepare(allq.data_ptr(), world, B, D, out.data_ptr(), out_r.data_ptr(), _stream()),
+          "avssl_ntxent_prepare")
     rows = torch.cat([torch.arange(rank * B, (rank + 1) * B, dtype=torch.int32, device=dev),
                       torch.arange(N + rank * B, N + (rank + 1) * B, dtype=torch.int32, device=dev)])
     n_loc = 2 * B
     ws = _workspace(dev, lib.avssl_ntxent_workspace_bytes(2 * N, D, n_loc), "ntxent")
     z_loc = torch.empty(n_loc, dtype=_f32, device=dev)
-    check(lib.avssl_ntxent_rowsum(out.data_ptr(), rows.data_ptr(), 2 * N, D, n_loc, float(T), z_loc.data_ptr(),
-                                  ws.data_ptr(), ws.numel(), int(impl), _stream()), "avssl_ntxent_rowsum")
+    check(lib.avssl_ntxent_rowsum(out.data_ptr(), out_r.data_ptr(), rows.data_ptr(), 2 * N, D, n_loc, float(T),
+                                  z_loc.data_ptr(), ws.data_ptr(), ws.numel(), int(impl), _stream()), "avssl_ntxent_rowsum")
     if world > 1:
         zg = torch.empty(world, 2, B, dtype=_f32, device=dev)
         dist.all_gather_into_tensor(zg.view(-1), z_loc)
@@ -609,8 +639,8 @@ def ntxent(feat1, feat2, T, gather=None, impl=_lib.IMPL_AUTO):
         z_all = z_loc
     loss = torch.empty(1, dtype=_f32, device=dev)
     dfeat = torch.empty(n_loc, D, dtype=_f32, device=dev)
-    check(lib.avssl_ntxent_grad(out.data_ptr(), rows.data_ptr(), z_all.data_ptr(), nrm.data_ptr(), 2 * N, D, n_loc,
-                                float(T), float(world), loss.data_ptr(), dfeat.data_ptr(), ws.data_ptr(),
+    check(lib.avssl_ntxent_grad(out.data_ptr(), out_r.data_ptr(), rows.data_ptr(), z_all.data_ptr(), nrm.data_ptr(),
+                                2 * N, D, n_loc, float(T), float(world), loss.data_ptr(), dfeat.data_ptr(), ws.data_ptr(),
                                 ws.numel(), int(impl), _stream()), "avssl_ntxent_grad")
     return loss, dfeat[:B], dfeat[B:]
 

@@ -354,34 +354,16 @@ def gpu_arm(args):
     loss_val = float(last["loss"].item()) if graphs is None else float(losses_static[(args.steps - 1) % POOL].item())
     model.check_device_status()
 
-    # ---- duration of the dominant kernel (the EMA) with CUDA events on its stream, inside the same step
-    # sequence, eager launches (event records cannot be timed inside a captured graph)
-    ema_events = []
-    plain_update = model._update_history
-
-    def timed_update(*a, **k):
-        t = Timer()
-        t.a.record()
-        plain_update(*a, **k)
-        t.b.record()
-        ema_events.append(t)
-
-    model._update_history = timed_update
-    for i in range(min(args.steps, 100)):
-        module_step(i % POOL)
-    sync_all()
-    del model._update_history
-    ema_ms = sum(t.ms() for t in ema_events) / len(ema_events)
-
     # ---- end-to-end through the same API: pinned host inputs in, loss out, every step
     loss_h = torch.empty(2).pin_memory()  # two slots: step i's loss is read while step i+1 runs
-    xq_in = torch.empty(B_PER_GPU, DIM, device=dev).requires_grad_(True)
-    xk_in = torch.empty(B_PER_GPU, DIM, device=dev)
+    # the step's two views travel as ONE pinned host tensor [2, B, D] (one copy per step), like a collated batch
+    both_h = [torch.stack([feats_h[s_], kfeat_h[s_]]).pin_memory() for s_ in range(POOL)]
+    both_in = torch.empty(2, B_PER_GPU, DIM, device=dev)
+    xq_in = both_in[0].detach().requires_grad_(True)  # views of the landing buffer: leaf for the query view
+    xk_in = both_in[1]
 
     def e2e_step(slot, out_slot=0):
-        with torch.no_grad():
-            xq_in.copy_(feats_h[slot], non_blocking=True)
-            xk_in.copy_(kfeat_h[slot], non_blocking=True)
+        both_in.copy_(both_h[slot], non_blocking=True)
         xq_in.grad = None
         _, _, loss, do_backward = C.contrastive_forward(model, cfg, [[xq_in], [xk_in]], index, time_in, 0.0)
         if do_backward:
@@ -456,13 +438,11 @@ def gpu_arm(args):
     model.check_device_status()
 
     # ================================================ the ops-level step (kernel-only, as in round 1)
-    ops_ms = None
-    ops_note = None
-    if not args.no_ops_level:
-        try:
-            ops_ms = ops_level(args, ops, dist, dev, world, rank, impl, queue0, feats_h, kfeat_h, model, sync_all)
-        except Exception as e:  # noqa: BLE001 - secondary number: report, do not fail the line
-            ops_note = "%s: %s" % (type(e).__name__, e)
+    # also yields the duration of the dominant kernel (the EMA): CUDA events around its launch inside the eager
+    # two-launch sequence, where the host keeps ahead of the GPU (event records cannot be timed inside a captured
+    # graph, and the eager MODULE step is host-bound, so events there would time launch gaps, not the kernel)
+    ops_ms, ema_ms = ops_level(args, ops, dist, dev, world, rank, impl, queue0, feats_h, kfeat_h, model, sync_all)
+    ops_note = None if ops_ms is not None else "--no-ops-level"
 
     # max over ranks
     if world > 1:
@@ -482,7 +462,9 @@ def gpu_arm(args):
     if not args.no_logits:
         step_bytes += 4 * B_PER_GPU * (QUEUE_LEN + 1)
     floor_us = step_bytes / (peak * 1e9) * 1e6
-    own_launches = 3 if (deferred_path or world == 1) else 4  # EMA, Normalize(+push), head(+wait+enqueue) [, wait_gather]
+    # own kernels per step: EMA, head(+Normalize of the keys, un-shuffle, enqueue) on one GPU; across GPUs one more
+    # launch normalises the keys and stores them into every rank's exchange buffer (or: Normalize, then NCCL)
+    own_launches = 2 if world == 1 else 3
 
     def per_step(ms):
         return {"value": clips / (ms / args.steps * 1e-3), "unit": UNIT, "ms_per_step": ms / args.steps}
@@ -504,8 +486,9 @@ def gpu_arm(args):
                    "e2e_cuda_graph": e2e_graphs is not None, "cuda_graph_error": graph_err,
                    "key_exchange": ("Normalize + NVLink peer stores in one launch; the head launch waits, un-shuffles by index "
                                     "and enqueues rank 0's rows" if deferred_path and world > 1 else
-                                    ("exchange buffer on one GPU (un-shuffle by index inside the head launch)" if deferred_path
-                                     else ("nccl all_gather + broadcast" if world > 1 else "none"))),
+                                    ("nccl all_gather of the normalised keys; the head launch un-shuffles by index and enqueues "
+                                     "rank 0's rows" if world > 1 else
+                                     "none (one GPU): the head launch normalises the raw key rows and un-shuffles by index")),
                    "clip_shuffle": "all-to-all of the key-encoder input rows on a side stream under the EMA" if world > 1
                                    else "local row gather on a side stream under the EMA",
                    "parallelism": "dp%d (queue/EMA replicated, batch sharded; exchanges: shuffle all-to-all, keys)" % n_gpus,
@@ -515,11 +498,13 @@ def gpu_arm(args):
                     note="pinned host embeddings -> H2D -> contrastive_forward + backward -> loss D2H to pinned memory, one host wait per step"),
         "e2e_strict": per_step(e2e_strict_ms),
         "ops_level": ({"ms_per_step": ops_ms / args.steps, "step_us": ops_ms / args.steps * 1e3,
+                       "roofline_frac": floor_us / (ops_ms / args.steps * 1e3),
                        "what": "EMA[+push] launch -> head launch driven through ops.* (no module, no autograd), CUDA-graph replay"}
                       if ops_ms is not None else {"skipped": ops_note or "--no-ops-level"}),
         "gpu_launches": own_launches * args.steps,
-        "gpu_launches_note": "own kernels per step: EMA, Normalize(+push), head(+wait+enqueue); plus torch's row gather of the "
-                             "shuffle and one elementwise multiply in backward",
+        "gpu_launches_note": "own kernels per step: EMA, [N>1: Normalize+push,] head(+key Normalize on one GPU, un-shuffle, "
+                             "wait, enqueue); plus torch's row gather of the shuffle (side stream) and autograd's ones-fill "
+                             "and elementwise multiply in backward",
         "clocks": clocks,
         "roofline": {"kernel": "ema_multi_tensor_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": EMA_DRAM_TRAFFIC,
@@ -569,13 +554,19 @@ def ops_level(args, ops, dist, dev, world, rank, impl, queue0, feats_h, kfeat_h,
     out = {}
     ws = torch.zeros(ops.moco_infonce_workspace_bytes(B_PER_GPU, DIM, QUEUE_LEN, 1), dtype=torch.uint8, device=dev)
 
-    def step(slot):
+    def step(slot, ema_timers=None):
         f, k = feats[slot], keys[slot]
         if gathered is not None:
             comm.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(comm):
                 dist.all_gather_into_tensor(gathered, k)
+        if ema_timers is not None:
+            tm = Timer()
+            tm.a.record()
         plan.run(MOMENTUM, it, bump_iter=True, first_iter=False, push=(xchg, k) if xchg is not None else None)
+        if ema_timers is not None:
+            tm.b.record()
+            ema_timers.append(tm)
         if xchg is not None:
             r = ops.moco_infonce(f, None, queue, TEMP, want_logits=not args.no_logits, impl=impl, out=out,
                                  enqueue=(ptr, status), workspace=ws, peer=xchg, peer_row_idx=restore[rank].contiguous(),
@@ -592,6 +583,13 @@ def ops_level(args, ops, dist, dev, world, rank, impl, queue0, feats_h, kfeat_h,
     for i in range(max(3, min(args.warmup, 10))):
         step(i % POOL)
     sync_all()
+    ema_t = []
+    for i in range(min(args.steps, 100)):
+        step(i % POOL, ema_t)
+    sync_all()
+    ema_ms = sum(t.ms() for t in ema_t) / len(ema_t)
+    if args.no_ops_level:
+        return None, ema_ms
     one, many = step, None
     if not args.no_graph:
         pool_graph = torch.cuda.CUDAGraph()
@@ -622,7 +620,7 @@ def ops_level(args, ops, dist, dev, world, rank, impl, queue0, feats_h, kfeat_h,
     t.b.record()
     sync_all()
     assert int(status.item()) == 0, "device status word set in the ops-level run: %d" % int(status.item())
-    return t.ms()
+    return t.ms(), ema_ms
 
 
 def main():

@@ -213,13 +213,24 @@ AVSSL_API int avssl_ce_target0_bwd(const float* logits, const float* row_lse, in
  *       the reference's all_reduce(SUM)-then-slice backward.
  * impl: AVSSL_IMPL_AUTO picks the tcgen05 kernels (single-pass tf32 with both operands rounded
  *   to nearest: loss ~1e-5, gradient ~3e-4 relative, inside the 1e-3 fp32 tolerance) when
- *   D is 32/64/96/128/256; AVSSL_IMPL_SIMT forces the exact-fp32 CUDA-core kernels.
+ *   D is 32/64/96/128/256 and out_tf32 is given; AVSSL_IMPL_SIMT forces the exact-fp32 CUDA-core
+ *   kernels (out_tf32 may then be NULL).
+ * out_tf32: `out` rounded to nearest tf32, the operand the tensor cores stream (written together
+ *   with `out` by avssl_ntxent_prepare, so the rounding costs no extra pass).
  * workspace: avssl_ntxent_workspace_bytes(), zero-filled once, reusable.
+ *
+ * avssl_ntxent_prepare assembles `out` from the all_gather result (C4, models/contrastive.py:771-775):
+ *   gathered is [world][2][B][D] (every rank's [q ; q2] block, what ncclAllGather delivers),
+ *   out[(v*world + w)*B + b] = gathered[w][v][b], out_tf32 = rn_tf32(out).  world = 1 just copies.
  */
 AVSSL_API size_t avssl_ntxent_workspace_bytes(int N2, int D, int n_loc);
-AVSSL_API int avssl_ntxent_rowsum(const float* out, const int* rows, int N2, int D, int n_loc, float T,
-                        float* z_loc_out, void* workspace, size_t workspace_bytes, int impl, void* stream);
-AVSSL_API int avssl_ntxent_grad(const float* out, const int* rows, const float* z_all, const float* norm_loc,
+AVSSL_API int avssl_ntxent_prepare(const float* gathered, int world, int B, int D, float* out, float* out_tf32,
+                         void* stream);
+AVSSL_API int avssl_ntxent_rowsum(const float* out, const float* out_tf32, const int* rows, int N2, int D, int n_loc,
+                        float T, float* z_loc_out, void* workspace, size_t workspace_bytes, int impl,
+                        void* stream);
+AVSSL_API int avssl_ntxent_grad(const float* out, const float* out_tf32, const int* rows, const float* z_all,
+                      const float* norm_loc,
                       int N2, int D, int n_loc, float T, float grad_scale, float* loss_out,
                       float* dfeat_out, void* workspace, size_t workspace_bytes, int impl, void* stream);
 
@@ -312,6 +323,19 @@ AVSSL_API int avssl_moco_infonce_fwd_bwd_enqueue_peer(const float* feat_q, const
                                             float* loss_out, float* dfeat_out, float* row_lse_out,
                                             float* logits_out, void* workspace, size_t workspace_bytes,
                                             int impl, void* stream);
+
+/* K2+K3+K4 with the un-shuffle (and optionally the key Normalize) folded in, for keys that live on THIS
+ * device (one GPU, or after an NCCL gather): key_rows is [n_key_rows, D]; query row i meets
+ * key_rows[row_idx ? row_idx[i] : i] (idx_restore[rank] of models/contrastive.py:209-230), the queue receives
+ * key_rows[enq_row_idx ? enq_row_idx[e] : e], e < n_enq.  keys_raw != 0: key_rows holds the key encoder's raw
+ * output and x / ||x|| (Normalize, :350, :923-934) is applied where the rows are read, bit-identical to
+ * avssl_l2norm_fwd.  tcgen05 kernels only.  ptr_dev may be NULL (no enqueue). */
+AVSSL_API int avssl_moco_infonce_fwd_bwd_enqueue_indexed(const float* feat_q, const float* key_rows, int n_key_rows,
+                                               int keys_raw, const int64_t* row_idx, const int64_t* enq_row_idx,
+                                               int n_enq, float* queue, int64_t* ptr_dev, uint32_t* status_dev,
+                                               int B, int D, int K, float T, float* q_out, float* loss_out,
+                                               float* dfeat_out, float* row_lse_out, float* logits_out,
+                                               void* workspace, size_t workspace_bytes, int impl, void* stream);
 
 /* ------------------------------------------- multi-tensor L2 norm
  * Replaces get_grad_norm_ (models/optimizer.py:375-397; one torch.norm per parameter, a stack and a

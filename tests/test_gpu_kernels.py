@@ -297,6 +297,64 @@ def test_infonce_fused_enqueue(name, impl, B, D, K, nk):
                          enqueue=(ptr, status))
 
 
+@pytest.mark.parametrize("raw", [False, True])
+@pytest.mark.parametrize("B,D,K,n_rows,n_enq", [(64, 128, 4096, 64, 64), (32, 64, 1024, 128, 32), (32, 64, 1024, 128, 128),
+                                               (16, 32, 256, 16, 16)])
+def test_infonce_indexed_keys(raw, B, D, K, n_rows, n_enq):
+    """The un-shuffle (models/contrastive.py:216-230), the key Normalize (:350) and the C9 choice of enqueued
+    rows folded into the head launch: query row i meets key_rows[row_idx[i]], the queue receives
+    key_rows[enq_idx[e]] -- same results, bit for bit in the queue, as normalising and gathering first."""
+    ops = _ops()
+    from advise_video_ssl_b200 import _lib
+    g = torch.Generator().manual_seed(B * 7 + n_rows + n_enq)
+    T = 0.1
+    queue_c = O.l2_normalize(torch.randn(K, D, generator=g))
+    table_c = torch.randn(n_rows, D, generator=g) * 3.0
+    if not raw:
+        table_c = O.l2_normalize(table_c)
+    perm = torch.randperm(n_rows, generator=g)
+    row_idx, enq_idx = perm[:B].contiguous(), perm[torch.randperm(n_rows, generator=g)[:n_enq]].contiguous()
+    feat = torch.randn(B, D, generator=g)
+    queue = queue_c.clone().cuda()
+    ptr = torch.full((1,), K - n_enq, dtype=torch.int64, device="cuda")  # the write lands exactly on K: wraps to 0
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    out = ops.moco_infonce(feat.cuda(), None, queue, T, True, _lib.IMPL_AUTO, enqueue=(ptr, status),
+                           key_rows=table_c.cuda(), keys_raw=raw, peer_row_idx=row_idx.cuda(), enq_row_idx=enq_idx.cuda())
+    # reference: the separate launches (Normalize kernel, torch gathers, plain head, K4)
+    norm_table = ops.l2norm_fwd(table_c.cuda(), 0.0)[0] if raw else table_c.cuda()
+    keys = norm_table[row_idx.cuda()].contiguous()
+    queue2 = queue_c.clone().cuda()
+    ptr2 = torch.full((1,), K - n_enq, dtype=torch.int64, device="cuda")
+    ref = ops.moco_infonce(feat.cuda(), [keys], queue2, T, True, _lib.IMPL_AUTO)
+    ops.queue_enqueue(queue2, ptr2, norm_table[enq_idx.cuda()].contiguous(), status)
+    for name in ("loss", "dfeat", "q", "logits", "lse"):
+        assert torch.equal(out[name], ref[name]), name
+    assert torch.equal(queue, queue2) and int(ptr.item()) == int(ptr2.item()) == 0 and int(status.item()) == 0
+    _check_infonce(out, feat, [O.l2_normalize(table_c)[row_idx] if raw else table_c[row_idx]], queue_c, T, *TOL["tc3x"])
+    # an index outside the table raises the status flag instead of reading out of bounds
+    bad = row_idx.clone()
+    bad[0] = n_rows
+    ops.moco_infonce(feat.cuda(), None, queue, T, False, _lib.IMPL_AUTO, key_rows=table_c.cuda(), keys_raw=raw,
+                     peer_row_idx=bad.cuda(), enqueue=(None, status))
+    assert int(status.item()) & _lib.DEVFLAG_BAD_INDEX
+
+
+def test_l2norm_push_is_bit_identical_to_normalize_then_push():
+    ops = _ops()
+    x = ops.PeerExchange(48, 64)  # no process group: world 1, the exchange targets its own buffer
+    try:
+        feat = torch.randn(48, 64, generator=torch.Generator().manual_seed(3)).cuda() * 5
+        keep = torch.empty_like(feat)
+        x.push_normalized(feat, 0.0, keep=keep)
+        got = x.wait_gather_all()
+        ref = ops.l2norm_fwd(feat, 0.0)[0]
+        assert torch.equal(got, ref) and torch.equal(keep, ref)
+        x.push(ref * 2)
+        assert torch.equal(x.wait_gather_all(), ref * 2)
+    finally:
+        x.close()
+
+
 def test_infonce_repeated_launches_are_deterministic():
     """The cooperative kernel's counters reset themselves: 20 back-to-back launches on the same
     inputs give identical bits (no floating-point atomics anywhere on the path)."""

@@ -98,10 +98,12 @@ for B, W in ((512, 1), (512, 8)):
                note="rowsum pass + gradient pass (2 GEMM-shaped sweeps + PV)")
     else:
         # per-rank work of the 8-GPU config on one GPU: this rank's 2B rows against 2N gathered columns
-        out = torch.nn.functional.normalize(torch.randn(2 * N, D, device=dev))
+        from advise_video_ssl_b200._lib import lib, check
+        gathered = torch.nn.functional.normalize(torch.randn(W, 2, B, D, device=dev), dim=-1)  # what the all_gather delivers
+        out = torch.empty(2 * N, D, device=dev)
+        out_r = torch.empty(2 * N, D, device=dev)
         rows = torch.cat([torch.arange(0, B, dtype=torch.int32, device=dev),
                           torch.arange(N, N + B, dtype=torch.int32, device=dev)])
-        from advise_video_ssl_b200._lib import lib, check
         n_loc = 2 * B
         ws = torch.zeros(lib.avssl_ntxent_workspace_bytes(2 * N, D, n_loc), dtype=torch.uint8, device=dev)
         z = torch.empty(n_loc, device=dev)
@@ -112,12 +114,15 @@ for B, W in ((512, 1), (512, 8)):
         st = torch.cuda.current_stream().cuda_stream
 
         def rank_work():
-            check(lib.avssl_ntxent_rowsum(out.data_ptr(), rows.data_ptr(), 2 * N, D, n_loc, T, z.data_ptr(), ws.data_ptr(),
-                                          ws.numel(), IMPL, st), "rowsum")
-            check(lib.avssl_ntxent_grad(out.data_ptr(), rows.data_ptr(), zall.data_ptr(), nrm.data_ptr(), 2 * N, D, n_loc, T,
-                                        float(W), loss.data_ptr(), dfe.data_ptr(), ws.data_ptr(), ws.numel(), IMPL, st), "grad")
+            check(lib.avssl_ntxent_prepare(gathered.data_ptr(), W, B, D, out.data_ptr(), out_r.data_ptr(), st), "prepare")
+            check(lib.avssl_ntxent_rowsum(out.data_ptr(), out_r.data_ptr(), rows.data_ptr(), 2 * N, D, n_loc, T, z.data_ptr(),
+                                          ws.data_ptr(), ws.numel(), IMPL, st), "rowsum")
+            check(lib.avssl_ntxent_grad(out.data_ptr(), out_r.data_ptr(), rows.data_ptr(), zall.data_ptr(), nrm.data_ptr(),
+                                        2 * N, D, n_loc, T, float(W), loss.data_ptr(), dfe.data_ptr(), ws.data_ptr(),
+                                        ws.numel(), IMPL, st), "grad")
         report("K6 NT-Xent per-rank work of cfg3: 2B=%d local rows x 2N=%d cols, D=%d" % (2 * B, 2 * N, D), rank_work,
-               flops=3 * 2 * (2 * B) * (2 * N) * D, note="rowsum + grad kernels only (collectives excluded)")
+               flops=3 * 2 * (2 * B) * (2 * N) * D,
+               note="assemble [q_all;q2_all] + tf32 copy, rowsum, grad, finalise (collectives excluded)")
 
 # ------------------------------------------------------------------ cfg5: SwAV
 for P in (3000, 1000):
