@@ -322,32 +322,42 @@ class ContrastiveModel(nn.Module):
         perm = torch.randperm(bsz * size)
         if self.num_gpus > 1:
             perm = broadcast_from_rank0(perm, x[0].device)
-        plan = ShufflePlan(perm.numpy(), size, rank, bsz, x[0].device)
+        # transport of the rows (C1): NVLink peer stores straight into the final positions when the ranks share
+        # a box, else an NCCL all-to-all; either way only the rows a rank keeps cross the fabric
+        scatters = [None] * len(x)
+        if size > 1 and x[0].is_cuda and self._peer_transport_on():
+            scatters = [self._peer_scatter(t) for t in x]
+        plan = ShufflePlan(perm.numpy(), size, rank, bsz, x[0].device, need_alltoall=any(s is None for s in scatters))
         if x[0].is_cuda and torch.cuda.is_current_stream_capturing():
-            # the captured upload nodes read the plan's pinned host buffers on every replay
+            # the captured upload node reads the plan's pinned host buffer on every replay
             self._const.setdefault("captured_plans", []).append(plan)
-        return [plan.shuffled(t, group) for t in x], plan.restore
+        return [plan.shuffled(t, group, sc, self._status) for t, sc in zip(x, scatters)], plan.restore
 
-    def _use_peer_exchange(self, x):
-        """Can the key gather for `x` go over NVLink peer memory?  Decided (collectively) once."""
-        if not (x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and x.shape[1] % 4 == 0):
-            return False
+    def _peer_transport_on(self):
+        """Do the ranks of the shuffle group exchange rows over NVLink peer memory (CUDA IPC) rather than NCCL?
+        Decided once, collectively: on when they share one box and a probe exchange can be set up."""
         if self._peer_exchange_on is None:
             group, size, _ = self._shuffle_scope()
             one_box = int(_opt(self.cfg, "NUM_SHARDS", 1)) == 1 or (self.cfg.CONTRASTIVE.LOCAL_SHUFFLE_BN and group is not None)
             on = bool(one_box) and size <= _lib.MAX_PEERS
             if on:
                 try:  # PeerExchange raises on every rank together or on none
-                    self._peer_xchg(x.shape[0], x.shape[1])
+                    ops.PeerExchange(1, 4, group=group).close()
                 except _lib.AvsslError as e:
-                    logger.warning("NVLink peer exchange unavailable, using NCCL all_gather: %s", e)
+                    logger.warning("NVLink peer exchange unavailable, using NCCL: %s", e)
                     on = False
             self._peer_exchange_on = on
         return bool(self._peer_exchange_on)
 
+    def _use_peer_exchange(self, x):
+        """Can the key rows `x` ([rows, D] fp32) go through the NVLink exchange buffers?"""
+        if not (x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and x.shape[1] % 4 == 0):
+            return False
+        return self._peer_transport_on()
+
     def enable_peer_exchange(self, on=True):
-        """Force the key exchange (C3) onto NVLink peer memory (`ops.PeerExchange`) or back onto NCCL.
-        Collective: call it on every rank."""
+        """Force the cross-GPU exchanges (C1 rows, C3 keys) onto NVLink peer memory (`ops.PeerExchange` /
+        `ops.PeerScatter`) or back onto NCCL.  Collective: call it on every rank."""
         self._peer_exchange_on = bool(on)
         if not on:
             for ex in self._peer_xchgs.values():
@@ -362,6 +372,18 @@ class ContrastiveModel(nn.Module):
             group, _, _ = self._shuffle_scope()
             ex = self._peer_xchgs[key] = ops.PeerExchange(rows, dim, group=group)
         return ex
+
+    def _peer_scatter(self, t):
+        """The scatter buffers for tensors shaped like `t` (None when its rows are not 16-byte multiples)."""
+        row_bytes = (t.numel() // max(t.shape[0], 1)) * t.element_size()
+        if t.shape[0] == 0 or row_bytes % 16 != 0:
+            return None
+        key = ("scatter", t.shape[0], row_bytes)
+        sc = self._peer_xchgs.get(key)
+        if sc is None:
+            group, _, _ = self._shuffle_scope()
+            sc = self._peer_xchgs[key] = ops.PeerScatter(t.shape[0], row_bytes, group=group)
+        return sc
 
     @torch.no_grad()
     def _batch_unshuffle(self, x, idx_restore):

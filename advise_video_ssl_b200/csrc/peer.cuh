@@ -73,9 +73,13 @@ __device__ __forceinline__ void peer_push_cta(const avssl_peer_xchg& x, const fl
     float4* out = reinterpret_cast<float4*>(out_f);
     for (int i = threadIdx.x; i < n4; i += blockDim.x) out[i] = __ldg(src + i);
   }
-  __threadfence_system();  // every thread's stores are performed at the destination before the flag
+  // Publication: the CTA barrier orders every thread's payload stores before thread 0's system-scope fence
+  // (release patterns are cumulative over barrier synchronisation in the PTX memory model -- the pattern of
+  // cooperative-groups grid sync), so ONE fence and one release store publish the whole block; a fence per
+  // thread cost a second NVLink round trip on the step's critical path.
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();
     st_release_sys_u64(&static_cast<PeerHdr*>(x.base[dst])->flags[x.rank], e);
     // every CTA has read `epoch` before it arrives here, so the last one may advance it
     const unsigned prev = atomicAdd(&me->done, 1u);

@@ -199,7 +199,7 @@ class PeerExchange:
         self.rows_per_rank, self.D = int(rows_per_rank), int(D)
         if self.world > _lib.MAX_PEERS:
             raise ValueError("PeerExchange supports at most %d ranks (one NVLink domain)" % _lib.MAX_PEERS)
-        nbytes = lib.avssl_peer_xchg_bytes(self.world, self.rows_per_rank, self.D)
+        nbytes = self._buffer_bytes()
         if nbytes == 0:
             raise ValueError("bad exchange geometry world=%d rows=%d D=%d" % (self.world, rows_per_rank, D))
         self.nbytes = int(nbytes)
@@ -254,6 +254,9 @@ class PeerExchange:
         if timeout_ms is None:
             timeout_ms = int(os.environ.get("AVSSL_PEER_TIMEOUT_MS", "30000"))
         self.desc.timeout_ms = max(0, int(timeout_ms))
+
+    def _buffer_bytes(self):
+        return lib.avssl_peer_xchg_bytes(self.world, self.rows_per_rank, self.D)
 
     def check_rows(self, rows):
         _req(rows, "rows")
@@ -312,6 +315,50 @@ class PeerExchange:
         if self._own is not None:
             lib.avssl_peer_free(self._own)
         self._own, self._opened = None, []
+
+
+class PeerScatter(PeerExchange):
+    """C1 over NVLink peer memory: the shuffle-BN exchange of the key encoder's input rows
+    (models/contrastive.py:174-214) as a scatter -- every rank writes each of its rows once, straight
+    into its final position in the destination rank's buffer; nothing is gathered first or reordered
+    on arrival.  Rows are opaque (any dtype, `row_bytes` a multiple of 16).
+
+        sc = PeerScatter(B, row_bytes)                       # collective set-up, once
+        sc.scatter(x, dest_pos)                              # dest_pos = argsort(perm)[rank*B:(rank+1)*B]
+        shuffled = sc.wait(out)                              # == cat_all_gather(x)[perm.view(W, -1)[rank]]
+    """
+
+    def __init__(self, rows_per_rank, row_bytes, group=None, device=None, timeout_ms=None):
+        if row_bytes % 16 != 0:
+            raise ValueError("row_bytes must be a multiple of 16, got %d" % row_bytes)
+        self.row_bytes = int(row_bytes)
+        super().__init__(rows_per_rank, row_bytes // 4, group=group, device=device, timeout_ms=timeout_ms)
+
+    def _buffer_bytes(self):
+        return lib.avssl_peer_scatter_bytes(self.rows_per_rank, self.row_bytes)
+
+    def _check(self, t, name):
+        if not t.is_cuda or not t.is_contiguous():
+            raise ValueError("%s must be a contiguous CUDA tensor" % name)
+        if t.shape[0] != self.rows_per_rank or t.numel() * t.element_size() != self.rows_per_rank * self.row_bytes:
+            raise ValueError("%s must hold %d rows of %d bytes, got %s %s" % (name, self.rows_per_rank, self.row_bytes,
+                                                                            tuple(t.shape), t.dtype))
+
+    def scatter(self, x, dest_pos, status=None):
+        self._check(x, "x")
+        _req(dest_pos, "dest_pos", torch.int64)
+        if dest_pos.numel() != self.rows_per_rank:
+            raise ValueError("dest_pos needs %d entries" % self.rows_per_rank)
+        check(lib.avssl_peer_scatter_rows(ctypes.addressof(self.desc), x.data_ptr(), dest_pos.data_ptr(),
+                                          status.data_ptr() if status is not None else None, _stream()),
+              "avssl_peer_scatter_rows")
+
+    def wait(self, out, status=None):
+        self._check(out, "out")
+        check(lib.avssl_peer_scatter_wait(ctypes.addressof(self.desc), out.data_ptr(),
+                                          status.data_ptr() if status is not None else None, _stream()),
+              "avssl_peer_scatter_wait")
+        return out
 
 
 # ---------------------------------------------------------------------------- K2+K3

@@ -61,52 +61,56 @@ def broadcast_from_rank0(values_cpu, device):
     return values_cpu
 
 
-def _upload(arr, device, keep):
-    t = torch.from_numpy(np.ascontiguousarray(arr))
-    if device.type != "cuda":
-        return t
-    host = t.pin_memory()
-    keep.append(host)  # the copy is asynchronous (and may be a captured graph node): the plan owns its source
-    return host.to(device, non_blocking=True)
-
-
 class ShufflePlan:
     """One draw of the shuffle permutation and what follows from it.
 
     perm      int64 [W*B] on the host: row r of rank d's shuffled batch is row perm[d*B + r] of the
               rank-major concatenation of all local batches (reference :204-207).
     restore   int64 [W, B] on the device = argsort(perm).view(W, B): `_batch_unshuffle`'s index
-              (:209-212); row i of rank d's ORIGINAL batch sits at gathered[restore[d, i]].
-    For this rank's side of the all-to-all: `send_rows` (device int64: local rows in the order they
-    are sent, grouped by destination), `send_counts` / `recv_counts` (host lists) and `place`
-    (device int64: where each row of the shuffled batch sits in the receive buffer).
+              (:209-212); row i of rank d's ORIGINAL batch sits at gathered[restore[d, i]].  Row
+              `rank` of it is also where this rank's local rows GO in the shuffled batch (the scatter's
+              destination positions).
+    For the NCCL all-to-all: `send_rows` (device int64: local rows in the order they are sent, grouped
+    by destination), `send_counts` / `recv_counts` (host lists) and `place` (device int64: where each
+    row of the shuffled batch sits in the receive buffer).
+    Every index array travels to the device in ONE copy from one pinned buffer, which the plan keeps
+    alive (the copy is asynchronous and may be a captured graph node).
     """
 
-    def __init__(self, perm, world, rank, bsz, device):
+    def __init__(self, perm, world, rank, bsz, device, need_alltoall=True):
         perm = np.asarray(perm, dtype=np.int64).reshape(world, bsz)
         self.world, self.rank, self.bsz, self.device = world, rank, bsz, device
         self.perm = perm
-        self._host = []
-        self.take = _upload(perm[rank], device, self._host)
-        self.restore = _upload(np.argsort(perm.reshape(-1), kind="stable").reshape(world, bsz), device, self._host)
-        if world == 1:
-            return
-        holder = perm // bsz  # rank that owns each wanted row
-        # np.nonzero walks row-major: destinations in ascending order, each in its own take order
-        dst, pos = np.nonzero(holder == rank)
-        self.send_rows = _upload(perm[dst, pos] % bsz, device, self._host)
-        self.send_counts = np.bincount(dst, minlength=world).tolist()
-        self.recv_counts = np.bincount(holder[rank], minlength=world).tolist()
-        # the receive buffer is grouped by source rank; inside a group rows keep this rank's take order
-        arrival = np.argsort(holder[rank], kind="stable")
-        place = np.empty(bsz, dtype=np.int64)
-        place[arrival] = np.arange(bsz)
-        self.place = _upload(place, device, self._host)
+        parts = [perm[rank], np.argsort(perm.reshape(-1), kind="stable")]
+        if world > 1 and need_alltoall:
+            holder = perm // bsz  # rank that owns each wanted row
+            # np.nonzero walks row-major: destinations in ascending order, each in its own take order
+            dst, pos = np.nonzero(holder == rank)
+            self.send_counts = np.bincount(dst, minlength=world).tolist()
+            self.recv_counts = np.bincount(holder[rank], minlength=world).tolist()
+            # the receive buffer is grouped by source rank; inside a group rows keep this rank's take order
+            arrival = np.argsort(holder[rank], kind="stable")
+            place = np.empty(bsz, dtype=np.int64)
+            place[arrival] = np.arange(bsz)
+            parts += [perm[dst, pos] % bsz, place]
+        packed = torch.from_numpy(np.ascontiguousarray(np.concatenate(parts)))
+        if device.type == "cuda":
+            self._host = packed.pin_memory()
+            packed = self._host.to(device, non_blocking=True)
+        self.take = packed[:bsz]
+        self.restore = packed[bsz:bsz + world * bsz].view(world, bsz)
+        if len(parts) == 4:
+            self.send_rows = packed[(world + 1) * bsz:(world + 2) * bsz]
+            self.place = packed[(world + 2) * bsz:]
 
-    def shuffled(self, x, group=None):
-        """This rank's shuffled batch: cat_all_gather(x)[perm[rank]] bit for bit, moving B rows."""
+    def shuffled(self, x, group=None, scatter=None, status=None):
+        """This rank's shuffled batch: cat_all_gather(x)[perm[rank]] bit for bit, moving B rows.
+        `scatter`: an ops.PeerScatter for x's row size -> NVLink peer stores instead of NCCL."""
         if self.world == 1:
             return x.index_select(0, self.take)
+        if scatter is not None:
+            scatter.scatter(x.contiguous(), self.restore[self.rank], status=status)
+            return scatter.wait(torch.empty_like(x, memory_format=torch.contiguous_format), status=status)
         outgoing = x.index_select(0, self.send_rows)
         incoming = torch.empty_like(x)
         dist.all_to_all_single(incoming, outgoing, output_split_sizes=self.recv_counts,

@@ -141,3 +141,43 @@ def test_fused_wait_needs_tensor_core_kernel():
         ops.moco_infonce(torch.randn(16, 48).cuda(), [k], torch.randn(256, 48).cuda(), 0.1)
     finally:
         x.close()
+
+
+@pytest.mark.parametrize("shape,dtype", [((64, 3, 4, 8), torch.float32), ((33, 40), torch.float16), ((5, 2), torch.int64)])
+def test_scatter_rows_bit_exact_over_epochs(shape, dtype):
+    """C1 as a scatter (models/contrastive.py:186-207): with one rank the rows land at argsort(perm) of its own
+    buffer, i.e. the result is x[perm]; several epochs exercise both slots, and a CUDA graph replays it."""
+    ops = _ops()
+    B = shape[0]
+    row_bytes = int(torch.empty(shape[1:], dtype=dtype).numel() * torch.empty(0, dtype=dtype).element_size())
+    sc = ops.PeerScatter(B, row_bytes)
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    try:
+        g = torch.Generator().manual_seed(11)
+        for step in range(4):
+            x = (torch.randn(shape, generator=g) * 100).to(dtype).cuda()
+            perm = torch.randperm(B, generator=g)
+            sc.scatter(x, torch.argsort(perm).cuda(), status=status)
+            out = sc.wait(torch.empty_like(x), status=status)
+            assert torch.equal(out, x[perm.cuda()]), step
+        # graph replay: fixed destination although the slot alternates
+        x = (torch.randn(shape, generator=g) * 100).to(dtype).cuda()
+        dest = torch.argsort(perm).cuda()
+        out = torch.empty_like(x)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            sc.scatter(x, dest, status=status)
+            sc.wait(out, status=status)
+        for rep in range(3):
+            x.copy_((torch.randn(shape, generator=g) * 100).to(dtype))
+            graph.replay()
+            assert torch.equal(out, x[perm.cuda()]), rep
+        bad = dest.clone()
+        bad[0] = B
+        sc.scatter(x, bad, status=status)
+        sc.wait(out, status=status)
+        assert int(status.item()) == 2
+    finally:
+        sc.close()
+    with pytest.raises(ValueError):
+        ops.PeerScatter(4, 24)  # rows must be 16-byte multiples

@@ -9,10 +9,16 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 import bench  # noqa: E402
 
-dev = torch.device("cuda", 0)
-torch.cuda.set_device(0)
+world = int(os.environ.get("WORLD_SIZE", "1"))
+rank = int(os.environ.get("RANK", "0"))
+local = int(os.environ.get("LOCAL_RANK", "0"))
+dev = torch.device("cuda", local)
+torch.cuda.set_device(local)
+if world > 1:  # torchrun --nproc-per-node N tools/step_timeline.py : rank 0 prints its timeline
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
 C = bench.register_stub_backbone()
-cfg = bench.head_cfg(1)
+cfg = bench.head_cfg(world)
 if os.environ.get("SHUFFLE", "1") == "0":
     cfg.BN.NORM_TYPE, cfg.BN.NUM_SYNC_DEVICES = "sync_batchnorm", 1
 model = C.ContrastiveModel(cfg).to(dev).train()
@@ -48,6 +54,9 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(4):
         g.replay()
     torch.cuda.synchronize()
+if rank != 0:
+    torch.cuda.synchronize()
+    os._exit(0)
 evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 evs.sort(key=lambda e: e.time_range.start)
 ema = [i for i, e in enumerate(evs) if "ema_multi_tensor" in e.name]
@@ -65,3 +74,6 @@ for e in evs[first:hi]:
     print("%-58s %9.2f %9.2f %7s" % (e.name[:58], (e.time_range.start - t0), (e.time_range.end - e.time_range.start),
                                      getattr(e, "stream", "?")))
 print("step (EMA start -> next EMA start): %.2f us" % (evs[hi].time_range.start - t0))
+if world > 1:
+    sys.stdout.flush()
+    os._exit(0)
