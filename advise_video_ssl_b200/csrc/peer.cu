@@ -51,7 +51,7 @@ peer_wait_gather_kernel(const avssl_peer_xchg x, const long long* __restrict__ r
 }
 
 // ---------------------------------------------------------------------------------------------------
-// C1 as a scatter over NVLink peer stores (the shuffle of models/contrastive.py:174-214).
+// C1 as a scatter over NVLink peer stores (the shuffle of models/contrastive.py:174-214), ONE launch.
 //
 // Geometry: the same header as the key exchange, then payload[2][rows_per_rank * D] (D = floats per row,
 // whatever the tensor's dtype): a rank receives exactly rows_per_rank rows per step, each written by the rank
@@ -59,68 +59,85 @@ peer_wait_gather_kernel(const avssl_peer_xchg x, const long long* __restrict__ r
 // goes to position dest_pos[j] = argsort(perm)[g] of the rank-major shuffled batch, i.e. to rank
 // dest_pos[j] / rows, row dest_pos[j] % rows.  One read of the source row, one NVLink write, no send-buffer
 // gather, no reordering on arrival (the reference all_gathers world x the bytes and discards (world-1)/world).
-// Flags: the LAST CTA of the scatter (gpu-scope counter, each CTA fences at system scope first) publishes
-// flags[rank] = epoch at every peer and advances the local epoch.
+//
+// Grid = world * M CTAs.  CTA (d, m) stores the m-th of M byte ranges of every local row destined to rank d,
+// then the last of the M CTAs of destination d (counter in the header) publishes flags[rank] = epoch at rank d.
+// Every CTA then waits for all `world` local flags (no rank's scatter depends on another's, so this cannot
+// deadlock) and copies its share of the received rows out of the slot to `out` -- the slot alternates with the
+// epoch, and a CUDA graph needs a fixed destination.  With small rows M = 1 and the dependent chain is
+// loads -> NVLink stores -> fence -> flag | poll -> copy: it has to fit under the EMA kernel it runs beside.
 __device__ __forceinline__ uint4* scatter_slot(void* base, int slot, const avssl_peer_xchg& x) {
   return reinterpret_cast<uint4*>(static_cast<char*>(base) + sizeof(PeerHdr)) + (size_t)slot * x.rows_per_rank * (x.D / 4);
 }
 
-__global__ void __launch_bounds__(256)
-peer_scatter_kernel(const avssl_peer_xchg x, const uint4* __restrict__ rows, const long long* __restrict__ dest_pos,
-                    uint32_t* status) {
+__global__ void __launch_bounds__(512)
+peer_scatter_exchange_kernel(const avssl_peer_xchg x, const uint4* __restrict__ rows, const long long* __restrict__ dest_pos,
+                             uint4* __restrict__ out, int M, uint32_t* status) {
   __shared__ unsigned long long s_epoch;
-  __shared__ unsigned s_last;
   PeerHdr* me = static_cast<PeerHdr*>(x.base[x.rank]);
   if (threadIdx.x == 0) s_epoch = *reinterpret_cast<volatile unsigned long long*>(&me->epoch) + 1ull;
   __syncthreads();
   const unsigned long long e = s_epoch;
   const int slot = (int)(e & 1ull);
+  const int d = blockIdx.x / M, m = blockIdx.x % M;
   const size_t row16 = (size_t)x.D / 4;  // 16-byte units per row
+  const size_t c_lo = row16 * m / M, c_hi = row16 * (m + 1) / M;
   const long long n_pos = (long long)x.world * x.rows_per_rank;
-  // CTA b takes rows b, b + grid, ...; a row is copied by the whole CTA with 128-bit accesses
-  for (int j = blockIdx.x; j < x.rows_per_rank; j += gridDim.x) {
-    const long long pos = dest_pos[j];
+  uint4* dst_slot = scatter_slot(x.base[d], slot, x);
+  for (int j = 0; j < x.rows_per_rank; ++j) {
+    const long long pos = __ldg(dest_pos + j);  // one address for the whole CTA: a broadcast load
     if (pos < 0 || pos >= n_pos) {
-      if (threadIdx.x == 0 && status) atomicOr(status, AVSSL_DEVFLAG_BAD_INDEX);
+      if (threadIdx.x == 0 && d == 0 && m == 0 && status) atomicOr(status, AVSSL_DEVFLAG_BAD_INDEX);
       continue;
     }
-    const int dst = (int)(pos / x.rows_per_rank), r = (int)(pos % x.rows_per_rank);
+    if ((int)(pos / x.rows_per_rank) != d) continue;
     const uint4* src = rows + (size_t)j * row16;
-    uint4* out = scatter_slot(x.base[dst], slot, x) + (size_t)r * row16;
-    for (size_t c = threadIdx.x; c < row16; c += blockDim.x) out[c] = __ldg(src + c);
+    uint4* o = dst_slot + (size_t)(pos % x.rows_per_rank) * row16;
+    for (size_t c = c_lo + threadIdx.x; c < c_hi; c += blockDim.x) o[c] = __ldg(src + c);
   }
-  __syncthreads();  // this CTA's stores are ordered before thread 0's fence (barrier + cumulativity)
+  __syncthreads();  // the CTA's stores are ordered before thread 0's fence (barrier + cumulativity)
   if (threadIdx.x == 0) {
     __threadfence_system();
-    s_last = (atomicAdd(&me->done, 1u) == gridDim.x - 1u) ? 1u : 0u;
-  }
-  __syncthreads();
-  if (s_last) {  // every CTA's rows have been performed at their destinations
-    if (threadIdx.x < (unsigned)x.world) {
-      __threadfence_system();
-      st_release_sys_u64(&static_cast<PeerHdr*>(x.base[threadIdx.x])->flags[x.rank], e);
+    bool publish = true;
+    if (M > 1) publish = atomicAdd(&me->pad_[d], 1u) == (unsigned)M - 1u;  // last CTA of destination d
+    if (publish) {
+      if (M > 1) {
+        me->pad_[d] = 0u;
+        __threadfence_system();
+      }
+      st_release_sys_u64(&static_cast<PeerHdr*>(x.base[d])->flags[x.rank], e);
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    // every CTA has read `epoch` before it arrives here, so the last one may advance it
+    if (atomicAdd(&me->done, 1u) == gridDim.x - 1u) {
       me->done = 0u;
       *reinterpret_cast<volatile unsigned long long*>(&me->epoch) = e;
       __threadfence();
     }
   }
-}
-
-// wait for every rank's scatter of the current epoch, then copy this rank's received rows out of the slot
-// (the slot alternates with the epoch, so a CUDA graph needs a fixed destination)
-__global__ void __launch_bounds__(256)
-peer_scatter_wait_kernel(const avssl_peer_xchg x, uint4* __restrict__ out, uint32_t* status) {
-  __shared__ int s_slot;
+  // ---- wait for every rank's rows of this epoch (bounded spin, see peer_wait_all_warp), then copy out
   if (threadIdx.x < 32) {
-    const int slot = peer_wait_all_warp(x, status);
-    if (threadIdx.x == 0) s_slot = slot;
+    const int lane = threadIdx.x;
+    if (lane < x.world) {
+      unsigned spins = 0;
+      unsigned long long t0 = 0ull;
+      while (ld_relaxed_sys_u64(&me->flags[lane]) < e) {
+        __nanosleep(32);
+        if (x.timeout_ms != 0u && (++spins & 1023u) == 0u) {
+          const unsigned long long now = global_timer_ns();
+          if (t0 == 0ull) t0 = now;
+          else if (now - t0 > (unsigned long long)x.timeout_ms * 1000000ull) {
+            if (status) atomicOr(status, AVSSL_DEVFLAG_PEER_TIMEOUT);
+            break;
+          }
+        }
+      }
+    }
+    __syncwarp();
+    __threadfence_system();
   }
   __syncthreads();
-  const uint4* src = scatter_slot(x.base[x.rank], s_slot, x);
-  const size_t n16 = (size_t)x.rows_per_rank * (x.D / 4);
+  const uint4* src = scatter_slot(x.base[x.rank], slot, x);
+  const size_t n16 = (size_t)x.rows_per_rank * row16;
   for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n16; c += (size_t)gridDim.x * blockDim.x)
     out[c] = __ldcg(src + c);
 }
@@ -200,32 +217,28 @@ extern "C" size_t avssl_peer_scatter_bytes(int rows_per_rank, int64_t row_bytes)
   return sizeof(PeerHdr) + 2ull * rows_per_rank * (size_t)row_bytes;
 }
 
-extern "C" int avssl_peer_scatter_rows(const avssl_peer_xchg* x, const void* rows, const int64_t* dest_pos_dev,
-                                       uint32_t* status_dev, void* stream) {
-  int rc = peer_check(x, "peer_scatter_rows");
+extern "C" int avssl_peer_scatter_exchange(const avssl_peer_xchg* x, const void* rows, const int64_t* dest_pos_dev,
+                                           void* out, uint32_t* status_dev, void* stream) {
+  int rc = peer_check(x, "peer_scatter_exchange");
   if (rc != AVSSL_OK) return rc;
-  AVSSL_REQUIRE(rows && dest_pos_dev && (reinterpret_cast<uintptr_t>(rows) & 15u) == 0, AVSSL_ERR_INVALID_ARGUMENT,
-                "peer_scatter_rows: rows / dest_pos null or rows not 16-byte aligned");
+  AVSSL_REQUIRE(rows && dest_pos_dev && out &&
+                    ((reinterpret_cast<uintptr_t>(rows) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0,
+                AVSSL_ERR_INVALID_ARGUMENT, "peer_scatter_exchange: null pointer, or rows / out not 16-byte aligned");
+  static_assert(sizeof(((PeerHdr*)nullptr)->pad_) >= AVSSL_MAX_PEERS * sizeof(unsigned), "per-destination counters");
+  // M CTAs per destination: one for small rows (latency-bound: the shortest dependent chain), more for large
+  // rows so that the stores keep NVLink busy (about 64 KiB per CTA), never more than 2 CTAs per SM
   const int sms = sm_count() > 0 ? sm_count() : 148;
-  // enough CTAs to keep NVLink busy for large rows, never more than one per row
-  const int grid = x->rows_per_rank < 2 * sms ? x->rows_per_rank : 2 * sms;
-  peer_scatter_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      *x, static_cast<const uint4*>(rows), reinterpret_cast<const long long*>(dest_pos_dev), status_dev);
-  AVSSL_LAUNCH_OK("peer_scatter_kernel");
-  return AVSSL_OK;
-}
-
-extern "C" int avssl_peer_scatter_wait(const avssl_peer_xchg* x, void* out, uint32_t* status_dev, void* stream) {
-  int rc = peer_check(x, "peer_scatter_wait");
-  if (rc != AVSSL_OK) return rc;
-  AVSSL_REQUIRE(out && (reinterpret_cast<uintptr_t>(out) & 15u) == 0, AVSSL_ERR_INVALID_ARGUMENT,
-                "peer_scatter_wait: out is null or not 16-byte aligned");
-  const size_t n16 = (size_t)x->rows_per_rank * (x->D / 4);
-  const int sms = sm_count() > 0 ? sm_count() : 148;
-  size_t grid = (n16 + 255) / 256;
-  if (grid > (size_t)4 * sms) grid = (size_t)4 * sms;
-  peer_scatter_wait_kernel<<<(int)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(*x, static_cast<uint4*>(out), status_dev);
-  AVSSL_LAUNCH_OK("peer_scatter_wait_kernel");
+  const size_t bytes_per_dest = (size_t)x->rows_per_rank * x->D * 4 / x->world;
+  int M = (int)((bytes_per_dest + 65535) / 65536);
+  // all CTAs spin on the peers' flags after their stores: the whole grid must be able to be co-resident
+  const int cap = 2 * sms / x->world > 1 ? 2 * sms / x->world : 1;
+  if (M > cap) M = cap;
+  if (M < 1) M = 1;
+  if ((size_t)M > (size_t)x->D / 4) M = x->D / 4;
+  peer_scatter_exchange_kernel<<<x->world * M, 512, 0, static_cast<cudaStream_t>(stream)>>>(
+      *x, static_cast<const uint4*>(rows), reinterpret_cast<const long long*>(dest_pos_dev), static_cast<uint4*>(out), M,
+      status_dev);
+  AVSSL_LAUNCH_OK("peer_scatter_exchange_kernel");
   return AVSSL_OK;
 }
 

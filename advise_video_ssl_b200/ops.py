@@ -324,8 +324,8 @@ class PeerScatter(PeerExchange):
     on arrival.  Rows are opaque (any dtype, `row_bytes` a multiple of 16).
 
         sc = PeerScatter(B, row_bytes)                       # collective set-up, once
-        sc.scatter(x, dest_pos)                              # dest_pos = argsort(perm)[rank*B:(rank+1)*B]
-        shuffled = sc.wait(out)                              # == cat_all_gather(x)[perm.view(W, -1)[rank]]
+        shuffled = sc.exchange(x, dest_pos)                  # dest_pos = argsort(perm)[rank*B:(rank+1)*B]
+                                                             # == cat_all_gather(x)[perm.view(W, -1)[rank]]
     """
 
     def __init__(self, rows_per_rank, row_bytes, group=None, device=None, timeout_ms=None):
@@ -344,20 +344,19 @@ class PeerScatter(PeerExchange):
             raise ValueError("%s must hold %d rows of %d bytes, got %s %s" % (name, self.rows_per_rank, self.row_bytes,
                                                                             tuple(t.shape), t.dtype))
 
-    def scatter(self, x, dest_pos, status=None):
+    def exchange(self, x, dest_pos, out=None, status=None):
+        """Scatter this rank's rows to their final positions, wait for everybody's, return the received rows
+        (one launch; collective: every rank of the group makes the call)."""
         self._check(x, "x")
         _req(dest_pos, "dest_pos", torch.int64)
         if dest_pos.numel() != self.rows_per_rank:
             raise ValueError("dest_pos needs %d entries" % self.rows_per_rank)
-        check(lib.avssl_peer_scatter_rows(ctypes.addressof(self.desc), x.data_ptr(), dest_pos.data_ptr(),
-                                          status.data_ptr() if status is not None else None, _stream()),
-              "avssl_peer_scatter_rows")
-
-    def wait(self, out, status=None):
+        if out is None:
+            out = torch.empty_like(x, memory_format=torch.contiguous_format)
         self._check(out, "out")
-        check(lib.avssl_peer_scatter_wait(ctypes.addressof(self.desc), out.data_ptr(),
-                                          status.data_ptr() if status is not None else None, _stream()),
-              "avssl_peer_scatter_wait")
+        check(lib.avssl_peer_scatter_exchange(ctypes.addressof(self.desc), x.data_ptr(), dest_pos.data_ptr(),
+                                              out.data_ptr(), status.data_ptr() if status is not None else None,
+                                              _stream()), "avssl_peer_scatter_exchange")
         return out
 
 

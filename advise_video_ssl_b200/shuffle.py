@@ -109,8 +109,7 @@ class ShufflePlan:
         if self.world == 1:
             return x.index_select(0, self.take)
         if scatter is not None:
-            scatter.scatter(x.contiguous(), self.restore[self.rank], status=status)
-            return scatter.wait(torch.empty_like(x, memory_format=torch.contiguous_format), status=status)
+            return scatter.exchange(x.contiguous(), self.restore[self.rank], status=status)
         outgoing = x.index_select(0, self.send_rows)
         incoming = torch.empty_like(x)
         dist.all_to_all_single(incoming, outgoing, output_split_sizes=self.recv_counts,

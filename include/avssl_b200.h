@@ -299,16 +299,16 @@ AVSSL_API int avssl_l2norm_push_rows(const avssl_peer_xchg* x, const float* feat
 AVSSL_API int avssl_peer_wait_gather(const avssl_peer_xchg* x, const int64_t* row_idx, int n_out, float* out,
                            uint32_t* status_dev, void* stream);
 /* C1 -- the shuffle-BN exchange of the key encoder's INPUT rows (models/contrastive.py:174-214: cat_all_gather of
- * the clip, then x[perm.view(W,-1)[rank]]) as a scatter over NVLink peer stores: every row is written by its owner
- * straight into its final position in the destination rank's buffer, once.  Uses an avssl_peer_xchg descriptor whose
- * buffers were allocated with avssl_peer_scatter_bytes(rows_per_rank, row_bytes) and D = row_bytes / 4 (rows are
- * opaque bytes; row_bytes % 16 == 0).  dest_pos_dev[j] = argsort(perm)[rank * rows_per_rank + j] (int64, device):
- * the position of local row j in the rank-major shuffled batch.  avssl_peer_scatter_wait waits for every rank's
- * scatter of the current epoch and copies this rank's rows_per_rank received rows to `out`.  Bit-exact. */
+ * the clip, then x[perm.view(W,-1)[rank]]) as a scatter over NVLink peer stores, ONE launch: every row is written by
+ * its owner straight into its final position in the destination rank's buffer, once; the same kernel then waits for
+ * every rank's rows of this epoch and copies this rank's rows_per_rank received rows to `out`.  Uses an
+ * avssl_peer_xchg descriptor whose buffers were allocated with avssl_peer_scatter_bytes(rows_per_rank, row_bytes)
+ * and D = row_bytes / 4 (rows are opaque bytes; row_bytes % 16 == 0).  dest_pos_dev[j] = argsort(perm)[rank *
+ * rows_per_rank + j] (int64, device): the position of local row j in the rank-major shuffled batch.  Bit-exact;
+ * every rank of the exchange must make the call (same sequence on every rank). */
 AVSSL_API size_t avssl_peer_scatter_bytes(int rows_per_rank, int64_t row_bytes);
-AVSSL_API int avssl_peer_scatter_rows(const avssl_peer_xchg* x, const void* rows, const int64_t* dest_pos_dev,
-                            uint32_t* status_dev, void* stream);
-AVSSL_API int avssl_peer_scatter_wait(const avssl_peer_xchg* x, void* out, uint32_t* status_dev, void* stream);
+AVSSL_API int avssl_peer_scatter_exchange(const avssl_peer_xchg* x, const void* rows, const int64_t* dest_pos_dev,
+                                void* out, uint32_t* status_dev, void* stream);
 /* K1 with the push fused into the same launch: `world` extra CTAs at the front of the EMA grid
  * push `rows` while the rest stream the parameters (north_star: the key exchange overlapped with
  * the EMA kernel).  Other arguments as avssl_ema_multi_tensor. */

@@ -143,7 +143,8 @@ def test_fused_wait_needs_tensor_core_kernel():
         x.close()
 
 
-@pytest.mark.parametrize("shape,dtype", [((64, 3, 4, 8), torch.float32), ((33, 40), torch.float16), ((5, 2), torch.int64)])
+@pytest.mark.parametrize("shape,dtype", [((64, 3, 4, 8), torch.float32), ((33, 40), torch.float16), ((5, 2), torch.int64),
+                                         ((16, 3, 8, 112, 112), torch.float32)])
 def test_scatter_rows_bit_exact_over_epochs(shape, dtype):
     """C1 as a scatter (models/contrastive.py:186-207): with one rank the rows land at argsort(perm) of its own
     buffer, i.e. the result is x[perm]; several epochs exercise both slots, and a CUDA graph replays it."""
@@ -157,8 +158,7 @@ def test_scatter_rows_bit_exact_over_epochs(shape, dtype):
         for step in range(4):
             x = (torch.randn(shape, generator=g) * 100).to(dtype).cuda()
             perm = torch.randperm(B, generator=g)
-            sc.scatter(x, torch.argsort(perm).cuda(), status=status)
-            out = sc.wait(torch.empty_like(x), status=status)
+            out = sc.exchange(x, torch.argsort(perm).cuda(), status=status)
             assert torch.equal(out, x[perm.cuda()]), step
         # graph replay: fixed destination although the slot alternates
         x = (torch.randn(shape, generator=g) * 100).to(dtype).cuda()
@@ -166,16 +166,14 @@ def test_scatter_rows_bit_exact_over_epochs(shape, dtype):
         out = torch.empty_like(x)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            sc.scatter(x, dest, status=status)
-            sc.wait(out, status=status)
+            sc.exchange(x, dest, out=out, status=status)
         for rep in range(3):
             x.copy_((torch.randn(shape, generator=g) * 100).to(dtype))
             graph.replay()
             assert torch.equal(out, x[perm.cuda()]), rep
         bad = dest.clone()
         bad[0] = B
-        sc.scatter(x, bad, status=status)
-        sc.wait(out, status=status)
+        sc.exchange(x, bad, out=out, status=status)
         assert int(status.item()) == 2
     finally:
         sc.close()
