@@ -84,16 +84,28 @@ peer_scatter_exchange_kernel(const avssl_peer_xchg x, const uint4* __restrict__ 
   const size_t c_lo = row16 * m / M, c_hi = row16 * (m + 1) / M;
   const long long n_pos = (long long)x.world * x.rows_per_rank;
   uint4* dst_slot = scatter_slot(x.base[d], slot, x);
-  for (int j = 0; j < x.rows_per_rank; ++j) {
-    const long long pos = __ldg(dest_pos + j);  // one address for the whole CTA: a broadcast load
-    if (pos < 0 || pos >= n_pos) {
-      if (threadIdx.x == 0 && d == 0 && m == 0 && status) atomicOr(status, AVSSL_DEVFLAG_BAD_INDEX);
-      continue;
+  // rows in batches of blockDim: one coalesced load of the destinations, then one WARP per row (all rows of
+  // a batch are in flight at once -- the launch runs beside a kernel that saturates HBM, so every dependent
+  // memory round trip costs microseconds)
+  __shared__ long long s_pos[512];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  for (int j0 = 0; j0 < x.rows_per_rank; j0 += (int)blockDim.x) {
+    const int nj = min((int)blockDim.x, x.rows_per_rank - j0);
+    __syncthreads();
+    if ((int)threadIdx.x < nj) s_pos[threadIdx.x] = __ldg(dest_pos + j0 + threadIdx.x);
+    __syncthreads();
+    for (int jj = warp; jj < nj; jj += n_warps) {
+      const long long pos = s_pos[jj];
+      if (pos < 0 || pos >= n_pos) {
+        if (lane == 0 && d == 0 && m == 0 && status) atomicOr(status, AVSSL_DEVFLAG_BAD_INDEX);
+        continue;
+      }
+      if ((int)(pos / x.rows_per_rank) != d) continue;
+      const uint4* src = rows + (size_t)(j0 + jj) * row16;
+      uint4* o = dst_slot + (size_t)(pos % x.rows_per_rank) * row16;
+#pragma unroll 4
+      for (size_t c = c_lo + lane; c < c_hi; c += 32) o[c] = __ldg(src + c);
     }
-    if ((int)(pos / x.rows_per_rank) != d) continue;
-    const uint4* src = rows + (size_t)j * row16;
-    uint4* o = dst_slot + (size_t)(pos % x.rows_per_rank) * row16;
-    for (size_t c = c_lo + threadIdx.x; c < c_hi; c += blockDim.x) o[c] = __ldg(src + c);
   }
   __syncthreads();  // the CTA's stores are ordered before thread 0's fence (barrier + cumulativity)
   if (threadIdx.x == 0) {
