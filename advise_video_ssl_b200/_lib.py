@@ -78,7 +78,7 @@ SIGNATURES = {
     "avssl_peer_free": (c_int, [c_void_p]),
     "avssl_peer_push_rows": (c_int, [c_void_p, c_void_p, c_void_p]),
     "avssl_peer_scatter_bytes": (c_size_t, [c_int, c_int64]),
-    "avssl_peer_scatter_exchange": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "avssl_peer_scatter_exchange": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "avssl_l2norm_push_rows": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
     "avssl_peer_wait_gather": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "avssl_ema_multi_tensor_push": (c_int, [c_void_p, c_int64, c_float, c_float, c_void_p, c_int, c_int, c_void_p,

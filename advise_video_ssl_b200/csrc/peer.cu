@@ -70,9 +70,18 @@ __device__ __forceinline__ uint4* scatter_slot(void* base, int slot, const avssl
   return reinterpret_cast<uint4*>(static_cast<char*>(base) + sizeof(PeerHdr)) + (size_t)slot * x.rows_per_rank * (x.D / 4);
 }
 
+// Destination positions passed BY VALUE in the kernel parameters (batches of up to kInlinePos rows): the launch then
+// depends on no host-to-device copy -- beside a kernel that saturates HBM, that copy and the scheduling gap behind it
+// cost ~15 us of the window the exchange has to fit in.
+constexpr int kInlinePos = 256;
+struct InlinePos {
+  uint32_t pos[kInlinePos];
+};
+
+template <bool kInline>
 __global__ void __launch_bounds__(512)
 peer_scatter_exchange_kernel(const avssl_peer_xchg x, const uint4* __restrict__ rows, const long long* __restrict__ dest_pos,
-                             uint4* __restrict__ out, int M, uint32_t* status) {
+                             const __grid_constant__ InlinePos inl, uint4* __restrict__ out, int M, uint32_t* status) {
   __shared__ unsigned long long s_epoch;
   PeerHdr* me = static_cast<PeerHdr*>(x.base[x.rank]);
   if (threadIdx.x == 0) s_epoch = *reinterpret_cast<volatile unsigned long long*>(&me->epoch) + 1ull;
@@ -92,7 +101,8 @@ peer_scatter_exchange_kernel(const avssl_peer_xchg x, const uint4* __restrict__ 
   for (int j0 = 0; j0 < x.rows_per_rank; j0 += (int)blockDim.x) {
     const int nj = min((int)blockDim.x, x.rows_per_rank - j0);
     __syncthreads();
-    if ((int)threadIdx.x < nj) s_pos[threadIdx.x] = __ldg(dest_pos + j0 + threadIdx.x);
+    if ((int)threadIdx.x < nj)
+      s_pos[threadIdx.x] = kInline ? (long long)inl.pos[j0 + threadIdx.x] : __ldg(dest_pos + j0 + threadIdx.x);
     __syncthreads();
     for (int jj = warp; jj < nj; jj += n_warps) {
       const long long pos = s_pos[jj];
@@ -230,10 +240,11 @@ extern "C" size_t avssl_peer_scatter_bytes(int rows_per_rank, int64_t row_bytes)
 }
 
 extern "C" int avssl_peer_scatter_exchange(const avssl_peer_xchg* x, const void* rows, const int64_t* dest_pos_dev,
-                                           void* out, uint32_t* status_dev, void* stream) {
+                                           const int64_t* dest_pos_host, void* out, uint32_t* status_dev,
+                                           void* stream) {
   int rc = peer_check(x, "peer_scatter_exchange");
   if (rc != AVSSL_OK) return rc;
-  AVSSL_REQUIRE(rows && dest_pos_dev && out &&
+  AVSSL_REQUIRE(rows && (dest_pos_dev || dest_pos_host) && out &&
                     ((reinterpret_cast<uintptr_t>(rows) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0,
                 AVSSL_ERR_INVALID_ARGUMENT, "peer_scatter_exchange: null pointer, or rows / out not 16-byte aligned");
   static_assert(sizeof(((PeerHdr*)nullptr)->pad_) >= AVSSL_MAX_PEERS * sizeof(unsigned), "per-destination counters");
@@ -247,9 +258,27 @@ extern "C" int avssl_peer_scatter_exchange(const avssl_peer_xchg* x, const void*
   if (M > cap) M = cap;
   if (M < 1) M = 1;
   if ((size_t)M > (size_t)x->D / 4) M = x->D / 4;
-  peer_scatter_exchange_kernel<<<x->world * M, 512, 0, static_cast<cudaStream_t>(stream)>>>(
-      *x, static_cast<const uint4*>(rows), reinterpret_cast<const long long*>(dest_pos_dev), static_cast<uint4*>(out), M,
-      status_dev);
+  InlinePos inl;
+  bool by_value = dest_pos_host != nullptr && x->rows_per_rank <= kInlinePos;
+  if (by_value) {
+    const int64_t n_pos = (int64_t)x->world * x->rows_per_rank;
+    for (int j = 0; j < x->rows_per_rank; ++j) {
+      AVSSL_REQUIRE(dest_pos_host[j] >= 0 && dest_pos_host[j] < n_pos, AVSSL_ERR_INVALID_ARGUMENT,
+                    "peer_scatter_exchange: dest_pos[%d] = %lld outside [0, %lld)", j, (long long)dest_pos_host[j],
+                    (long long)n_pos);
+      inl.pos[j] = (uint32_t)dest_pos_host[j];
+    }
+  }
+  AVSSL_REQUIRE(by_value || dest_pos_dev, AVSSL_ERR_INVALID_ARGUMENT,
+                "peer_scatter_exchange: more than %d rows per rank need the device copy of dest_pos", kInlinePos);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (by_value)
+    peer_scatter_exchange_kernel<true><<<x->world * M, 512, 0, st>>>(*x, static_cast<const uint4*>(rows), nullptr, inl,
+                                                                      static_cast<uint4*>(out), M, status_dev);
+  else
+    peer_scatter_exchange_kernel<false><<<x->world * M, 512, 0, st>>>(
+        *x, static_cast<const uint4*>(rows), reinterpret_cast<const long long*>(dest_pos_dev), inl, static_cast<uint4*>(out),
+        M, status_dev);
   AVSSL_LAUNCH_OK("peer_scatter_exchange_kernel");
   return AVSSL_OK;
 }

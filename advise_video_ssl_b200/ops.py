@@ -344,17 +344,28 @@ class PeerScatter(PeerExchange):
             raise ValueError("%s must hold %d rows of %d bytes, got %s %s" % (name, self.rows_per_rank, self.row_bytes,
                                                                             tuple(t.shape), t.dtype))
 
-    def exchange(self, x, dest_pos, out=None, status=None):
+    def exchange(self, x, dest_pos, out=None, status=None, dest_pos_host=None):
         """Scatter this rank's rows to their final positions, wait for everybody's, return the received rows
-        (one launch; collective: every rank of the group makes the call)."""
+        (one launch; collective: every rank of the group makes the call).  `dest_pos_host` (numpy int64, the
+        same values): small batches then carry the positions in the kernel parameters and `dest_pos` may be None."""
         self._check(x, "x")
-        _req(dest_pos, "dest_pos", torch.int64)
-        if dest_pos.numel() != self.rows_per_rank:
-            raise ValueError("dest_pos needs %d entries" % self.rows_per_rank)
+        host_ptr = None
+        if dest_pos_host is not None:
+            dest_pos_host = np.ascontiguousarray(dest_pos_host, dtype=np.int64)
+            if dest_pos_host.size != self.rows_per_rank:
+                raise ValueError("dest_pos_host needs %d entries" % self.rows_per_rank)
+            host_ptr = dest_pos_host.ctypes.data
+        if dest_pos is not None:
+            _req(dest_pos, "dest_pos", torch.int64)
+            if dest_pos.numel() != self.rows_per_rank:
+                raise ValueError("dest_pos needs %d entries" % self.rows_per_rank)
+        elif host_ptr is None:
+            raise ValueError("need dest_pos or dest_pos_host")
         if out is None:
             out = torch.empty_like(x, memory_format=torch.contiguous_format)
         self._check(out, "out")
-        check(lib.avssl_peer_scatter_exchange(ctypes.addressof(self.desc), x.data_ptr(), dest_pos.data_ptr(),
+        check(lib.avssl_peer_scatter_exchange(ctypes.addressof(self.desc), x.data_ptr(),
+                                              dest_pos.data_ptr() if dest_pos is not None else None, host_ptr,
                                               out.data_ptr(), status.data_ptr() if status is not None else None,
                                               _stream()), "avssl_peer_scatter_exchange")
         return out

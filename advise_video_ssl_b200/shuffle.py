@@ -81,7 +81,9 @@ class ShufflePlan:
         perm = np.asarray(perm, dtype=np.int64).reshape(world, bsz)
         self.world, self.rank, self.bsz, self.device = world, rank, bsz, device
         self.perm = perm
-        parts = [perm[rank], np.argsort(perm.reshape(-1), kind="stable")]
+        restore_host = np.argsort(perm.reshape(-1), kind="stable")
+        self.dest_host = np.ascontiguousarray(restore_host.reshape(world, bsz)[rank])  # where this rank's rows go
+        parts = [perm[rank], restore_host]
         if world > 1 and need_alltoall:
             holder = perm // bsz  # rank that owns each wanted row
             # np.nonzero walks row-major: destinations in ascending order, each in its own take order
@@ -93,15 +95,36 @@ class ShufflePlan:
             place = np.empty(bsz, dtype=np.int64)
             place[arrival] = np.arange(bsz)
             parts += [perm[dst, pos] % bsz, place]
-        packed = torch.from_numpy(np.ascontiguousarray(np.concatenate(parts)))
+        self._n_parts = len(parts)
+        self._host = torch.from_numpy(np.ascontiguousarray(np.concatenate(parts)))
         if device.type == "cuda":
-            self._host = packed.pin_memory()
-            packed = self._host.to(device, non_blocking=True)
-        self.take = packed[:bsz]
-        self.restore = packed[bsz:bsz + world * bsz].view(world, bsz)
-        if len(parts) == 4:
-            self.send_rows = packed[(world + 1) * bsz:(world + 2) * bsz]
-            self.place = packed[(world + 2) * bsz:]
+            self._host = self._host.pin_memory()
+        self._dev = None
+
+    def _packed(self):
+        """The index arrays on the device: ONE asynchronous copy from the pinned buffer, issued on first use (the
+        NVLink scatter carries its positions in the kernel parameters and runs before it)."""
+        if self._dev is None:
+            self._dev = self._host.to(self.device, non_blocking=True) if self.device.type == "cuda" else self._host
+        return self._dev
+
+    @property
+    def take(self):
+        return self._packed()[:self.bsz]
+
+    @property
+    def restore(self):
+        return self._packed()[self.bsz:(self.world + 1) * self.bsz].view(self.world, self.bsz)
+
+    @property
+    def send_rows(self):
+        assert self._n_parts == 4
+        return self._packed()[(self.world + 1) * self.bsz:(self.world + 2) * self.bsz]
+
+    @property
+    def place(self):
+        assert self._n_parts == 4
+        return self._packed()[(self.world + 2) * self.bsz:]
 
     def shuffled(self, x, group=None, scatter=None, status=None):
         """This rank's shuffled batch: cat_all_gather(x)[perm[rank]] bit for bit, moving B rows.
@@ -109,7 +132,9 @@ class ShufflePlan:
         if self.world == 1:
             return x.index_select(0, self.take)
         if scatter is not None:
-            return scatter.exchange(x.contiguous(), self.restore[self.rank], status=status)
+            small = self.bsz <= 256  # positions ride in the kernel parameters: no dependence on the index upload
+            return scatter.exchange(x.contiguous(), None if small else self.restore[self.rank], status=status,
+                                    dest_pos_host=self.dest_host)
         outgoing = x.index_select(0, self.send_rows)
         incoming = torch.empty_like(x)
         dist.all_to_all_single(incoming, outgoing, output_split_sizes=self.recv_counts,

@@ -304,11 +304,13 @@ AVSSL_API int avssl_peer_wait_gather(const avssl_peer_xchg* x, const int64_t* ro
  * every rank's rows of this epoch and copies this rank's rows_per_rank received rows to `out`.  Uses an
  * avssl_peer_xchg descriptor whose buffers were allocated with avssl_peer_scatter_bytes(rows_per_rank, row_bytes)
  * and D = row_bytes / 4 (rows are opaque bytes; row_bytes % 16 == 0).  dest_pos_dev[j] = argsort(perm)[rank *
- * rows_per_rank + j] (int64, device): the position of local row j in the rank-major shuffled batch.  Bit-exact;
+ * rows_per_rank + j] (int64, device): the position of local row j in the rank-major shuffled batch.
+ * dest_pos_host (optional, same values on the host): with at most 256 rows per rank the positions travel in the
+ * kernel parameters and the launch depends on no host-to-device copy (dest_pos_dev may then be NULL).  Bit-exact;
  * every rank of the exchange must make the call (same sequence on every rank). */
 AVSSL_API size_t avssl_peer_scatter_bytes(int rows_per_rank, int64_t row_bytes);
 AVSSL_API int avssl_peer_scatter_exchange(const avssl_peer_xchg* x, const void* rows, const int64_t* dest_pos_dev,
-                                void* out, uint32_t* status_dev, void* stream);
+                                const int64_t* dest_pos_host, void* out, uint32_t* status_dev, void* stream);
 /* K1 with the push fused into the same launch: `world` extra CTAs at the front of the EMA grid
  * push `rows` while the rest stream the parameters (north_star: the key exchange overlapped with
  * the EMA kernel).  Other arguments as avssl_ema_multi_tensor. */
