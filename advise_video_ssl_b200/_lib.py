@@ -84,7 +84,7 @@ SIGNATURES = {
     "avssl_ema_multi_tensor_push": (c_int, [c_void_p, c_int64, c_float, c_float, c_void_p, c_int, c_int, c_void_p,
                                             c_void_p, c_void_p, c_void_p]),
     "avssl_moco_infonce_fwd_bwd_enqueue_peer": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
-                                                        c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                                                        c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
                                                         c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "avssl_moco_infonce_fwd_bwd_enqueue_indexed": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int,
                                                            c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,

@@ -93,8 +93,9 @@ class _KeyBatch:
     `local` (when set) holds this rank's normalised keys in the original row order.  Otherwise the rows
     are still where the encoder / the exchange left them and consumers index them instead of
     materialising an un-shuffled copy:
-      xchg   every rank's normalised rows in the NVLink exchange buffers (encoder order, rank-major), or
-      table  a [world * rows, D] tensor on this device in the same order (`raw`: still un-normalised);
+      xchg   every rank's normalised rows in the NVLink exchange buffers (encoder order, rank-major) -- when
+             `table` is set as well, this rank's raw rows that the head launch still has to normalise and push;
+      table  otherwise a [world * rows, D] tensor on this device in the same order (`raw`: un-normalised);
       restore ([W, B] device int64, None without shuffle) maps original rows to that order.
     """
 
@@ -460,10 +461,10 @@ class ContrastiveModel(nn.Module):
         crosses = shuffled or (defer and self.queue_mode != "local")
         if crosses and self._use_peer_exchange(feats):
             ex = self._peer_xchg(n, feats.shape[1])
+            if defer:  # the head launch normalises and pushes the rows itself (one extra CTA), then waits for everybody's
+                return _KeyBatch(xchg=ex, table=feats.contiguous(), raw=True, restore=restore, rank=rank, rows=n, world=size)
             ex.push_normalized(feats.contiguous(), 0.0)
             pending = _KeyBatch(xchg=ex, restore=restore, rank=rank, rows=n, world=size)
-            if defer:
-                return pending
             return _KeyBatch(local=ex.wait_gather(self._local_rows(pending, feats.device), status=self._status))
         keys = self.l2_norm(feats)
         if not crosses:
@@ -643,7 +644,7 @@ class ContrastiveModel(nn.Module):
             head_kw.update(peer_row_idx=self._local_rows(deferred, feat_q.device),
                            enq_row_idx=self._queue_rows(deferred, feat_q.device), enqueue=(self.ptr, self._status))
             if deferred.xchg is not None:
-                head_kw["peer"] = deferred.xchg
+                head_kw.update(peer=deferred.xchg, push_rows=deferred.table)
             else:
                 head_kw.update(key_rows=deferred.table, keys_raw=deferred.raw)
             plan = {"keys": None, "kw": head_kw}

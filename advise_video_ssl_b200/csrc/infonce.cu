@@ -53,7 +53,8 @@ int moco_infonce_run(const float* feat_q, const float* const* keys_host, int n_k
                      float* q_out, float* loss_out, float* dfeat_out, float* row_lse_out, float* logits_out,
                      void* workspace, size_t workspace_bytes, int impl, void* stream,
                      const avssl_peer_xchg* peer = nullptr, const int64_t* peer_row_idx = nullptr,
-                     const int64_t* enq_row_idx = nullptr, int n_enq = 0, int n_key_rows = 0, int keys_raw = 0) {
+                     const int64_t* enq_row_idx = nullptr, int n_enq = 0, int n_key_rows = 0, int keys_raw = 0,
+                     const float* push_feat = nullptr) {
   AVSSL_REQUIRE(feat_q && (keys_host || peer) && queue && q_out && loss_out && dfeat_out && workspace,
                 AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: null pointer");
   AVSSL_REQUIRE(B > 0 && D > 0 && K > 0, AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: bad sizes B=%d D=%d K=%d", B, D, K);
@@ -78,6 +79,10 @@ int moco_infonce_run(const float* feat_q, const float* const* keys_host, int n_k
   p.n_enq = (ptr_dev && n_enq > 0) ? n_enq : B;
   p.n_key_rows = n_key_rows > 0 ? n_key_rows : B;
   p.keys_raw = keys_raw ? 1 : 0;
+  p.push_feat = push_feat;
+  p.push_eps = 0.f;  // Normalize has no epsilon (models/contrastive.py:929-934)
+  AVSSL_REQUIRE(!push_feat || (peer && (reinterpret_cast<uintptr_t>(push_feat) & 15u) == 0), AVSSL_ERR_INVALID_ARGUMENT,
+                "moco_infonce_peer: push_feat needs an exchange descriptor and 16-byte alignment");
   const bool indexed = !peer && (peer_row_idx || enq_row_idx || keys_raw || p.n_key_rows != B);
   AVSSL_REQUIRE(!indexed || n_keys == 1, AVSSL_ERR_INVALID_ARGUMENT,
                 "moco_infonce_indexed: one key tensor only (got %d)", n_keys);
@@ -129,7 +134,8 @@ int moco_infonce_run(const float* feat_q, const float* const* keys_host, int n_k
   const int tile = (use == AVSSL_IMPL_SIMT) ? kSimtTileRows : kTcTileRows;
   const int n_tiles = (K + tile - 1) / tile;
   const int row_blocks = (use == AVSSL_IMPL_SIMT) ? (B + 63) / 64 : (B + 127) / 128;
-  int S = sms / row_blocks;
+  // (the fused key push takes one more column of CTAs: leave it an SM, the launch is cooperative)
+  int S = (push_feat ? sms - row_blocks : sms) / row_blocks;
   if (S < 1) S = 1;
   if (S > n_tiles) S = n_tiles;
   const int tiles_per_split = (n_tiles + S - 1) / S;
@@ -181,7 +187,7 @@ extern "C" int avssl_moco_infonce_fwd_bwd_enqueue(const float* feat_q, const flo
 
 extern "C" int avssl_moco_infonce_fwd_bwd_enqueue_peer(const float* feat_q, const avssl_peer_xchg* x,
                                                        const int64_t* row_idx, const int64_t* enq_row_idx, int n_enq,
-                                                       float* queue, int64_t* ptr_dev,
+                                                       const float* push_feat, float* queue, int64_t* ptr_dev,
                                                        uint32_t* status_dev, int B, int D, int K, float T,
                                                        float* q_out, float* loss_out, float* dfeat_out,
                                                        float* row_lse_out, float* logits_out, void* workspace,
@@ -189,7 +195,7 @@ extern "C" int avssl_moco_infonce_fwd_bwd_enqueue_peer(const float* feat_q, cons
   AVSSL_REQUIRE(x, AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce_peer: exchange descriptor is null");
   return moco_infonce_run(feat_q, nullptr, 1, queue, ptr_dev ? queue : nullptr, ptr_dev, status_dev, B, D, K, T, q_out,
                           loss_out, dfeat_out, row_lse_out, logits_out, workspace, workspace_bytes, impl, stream, x,
-                          row_idx, enq_row_idx, n_enq);
+                          row_idx, enq_row_idx, n_enq, 0, 0, push_feat);
 }
 
 extern "C" int avssl_moco_infonce_fwd_bwd_enqueue_indexed(const float* feat_q, const float* key_rows, int n_key_rows,

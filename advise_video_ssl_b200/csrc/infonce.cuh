@@ -54,6 +54,10 @@ struct InfoNceParams {
   // (positive logit and enqueue), with the arithmetic of l2norm_fwd_kernel.
   int n_key_rows;
   int keys_raw;
+  // fused C3 push (tcgen05 kernel with use_peer): this rank's RAW key rows [peer.rows_per_rank, D]; one extra CTA
+  // of the launch normalises them (eps as Normalize: 0) and stores them into every rank's exchange buffer
+  const float* push_feat;
+  float push_eps;
   avssl_peer_xchg peer;
 };
 

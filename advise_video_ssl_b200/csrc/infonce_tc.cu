@@ -142,6 +142,15 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
     }
   }
 
+  // The launch may carry one EXTRA column of CTAs (blockIdx.x == n_splits) that owns no queue split: its first
+  // CTA normalises this rank's raw key rows and stores them into every rank's exchange buffer (C3 push, the
+  // Normalize of models/contrastive.py:350 fused in) while the others sweep the queue; the merge below waits
+  // for every rank's rows after the sweep.  The step then has no launch between the key encoder and the head.
+  const bool exch_cta = p.push_feat != nullptr && blockIdx.x == (unsigned)p.n_splits;
+  if (exch_cta) {
+    __shared__ unsigned long long s_epoch;
+    if (blockIdx.y == 0) peer_push_all_cta(p.peer, p.push_feat, p.push_eps, &s_epoch);
+  } else {
   // ------------------------------------------------------------------ one-time setup
   if (warp == 0 && lane == 0) {
     ptx::tma_prefetch_desc(&tmap);
@@ -582,6 +591,8 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
     ptx::tmem_dealloc(tmem, C::kTmemCols);
   }
 
+  }  // !exch_cta
+
   // --------------------------------------------------------------------- grid barrier
   // Cooperative launch: all CTAs are co-resident, so spinning on a global counter is safe.
   const unsigned n_ctas = gridDim.x * gridDim.y;
@@ -723,7 +734,7 @@ int launch_tc(const InfoNceParams& p, cudaStream_t s) {
     AVSSL_CUDA_OK(cudaFuncSetAttribute(infonce_tc_kernel<D, kThreeTerm>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)C::kSmemBytes));
   }
-  dim3 grid(p.n_splits, (p.B + kM - 1) / kM);
+  dim3 grid(p.n_splits + (p.push_feat ? 1 : 0), (p.B + kM - 1) / kM);
   AVSSL_REQUIRE((int)(grid.x * grid.y) <= sm_count(), AVSSL_ERR_INVALID_ARGUMENT,
                 "moco_infonce: %u CTAs cannot be co-resident on %d SMs", grid.x * grid.y, sm_count());
   // cooperative: the kernel contains a grid-wide barrier (all CTAs must be co-resident)

@@ -91,6 +91,37 @@ __device__ __forceinline__ void peer_push_cta(const avssl_peer_xchg& x, const fl
   }
 }
 
+// All threads of ONE CTA: normalise this rank's raw rows and store them to EVERY rank of the exchange (one push by
+// a single CTA: the extra CTA of the head launch).  Same arithmetic as peer_push_cta<true>; `world` threads publish
+// the flags after the barrier, the epoch advances locally.
+__device__ __forceinline__ void peer_push_all_cta(const avssl_peer_xchg& x, const float* __restrict__ rows, float eps,
+                                                  unsigned long long* s_epoch) {
+  PeerHdr* me = static_cast<PeerHdr*>(x.base[x.rank]);
+  if (threadIdx.x == 0) *s_epoch = *reinterpret_cast<volatile unsigned long long*>(&me->epoch) + 1ull;
+  __syncthreads();
+  const unsigned long long e = *s_epoch;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  const size_t block_off = (size_t)x.rank * x.rows_per_rank * x.D;
+  for (int r = warp; r < x.rows_per_rank; r += n_warps) {
+    const float* xr = rows + (size_t)r * x.D;
+    const float den = fmaxf(sqrtf(row_sumsq(xr, x.D, lane)), eps);
+    for (int c = lane; c < x.D; c += 32) {
+      const float y = xr[c] / den;
+      for (int d = 0; d < x.world; ++d) peer_payload(x.base[d], (int)(e & 1ull), x)[block_off + (size_t)r * x.D + c] = y;
+    }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < x.world) {
+    __threadfence_system();
+    st_release_sys_u64(&static_cast<PeerHdr*>(x.base[threadIdx.x])->flags[x.rank], e);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *reinterpret_cast<volatile unsigned long long*>(&me->epoch) = e;
+    __threadfence();
+  }
+}
+
 __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");

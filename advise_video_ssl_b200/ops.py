@@ -395,7 +395,7 @@ def _workspace(device, nbytes, op):
 
 
 def moco_infonce(feat_q, keys, queue, T, want_logits=True, impl=_lib.IMPL_AUTO, out=None, enqueue=None, workspace=None,
-                 peer=None, peer_row_idx=None, enq_row_idx=None, key_rows=None, keys_raw=False):
+                 peer=None, peer_row_idx=None, enq_row_idx=None, key_rows=None, keys_raw=False, push_rows=None):
     """Fused l2-norm + logits + InfoNCE forward/backward (K2+K3).
 
     Returns dict(loss[1], dfeat[B,D], q[B,D], lse[n_keys*B], logits[n_keys*B,K+1] or None).
@@ -411,6 +411,8 @@ def moco_infonce(feat_q, keys, queue, T, want_logits=True, impl=_lib.IMPL_AUTO, 
     `enq_row_idx` (peer only, int64): the rows of the gathered buffer that the fused enqueue writes,
     ptr advancing by their count (C9: rank 0's rows on every rank = the reference's effective
     semantics under DDP's buffer broadcast; all rows = canonical MoCo).  Default: this rank's block.
+    `push_rows` (peer only, [rows_per_rank, D]): this rank's RAW key-encoder output; one extra CTA of the
+    launch normalises it and performs this step's push into every rank's buffer, so the caller pushes nothing.
     `key_rows` ([n, D], `keys` must be None): keys that live on this device but are still in the key
     encoder's row order -- query row i meets key_rows[peer_row_idx[i]] and the queue receives
     key_rows[enq_row_idx[e]] (the un-shuffle folded into the launch); with `keys_raw` they are the
@@ -480,9 +482,12 @@ def moco_infonce(feat_q, keys, queue, T, want_logits=True, impl=_lib.IMPL_AUTO, 
             "avssl_moco_infonce_fwd_bwd_enqueue_indexed")
         return {"loss": loss, "dfeat": dfeat, "q": q, "lse": lse, "logits": logits}
     if peer is not None:
+        if push_rows is not None:
+            peer.check_rows(push_rows)
         check(lib.avssl_moco_infonce_fwd_bwd_enqueue_peer(
             feat_q.data_ptr(), ctypes.addressof(peer.desc), peer_row_idx.data_ptr() if peer_row_idx is not None else None,
             enq_row_idx.data_ptr() if enq_row_idx is not None else None, n_enq,
+            push_rows.data_ptr() if push_rows is not None else None,
             queue.data_ptr(), ptr.data_ptr() if ptr is not None else None,
             status.data_ptr() if status is not None else None, B, D, K, float(T),
             q.data_ptr(), loss.data_ptr(), dfeat.data_ptr(), lse.data_ptr(),

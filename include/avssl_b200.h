@@ -328,10 +328,14 @@ AVSSL_API int avssl_ema_multi_tensor_push(const avssl_ema_chunk* table_dev, int6
  * queue are gathered[enq_row_idx[e]], e < n_enq, and ptr advances by n_enq (K % n_enq == 0).
  * enq_row_idx NULL: this rank's own block (n_enq must be B).  With enq_row_idx = rank 0's rows on
  * every rank the queues stay bit-identical without any broadcast; with all world*B rows it is
- * canonical MoCo. */
+ * canonical MoCo.
+ * push_feat (optional, [rows_per_rank, D]): this rank's RAW key-encoder output.  One extra CTA of the launch then
+ * performs the push of this step itself -- Normalize (models/contrastive.py:350) and the stores into every rank's
+ * buffer -- while the others sweep the queue, so no launch sits between the key encoder and the head; without it the
+ * caller must have pushed (avssl_peer_push_rows / avssl_l2norm_push_rows / the EMA-fused push) before this call. */
 AVSSL_API int avssl_moco_infonce_fwd_bwd_enqueue_peer(const float* feat_q, const avssl_peer_xchg* x,
                                             const int64_t* row_idx, const int64_t* enq_row_idx, int n_enq,
-                                            float* queue, int64_t* ptr_dev,
+                                            const float* push_feat, float* queue, int64_t* ptr_dev,
                                             uint32_t* status_dev, int B, int D, int K, float T, float* q_out,
                                             float* loss_out, float* dfeat_out, float* row_lse_out,
                                             float* logits_out, void* workspace, size_t workspace_bytes,

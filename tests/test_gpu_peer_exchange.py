@@ -179,3 +179,37 @@ def test_scatter_rows_bit_exact_over_epochs(shape, dtype):
         sc.close()
     with pytest.raises(ValueError):
         ops.PeerScatter(4, 24)  # rows must be 16-byte multiples
+
+
+@pytest.mark.parametrize("B,D,K", [(64, 128, 4096), (32, 64, 1024)])
+def test_head_launch_pushes_its_own_keys(B, D, K):
+    """C3 push fused into the head launch: an extra CTA normalises this rank's raw key rows and stores them into the
+    exchange buffers while the others sweep; same bits as Normalize -> push -> head(wait), over both payload slots."""
+    ops = _ops()
+    from advise_video_ssl_b200 import _lib
+    g = torch.Generator().manual_seed(B + D)
+    T = 0.1
+    queue_c = O.l2_normalize(torch.randn(K, D, generator=g))
+    x1, x2 = ops.PeerExchange(B, D), ops.PeerExchange(B, D)
+    try:
+        q1, q2 = queue_c.clone().cuda(), queue_c.clone().cuda()
+        p1 = torch.zeros(1, dtype=torch.int64, device="cuda")
+        p2 = torch.zeros(1, dtype=torch.int64, device="cuda")
+        status = torch.zeros(1, dtype=torch.int32, device="cuda")
+        for step in range(3):
+            feat = torch.randn(B, D, generator=g).cuda()
+            raw = (torch.randn(B, D, generator=g) * 4).cuda()
+            perm = torch.randperm(B, generator=g).cuda()
+            a = ops.moco_infonce(feat, None, q1, T, True, _lib.IMPL_AUTO, enqueue=(p1, status), peer=x1, push_rows=raw,
+                                 peer_row_idx=perm, enq_row_idx=perm)
+            x2.push_normalized(raw, 0.0)
+            b = ops.moco_infonce(feat, None, q2, T, True, _lib.IMPL_AUTO, enqueue=(p2, status), peer=x2,
+                                 peer_row_idx=perm, enq_row_idx=perm)
+            for name in ("loss", "dfeat", "q", "logits", "lse"):
+                assert torch.equal(a[name], b[name]), (step, name)
+            assert torch.equal(q1, q2) and torch.equal(p1, p2)
+            assert torch.equal(x1.wait_gather_all(), ops.l2norm_fwd(raw, 0.0)[0])
+        assert int(status.item()) == 0
+    finally:
+        x1.close()
+        x2.close()
