@@ -464,7 +464,9 @@ def gpu_arm(args):
     floor_us = step_bytes / (peak * 1e9) * 1e6
     # own kernels per step: EMA, head(+Normalize of the keys, un-shuffle, enqueue) on one GPU; across GPUs one more
     # launch normalises the keys and stores them into every rank's exchange buffer (or: Normalize, then NCCL)
-    own_launches = 2 if world == 1 else 3
+    own_launches = 2 if (world == 1 or deferred_path) else 3
+    if world > 1:
+        own_launches += 1  # the NVLink scatter of the key-encoder input rows (side stream, under the EMA)
 
     def per_step(ms):
         return {"value": clips / (ms / args.steps * 1e-3), "unit": UNIT, "ms_per_step": ms / args.steps}
@@ -484,13 +486,16 @@ def gpu_arm(args):
                    "shuffle_perm": "drawn per captured step (frozen in its graph); %d input slots" % POOL,
                    "rank_alignment": "one untimed step between the barrier and the first timed event (N>1)" if world > 1 else None,
                    "e2e_cuda_graph": e2e_graphs is not None, "cuda_graph_error": graph_err,
-                   "key_exchange": ("Normalize + NVLink peer stores in one launch; the head launch waits, un-shuffles by index "
-                                    "and enqueues rank 0's rows" if deferred_path and world > 1 else
+                   "key_exchange": ("inside the head launch: one extra CTA normalises this rank's key rows and stores them into "
+                                    "every rank's buffer over NVLink while the others sweep the queue; the merge waits, "
+                                    "un-shuffles by index and enqueues rank 0's rows" if deferred_path and world > 1 else
                                     ("nccl all_gather of the normalised keys; the head launch un-shuffles by index and enqueues "
                                      "rank 0's rows" if world > 1 else
                                      "none (one GPU): the head launch normalises the raw key rows and un-shuffles by index")),
-                   "clip_shuffle": "all-to-all of the key-encoder input rows on a side stream under the EMA" if world > 1
-                                   else "local row gather on a side stream under the EMA",
+                   "clip_shuffle": ("NVLink row scatter (each row written once into its final position on the destination rank) "
+                                    "on a side stream under the EMA" if deferred_path and world > 1 else
+                                    ("NCCL all-to-all on a side stream under the EMA" if world > 1
+                                     else "local row gather on a side stream under the EMA")),
                    "parallelism": "dp%d (queue/EMA replicated, batch sharded; exchanges: shuffle all-to-all, keys)" % n_gpus,
                    "l2": "no explicit flush: one step streams %.0f MB (> 126 MB L2) so nothing survives between steps" % (step_bytes / 1e6)},
         "e2e": dict(per_step(e2e_ms), h2d_bytes_per_step=2 * 4 * B_PER_GPU * DIM, d2h_bytes_per_step=4, mode=e2e_mode,
@@ -502,9 +507,9 @@ def gpu_arm(args):
                        "what": "EMA[+push] launch -> head launch driven through ops.* (no module, no autograd), CUDA-graph replay"}
                       if ops_ms is not None else {"skipped": ops_note or "--no-ops-level"}),
         "gpu_launches": own_launches * args.steps,
-        "gpu_launches_note": "own kernels per step: EMA, [N>1: Normalize+push,] head(+key Normalize on one GPU, un-shuffle, "
-                             "wait, enqueue); plus torch's row gather of the shuffle (side stream) and autograd's ones-fill "
-                             "and elementwise multiply in backward",
+        "gpu_launches_note": "own kernels per step: EMA, head(+key Normalize, [N>1: key push over NVLink + wait,] un-shuffle, "
+                             "enqueue) [, N>1: row scatter of the shuffle, side stream]; plus torch's row gather of the "
+                             "shuffle on one GPU and autograd's ones-fill and elementwise multiply in backward",
         "clocks": clocks,
         "roofline": {"kernel": "ema_multi_tensor_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": EMA_DRAM_TRAFFIC,
