@@ -743,17 +743,35 @@ class ContrastiveModel(nn.Module):
         return self._cached_dummy_logits(len(index), scores.device), loss
 
     def _swav_queue_step(self, slot, emb, out, proto_w):
-        """K12 (:642-664): once the feature queue of this crop is full its scores are prepended to the
-        batch's, then the batch's embeddings enter the queue, newest first."""
+        """K12 (:642-664): once the feature queue of this crop is full its scores are prepended to the batch's,
+        then the batch's embeddings enter the queue, newest first.
+
+        The reference decides "full" by reading the queue's last row back to the host on every step until it is
+        non-zero (:651).  The queue starts as zeros and every step pushes `bs` rows at the front, so it is full
+        after ceil(L / bs) pushes: a host-side push counter answers the question without touching the device.  The
+        counter is unknown after a checkpoint load (or any other torch-side write to the buffer, seen through its
+        version counter): one read-back then re-seeds it.
+        The buffer keeps the reference's physical layout (newest first) -- it is part of the checkpoint contract --
+        so the push is the same front insertion; at the cfg5 size (L = 3840 / 8 ranks, D = 128: 245 KB per crop)
+        that is one ~2 us copy, far below the step's other costs, and a ring with a moving head would buy nothing
+        while breaking the layout."""
         queue = self.queue_swav[slot]
-        bs = emb.shape[0]
+        bs, rows = emb.shape[0], queue.shape[0]
         if not self.swav_use_the_queue:
-            # the queue starts as zeros and fills from the front: full <=> its last row is non-zero.  One
-            # host read per step until that happens, as in the reference (:651)
-            self.swav_use_the_queue = bool(torch.any(queue[-1] != 0).item())
+            tag = (self.queue_swav.data_ptr(), self.queue_swav._version)
+            seen = self._const.get("swav_pushes")
+            if seen is None or seen[0] != tag:
+                full = bool(torch.any(queue[-1] != 0).item())  # once per (re)start
+                seen = [tag, [rows if full else 0] * self.queue_swav.shape[0]]
+            self.swav_use_the_queue = seen[1][slot] >= rows
+            self._const["swav_pushes"] = seen
         if self.swav_use_the_queue:
             out = torch.cat((queue @ proto_w.t(), out))
         self.queue_swav[slot] = torch.cat((emb, queue[:-bs]))
+        seen = self._const.get("swav_pushes")
+        if seen is not None:
+            seen[1][slot] = min(rows, seen[1][slot] + bs)
+            seen[0] = (self.queue_swav.data_ptr(), self.queue_swav._version)  # our own write is not a foreign one
         return out
 
     # ---- simclr (:733-802; `distributed_loss` is False in the reference, so: gather with gradient)
