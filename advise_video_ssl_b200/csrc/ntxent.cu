@@ -13,6 +13,8 @@
 // where the reference's raw exp overflows for T < 0.0113.
 // Both passes are split over column ranges; partials are reduced in a fixed order.
 // CUDA-core kernels (fp32 exact) = AVSSL_IMPL_SIMT; the tcgen05 kernels are in ntxent_tc.cu.
+#include <cuda_fp16.h>
+
 #include "ntxent.cuh"
 #include "simt_tile.cuh"
 
@@ -20,11 +22,7 @@ namespace avssl {
 
 constexpr float kLog2eN = 1.4426950408889634f;
 
-__device__ __forceinline__ float ptx_round_tf32(float x) {  // round to nearest tf32 (10 explicit mantissa bits)
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
+
 
 template <int DP>
 __device__ __forceinline__ void ntx_load_rows(float* qs, const NtxArgs& a, int i_base) {
@@ -295,7 +293,7 @@ extern "C" size_t avssl_ntxent_workspace_bytes(int N2, int D, int n_loc) {
   return 256 + 4 * ((size_t)N2 + 64) + 4 * 64 * ((size_t)n_loc + 64) + 4 * 64 * (size_t)n_loc * D + 1024;
 }
 
-static int ntx_setup(NtxArgs& a, const float* out, const float* out_tf32, const int* rows, const float* z_all, int N2, int D, int n_loc,
+static int ntx_setup(NtxArgs& a, const float* out, const void* out_f16, const int* rows, const float* z_all, int N2, int D, int n_loc,
                      float T, void* workspace, size_t workspace_bytes, int impl, bool* use_tc, const char* who) {
   AVSSL_REQUIRE(out && rows && workspace, AVSSL_ERR_INVALID_ARGUMENT, "%s: null pointer", who);
   AVSSL_REQUIRE(N2 > 0 && (N2 % 2) == 0 && n_loc > 0 && n_loc <= N2 && T > 0.f, AVSSL_ERR_INVALID_ARGUMENT,
@@ -303,7 +301,7 @@ static int ntx_setup(NtxArgs& a, const float* out, const float* out_tf32, const 
   AVSSL_REQUIRE(D % 4 == 0 && D >= 4 && D <= 256, AVSSL_ERR_UNSUPPORTED, "%s: D=%d unsupported (D %% 4 == 0, D <= 256)", who, D);
   AVSSL_REQUIRE(workspace_bytes >= avssl_ntxent_workspace_bytes(N2, D, n_loc), AVSSL_ERR_WORKSPACE, "%s: workspace too small", who);
   a.out = out;
-  a.out_tf32 = out_tf32;
+  a.out_f16 = static_cast<const uint16_t*>(out_f16);
   a.rows = rows;
   a.z_all = z_all;
   a.N2 = N2;
@@ -312,10 +310,10 @@ static int ntx_setup(NtxArgs& a, const float* out, const float* out_tf32, const 
   a.inv_T = 1.f / T;
   AVSSL_REQUIRE(impl == AVSSL_IMPL_AUTO || impl == AVSSL_IMPL_SIMT || impl == AVSSL_IMPL_TC1X, AVSSL_ERR_INVALID_ARGUMENT,
                 "%s: impl must be AVSSL_IMPL_AUTO, AVSSL_IMPL_SIMT or AVSSL_IMPL_TC1X (got %d)", who, impl);
-  *use_tc = impl != AVSSL_IMPL_SIMT && ntxent_tc_supported(N2, D, n_loc) && out_tf32 != nullptr &&
-            (reinterpret_cast<uintptr_t>(out_tf32) & 15u) == 0;
+  *use_tc = impl != AVSSL_IMPL_SIMT && ntxent_tc_supported(N2, D, n_loc) && out_f16 != nullptr &&
+            (reinterpret_cast<uintptr_t>(out_f16) & 15u) == 0;
   AVSSL_REQUIRE(*use_tc || impl != AVSSL_IMPL_TC1X, AVSSL_ERR_UNSUPPORTED,
-                "%s: the tcgen05 kernel needs D in {32,64,96,128,256} and a 16-byte aligned tf32-rounded copy of `out` "
+                "%s: the tcgen05 kernel needs D in {64,128,256} and a 16-byte aligned fp16 copy of `out` "
                 "(avssl_ntxent_prepare) (D=%d)", who, D);
   AVSSL_REQUIRE((*use_tc ? ntxent_tc_plan(N2, n_loc, &a.n_splits, &a.cols_per_split)
                          : plan_splits(N2, n_loc, &a.n_splits, &a.cols_per_split)) == 0,
@@ -331,10 +329,10 @@ static int ntx_setup(NtxArgs& a, const float* out, const float* out_tf32, const 
 }
 
 // out[(v * W + w) * B + b] = gathered[w][v][b] ([q_all ; q2_all], models/contrastive.py:771-775) and its
-// tf32-rounded copy, one pass: 128-bit loads, two 128-bit stores per element group.
+// fp16 copy (round to nearest), one pass: 128-bit loads, a 128-bit and a 64-bit store per element group.
 __global__ void __launch_bounds__(256)
 ntxent_prepare_kernel(const float4* __restrict__ gathered, int W, int B, int D4, float4* __restrict__ out,
-                      float4* __restrict__ out_tf32) {
+                      uint2* __restrict__ out_f16) {
   const size_t total = (size_t)2 * W * B * D4;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const size_t row = e / D4;               // destination row (v * W + w) * B + b
@@ -344,16 +342,17 @@ ntxent_prepare_kernel(const float4* __restrict__ gathered, int W, int B, int D4,
     const int w = vw % W, v = vw / W;
     const float4 x = __ldg(gathered + (((size_t)w * 2 + v) * B + b) * D4 + c);
     out[e] = x;
-    out_tf32[e] = make_float4(ptx_round_tf32(x.x), ptx_round_tf32(x.y), ptx_round_tf32(x.z), ptx_round_tf32(x.w));
+    const __half2 lo = __floats2half2_rn(x.x, x.y), hi = __floats2half2_rn(x.z, x.w);
+    out_f16[e] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
   }
 }
 
-extern "C" int avssl_ntxent_prepare(const float* gathered, int world, int B, int D, float* out, float* out_tf32,
+extern "C" int avssl_ntxent_prepare(const float* gathered, int world, int B, int D, float* out, void* out_f16,
                                     void* stream) {
-  AVSSL_REQUIRE(gathered && out && out_tf32 && world > 0 && B > 0 && D > 0 && D % 4 == 0, AVSSL_ERR_INVALID_ARGUMENT,
+  AVSSL_REQUIRE(gathered && out && out_f16 && world > 0 && B > 0 && D > 0 && D % 4 == 0, AVSSL_ERR_INVALID_ARGUMENT,
                 "ntxent_prepare: bad arguments (world=%d B=%d D=%d, D %% 4 == 0)", world, B, D);
   AVSSL_REQUIRE(((reinterpret_cast<uintptr_t>(gathered) | reinterpret_cast<uintptr_t>(out) |
-                  reinterpret_cast<uintptr_t>(out_tf32)) & 15u) == 0,
+                  reinterpret_cast<uintptr_t>(out_f16)) & 15u) == 0,
                 AVSSL_ERR_INVALID_ARGUMENT, "ntxent_prepare: pointers must be 16-byte aligned");
   const size_t total = (size_t)2 * world * B * (D / 4);
   int grid = (int)((total + 255) / 256);
@@ -361,16 +360,16 @@ extern "C" int avssl_ntxent_prepare(const float* gathered, int world, int B, int
   if (grid > cap) grid = cap;
   ntxent_prepare_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float4*>(gathered), world, B, D / 4, reinterpret_cast<float4*>(out),
-      reinterpret_cast<float4*>(out_tf32));
+      reinterpret_cast<uint2*>(out_f16));
   AVSSL_LAUNCH_OK("ntxent_prepare_kernel");
   return AVSSL_OK;
 }
 
-extern "C" int avssl_ntxent_rowsum(const float* out, const float* out_tf32, const int* rows, int N2, int D, int n_loc, float T,
+extern "C" int avssl_ntxent_rowsum(const float* out, const void* out_f16, const int* rows, int N2, int D, int n_loc, float T,
                                    float* z_loc_out, void* workspace, size_t workspace_bytes, int impl, void* stream) {
   NtxArgs a;
   bool use_tc = false;
-  int rc = ntx_setup(a, out, out_tf32, rows, nullptr, N2, D, n_loc, T, workspace, workspace_bytes, impl, &use_tc, "ntxent_rowsum");
+  int rc = ntx_setup(a, out, out_f16, rows, nullptr, N2, D, n_loc, T, workspace, workspace_bytes, impl, &use_tc, "ntxent_rowsum");
   if (rc) return rc;
   AVSSL_REQUIRE(z_loc_out, AVSSL_ERR_INVALID_ARGUMENT, "ntxent_rowsum: null output");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -381,12 +380,12 @@ extern "C" int avssl_ntxent_rowsum(const float* out, const float* out_tf32, cons
   return AVSSL_OK;
 }
 
-extern "C" int avssl_ntxent_grad(const float* out, const float* out_tf32, const int* rows, const float* z_all, const float* norm_loc, int N2,
+extern "C" int avssl_ntxent_grad(const float* out, const void* out_f16, const int* rows, const float* z_all, const float* norm_loc, int N2,
                                  int D, int n_loc, float T, float grad_scale, float* loss_out, float* dfeat_out,
                                  void* workspace, size_t workspace_bytes, int impl, void* stream) {
   NtxArgs a;
   bool use_tc = false;
-  int rc = ntx_setup(a, out, out_tf32, rows, z_all, N2, D, n_loc, T, workspace, workspace_bytes, impl, &use_tc, "ntxent_grad");
+  int rc = ntx_setup(a, out, out_f16, rows, z_all, N2, D, n_loc, T, workspace, workspace_bytes, impl, &use_tc, "ntxent_grad");
   if (rc) return rc;
   AVSSL_REQUIRE(z_all && norm_loc && loss_out && dfeat_out, AVSSL_ERR_INVALID_ARGUMENT, "ntxent_grad: null pointer");
   AVSSL_REQUIRE(((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(dfeat_out)) & 15u) == 0,

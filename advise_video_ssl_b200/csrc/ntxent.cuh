@@ -8,7 +8,7 @@ namespace avssl {
 
 struct NtxArgs {
   const float* out;     // [N2, D] unit rows, global order
-  const float* out_tf32;  // the same rows rounded to nearest tf32 (operands of the tcgen05 kernels); may be null for SIMT
+  const uint16_t* out_f16;  // the same rows as fp16 (operands of the tcgen05 kernels); may be null for SIMT
   const int* rows;      // [n_loc] global row ids handled here
   const float* z_all;   // [N2] (pass 2)
   int N2, D, n_loc;

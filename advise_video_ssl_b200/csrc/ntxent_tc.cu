@@ -3,25 +3,30 @@
 // CUDA-core reference kernels, whose partial layout and finalisation kernels are reused).
 //
 // One CTA = 128 local rows x one range of columns.  Per 64-column tile of `out`:
-//     S  = Q . tile^T                       (M=128 x N=64, K=D, kind::tf32, A = Q in TMEM)
+//     S  = Q . tile^T                       (M=128 x N=64, K=D;   kind::f16, A = Q in TMEM, B = tile K-major)
 //     e  = 2^((S - 1) log2e / T)            (softmax warps: tcgen05.ld -> exp2; diagonal masked)
 //   pass 1 (rowsum):  z_r += sum_c e_rc
-//   pass 2 (grad):    P = e (1/Z_r + 1/Z_c) -> TMEM;  acc += P . tile   (M=128 x N<=128, K=64)
-// With D = 256 the accumulator of pass 2 (256 TMEM columns) does not fit beside Q (256) and the
-// double-buffered S/P tile (128), so pass 2 sweeps the columns once per 128-wide half of D and
-// recomputes S for the second half (tensor time is cheap here: 28 k cycles per CTA at cfg3).
+//   pass 2 (grad):    P = e (1/Z_r + 1/Z_c) -> TMEM;  acc += P . tile   (M=128 x N=D, K=64, B = tile MN-major)
 //
-// Precision: single-pass tf32 with BOTH operands rounded to nearest, so there is no truncation
-// bias; measured errors are ~1e-5 (loss) and ~3e-4 (gradient), inside the 1e-3 fp32 tolerance.
-// The rounding happens ONCE, when `out` is assembled from the gathered rows (avssl_ntxent_prepare
-// writes the exact rows and a tf32-rounded copy): the tiles go from TMA straight to the tensor core.
-// (Round 1 re-rounded every tile in shared memory with eight helper warps: 128 KB of extra
-// shared-memory traffic per 64 KB tile and one more hop in the role chain; ncu showed the tensor
-// pipe 22-32 % active.)  The CUDA-core kernels (AVSSL_IMPL_SIMT) remain the exact-fp32 reference.
+// Operands are fp16 copies of the unit-length rows (avssl_ntxent_prepare writes them next to the exact
+// fp32 rows): on [-1, 1] fp16 carries the same 11 significant bits as tf32, so the accuracy is that of
+// round-to-nearest tf32 (measured ~1e-5 loss, ~3e-4 gradient, inside the 1e-3 fp32 tolerance), while
+//   * one MMA covers K = 16 instead of 8: half the instructions for the same flops (the tf32 kernel was
+//     bound by the ~50-cycle issue interval of its N = 64 MMAs, tensor pipe 22-31 % active),
+//   * a tile is half the bytes, and with 16-bit elements the plain 128-byte swizzle serves BOTH operand
+//     roles (K-major for S, MN-major for P.V): ONE shared-memory copy per tile instead of two,
+//   * Q takes D/2 TMEM columns, so the whole D = 256 accumulator fits beside it (128 + 128 + 256 = 512):
+//     pass 2 no longer recomputes S for a second half of D.
+// P = e (1/Z_r + 1/Z_c) is the sum of two softmax probabilities, hence <= 2: it is scaled by 2^14 before
+// the conversion to fp16 (<= 32768, no overflow; probabilities down to 4e-9 keep full precision) and the
+// accumulator is scaled back in the epilogue.  The CUDA-core kernels (AVSSL_IMPL_SIMT) remain the exact-fp32
+// reference and serve every D that is not a multiple of 64.
 //
 // Warp roles (320 threads, 1 CTA / SM): 0 TMA producer | 1 MMA issuer + TMEM allocator |
 // 2-9 softmax + epilogue: thread = row, and the two warps that share a TMEM sub-partition (w, w+4)
 // split every tile's 64 columns (and the accumulator read-out) between them.
+#include <cuda_fp16.h>
+
 #include "ntxent.cuh"
 #include "sm100_ptx.cuh"
 
@@ -33,31 +38,33 @@ constexpr int kBJ = 64;    // columns of `out` per tile
 constexpr int kMt = 128;   // local rows per CTA
 constexpr int kNtThreads = 320;
 constexpr int kSoftmax = 256;
-constexpr int kMaxSlots = 4;
+constexpr int kMaxSlots = 6;
 constexpr int kHalfCols = kBJ / 2;  // columns of a tile per softmax warp
 constexpr float kLog2eT = 1.4426950408889634f;
+constexpr float kPScale = 16384.f, kPUnscale = 1.f / 16384.f;
+
+// UMMA instruction descriptor for kind::f16 with fp16 operands (a/b format 0) and fp32 accumulate
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
 
 template <int D, bool kGrad>
 struct NtCfg {
-  static constexpr int kKB = D / 32;                 // 128-byte k-blocks per row
+  static_assert(D % 64 == 0 && D <= 256, "whole 128-byte boxes of fp16");
+  static constexpr int kKB = D / 64;                 // 128-byte boxes (64 fp16) per row
   static constexpr int kBoxBytes = kBJ * 128;        // one TMA box: 64 rows x 128 B
-  static constexpr int kTileBytes = kKB * kBoxBytes; // S tile: 64 KiB at D = 256
-  static constexpr int kAcc = D < 128 ? D : 128;     // accumulator columns per sweep
-  static constexpr int kHalves = kGrad ? D / kAcc : 1;
-  static constexpr int kVBytes = kGrad ? (kAcc / 32) * kBoxBytes : 0;  // V tile of one half
-  static constexpr int kColQ = 0, kColS = D, kColAcc = D + 2 * kBJ;
-  static constexpr int kColsNeeded = D + 2 * kBJ + (kGrad ? kAcc : 0);
+  static constexpr int kTileBytes = kKB * kBoxBytes; // 32 KiB at D = 256
+  static constexpr int kColQ = 0, kColS = D / 2, kColAcc = D / 2 + 2 * kBJ;
+  static constexpr int kColsNeeded = D / 2 + 2 * kBJ + (kGrad ? D : 0);
   static constexpr int kTmemCols = kColsNeeded <= 128 ? 128 : (kColsNeeded <= 256 ? 256 : 512);
   static_assert(kColsNeeded <= 512, "TMEM budget");
-  static constexpr int kSlotBytes = kTileBytes + kVBytes;
-  static constexpr int kSlots = (200 * 1024 / kSlotBytes) < kMaxSlots ? (200 * 1024 / kSlotBytes) : kMaxSlots;
-  static_assert(kSlots >= 2, "at least a double buffer");
-  static constexpr size_t kSmemBytes = 1024 + (size_t)kSlots * kSlotBytes + 8 * kHalfCols * 4 + 512;
+  static constexpr int kSlots = (192 * 1024 / kTileBytes) < kMaxSlots ? (192 * 1024 / kTileBytes) : kMaxSlots;
+  static constexpr size_t kSmemBytes = 1024 + (size_t)kSlots * kTileBytes + 8 * kHalfCols * 4 + 512;
 };
 
 struct NtBarriers {
-  uint64_t s_full[kMaxSlots], s_free[kMaxSlots];
-  uint64_t v_full[kMaxSlots], v_free[kMaxSlots];
+  uint64_t s_full[kMaxSlots], s_free[kMaxSlots];  // tile landed / both MMAs that read it have retired
   uint64_t s_ready[2], p_ready[2];
   uint64_t q_ready, acc_done;
   uint32_t tmem_base;
@@ -65,15 +72,14 @@ struct NtBarriers {
 
 template <int D, bool kGrad>
 __global__ void __launch_bounds__(kNtThreads, 1)
-ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_v) {
+ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap) {
   using C = NtCfg<D, kGrad>;
   constexpr int kSlots = C::kSlots;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
-  uint8_t* s_ring = smem;
-  uint8_t* v_ring = smem + kSlots * C::kTileBytes;
-  float* invz_c = reinterpret_cast<float*>(smem + kSlots * C::kSlotBytes);  // [8 softmax warps][32]: 1/Z of the warp's columns
-  NtBarriers* bar = reinterpret_cast<NtBarriers*>(smem + kSlots * C::kSlotBytes + 8 * kHalfCols * 4);
+  uint8_t* ring = smem;
+  float* invz_c = reinterpret_cast<float*>(smem + kSlots * C::kTileBytes);  // [8 softmax warps][32]: 1/Z of the warp's columns
+  NtBarriers* bar = reinterpret_cast<NtBarriers*>(smem + kSlots * C::kTileBytes + 8 * kHalfCols * 4);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int split = blockIdx.x;
@@ -81,16 +87,12 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
   const int j_begin = split * a.cols_per_split;
   const int j_end = min(a.N2, j_begin + a.cols_per_split);
   const int n_tiles = (j_end - j_begin + kBJ - 1) / kBJ;
-  const int n_steps = n_tiles * C::kHalves;  // pass 2 with D = 256: every tile is visited once per half of D
 
   if (warp == 0 && lane == 0) {
     ptx::tma_prefetch_desc(&tmap);
-    if (kGrad) ptx::tma_prefetch_desc(&tmap_v);
     for (int s = 0; s < kSlots; ++s) {
       ptx::mbar_init(&bar->s_full[s], 1);
       ptx::mbar_init(&bar->s_free[s], 1);
-      ptx::mbar_init(&bar->v_full[s], 1);
-      ptx::mbar_init(&bar->v_free[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&bar->s_ready[b], 1);
@@ -109,72 +111,64 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
   if (warp == 0) {
     // ================================================================ TMA producer
     if (lane == 0) {
-      for (int u = 0; u < n_steps; ++u) {
-        const int t = u % n_tiles, h = u / n_tiles, sl = u % kSlots;
-        const int j0 = j_begin + t * kBJ;
-        if (u >= kSlots) ptx::mbar_wait(&bar->s_free[sl], ((u / kSlots) - 1) & 1);
+      for (int t = 0; t < n_tiles; ++t) {
+        const int sl = t % kSlots;
+        if (t >= kSlots) ptx::mbar_wait(&bar->s_free[sl], ((t / kSlots) - 1) & 1);
         ptx::mbar_arrive_expect_tx(&bar->s_full[sl], C::kTileBytes);
-        uint8_t* dst = s_ring + (size_t)sl * C::kTileBytes;
+        uint8_t* dst = ring + (size_t)sl * C::kTileBytes;
 #pragma unroll
-        for (int kb = 0; kb < C::kKB; ++kb) ptx::tma_load_2d(dst + kb * C::kBoxBytes, &tmap, &bar->s_full[sl], kb * 32, j0);
-        if (kGrad) {
-          if (u >= kSlots) ptx::mbar_wait(&bar->v_free[sl], ((u / kSlots) - 1) & 1);
-          ptx::mbar_arrive_expect_tx(&bar->v_full[sl], C::kVBytes);
-          uint8_t* dv = v_ring + (size_t)sl * C::kVBytes;
-#pragma unroll
-          for (int kb = 0; kb < C::kAcc / 32; ++kb)
-            ptx::tma_load_2d(dv + kb * C::kBoxBytes, &tmap_v, &bar->v_full[sl], (h * (C::kAcc / 32) + kb) * 32, j0);
-        }
+        for (int kb = 0; kb < C::kKB; ++kb)
+          ptx::tma_load_2d(dst + kb * C::kBoxBytes, &tmap, &bar->s_full[sl], kb * 64, j_begin + t * kBJ);
       }
     }
   } else if (warp == 1) {
     // ================================================================== MMA issuer
-    constexpr uint32_t idesc_s = ptx::umma_idesc_tf32(kMt, kBJ, 0, 0);      // B = tile, K-major
-    constexpr uint32_t idesc_pv = ptx::umma_idesc_tf32(kMt, C::kAcc, 0, 1);  // B = tile half, MN-major
+    constexpr uint32_t idesc_s = umma_idesc_f16(kMt, kBJ, 0, 0);  // B = tile, K-major
+    constexpr uint32_t idesc_pv = umma_idesc_f16(kMt, D, 0, 1);   // B = the same tile, MN-major
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
-    const uint32_t s_ring0 = __shfl_sync(0xffffffffu, ptx::smem_u32(s_ring), 0);
-    const uint32_t v_ring0 = __shfl_sync(0xffffffffu, ptx::smem_u32(v_ring), 0);
+    const uint32_t ring0 = __shfl_sync(0xffffffffu, ptx::smem_u32(ring), 0);
     ptx::mbar_wait_relaxed(&bar->q_ready, 0);
     ptx::tc_fence_after();
-    auto issue_pv = [&](int u) {
-      const int sl = u % kSlots, b = u & 1, t = u % n_tiles;
-      ptx::mbar_wait(&bar->v_full[sl], (u / kSlots) & 1);
-      ptx::mbar_wait(&bar->p_ready[b], (u >> 1) & 1);
+    auto issue_pv = [&](int t) {
+      const int sl = t % kSlots, b = t & 1;
+      ptx::mbar_wait(&bar->p_ready[b], (t >> 1) & 1);
       ptx::tc_fence_after();
-      // MN-major, 32B-atom swizzle: 8 rows per k-step (1024 B) = two 4-row atoms 512 B apart (SBO);
-      // the 32-float column blocks (one TMA box each) are kBoxBytes apart (LBO)
-      const uint64_t bd0 = ptx::umma_smem_desc(v_ring0 + sl * C::kVBytes, C::kBoxBytes, 512, ptx::kUmmaSwizzle128BBase32B);
+      // MN-major, 128-byte swizzle, 16-bit elements: one k-step = 16 tile rows = two 8-row atoms 1024 B apart
+      // (SBO); the 64-element column blocks of N (one TMA box each) are kBoxBytes apart (LBO)
+      const uint64_t bd0 = ptx::umma_smem_desc(ring0 + sl * C::kTileBytes, C::kBoxBytes, 1024, ptx::kUmmaSwizzle128B);
       const uint32_t a0 = tm + C::kColS + b * kBJ;
       if (ptx::elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < kBJ / 8; ++ks)
-          ptx::mma_tf32_ts(tm + C::kColAcc, a0 + ks * 8, bd0 + (uint64_t)(ks * 1024 >> 4), idesc_pv, (t > 0 || ks > 0) ? 1u : 0u);
-        ptx::tc_commit(&bar->v_free[sl]);
-        if (t == n_tiles - 1) ptx::tc_commit(&bar->acc_done);  // this half of the accumulator is complete
+        for (int ks = 0; ks < kBJ / 16; ++ks)  // P of columns 32h..32h+31 sits packed in TMEM columns 32h..32h+15
+          ptx::mma_f16_ts(tm + C::kColAcc, a0 + (ks >> 1) * kHalfCols + (ks & 1) * 8, bd0 + (uint64_t)(ks * 2048 >> 4),
+                          idesc_pv, (t > 0 || ks > 0) ? 1u : 0u);
+        ptx::tc_commit(&bar->s_free[sl]);  // S(t) retired before PV(t) was issued: the slot is free
+        if (t == n_tiles - 1) ptx::tc_commit(&bar->acc_done);
       }
       __syncwarp();
     };
-    for (int u = 0; u < n_steps; ++u) {
-      const int sl = u % kSlots, b = u & 1;
-      ptx::mbar_wait(&bar->s_full[sl], (u / kSlots) & 1);
-      // S(u) overwrites the TMEM buffer of step u-2: its exponentials must have been read (pass 2 gets
-      // this ordering for free from PV(u-2), which waited for the same barrier)
-      if (!kGrad && u >= 2) ptx::mbar_wait(&bar->p_ready[b], ((u - 2) >> 1) & 1);
+    for (int t = 0; t < n_tiles; ++t) {
+      const int sl = t % kSlots, b = t & 1;
+      ptx::mbar_wait(&bar->s_full[sl], (t / kSlots) & 1);
+      // S(t) overwrites the TMEM buffer of tile t-2: its exponentials must have been read (pass 2 gets this
+      // ordering for free from PV(t-2), which waited for the same barrier)
+      if (!kGrad && t >= 2) ptx::mbar_wait(&bar->p_ready[b], ((t - 2) >> 1) & 1);
       ptx::tc_fence_after();
-      const uint64_t sd0 = ptx::umma_smem_desc(s_ring0 + sl * C::kTileBytes, 16, 1024, ptx::kUmmaSwizzle128B);
+      // K-major: box ks/4 (64 fp16 = 128 B), 16 elements = 32 bytes per k-step inside the 128-byte row
+      const uint64_t sd0 = ptx::umma_smem_desc(ring0 + sl * C::kTileBytes, 16, 1024, ptx::kUmmaSwizzle128B);
       const uint32_t d_s = tm + C::kColS + b * kBJ;
       if (ptx::elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < D / 8; ++ks)
-          ptx::mma_tf32_ts(d_s, tm + C::kColQ + ks * 8, sd0 + (uint64_t)(((ks >> 2) * C::kBoxBytes + (ks & 3) * 32) >> 4), idesc_s,
-                           ks > 0 ? 1u : 0u);
+        for (int ks = 0; ks < D / 16; ++ks)
+          ptx::mma_f16_ts(d_s, tm + C::kColQ + ks * 8, sd0 + (uint64_t)(((ks >> 2) * C::kBoxBytes + (ks & 3) * 32) >> 4), idesc_s,
+                          ks > 0 ? 1u : 0u);
         ptx::tc_commit(&bar->s_ready[b]);
-        ptx::tc_commit(&bar->s_free[sl]);
+        if (!kGrad) ptx::tc_commit(&bar->s_free[sl]);
       }
       __syncwarp();
-      if (kGrad && u > 0) issue_pv(u - 1);
+      if (kGrad && t > 0) issue_pv(t - 1);
     }
-    if (kGrad && n_steps > 0) issue_pv(n_steps - 1);
+    if (kGrad && n_tiles > 0) issue_pv(n_tiles - 1);
   } else {
     // ================= softmax + epilogue: thread = local row; warp pair (w, w+4) shares a sub-partition
     const int sw = warp - 2;                    // 0..7
@@ -188,24 +182,26 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
     const float invz_r = (kGrad && row_valid) ? 1.f / __ldg(a.z_all + rid) : 0.f;
     float* iz = invz_c + sw * kHalfCols;        // this warp's staging of 1/Z_c (private: __syncwarp suffices)
 
-    // ---- A operand: this row of `out` (unit length, already rounded to tf32) into TMEM; the pair splits
-    // the D / 32 column blocks
+    // ---- A operand: this row of `out` in fp16 into TMEM, two consecutive elements per 32-bit column (the
+    // memory image of the row); the pair splits the 32-column chunks
     {
-      const float4* src = reinterpret_cast<const float4*>(a.out_tf32 + (size_t)(row_valid ? rid : 0) * D);
-      constexpr int kCb = D / 32;
+      const uint4* src = reinterpret_cast<const uint4*>(a.out_f16 + (size_t)(row_valid ? rid : 0) * D);
+      constexpr int kChunks = (D / 2 + 31) / 32;     // chunks of 32 TMEM columns = 64 elements = 8 uint4
+      constexpr int kWords = D / 2 < 32 ? D / 2 : 32;  // columns per chunk (D = 64: one chunk of 32)
+      static_assert(kWords == 32, "D >= 64");
 #pragma unroll 1
-      for (int cb = hc; cb < kCb; cb += 2) {
+      for (int ch = hc; ch < kChunks; ch += 2) {
         uint32_t v[32];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row_valid) x = __ldg(src + cb * 8 + k);
-          v[4 * k + 0] = __float_as_uint(x.x);
-          v[4 * k + 1] = __float_as_uint(x.y);
-          v[4 * k + 2] = __float_as_uint(x.z);
-          v[4 * k + 3] = __float_as_uint(x.w);
+          uint4 x = make_uint4(0u, 0u, 0u, 0u);
+          if (row_valid) x = __ldg(src + ch * 8 + k);
+          v[4 * k + 0] = x.x;
+          v[4 * k + 1] = x.y;
+          v[4 * k + 2] = x.z;
+          v[4 * k + 3] = x.w;
         }
-        ptx::tmem_st32(lane_base + C::kColQ + cb * 32, v);
+        ptx::tmem_st32(lane_base + C::kColQ + ch * 32, v);
       }
       ptx::tc_wait_st();
       ptx::tc_fence_before();
@@ -214,15 +210,15 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
     const float scale2 = a.inv_T * kLog2eT;
     float zs[4] = {0.f, 0.f, 0.f, 0.f};
 
-    for (int u = 0; u < n_steps; ++u) {
-      const int t = u % n_tiles, h = u / n_tiles, b = u & 1;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int b = t & 1;
       const int j0 = j_begin + t * kBJ + hc * kHalfCols;  // first column of this warp's half tile
-      if (kGrad) {  // 1/Z of this warp's 32 columns, staged while S(u) is still being computed
+      if (kGrad) {  // 1/Z of this warp's 32 columns, staged while S(t) is still being computed
         __syncwarp();
         iz[lane] = (j0 + lane < j_end) ? 1.f / __ldg(a.z_all + j0 + lane) : 0.f;
         __syncwarp();
       }
-      ptx::mbar_wait(&bar->s_ready[b], (u >> 1) & 1);
+      ptx::mbar_wait(&bar->s_ready[b], (t >> 1) & 1);
       ptx::tc_fence_after();
       const uint32_t s_col = lane_base + C::kColS + b * kBJ + hc * kHalfCols;
       uint32_t sv[kHalfCols];
@@ -230,46 +226,50 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
       ptx::tc_wait_ld();
       const int diag = rid - j0;            // column of this half tile that is the row itself (masked), if in [0, 32)
       const int valid = row_valid ? min(kHalfCols, j_end - j0) : 0;
+      uint32_t pk[kHalfCols / 2];
 #pragma unroll
-      for (int c = 0; c < kHalfCols; ++c) {
-        // e^{(s - 1)/T}: unit rows give s <= 1, so the exponent is <= 0
-        float e;
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((__uint_as_float(sv[c]) - 1.f) * scale2));
-        e = (c < valid && c != diag) ? e : 0.f;
+      for (int c = 0; c < kHalfCols; c += 2) {
+        float e[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          // e^{(s - 1)/T}: unit rows give s <= 1, so the exponent is <= 0
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[u]) : "f"((__uint_as_float(sv[c + u]) - 1.f) * scale2));
+          e[u] = (c + u < valid && c + u != diag) ? e[u] : 0.f;
+        }
         if (kGrad) {
-          sv[c] = __float_as_uint(ptx::round_tf32(e * (invz_r + iz[c])));
+          const __half2 h = __floats2half2_rn(e[0] * (invz_r + iz[c]) * kPScale, e[1] * (invz_r + iz[c + 1]) * kPScale);
+          pk[c >> 1] = *reinterpret_cast<const uint32_t*>(&h);  // low half = even k
         } else {
-          zs[c & 3] += e;
+          zs[c & 3] += e[0];
+          zs[(c + 1) & 3] += e[1];
         }
       }
       if (kGrad) {
-        ptx::tmem_st32(s_col, sv);
+        ptx::tmem_st16(s_col, pk);  // over the first 16 columns of this warp's own 32 (the pair never overlaps)
         ptx::tc_wait_st();
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&bar->p_ready[b]);
-
-      if (kGrad && t == n_tiles - 1) {
-        // ---- this half of the gradient partial is complete once its last PV retires
-        ptx::mbar_wait(&bar->acc_done, h & 1);
-        ptx::tc_fence_after();
-#pragma unroll 1
-        for (int cb = hc; cb < C::kAcc / 32; cb += 2) {
-          uint32_t av[32];
-          ptx::tmem_ld32(lane_base + C::kColAcc + cb * 32, av);
-          ptx::tc_wait_ld();
-          if (row_valid) {
-            float4* dst = reinterpret_cast<float4*>(a.part_g + ((size_t)split * a.n_loc + i) * D + h * C::kAcc + cb * 32);
-#pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4)
-              dst[c4] = make_float4(__uint_as_float(av[c4 * 4]), __uint_as_float(av[c4 * 4 + 1]),
-                                    __uint_as_float(av[c4 * 4 + 2]), __uint_as_float(av[c4 * 4 + 3]));
-          }
-        }
-        ptx::tc_fence_before();
-      }
     }
-    if (!kGrad) {
+    if (kGrad) {
+      // ---- the gradient partial is complete once the last PV retires; the pair splits the 32-column chunks
+      ptx::mbar_wait(&bar->acc_done, 0);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int cb = hc; cb < D / 32; cb += 2) {
+        uint32_t av[32];
+        ptx::tmem_ld32(lane_base + C::kColAcc + cb * 32, av);
+        ptx::tc_wait_ld();
+        if (row_valid) {
+          float4* dst = reinterpret_cast<float4*>(a.part_g + ((size_t)split * a.n_loc + i) * D + cb * 32);
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4)
+            dst[c4] = make_float4(__uint_as_float(av[c4 * 4]) * kPUnscale, __uint_as_float(av[c4 * 4 + 1]) * kPUnscale,
+                                  __uint_as_float(av[c4 * 4 + 2]) * kPUnscale, __uint_as_float(av[c4 * 4 + 3]) * kPUnscale);
+        }
+      }
+      ptx::tc_fence_before();
+    } else {
       // the pair's two partial row sums meet in shared memory (the 1/Z staging area is unused in this pass)
       const float z = (zs[0] + zs[1]) + (zs[2] + zs[3]);
       float* zx = invz_c;  // [128] floats: one per row
@@ -305,31 +305,27 @@ EncodeTiledFn nt_encode_fn() {
 }
 
 struct NtTmapCache {
-  const float* out = nullptr;
+  const void* out = nullptr;
   int N2 = 0, D = 0;
-  CUtensorMap s, v;
+  CUtensorMap s;
 };
 
 template <int D, bool kGrad>
 int launch_nt(const NtxArgs& a, cudaStream_t st) {
   using C = NtCfg<D, kGrad>;
   static thread_local NtTmapCache cache;
-  if (cache.out != a.out_tf32 || cache.N2 != a.N2 || cache.D != D) {
+  if (cache.out != a.out_f16 || cache.N2 != a.N2 || cache.D != D) {
     EncodeTiledFn enc = nt_encode_fn();
     AVSSL_REQUIRE(enc, AVSSL_ERR_CUDA, "ntxent: cuTensorMapEncodeTiled is not available from the driver");
     const cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)a.N2};
-    const cuuint64_t gstride[1] = {(cuuint64_t)D * sizeof(float)};
-    const cuuint32_t box[2] = {32u, (cuuint32_t)kBJ};
+    const cuuint64_t gstride[1] = {(cuuint64_t)D * sizeof(uint16_t)};
+    const cuuint32_t box[2] = {64u, (cuuint32_t)kBJ};  // 64 fp16 = 128 bytes x 64 rows
     const cuuint32_t estride[2] = {1u, 1u};
-    CUresult r = enc(&cache.s, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a.out_tf32), gdim, gstride, box, estride,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    CUresult r = enc(&cache.s, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<uint16_t*>(a.out_f16), gdim, gstride, box,
+                     estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     AVSSL_REQUIRE(r == CUDA_SUCCESS, AVSSL_ERR_CUDA, "ntxent: cuTensorMapEncodeTiled failed (%d)", (int)r);
-    r = enc(&cache.v, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a.out_tf32), gdim, gstride, box, estride,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    AVSSL_REQUIRE(r == CUDA_SUCCESS, AVSSL_ERR_CUDA, "ntxent: cuTensorMapEncodeTiled (32B atoms) failed (%d)", (int)r);
-    cache.out = a.out_tf32;
+    cache.out = a.out_f16;
     cache.N2 = a.N2;
     cache.D = D;
   }
@@ -338,7 +334,7 @@ int launch_nt(const NtxArgs& a, cudaStream_t st) {
     AVSSL_CUDA_OK(cudaFuncSetAttribute(ntxent_tc_kernel<D, kGrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes));
   }
   dim3 grid(a.n_splits, (a.n_loc + kMt - 1) / kMt);
-  ntxent_tc_kernel<D, kGrad><<<grid, kNtThreads, C::kSmemBytes, st>>>(a, cache.s, cache.v);
+  ntxent_tc_kernel<D, kGrad><<<grid, kNtThreads, C::kSmemBytes, st>>>(a, cache.s);
   AVSSL_LAUNCH_OK("ntxent_tc_kernel");
   return AVSSL_OK;
 }
@@ -347,7 +343,7 @@ int launch_nt(const NtxArgs& a, cudaStream_t st) {
 
 bool ntxent_tc_supported(int N2, int D, int n_loc) {
   (void)n_loc;
-  return (D == 32 || D == 64 || D == 96 || D == 128 || D == 256) && N2 >= 2;
+  return (D == 64 || D == 128 || D == 256) && N2 >= 2;
 }
 
 // Column split of the tcgen05 kernels: whole 64-column tiles, at most 64 splits (workspace layout),
@@ -372,9 +368,7 @@ int launch_ntxent_tc(const NtxArgs& a, bool grad, cudaStream_t s) {
   case DD:                \
     return grad ? launch_nt<DD, true>(a, s) : launch_nt<DD, false>(a, s);
   switch (a.D) {
-    AVSSL_NT_CASE(32)
     AVSSL_NT_CASE(64)
-    AVSSL_NT_CASE(96)
     AVSSL_NT_CASE(128)
     AVSSL_NT_CASE(256)
   }

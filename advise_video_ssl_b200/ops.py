@@ -680,10 +680,10 @@ def ntxent(feat1, feat2, T, gather=None, impl=_lib.IMPL_AUTO):
         dist.all_gather_into_tensor(allq.view(world * 2 * B, D), y)
     else:
         allq = y
-    # [q_all ; q2_all] and its tf32-rounded copy (the tensor cores' operand) in one pass over the gathered rows
+    # [q_all ; q2_all] and its fp16 copy (the tensor cores' operand) in one pass over the gathered rows
     N = world * B
     out = torch.empty(2 * N, D, dtype=_f32, device=dev)
-    out_r = torch.empty(2 * N, D, dtype=_f32, device=dev)
+    out_r = torch.empty(2 * N, D, dtype=torch.float16, device=dev)
     check(lib.avssl_ntxent_prepare(allq.data_ptr(), world, B, D, out.data_ptr(), out_r.data_ptr(), _stream()),
           "avssl_ntxent_prepare")
     rows = torch.cat([torch.arange(rank * B, (rank + 1) * B, dtype=torch.int32, device=dev),

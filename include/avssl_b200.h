@@ -211,25 +211,25 @@ AVSSL_API int avssl_ce_target0_bwd(const float* logits, const float* row_lse, in
  *       and dfeat[i] = grad_scale * dLoss/dout_{r_i} chained through the row
  *       l2-normalisation (norm_loc[i] = ||f_i||).  grad_scale = world size reproduces
  *       the reference's all_reduce(SUM)-then-slice backward.
- * impl: AVSSL_IMPL_AUTO picks the tcgen05 kernels (single-pass tf32 with both operands rounded
- *   to nearest: loss ~1e-5, gradient ~3e-4 relative, inside the 1e-3 fp32 tolerance) when
- *   D is 32/64/96/128/256 and out_tf32 is given; AVSSL_IMPL_SIMT forces the exact-fp32 CUDA-core
- *   kernels (out_tf32 may then be NULL).
- * out_tf32: `out` rounded to nearest tf32, the operand the tensor cores stream (written together
- *   with `out` by avssl_ntxent_prepare, so the rounding costs no extra pass).
+ * impl: AVSSL_IMPL_AUTO picks the tcgen05 kernels (kind::f16 on fp16 copies of the unit rows -- on [-1, 1]
+ *   the 11 significant bits of round-to-nearest tf32 -- with fp32 accumulation: loss ~1e-5, gradient ~3e-4
+ *   relative, inside the 1e-3 fp32 tolerance) when D is 64/128/256 and out_f16 is given; AVSSL_IMPL_SIMT
+ *   forces the exact-fp32 CUDA-core kernels (out_f16 may then be NULL), which also serve every other D.
+ * out_f16: `out` as IEEE fp16 ([N2, D], 2 bytes per element), the operand the tensor cores stream (written
+ *   together with `out` by avssl_ntxent_prepare, so the conversion costs no extra pass).
  * workspace: avssl_ntxent_workspace_bytes(), zero-filled once, reusable.
  *
  * avssl_ntxent_prepare assembles `out` from the all_gather result (C4, models/contrastive.py:771-775):
  *   gathered is [world][2][B][D] (every rank's [q ; q2] block, what ncclAllGather delivers),
- *   out[(v*world + w)*B + b] = gathered[w][v][b], out_tf32 = rn_tf32(out).  world = 1 just copies.
+ *   out[(v*world + w)*B + b] = gathered[w][v][b], out_f16 = rn_fp16(out).  world = 1 just copies.
  */
 AVSSL_API size_t avssl_ntxent_workspace_bytes(int N2, int D, int n_loc);
-AVSSL_API int avssl_ntxent_prepare(const float* gathered, int world, int B, int D, float* out, float* out_tf32,
+AVSSL_API int avssl_ntxent_prepare(const float* gathered, int world, int B, int D, float* out, void* out_f16,
                          void* stream);
-AVSSL_API int avssl_ntxent_rowsum(const float* out, const float* out_tf32, const int* rows, int N2, int D, int n_loc,
+AVSSL_API int avssl_ntxent_rowsum(const float* out, const void* out_f16, const int* rows, int N2, int D, int n_loc,
                         float T, float* z_loc_out, void* workspace, size_t workspace_bytes, int impl,
                         void* stream);
-AVSSL_API int avssl_ntxent_grad(const float* out, const float* out_tf32, const int* rows, const float* z_all,
+AVSSL_API int avssl_ntxent_grad(const float* out, const void* out_f16, const int* rows, const float* z_all,
                       const float* norm_loc,
                       int N2, int D, int n_loc, float T, float grad_scale, float* loss_out,
                       float* dfeat_out, void* workspace, size_t workspace_bytes, int impl, void* stream);

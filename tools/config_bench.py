@@ -101,7 +101,7 @@ for B, W in ((512, 1), (512, 8)):
         from advise_video_ssl_b200._lib import lib, check
         gathered = torch.nn.functional.normalize(torch.randn(W, 2, B, D, device=dev), dim=-1)  # what the all_gather delivers
         out = torch.empty(2 * N, D, device=dev)
-        out_r = torch.empty(2 * N, D, device=dev)
+        out_r = torch.empty(2 * N, D, device=dev, dtype=torch.float16)
         rows = torch.cat([torch.arange(0, B, dtype=torch.int32, device=dev),
                           torch.arange(N, N + B, dtype=torch.int32, device=dev)])
         n_loc = 2 * B

@@ -6,7 +6,7 @@ dev = torch.device("cuda")
 B, W, D, T = 512, 8, 256, 0.1
 N = B * W
 gathered = torch.nn.functional.normalize(torch.randn(W, 2, B, D, device=dev), dim=-1)
-out = torch.empty(2 * N, D, device=dev); out_r = torch.empty(2 * N, D, device=dev)
+out = torch.empty(2 * N, D, device=dev); out_r = torch.empty(2 * N, D, device=dev, dtype=torch.float16)
 rows = torch.cat([torch.arange(0, B, dtype=torch.int32, device=dev), torch.arange(N, N + B, dtype=torch.int32, device=dev)])
 n_loc = 2 * B
 ws = torch.zeros(lib.avssl_ntxent_workspace_bytes(2 * N, D, n_loc), dtype=torch.uint8, device=dev)
