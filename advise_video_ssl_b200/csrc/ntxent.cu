@@ -135,20 +135,27 @@ __global__ void __launch_bounds__(kSimtThreads, 1) ntxent_pass_kernel(const NtxA
 __global__ void ntxent_sum_z_kernel(const float* __restrict__ part_z, int n_splits, int n_loc, float* __restrict__ z_loc) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_loc) return;
+  // fixed summation order (deterministic); eight split rows in flight per thread
   float z = 0.f;
-  for (int s = 0; s < n_splits; ++s) z += part_z[(size_t)s * n_loc + i];
+  for (int s0 = 0; s0 < n_splits; s0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = s0 + u < n_splits ? __ldcg(part_z + (size_t)(s0 + u) * n_loc + i) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) z += v[u];
+  }
   z_loc[i] = z;
 }
 
-// Finalisation of pass 2 in ONE launch (4 warps per CTA, one warp per unit of work):
+// Finalisation of pass 2 in ONE launch (8 warps per CTA):
 //   CTAs [0, comb_blocks):  one warp per local row -- merge the gradient partials in split order
 //     (deterministic; 128-bit loads, 8 split rows in flight per lane), subtract the positive term,
 //     apply 1/(2N T) and the world-size factor, then chain through the l2-normalisation.
 //     D <= 256: lane l owns columns 4l..4l+3 and 128+4l..128+4l+3.
-//   CTAs [comb_blocks, ...): one warp per PAIR (r, r+) of all 2N rows -- both rows share the same
-//     dot product: loss = mean_r( log Z_r + 1/T - out_r . out_{r+} / T ); the last of these CTAs
-//     to finish takes the mean in row order.
-constexpr int kFinWarps = 4;
+//   CTAs [comb_blocks, ...): about one per SM; every warp walks its share of the PAIRS (r, r+) of all 2N rows --
+//     both rows share the same dot product: loss = mean_r( log Z_r + 1/T - out_r . out_{r+} / T ); the last of
+//     these CTAs to finish folds the per-CTA sums in CTA order.
+constexpr int kFinWarps = 8;
 
 __global__ void __launch_bounds__(kFinWarps * 32)
 ntxent_finish_kernel(const NtxArgs a, const float* __restrict__ norm_loc, float gscale, float* __restrict__ dfeat,
@@ -206,41 +213,40 @@ ntxent_finish_kernel(const NtxArgs a, const float* __restrict__ norm_loc, float 
     return;
   }
 
+  // ---- loss: mean_r( log Z_r + 1/T - out_r . out_{r+} / T ) over ALL 2N rows.  A few fat CTAs: every warp walks
+  // its share of the pairs (both rows of a pair share the dot product) and keeps a running sum, the CTA folds its
+  // warps' sums in a fixed order, and the last CTA to arrive folds the per-CTA sums -- deterministic, one atomic
+  // per CTA and no per-row round trip through memory.
   const int n_loss_blocks = gridDim.x - comb_blocks;
-  const int r = ((int)blockIdx.x - comb_blocks) * kFinWarps + warp;  // pair index
-  if (r < half) {
+  const int lb = (int)blockIdx.x - comb_blocks;
+  const bool in0 = 4 * lane < D, in1 = 128 + 4 * lane < D;
+  float wsum = 0.f;
+  for (int r = lb * kFinWarps + warp; r < half; r += n_loss_blocks * kFinWarps) {  // pair index
     const float4* x4 = reinterpret_cast<const float4*>(a.out + (size_t)r * D);
     const float4* y4 = reinterpret_cast<const float4*>(a.out + (size_t)(r + half) * D);
-    const bool in0 = 4 * lane < D, in1 = 128 + 4 * lane < D;
     const float4 x0 = in0 ? __ldg(x4 + lane) : zero4, y0 = in0 ? __ldg(y4 + lane) : zero4;
     const float4 x1 = in1 ? __ldg(x4 + 32 + lane) : zero4, y1 = in1 ? __ldg(y4 + 32 + lane) : zero4;
     const float za = a.z_all[r], zb = a.z_all[r + half];
     float dot = (x0.x * y0.x + x0.y * y0.y) + (x0.z * y0.z + x0.w * y0.w) + (x1.x * y1.x + x1.y * y1.y) +
                 (x1.z * y1.z + x1.w * y1.w);
     dot = warp_sum(dot);
-    if (lane == 0) {
-      row_term[r] = logf(za) + a.inv_T - dot * a.inv_T;
-      row_term[r + half] = logf(zb) + a.inv_T - dot * a.inv_T;
-    }
+    wsum += (logf(za) + a.inv_T - dot * a.inv_T) + (logf(zb) + a.inv_T - dot * a.inv_T);
   }
+  if (lane == 0) s_red[warp] = wsum;
   __syncthreads();
   if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < kFinWarps; ++w) t += s_red[w];
+    row_term[lb] = t;
     __threadfence();
     s_last = (atomicAdd(counter, 1u) == (unsigned)n_loss_blocks - 1u) ? 1u : 0u;
   }
   __syncthreads();
   if (s_last) {
     __threadfence();
-    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-    int k = threadIdx.x;
-    for (; k + 3 * (int)blockDim.x < a.N2; k += 4 * blockDim.x) {
-      t0 += __ldcg(row_term + k);
-      t1 += __ldcg(row_term + k + blockDim.x);
-      t2 += __ldcg(row_term + k + 2 * blockDim.x);
-      t3 += __ldcg(row_term + k + 3 * blockDim.x);
-    }
-    for (; k < a.N2; k += blockDim.x) t0 += __ldcg(row_term + k);
-    const float tot = block_sum((t0 + t1) + (t2 + t3), s_red);
+    float t = 0.f;
+    for (int k = threadIdx.x; k < n_loss_blocks; k += blockDim.x) t += __ldcg(row_term + k);
+    const float tot = block_sum(t, s_red);
     if (threadIdx.x == 0) {
       *loss_out = tot / (float)a.N2;
       *counter = 0u;
@@ -333,17 +339,21 @@ static int ntx_setup(NtxArgs& a, const float* out, const void* out_f16, const in
 __global__ void __launch_bounds__(256)
 ntxent_prepare_kernel(const float4* __restrict__ gathered, int W, int B, int D4, float4* __restrict__ out,
                       uint2* __restrict__ out_f16) {
-  const size_t total = (size_t)2 * W * B * D4;
-  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-    const size_t row = e / D4;               // destination row (v * W + w) * B + b
-    const int c = (int)(e - row * D4);
-    const int b = (int)(row % B);
-    const int vw = (int)(row / B);
+  // one warp per destination row (v * W + w) * B + b; the row index arithmetic is per warp, not per element
+  const int lane = threadIdx.x & 31;
+  const int n_rows = 2 * W * B;
+  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n_rows; row += gridDim.x * (blockDim.x >> 5)) {
+    const int b = row % B, vw = row / B;
     const int w = vw % W, v = vw / W;
-    const float4 x = __ldg(gathered + (((size_t)w * 2 + v) * B + b) * D4 + c);
-    out[e] = x;
-    const __half2 lo = __floats2half2_rn(x.x, x.y), hi = __floats2half2_rn(x.z, x.w);
-    out_f16[e] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+    const float4* src = gathered + ((size_t)(w * 2 + v) * B + b) * D4;
+    float4* o = out + (size_t)row * D4;
+    uint2* oh = out_f16 + (size_t)row * D4;
+    for (int c = lane; c < D4; c += 32) {
+      const float4 x = __ldg(src + c);
+      o[c] = x;
+      const __half2 lo = __floats2half2_rn(x.x, x.y), hi = __floats2half2_rn(x.z, x.w);
+      oh[c] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+    }
   }
 }
 
@@ -354,9 +364,8 @@ extern "C" int avssl_ntxent_prepare(const float* gathered, int world, int B, int
   AVSSL_REQUIRE(((reinterpret_cast<uintptr_t>(gathered) | reinterpret_cast<uintptr_t>(out) |
                   reinterpret_cast<uintptr_t>(out_f16)) & 15u) == 0,
                 AVSSL_ERR_INVALID_ARGUMENT, "ntxent_prepare: pointers must be 16-byte aligned");
-  const size_t total = (size_t)2 * world * B * (D / 4);
-  int grid = (int)((total + 255) / 256);
-  const int cap = 8 * (sm_count() > 0 ? sm_count() : 148);
+  int grid = (2 * world * B + 7) / 8;  // 8 warps = 8 rows per CTA
+  const int cap = 16 * (sm_count() > 0 ? sm_count() : 148);
   if (grid > cap) grid = cap;
   ntxent_prepare_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float4*>(gathered), world, B, D / 4, reinterpret_cast<float4*>(out),
@@ -375,7 +384,7 @@ extern "C" int avssl_ntxent_rowsum(const float* out, const void* out_f16, const 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   rc = use_tc ? launch_ntxent_tc(a, false, s) : launch_pass_d<false>(a, s);
   if (rc) return rc;
-  ntxent_sum_z_kernel<<<(n_loc + 255) / 256, 256, 0, s>>>(a.part_z, a.n_splits, n_loc, z_loc_out);
+  ntxent_sum_z_kernel<<<(n_loc + 63) / 64, 64, 0, s>>>(a.part_z, a.n_splits, n_loc, z_loc_out);
   AVSSL_LAUNCH_OK("ntxent_sum_z_kernel");
   return AVSSL_OK;
 }
@@ -397,7 +406,8 @@ extern "C" int avssl_ntxent_grad(const float* out, const void* out_f16, const in
   unsigned* counter = static_cast<unsigned*>(workspace);
   float* row_term = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
   const int comb_blocks = (n_loc + kFinWarps - 1) / kFinWarps;
-  const int loss_blocks = (N2 / 2 + kFinWarps - 1) / kFinWarps;
+  int loss_blocks = (N2 / 2 + kFinWarps - 1) / kFinWarps;  // a few pairs per warp: about one CTA per SM
+  if (loss_blocks > (sm_count() > 0 ? sm_count() : 148)) loss_blocks = sm_count() > 0 ? sm_count() : 148;
   ntxent_finish_kernel<<<comb_blocks + loss_blocks, kFinWarps * 32, 0, s>>>(a, norm_loc, gscale, dfeat_out, comb_blocks,
                                                                            loss_out, row_term, counter);
   AVSSL_LAUNCH_OK("ntxent_finish_kernel");
