@@ -584,6 +584,138 @@ def gpu_arm(args):
     return 0
 
 
+def simclr_arm(args):
+    """--workload simclr: BASELINE configs[2] (SimCLR, global all_gather negatives, 512 clips per GPU -> total batch
+    4096 at 8 GPUs, dim 256, T = 0.1) through the same module API: ContrastiveModel(simclr)([[f1], [f2]], index) +
+    loss.backward(), the two all_gathers (C4: rows, row sums) inside the timed region, CUDA-graph replay.
+    Not the headline (that is the MoCo step); one JSON line of the same shape, `roofline` on the tensor pipe."""
+    import torch.distributed as dist
+    import torch.nn as nn
+    from advise_video_ssl_b200 import contrastive as C
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the contrastive hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    json_out = sys.stdout
+    if world > 1:
+        sys.stdout.flush()
+        json_out = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        dist.init_process_group("nccl", device_id=dev)
+    B, D, T = 512, 256, 0.1
+
+    class Identity(nn.Module):
+        def __init__(self, cfg):
+            super().__init__()
+            self.dummy = nn.Parameter(torch.zeros(4))
+
+        def forward(self, x):
+            return x[0] if isinstance(x, (list, tuple)) else x
+
+    C._MODEL_TYPES["identity_embed"] = Identity
+    cfg = head_cfg(world)
+    cfg.MODEL.ARCH = "identity_embed"
+    cfg.CONTRASTIVE.TYPE, cfg.CONTRASTIVE.DIM, cfg.CONTRASTIVE.T = "simclr", D, T
+    cfg.CONTRASTIVE.QUEUE_LEN = 64
+    cfg.TRAIN.BATCH_SIZE = B * world
+    model = C.ContrastiveModel(cfg).to(dev).train()
+    g = torch.Generator().manual_seed(2000 + rank)
+    f1 = [torch.randn(B, D, generator=g).to(dev).requires_grad_(True) for _ in range(POOL)]
+    f2 = [torch.randn(B, D, generator=g).to(dev).requires_grad_(True) for _ in range(POOL)]
+    index = torch.arange(B, device=dev)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step(slot):
+        f1[slot].grad, f2[slot].grad = None, None
+        _, loss = model([[f1[slot]], [f2[slot]]], index, None, 0.0)
+        loss.backward()
+        return loss
+
+    for i in range(args.warmup):
+        step(i % POOL)
+    sync_all()
+    graph, graph_err, loss_t = None, None, None
+    if not args.no_graph:
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                for slot in range(POOL):
+                    loss_t = step(slot)
+            graph.replay()
+            sync_all()
+        except Exception as e:  # noqa: BLE001
+            graph, graph_err = None, "%s: %s" % (type(e).__name__, e)
+            torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sync_all()
+    if rank == 0:
+        sampler.start()
+    n_launch = (args.steps + POOL - 1) // POOL  # whole pools: steps rounded up to a multiple of POOL
+    steps = n_launch * POOL
+    t = Timer()
+    if world > 1 and graph is not None:
+        graph.replay()
+    t.a.record()
+    for i in range(n_launch):
+        if graph is not None:
+            graph.replay()
+        else:
+            for slot in range(POOL):
+                loss_t = step(slot)
+    t.b.record()
+    sync_all()
+    clocks = sampler.stop()
+    ms = t.ms()
+    if world > 1:
+        tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    per = ms / steps
+    N = B * world
+    flops = 3 * 2 * (2 * B) * (2 * N) * D  # this rank's rows: S for the row sums, S again and P.V for the gradient
+    peaks = {}
+    pth = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pth):
+        with open(pth) as f:
+            peaks = json.load(f)
+    peak_tf = float(peaks.get("bf16_tflops", 1590.0))
+    ach = flops / (per * 1e-3) / 1e12
+    if rank == 0:
+        json_out.write(json.dumps({
+            "metric": METRIC, "value": world * B / (per * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": per, "step_us": per * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 (kind::f16 operands on unit rows, fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": "configs[2] head: SimCLR NT-Xent, global all_gather negatives, 512 clips/GPU (total batch "
+                                   "%d), dim 256, T 0.1; l2norm + all_gather + row sums + all_gather + gradient + finalise; "
+                                   "backbone excluded" % N,
+                       "api": "ContrastiveModel(simclr).forward + loss.backward()", "cuda_graph": graph is not None,
+                       "cuda_graph_error": graph_err, "collectives": "2 x ncclAllGather per step inside the timed region" if world > 1 else "none",
+                       "parallelism": "dp%d, rows sharded: each rank computes its 2B rows against all 2N columns" % world},
+            "gpu_launches": 6 * steps,
+            "gpu_launches_note": "l2norm, prepare, rowsum, sum_z, grad, finish per step (+ torch cat / mul, NCCL)",
+            "clocks": clocks,
+            "roofline": {"kernel": "ntxent step (per-rank useful flops 3*2*(2B)(2N)D)", "bound": "tensor", "achieved": ach,
+                         "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops (kind::f16 runs at the bf16 rate)"},
+            "loss": float(loss_t.item()) if loss_t is not None else None}) + "\n")
+        json_out.flush()
+    if world > 1:
+        sync_all()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+    return 0
+
+
 def ops_level(args, ops, dist, dev, world, rank, impl, queue0, feats_h, kfeat_h, model, sync_all):
     """The two-launch kernel-only step of round 1, for comparison: EMA (+ the key push riding in the same
     launch) -> head (+ wait + enqueue).  Keys are pre-normalised device tensors, no autograd, no shuffle."""
@@ -685,6 +817,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ops-level", action="store_true", help="skip the secondary kernel-only (ops.*) measurement")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--workload", default="moco", choices=["moco", "simclr"],
+                    help="moco = BASELINE configs[1] (the headline); simclr = configs[2], an extra line")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: cross-GPU key gather over NVLink peer memory (default) or NCCL all_gather")
     args = ap.parse_args()
@@ -692,6 +826,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         return reference_arm(args)
+    if args.workload == "simclr":
+        return simclr_arm(args)
     return gpu_arm(args)
 
 
