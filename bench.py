@@ -42,7 +42,7 @@ import torch  # noqa: E402
 
 B_PER_GPU, DIM, QUEUE_LEN, TEMP, MOMENTUM = 64, 128, 65536, 0.1, 0.999
 POOL = 8  # distinct synthetic batches rotated through the steps
-EMA_DRAM_TRAFFIC = 383_585_280  # bytes per launch of the EMA kernel measured by ncu (289.0 MB read + 94.6 MB written, profiles/r1_ema_ncu.md)
+EMA_DRAM_TRAFFIC = 383_306_752  # bytes per launch of the EMA kernel measured by ncu (289.0 MB read + 94.3 MB written, profiles/r2_ema_ncu.md)
 WORKLOAD = ("configs[1] head: Slow-R50 MoCo, 2 views/clip, queue 65536, dim 128, batch 64/GPU; "
             "EMA(164 tensors, 36.1M fp32) + l2norm + logits + InfoNCE fwd/bwd + enqueue; backbone excluded")
 METRIC, UNIT = "contrastive_head_clips_per_sec", "clips/s"
@@ -560,7 +560,7 @@ def gpu_arm(args):
         "roofline": {"kernel": "ema_multi_tensor_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": EMA_DRAM_TRAFFIC,
                      "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch "
-                                       "(profiles/r1_ema_ncu.md)",
+                                       "(profiles/r2_ema_ncu.md)",
                      "bytes_per_launch": ema_bytes, "us_per_launch": ema_ms * 1e3, "peak_source": peak_src},
         "step_roofline": {"bytes_per_step": step_bytes, "floor_us": floor_us, "frac": floor_us / (ms_per_step * 1e3)},
         "loss": loss_val,

@@ -70,3 +70,37 @@ def test_committed_bench_lines_carry_every_contract_key():
             assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
         else:
             assert d["config"]["key_exchange_verified_vs_nccl"] is True
+
+
+def test_round2_bench_lines_go_through_the_module_api():
+    """Round 2: `value` / `e2e` are measured through contrastive_forward + backward; the kernel-only number sits
+    beside them, the strict end-to-end number is at the top level, and the N > 1 lines record the exchanges."""
+    prof = os.path.join(ROOT, "profiles")
+    top = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+           "vs_baseline", "dtype", "data", "config", "e2e", "e2e_strict", "ops_level", "gpu_launches", "clocks", "roofline",
+           "step_roofline"}
+    vals = {}
+    for n in (1, 2, 4, 8):
+        d = json.loads(open(os.path.join(prof, "r2_bench_n%d.json" % n)).read().strip().splitlines()[-1])
+        assert top <= set(d), (n, top - set(d))
+        assert d["n_gpus"] == n and d["metric"] == "contrastive_head_clips_per_sec" and d["dtype"] == "f32"
+        assert "contrastive_forward" in d["config"]["api"] and d["config"]["cuda_graph"] is True
+        assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+        assert d["e2e"]["value"] < d["value"] and d["e2e_strict"]["value"] <= d["e2e"]["value"]
+        assert d["ops_level"]["step_us"] < d["step_us"]  # the module adds autograd and the shuffle, never removes work
+        assert abs(d["value"] - n * 64 / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        r = d["roofline"]
+        assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0.5 < r["frac"] < 1.0
+        assert d["gpu_launches"] > 0
+        vals[n] = d["value"]
+        if n == 1:
+            assert d["step_roofline"]["frac"] >= 0.75
+            assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
+        else:
+            assert "NVLink" in d["config"]["key_exchange"]
+    assert vals[8] / (8 * vals[1]) >= 0.85  # north_star: weak-scaling efficiency at 8 GPUs
+    for n in (2, 8):
+        rep = json.loads(open(os.path.join(prof, "r2_multirank_parity_n%d.json" % n)).read())
+        assert rep["ok"] and rep["world"] == n and {"shuffle", "moco", "simclr", "bank"} <= set(rep)
+        assert all(v["queues_identical"] for k, v in rep["moco"].items() if not k.startswith("local"))
