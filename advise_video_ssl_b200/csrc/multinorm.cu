@@ -4,8 +4,10 @@
 //
 // Same flat chunk table as the momentum update (K1): one 256-thread CTA per four 4096-element
 // chunks, sixteen independent 128-bit streaming loads per thread, fp32 sum of squares per chunk written to a
-// partial array; a second one-CTA launch folds the partials per tensor (chunk order) and the
-// per-tensor norms into the total, all in a fixed order (deterministic, no fp atomics).
+// partial array.  The fold rides in the same launch: the CTA that completes the LAST chunk of a tensor (a per-tensor
+// arrival counter) sums that tensor's partials in chunk order, and the CTA that completes the last tensor adds the
+// squared norms in tensor order -- every sum has a fixed shape, so the result is deterministic (no fp atomics), and
+// there is no second launch behind the 144 MB stream (round 1: two launches, 0.59 of HBM).
 // HBM-bound: 4 bytes per element, read once.
 #include "common.cuh"
 
@@ -33,9 +35,21 @@ __device__ __forceinline__ void norm_block_sum_n(float (&v)[kN], float* scratch 
   }
 }
 
+__device__ __forceinline__ int tensor_of_chunk(const int* __restrict__ first_chunk, int n_tensors, int c) {
+  int lo = 0, hi = n_tensors;  // first_chunk[lo] <= c < first_chunk[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(first_chunk + mid) <= c) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
 __global__ void __launch_bounds__(kNormThreads)
-multi_l2norm_kernel(const avssl_ema_chunk* __restrict__ table, int n_chunks, float* __restrict__ partial) {
+multi_l2norm_kernel(const avssl_ema_chunk* __restrict__ table, int n_chunks, const int* __restrict__ first_chunk,
+                    int n_tensors, float* __restrict__ partial, float* __restrict__ sq, unsigned* __restrict__ tensor_done,
+                    unsigned* counter, float* __restrict__ per_tensor, float* __restrict__ total) {
   __shared__ float s_red[8 * kNormChunksPerCta];
+  __shared__ int s_fold[kNormChunksPerCta + 1];  // tensors this CTA has to fold (-1 = none), [last] = fold the total
   const int tid = threadIdx.x;
   const int c0 = blockIdx.x * kNormChunksPerCta;
   avssl_ema_chunk c[kNormChunksPerCta];
@@ -85,43 +99,77 @@ multi_l2norm_kernel(const avssl_ema_chunk* __restrict__ table, int n_chunks, flo
     for (int u = 1; u < kNormChunksPerCta; ++u) out = tid == u ? ss[u] : out;
     partial[c0 + tid] = out;
   }
-}
-
-// Second launch: one warp per tensor (lanes stride over its chunks in a fixed order) across
-// ceil(n_tensors / 8) CTAs; the last CTA to finish adds the squared norms in tensor order.
-constexpr int kFoldThreads = 256;
-__global__ void __launch_bounds__(kFoldThreads)
-multi_l2norm_fold_kernel(const int* __restrict__ first_chunk, int n_tensors, const float* __restrict__ partial,
-                         float* __restrict__ sq, float* __restrict__ per_tensor, float* __restrict__ total,
-                         unsigned* counter) {
-  __shared__ float s_red[32];
-  __shared__ unsigned s_last;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int t = blockIdx.x * (kFoldThreads / 32) + (tid >> 5);
-  if (t < n_tensors) {
-    const int k0 = __ldg(first_chunk + t), k1 = __ldg(first_chunk + t + 1);
-    float s = 0.f;
-    for (int k = k0 + lane; k < k1; k += 32) s += __ldcg(partial + k);
-    s = warp_sum(s);
-    if (lane == 0) {
-      sq[t] = s;
-      if (per_tensor) per_tensor[t] = sqrtf(s);
+  // ---- arrival: which tensors did this CTA complete?
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();  // this CTA's partials are visible before its arrivals
+    int n_fold = 0;
+    int u = 0;
+    while (u < kNormChunksPerCta && c0 + u < n_chunks) {
+      const int t = tensor_of_chunk(first_chunk, n_tensors, c0 + u);
+      const int t_end = __ldg(first_chunk + t + 1), t_begin = __ldg(first_chunk + t);
+      int cnt = 1;
+      while (u + cnt < kNormChunksPerCta && c0 + u + cnt < t_end) ++cnt;  // my chunks inside tensor t
+      const unsigned before = atomicAdd(tensor_done + t, (unsigned)cnt);
+      if (before + (unsigned)cnt == (unsigned)(t_end - t_begin)) s_fold[n_fold++] = t;
+      u += cnt;
     }
+    for (int k = n_fold; k < kNormChunksPerCta; ++k) s_fold[k] = -1;
+    s_fold[kNormChunksPerCta] = 0;
   }
   __syncthreads();
-  if (tid == 0) {
+  int n_arrived = 0;  // tensors this CTA reports complete beyond those it folds (thread 0's value is the one used)
+  if (blockIdx.x == 0) {
+    // tensors without elements own no chunk and would never arrive: CTA 0 reports them (norm 0)
+    int empties = 0;
+    for (int t = tid; t < n_tensors; t += kNormThreads) {
+      if (__ldg(first_chunk + t + 1) == __ldg(first_chunk + t)) {
+        ++empties;
+        sq[t] = 0.f;
+        if (per_tensor) per_tensor[t] = 0.f;
+      }
+    }
+    __syncthreads();
+    n_arrived = (int)(block_sum((float)empties, s_red) + 0.5f);
+  }
+  bool folded_any = blockIdx.x == 0 && n_arrived > 0;
+  for (int k = 0; k < kNormChunksPerCta; ++k) {
+    const int t = s_fold[k];
+    if (t < 0) break;  // uniform over the CTA
     __threadfence();
-    s_last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+    const int k0 = __ldg(first_chunk + t), k1 = __ldg(first_chunk + t + 1);
+    float a = 0.f;
+    for (int j = k0 + tid; j < k1; j += kNormThreads) a += __ldcg(partial + j);  // fixed thread <- chunk assignment
+    __syncthreads();
+    a = block_sum(a, s_red);
+    if (tid == 0) {
+      sq[t] = a;
+      if (per_tensor) per_tensor[t] = sqrtf(a);
+      tensor_done[t] = 0u;  // reusable: every chunk of t has arrived
+    }
+    folded_any = true;
   }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  float a = 0.f;
-  for (int k = tid; k < n_tensors; k += kFoldThreads) a += __ldcg(sq + k);
-  a = block_sum(a, s_red);
-  if (tid == 0) {
-    *total = sqrtf(a);  // norm(stack(norm_t)) = sqrt(sum_t norm_t^2)
-    *counter = 0u;
+  if (folded_any) {
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      int n = n_arrived;
+      for (int k = 0; k < kNormChunksPerCta; ++k) n += s_fold[k] >= 0;
+      const unsigned before = atomicAdd(counter, (unsigned)n);
+      s_fold[kNormChunksPerCta] = (before + (unsigned)n == (unsigned)n_tensors) ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_fold[kNormChunksPerCta]) {  // the last tensor is complete: norm(stack(norm_t)) = sqrt(sum_t norm_t^2)
+      __threadfence();
+      float a = 0.f;
+      for (int t = tid; t < n_tensors; t += kNormThreads) a += __ldcg(sq + t);
+      __syncthreads();
+      a = block_sum(a, s_red);
+      if (tid == 0) {
+        *total = sqrtf(a);
+        *counter = 0u;
+      }
+    }
   }
 }
 
@@ -133,7 +181,8 @@ using namespace avssl;
 
 extern "C" size_t avssl_multi_l2norm_workspace_bytes(int64_t n_chunks, int n_tensors) {
   if (n_chunks < 0 || n_tensors < 0) return 0;
-  return 256 + 4 * (size_t)n_chunks + 4 * (size_t)n_tensors + 256;  // counter | partial[n_chunks] | sq[n_tensors]
+  // counter | partial[n_chunks] | sq[n_tensors] | tensor_done[n_tensors]
+  return 256 + 4 * (size_t)n_chunks + 8 * (size_t)n_tensors + 256;
 }
 
 extern "C" int avssl_multi_l2norm(const avssl_ema_chunk* table_dev, int64_t n_chunks, const int32_t* first_chunk_dev,
@@ -154,12 +203,11 @@ extern "C" int avssl_multi_l2norm(const avssl_ema_chunk* table_dev, int64_t n_ch
   AVSSL_REQUIRE(table_dev && first_chunk_dev && n_tensors > 0, AVSSL_ERR_INVALID_ARGUMENT, "multi_l2norm: null table");
   float* partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
   const unsigned grid = (unsigned)((n_chunks + kNormChunksPerCta - 1) / kNormChunksPerCta);
-  multi_l2norm_kernel<<<grid, kNormThreads, 0, s>>>(table_dev, (int)n_chunks, partial);
-  AVSSL_LAUNCH_OK("multi_l2norm_kernel");
   float* sq = partial + n_chunks;
+  unsigned* tensor_done = reinterpret_cast<unsigned*>(sq + n_tensors);  // zero-filled once with the workspace, self-resetting
   unsigned* counter = static_cast<unsigned*>(workspace);
-  multi_l2norm_fold_kernel<<<(n_tensors + kFoldThreads / 32 - 1) / (kFoldThreads / 32), kFoldThreads, 0, s>>>(
-      first_chunk_dev, n_tensors, partial, sq, per_tensor_norm_out, total_norm_out, counter);
-  AVSSL_LAUNCH_OK("multi_l2norm_fold_kernel");
+  multi_l2norm_kernel<<<grid, kNormThreads, 0, s>>>(table_dev, (int)n_chunks, first_chunk_dev, n_tensors, partial, sq,
+                                                    tensor_done, counter, per_tensor_norm_out, total_norm_out);
+  AVSSL_LAUNCH_OK("multi_l2norm_kernel");
   return AVSSL_OK;
 }

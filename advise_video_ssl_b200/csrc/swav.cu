@@ -5,6 +5,7 @@
 #include <cooperative_groups.h>
 
 #include "common.cuh"
+#include "sm100_ptx.cuh"
 
 namespace avssl {
 
@@ -457,6 +458,154 @@ __global__ void __launch_bounds__(256) swav_ce_reg_kernel(const SwavCeArgs a) {
   }
 }
 
+
+// Persistent, pipelined variant of the register-resident kernel (the hot one at cfg5): about three CTAs per SM
+// walk the score rows; while a CTA reduces row i out of shared memory, ONE elected thread has the bulk-copy
+// engine (cp.async.bulk, completion on an mbarrier) landing row i+1 -- its scores and the code rows it needs --
+// in the other stage.  The one-CTA-per-row kernel only had loads in flight at the start of each CTA's short life
+// (load -> reduce -> reduce -> store, 1536 CTAs: 0.33 of HBM); here the loads of the next row overlap the two
+// block reductions and the store of the current one.  Per-thread arithmetic and the shape of every reduction are
+// those of swav_ce_reg_kernel, so the results are bit-identical to it.
+template <int kA>
+__global__ void __launch_bounds__(256) swav_ce_pipe_kernel(const SwavCeArgs a) {
+  extern __shared__ __align__(16) uint8_t pipe_smem[];
+  __shared__ float s_red[32 * (1 + 2 * kA)];
+  __shared__ unsigned s_last;
+  __shared__ __align__(8) uint64_t full[2];
+  const int tid = threadIdx.x;
+  const int P4 = a.P >> 2;
+  const int n_rows = a.n_crops * a.bs;
+  const uint32_t row_bytes = (uint32_t)a.P * 4u;
+  auto stage_ptr = [&](int st, int which) {  // which: 0 = scores, 1 + as = code set as
+    return reinterpret_cast<float4*>(pipe_smem + ((size_t)st * (1 + kA) + which) * row_bytes);
+  };
+  auto issue = [&](int row, int st) {  // thread 0 only
+    const int v = row / a.bs, r = row % a.bs;
+    uint32_t bytes = row_bytes;
+#pragma unroll
+    for (int as = 0; as < kA; ++as)
+      if (as < a.n_assign && a.w[as * a.n_crops + v] != 0.f) bytes += row_bytes;
+    ptx::mbar_arrive_expect_tx(&full[st], bytes);
+    ptx::bulk_load(stage_ptr(st, 0), a.scores + (size_t)row * a.P, row_bytes, &full[st]);
+#pragma unroll
+    for (int as = 0; as < kA; ++as)
+      if (as < a.n_assign && a.w[as * a.n_crops + v] != 0.f)
+        ptx::bulk_load(stage_ptr(st, 1 + as), a.codes + ((size_t)as * a.bs + r) * a.P, row_bytes, &full[st]);
+  };
+  if (tid == 0) {
+    ptx::mbar_init(&full[0], 1);
+    ptx::mbar_init(&full[1], 1);
+    ptx::mbar_fence_init();
+    if ((int)blockIdx.x < n_rows) issue(blockIdx.x, 0);
+  }
+  __syncthreads();
+
+  int it = 0;
+  for (int row = blockIdx.x; row < n_rows; row += gridDim.x, ++it) {
+    const int st = it & 1;
+    const int v = row / a.bs;
+    if (tid == 0 && row + (int)gridDim.x < n_rows) issue(row + gridDim.x, st ^ 1);  // stage st^1 was released by the barrier below
+    ptx::mbar_wait(&full[st], (it >> 1) & 1);
+
+    const float4* xs = stage_ptr(st, 0);
+    float4 x[kCeVec];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kCeVec; ++j) {
+      const int c = tid + j * 256;
+      if (c < P4) {
+        x[j] = xs[c];
+        x[j].x *= a.inv_T; x[j].y *= a.inv_T; x[j].z *= a.inv_T; x[j].w *= a.inv_T;
+        mx = fmaxf(mx, fmaxf(fmaxf(x[j].x, x[j].y), fmaxf(x[j].z, x[j].w)));
+      } else {
+        x[j] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      }
+    }
+    float wa[kA];
+    float4 cd[kA][kCeVec];
+#pragma unroll
+    for (int as = 0; as < kA; ++as) {
+      wa[as] = as < a.n_assign ? a.w[as * a.n_crops + v] : 0.f;
+      const float4* c4 = stage_ptr(st, 1 + as);
+#pragma unroll
+      for (int j = 0; j < kCeVec; ++j) {
+        const int c = tid + j * 256;
+        cd[as][j] = (wa[as] != 0.f && c < P4) ? c4[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    mx = warp_max(mx);
+    __syncthreads();  // s_red of the previous row is dead
+    if ((tid & 31) == 0) s_red[tid >> 5] = mx;
+    __syncthreads();  // ... and every thread has read stage st: it may be refilled after the next iteration's issue
+    mx = s_red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, s_red[w]);
+
+    float red[1 + 2 * kA];
+#pragma unroll
+    for (int i = 0; i < 1 + 2 * kA; ++i) red[i] = 0.f;
+    float4 e[kCeVec];
+#pragma unroll
+    for (int j = 0; j < kCeVec; ++j) {
+      e[j] = make_float4(__expf(x[j].x - mx), __expf(x[j].y - mx), __expf(x[j].z - mx), __expf(x[j].w - mx));
+      red[0] += (e[j].x + e[j].y) + (e[j].z + e[j].w);
+      const bool in = tid + j * 256 < P4;
+#pragma unroll
+      for (int as = 0; as < kA; ++as) {
+        const float4 c = cd[as][j];
+        if (in) {
+          red[1 + 2 * as] = fmaf(c.x, x[j].x, fmaf(c.y, x[j].y, fmaf(c.z, x[j].z, fmaf(c.w, x[j].w, red[1 + 2 * as]))));
+          red[2 + 2 * as] += (c.x + c.y) + (c.z + c.w);
+        }
+      }
+    }
+    block_sum_n<1 + 2 * kA>(red, s_red);
+    const float lse = mx + logf(red[0]);
+    float loss = 0.f, wsum = 0.f;
+#pragma unroll
+    for (int as = 0; as < kA; ++as) {
+      loss += wa[as] * (lse * red[2 + 2 * as] - red[1 + 2 * as]);
+      wsum += wa[as] * red[2 + 2 * as];
+    }
+    if (a.dscores) {
+      float4* d4 = reinterpret_cast<float4*>(a.dscores + (size_t)row * a.P);
+      const float pscale = wsum / red[0];
+#pragma unroll
+      for (int j = 0; j < kCeVec; ++j) {
+        const int c = tid + j * 256;
+        if (c < P4) {
+          float4 g = make_float4(e[j].x * pscale, e[j].y * pscale, e[j].z * pscale, e[j].w * pscale);
+#pragma unroll
+          for (int as = 0; as < kA; ++as) {
+            g.x = fmaf(-wa[as], cd[as][j].x, g.x);
+            g.y = fmaf(-wa[as], cd[as][j].y, g.y);
+            g.z = fmaf(-wa[as], cd[as][j].z, g.z);
+            g.w = fmaf(-wa[as], cd[as][j].w, g.w);
+          }
+          st_stream(d4 + c, make_float4(g.x * a.inv_T, g.y * a.inv_T, g.z * a.inv_T, g.w * a.inv_T));
+        }
+      }
+    }
+    if (tid == 0) a.row_loss[row] = loss;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    s_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    float tot = 0.f;
+    for (int i = tid; i < n_rows; i += blockDim.x) tot += __ldcg(a.row_loss + i);
+    tot = block_sum(tot, s_red);
+    if (tid == 0) {
+      *a.loss_out = tot;
+      *a.counter = 0u;
+    }
+  }
+}
+
 }  // namespace avssl
 
 using namespace avssl;
@@ -593,7 +742,19 @@ extern "C" int avssl_swav_ce_fwd_bwd(const float* scores, const float* codes, in
                         ((reinterpret_cast<uintptr_t>(scores) | reinterpret_cast<uintptr_t>(codes) |
                           reinterpret_cast<uintptr_t>(dscores_out)) & 15u) == 0;
   // more than two code sets (never produced by the reference: two global crops) take the generic kernel
-  if (reg_path && n_assign <= 2)
+  const size_t pipe_smem = (size_t)2 * 3 * P * 4;  // two stages x (scores + two code rows)
+  if (reg_path && n_assign <= 2 && pipe_smem <= 200 * 1024 && n_crops * bs >= 2 * sm_count()) {
+    // persistent + bulk-copy pipeline: as many CTAs as fit (about three per SM at P = 3000)
+    static unsigned long long configured = 0ull;
+    if (first_use_on_device(configured))
+      AVSSL_CUDA_OK(cudaFuncSetAttribute(swav_ce_pipe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    int per_sm = (int)((220 * 1024) / (pipe_smem + 2048));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    int grid = sm_count() * per_sm;
+    if (grid > n_crops * bs) grid = n_crops * bs;
+    swav_ce_pipe_kernel<2><<<grid, 256, pipe_smem, static_cast<cudaStream_t>(stream)>>>(a);
+  } else if (reg_path && n_assign <= 2)
     swav_ce_reg_kernel<2><<<n_crops * bs, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   else
     swav_ce_kernel<<<n_crops * bs, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
