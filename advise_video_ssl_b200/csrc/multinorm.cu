@@ -35,104 +35,18 @@ __device__ __forceinline__ void norm_block_sum_n(float (&v)[kN], float* scratch 
   }
 }
 
-__device__ __forceinline__ int tensor_of_chunk(const int* __restrict__ first_chunk, int n_tensors, int c) {
-  int lo = 0, hi = n_tensors;  // first_chunk[lo] <= c < first_chunk[hi]
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (__ldg(first_chunk + mid) <= c) lo = mid; else hi = mid;
-  }
-  return lo;
-}
-
-__global__ void __launch_bounds__(kNormThreads)
-multi_l2norm_kernel(const avssl_ema_chunk* __restrict__ table, int n_chunks, const int* __restrict__ first_chunk,
-                    int n_tensors, float* __restrict__ partial, float* __restrict__ sq, unsigned* __restrict__ tensor_done,
-                    unsigned* counter, float* __restrict__ per_tensor, float* __restrict__ total) {
-  __shared__ float s_red[8 * kNormChunksPerCta];
-  __shared__ int s_fold[kNormChunksPerCta + 1];  // tensors this CTA has to fold (-1 = none), [last] = fold the total
+// Persistent kernel: 2 CTAs per SM walk groups of kNormChunksPerCta chunks.  Per group: 16 independent 128-bit
+// streaming loads per thread, a block reduction per chunk, the partials to memory -- and then ONE thread does the
+// arrival bookkeeping (a counter per tensor; the chunk table carries the tensor index in flags[31:8]) while the
+// other threads already issue the loads of the next group, so the bookkeeping latency hides under the stream.
+// Whatever tensors the arrivals completed are folded (by the whole CTA, in chunk order) one iteration later.
+__device__ __forceinline__ void norm_fold_tensors(const int* s_fold, const int* __restrict__ first_chunk, int n_tensors,
+                                                  const float* __restrict__ partial, float* __restrict__ sq,
+                                                  unsigned* __restrict__ tensor_done, unsigned* counter,
+                                                  float* __restrict__ per_tensor, float* __restrict__ total, float* s_red,
+                                                  int* s_flag, int extra_arrivals) {
   const int tid = threadIdx.x;
-  const int c0 = blockIdx.x * kNormChunksPerCta;
-  avssl_ema_chunk c[kNormChunksPerCta];
-  bool fast = true;
-#pragma unroll
-  for (int u = 0; u < kNormChunksPerCta; ++u) {
-    if (c0 + u < n_chunks) {
-      c[u] = table[c0 + u];
-    } else {
-      c[u].online = nullptr;
-      c[u].n = 0;
-      c[u].flags = 1u;
-    }
-    fast = fast && (c[u].flags & 1u) && c[u].n == (uint32_t)kNormChunk;
-  }
-  float ss[kNormChunksPerCta];
-  if (fast) {  // all loads of the CTA's chunks in flight before the first use
-    float4 v[kNormChunksPerCta][4];
-#pragma unroll
-    for (int u = 0; u < kNormChunksPerCta; ++u) {
-      const float4* x4 = reinterpret_cast<const float4*>(c[u].online) + tid;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) v[u][k] = ldg_stream(x4 + k * kNormThreads);
-    }
-#pragma unroll
-    for (int u = 0; u < kNormChunksPerCta; ++u) {
-      float a[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) a[k] = v[u][k].x * v[u][k].x + v[u][k].y * v[u][k].y + v[u][k].z * v[u][k].z + v[u][k].w * v[u][k].w;
-      ss[u] = (a[0] + a[1]) + (a[2] + a[3]);
-    }
-  } else {
-#pragma unroll
-    for (int u = 0; u < kNormChunksPerCta; ++u) {
-      float a = 0.f;
-      for (uint32_t i = tid; i < c[u].n; i += kNormThreads) {
-        const float x = c[u].online[i];
-        a = fmaf(x, x, a);
-      }
-      ss[u] = a;
-    }
-  }
-  norm_block_sum_n<kNormChunksPerCta>(ss, s_red);
-  if (tid < kNormChunksPerCta && c0 + tid < n_chunks) {
-    float out = ss[0];
-#pragma unroll
-    for (int u = 1; u < kNormChunksPerCta; ++u) out = tid == u ? ss[u] : out;
-    partial[c0 + tid] = out;
-  }
-  // ---- arrival: which tensors did this CTA complete?
-  __syncthreads();
-  if (tid == 0) {
-    __threadfence();  // this CTA's partials are visible before its arrivals
-    int n_fold = 0;
-    int u = 0;
-    while (u < kNormChunksPerCta && c0 + u < n_chunks) {
-      const int t = tensor_of_chunk(first_chunk, n_tensors, c0 + u);
-      const int t_end = __ldg(first_chunk + t + 1), t_begin = __ldg(first_chunk + t);
-      int cnt = 1;
-      while (u + cnt < kNormChunksPerCta && c0 + u + cnt < t_end) ++cnt;  // my chunks inside tensor t
-      const unsigned before = atomicAdd(tensor_done + t, (unsigned)cnt);
-      if (before + (unsigned)cnt == (unsigned)(t_end - t_begin)) s_fold[n_fold++] = t;
-      u += cnt;
-    }
-    for (int k = n_fold; k < kNormChunksPerCta; ++k) s_fold[k] = -1;
-    s_fold[kNormChunksPerCta] = 0;
-  }
-  __syncthreads();
-  int n_arrived = 0;  // tensors this CTA reports complete beyond those it folds (thread 0's value is the one used)
-  if (blockIdx.x == 0) {
-    // tensors without elements own no chunk and would never arrive: CTA 0 reports them (norm 0)
-    int empties = 0;
-    for (int t = tid; t < n_tensors; t += kNormThreads) {
-      if (__ldg(first_chunk + t + 1) == __ldg(first_chunk + t)) {
-        ++empties;
-        sq[t] = 0.f;
-        if (per_tensor) per_tensor[t] = 0.f;
-      }
-    }
-    __syncthreads();
-    n_arrived = (int)(block_sum((float)empties, s_red) + 0.5f);
-  }
-  bool folded_any = blockIdx.x == 0 && n_arrived > 0;
+  int n_done = extra_arrivals;
   for (int k = 0; k < kNormChunksPerCta; ++k) {
     const int t = s_fold[k];
     if (t < 0) break;  // uniform over the CTA
@@ -147,30 +61,134 @@ multi_l2norm_kernel(const avssl_ema_chunk* __restrict__ table, int n_chunks, con
       if (per_tensor) per_tensor[t] = sqrtf(a);
       tensor_done[t] = 0u;  // reusable: every chunk of t has arrived
     }
-    folded_any = true;
+    ++n_done;
   }
-  if (folded_any) {
+  if (n_done == 0) return;
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    const unsigned before = atomicAdd(counter, (unsigned)n_done);
+    *s_flag = (before + (unsigned)n_done == (unsigned)n_tensors) ? 1 : 0;
+  }
+  __syncthreads();
+  if (*s_flag) {  // the last tensor is complete: norm(stack(norm_t)) = sqrt(sum_t norm_t^2), tensor order
+    __threadfence();
+    float a = 0.f;
+    for (int t = tid; t < n_tensors; t += kNormThreads) a += __ldcg(sq + t);
     __syncthreads();
+    a = block_sum(a, s_red);
     if (tid == 0) {
-      __threadfence();
-      int n = n_arrived;
-      for (int k = 0; k < kNormChunksPerCta; ++k) n += s_fold[k] >= 0;
-      const unsigned before = atomicAdd(counter, (unsigned)n);
-      s_fold[kNormChunksPerCta] = (before + (unsigned)n == (unsigned)n_tensors) ? 1 : 0;
+      *total = sqrtf(a);
+      *counter = 0u;
     }
-    __syncthreads();
-    if (s_fold[kNormChunksPerCta]) {  // the last tensor is complete: norm(stack(norm_t)) = sqrt(sum_t norm_t^2)
-      __threadfence();
-      float a = 0.f;
-      for (int t = tid; t < n_tensors; t += kNormThreads) a += __ldcg(sq + t);
-      __syncthreads();
-      a = block_sum(a, s_red);
-      if (tid == 0) {
-        *total = sqrtf(a);
-        *counter = 0u;
+  }
+}
+
+__global__ void __launch_bounds__(kNormThreads, 2)
+multi_l2norm_kernel(const avssl_ema_chunk* __restrict__ table, int n_chunks, const int* __restrict__ first_chunk,
+                    int n_tensors, float* __restrict__ partial, float* __restrict__ sq, unsigned* __restrict__ tensor_done,
+                    unsigned* counter, float* __restrict__ per_tensor, float* __restrict__ total) {
+  __shared__ float s_red[8 * kNormChunksPerCta + 32];
+  __shared__ int s_fold[2][kNormChunksPerCta];  // tensors completed by this CTA's arrivals of the previous iteration
+  __shared__ int s_flag;
+  const int tid = threadIdx.x;
+  const int n_groups = (n_chunks + kNormChunksPerCta - 1) / kNormChunksPerCta;
+  if (tid < 2 * kNormChunksPerCta) (&s_fold[0][0])[tid] = -1;
+
+  // tensors without elements own no chunk and would never arrive: CTA 0 reports them (norm 0)
+  int empties = 0;
+  if (blockIdx.x == 0) {
+    for (int t = tid; t < n_tensors; t += kNormThreads) {
+      if (__ldg(first_chunk + t + 1) == __ldg(first_chunk + t)) {
+        ++empties;
+        sq[t] = 0.f;
+        if (per_tensor) per_tensor[t] = 0.f;
       }
     }
+    __syncthreads();
+    empties = (int)(block_sum((float)empties, s_red) + 0.5f);
   }
+  __syncthreads();
+
+  int it = 0;
+  for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++it) {
+    const int c0 = g * kNormChunksPerCta;
+    // ---- issue this group's loads
+    avssl_ema_chunk c[kNormChunksPerCta];
+    bool fast = true;
+#pragma unroll
+    for (int u = 0; u < kNormChunksPerCta; ++u) {
+      if (c0 + u < n_chunks) {
+        c[u] = table[c0 + u];
+      } else {
+        c[u].online = nullptr;
+        c[u].n = 0;
+        c[u].flags = 1u;
+      }
+      fast = fast && (c[u].flags & 1u) && c[u].n == (uint32_t)kNormChunk;
+    }
+    float4 v[kNormChunksPerCta][4];
+    if (fast) {
+#pragma unroll
+      for (int u = 0; u < kNormChunksPerCta; ++u) {
+        const float4* x4 = reinterpret_cast<const float4*>(c[u].online) + tid;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[u][k] = ldg_stream(x4 + k * kNormThreads);
+      }
+    }
+    // ---- fold what the previous iteration's arrivals completed (its bookkeeping ran under the loads above)
+    __syncthreads();
+    norm_fold_tensors(s_fold[(it + 1) & 1], first_chunk, n_tensors, partial, sq, tensor_done, counter, per_tensor, total,
+                      s_red + 8 * kNormChunksPerCta, &s_flag, 0);
+    // ---- this group's sums of squares
+    float ss[kNormChunksPerCta];
+    if (fast) {
+#pragma unroll
+      for (int u = 0; u < kNormChunksPerCta; ++u) {
+        float a[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a[k] = v[u][k].x * v[u][k].x + v[u][k].y * v[u][k].y + v[u][k].z * v[u][k].z + v[u][k].w * v[u][k].w;
+        ss[u] = (a[0] + a[1]) + (a[2] + a[3]);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < kNormChunksPerCta; ++u) {
+        float a = 0.f;
+        for (uint32_t i = tid; i < c[u].n; i += kNormThreads) {
+          const float x = c[u].online[i];
+          a = fmaf(x, x, a);
+        }
+        ss[u] = a;
+      }
+    }
+    __syncthreads();  // s_red of the fold above is dead
+    norm_block_sum_n<kNormChunksPerCta>(ss, s_red);
+    if (tid < kNormChunksPerCta && c0 + tid < n_chunks) {
+      float out = ss[0];
+#pragma unroll
+      for (int u = 1; u < kNormChunksPerCta; ++u) out = tid == u ? ss[u] : out;
+      partial[c0 + tid] = out;
+    }
+    __syncthreads();  // the partials of this group are written (ordered before thread 0's fence)
+    if (tid == 0) {   // arrival bookkeeping; everybody else runs ahead into the next group's loads
+      __threadfence();
+      int n_fold = 0, u = 0;
+      int* out = s_fold[it & 1];
+      while (u < kNormChunksPerCta && c0 + u < n_chunks) {
+        const int t = (int)(c[u].flags >> 8);
+        int cnt = 1;
+        while (u + cnt < kNormChunksPerCta && c0 + u + cnt < n_chunks && (int)(c[u + cnt].flags >> 8) == t) ++cnt;
+        const unsigned len = (unsigned)(__ldg(first_chunk + t + 1) - __ldg(first_chunk + t));
+        if (atomicAdd(tensor_done + t, (unsigned)cnt) + (unsigned)cnt == len) out[n_fold++] = t;
+        u += cnt;
+      }
+      for (int k = n_fold; k < kNormChunksPerCta; ++k) out[k] = -1;
+    }
+  }
+  // ---- what the last iteration completed (and CTA 0's empty tensors)
+  __syncthreads();
+  norm_fold_tensors(s_fold[(it + 1) & 1], first_chunk, n_tensors, partial, sq, tensor_done, counter, per_tensor, total,
+                    s_red + 8 * kNormChunksPerCta, &s_flag, blockIdx.x == 0 ? empties : 0);
 }
 
 __global__ void multi_l2norm_empty_kernel(float* total) { *total = 0.f; }
@@ -202,7 +220,9 @@ extern "C" int avssl_multi_l2norm(const avssl_ema_chunk* table_dev, int64_t n_ch
   }
   AVSSL_REQUIRE(table_dev && first_chunk_dev && n_tensors > 0, AVSSL_ERR_INVALID_ARGUMENT, "multi_l2norm: null table");
   float* partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
-  const unsigned grid = (unsigned)((n_chunks + kNormChunksPerCta - 1) / kNormChunksPerCta);
+  const unsigned n_groups = (unsigned)((n_chunks + kNormChunksPerCta - 1) / kNormChunksPerCta);
+  const unsigned cap = 2u * (unsigned)sm_count();  // persistent: two CTAs per SM (64 KiB in flight each)
+  const unsigned grid = n_groups < cap ? n_groups : cap;
   float* sq = partial + n_chunks;
   unsigned* tensor_done = reinterpret_cast<unsigned*>(sq + n_tensors);  // zero-filled once with the workspace, self-resetting
   unsigned* counter = static_cast<unsigned*>(workspace);
