@@ -156,7 +156,7 @@ extern "C" int avssl_ema_plan_fill(const uint64_t* online_ptrs_host, const uint6
       c.online = reinterpret_cast<const float*>(po + 4ull * off);
       c.hist = reinterpret_cast<float*>(ph + 4ull * off);
       c.n = (uint32_t)n;
-      c.flags = ((((po + 4ull * off) | (ph + 4ull * off)) & 15u) == 0 ? 1u : 0u) | ((uint32_t)t << 8);
+      c.flags = (((po + 4ull * off) | (ph + 4ull * off)) & 15u) == 0 ? 1u : 0u;
     }
   }
   return AVSSL_OK;

@@ -68,7 +68,7 @@ typedef struct {
   const float* online; /* start of this chunk in the online (query) encoder tensor */
   float* hist;         /* same offset in the momentum (key) encoder tensor         */
   uint32_t n;          /* elements in this chunk (<= chunk_elems)                  */
-  uint32_t flags;      /* bit0: both pointers 16-byte aligned; bits [31:8]: index of the tensor */
+  uint32_t flags;      /* bit0: both pointers 16-byte aligned                      */
 } avssl_ema_chunk;
 
 /* Elements per chunk used by the kernel's fast path. */
