@@ -482,6 +482,15 @@ def gpu_arm(args):
     e2e_mode = "one step in flight: step i+1 is submitted before the host waits for and reads the loss of step i"
     model.check_device_status()
 
+    # ---- C9 evidence in the line itself: after all those steps every rank must hold the same queue / ptr / iter
+    queue_consistent = None
+    if world > 1:
+        probe = torch.stack([model.queue_x.view(torch.int32).to(torch.int64).sum(), model.ptr[0], model.iter[0],
+                             (model.queue_x.view(torch.int32).to(torch.int64) * torch.arange(1, DIM + 1, device=dev)).sum()])
+        allp = [torch.empty_like(probe) for _ in range(world)]
+        dist.all_gather(allp, probe)
+        queue_consistent = bool(all(torch.equal(allp[0], t_) for t_ in allp))
+
     # ================================================ the ops-level step (kernel-only, as in round 1)
     # also yields the duration of the dominant kernel (the EMA): CUDA events around its launch inside the eager
     # two-launch sequence, where the host keeps ahead of the GPU (event records cannot be timed inside a captured
@@ -541,7 +550,8 @@ def gpu_arm(args):
                                     "on a side stream under the EMA" if deferred_path and world > 1 else
                                     ("NCCL all-to-all on a side stream under the EMA" if world > 1
                                      else "local row gather on a side stream under the EMA")),
-                   "parallelism": "dp%d (queue/EMA replicated, batch sharded; exchanges: shuffle all-to-all, keys)" % n_gpus,
+                   "queue_ptr_iter_identical_across_ranks": queue_consistent,
+                   "parallelism": "dp%d (queue/EMA replicated, batch sharded; exchanges: shuffle rows, keys)" % n_gpus,
                    "l2": "no explicit flush: one step streams %.0f MB (> 126 MB L2) so nothing survives between steps" % (step_bytes / 1e6)},
         "e2e": dict(per_step(e2e_ms), h2d_bytes_per_step=2 * 4 * B_PER_GPU * DIM, d2h_bytes_per_step=4, mode=e2e_mode,
                     strict_sync=per_step(e2e_strict_ms),
