@@ -65,9 +65,9 @@ SIGNATURES = {
     "avssl_ce_target0_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "avssl_ntxent_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "avssl_ntxent_prepare": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
-    "avssl_ntxent_rowsum": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_size_t,
+    "avssl_ntxent_rowsum": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_size_t,
                                     c_int, c_void_p]),
-    "avssl_ntxent_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float,
+    "avssl_ntxent_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float,
                                   c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "avssl_sinkhorn_workspace_bytes": (c_size_t, [c_int, c_int]),
     "avssl_sinkhorn": (c_int, [c_void_p, c_int, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -299,7 +299,7 @@ extern "C" size_t avssl_ntxent_workspace_bytes(int N2, int D, int n_loc) {
   return 256 + 4 * ((size_t)N2 + 64) + 4 * 64 * ((size_t)n_loc + 64) + 4 * 64 * (size_t)n_loc * D + 1024;
 }
 
-static int ntx_setup(NtxArgs& a, const float* out, const void* out_f16, const int* rows, const float* z_all, int N2, int D, int n_loc,
+static int ntx_setup(NtxArgs& a, const float* out, const void* out_f16, const int* rows, int row0_first, int row1_first, const float* z_all, int N2, int D, int n_loc,
                      float T, void* workspace, size_t workspace_bytes, int impl, bool* use_tc, const char* who) {
   AVSSL_REQUIRE(out && rows && workspace, AVSSL_ERR_INVALID_ARGUMENT, "%s: null pointer", who);
   AVSSL_REQUIRE(N2 > 0 && (N2 % 2) == 0 && n_loc > 0 && n_loc <= N2 && T > 0.f, AVSSL_ERR_INVALID_ARGUMENT,
@@ -309,6 +309,8 @@ static int ntx_setup(NtxArgs& a, const float* out, const void* out_f16, const in
   a.out = out;
   a.out_f16 = static_cast<const uint16_t*>(out_f16);
   a.rows = rows;
+  a.q_row0 = row0_first;
+  a.q_row1 = row1_first;
   a.z_all = z_all;
   a.N2 = N2;
   a.D = D;
@@ -316,7 +318,8 @@ static int ntx_setup(NtxArgs& a, const float* out, const void* out_f16, const in
   a.inv_T = 1.f / T;
   AVSSL_REQUIRE(impl == AVSSL_IMPL_AUTO || impl == AVSSL_IMPL_SIMT || impl == AVSSL_IMPL_TC1X, AVSSL_ERR_INVALID_ARGUMENT,
                 "%s: impl must be AVSSL_IMPL_AUTO, AVSSL_IMPL_SIMT or AVSSL_IMPL_TC1X (got %d)", who, impl);
-  *use_tc = impl != AVSSL_IMPL_SIMT && ntxent_tc_supported(N2, D, n_loc) && out_f16 != nullptr &&
+  *use_tc = impl != AVSSL_IMPL_SIMT && ntxent_tc_supported(N2, D, n_loc) && out_f16 != nullptr && row0_first >= 0 && row1_first >= 0 &&
+            n_loc % 2 == 0 && row0_first + n_loc / 2 <= N2 && row1_first + n_loc / 2 <= N2 &&
             (reinterpret_cast<uintptr_t>(out_f16) & 15u) == 0;
   AVSSL_REQUIRE(*use_tc || impl != AVSSL_IMPL_TC1X, AVSSL_ERR_UNSUPPORTED,
                 "%s: the tcgen05 kernel needs D in {64,128,256} and a 16-byte aligned fp16 copy of `out` "
@@ -374,11 +377,12 @@ extern "C" int avssl_ntxent_prepare(const float* gathered, int world, int B, int
   return AVSSL_OK;
 }
 
-extern "C" int avssl_ntxent_rowsum(const float* out, const void* out_f16, const int* rows, int N2, int D, int n_loc, float T,
+extern "C" int avssl_ntxent_rowsum(const float* out, const void* out_f16, const int* rows, int row0_first,
+                                   int row1_first, int N2, int D, int n_loc, float T,
                                    float* z_loc_out, void* workspace, size_t workspace_bytes, int impl, void* stream) {
   NtxArgs a;
   bool use_tc = false;
-  int rc = ntx_setup(a, out, out_f16, rows, nullptr, N2, D, n_loc, T, workspace, workspace_bytes, impl, &use_tc, "ntxent_rowsum");
+  int rc = ntx_setup(a, out, out_f16, rows, row0_first, row1_first, nullptr, N2, D, n_loc, T, workspace, workspace_bytes, impl, &use_tc, "ntxent_rowsum");
   if (rc) return rc;
   AVSSL_REQUIRE(z_loc_out, AVSSL_ERR_INVALID_ARGUMENT, "ntxent_rowsum: null output");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -389,12 +393,13 @@ extern "C" int avssl_ntxent_rowsum(const float* out, const void* out_f16, const 
   return AVSSL_OK;
 }
 
-extern "C" int avssl_ntxent_grad(const float* out, const void* out_f16, const int* rows, const float* z_all, const float* norm_loc, int N2,
+extern "C" int avssl_ntxent_grad(const float* out, const void* out_f16, const int* rows, int row0_first,
+                                 int row1_first, const float* z_all, const float* norm_loc, int N2,
                                  int D, int n_loc, float T, float grad_scale, float* loss_out, float* dfeat_out,
                                  void* workspace, size_t workspace_bytes, int impl, void* stream) {
   NtxArgs a;
   bool use_tc = false;
-  int rc = ntx_setup(a, out, out_f16, rows, z_all, N2, D, n_loc, T, workspace, workspace_bytes, impl, &use_tc, "ntxent_grad");
+  int rc = ntx_setup(a, out, out_f16, rows, row0_first, row1_first, z_all, N2, D, n_loc, T, workspace, workspace_bytes, impl, &use_tc, "ntxent_grad");
   if (rc) return rc;
   AVSSL_REQUIRE(z_all && norm_loc && loss_out && dfeat_out, AVSSL_ERR_INVALID_ARGUMENT, "ntxent_grad: null pointer");
   AVSSL_REQUIRE(((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(dfeat_out)) & 15u) == 0,

@@ -10,6 +10,7 @@ struct NtxArgs {
   const float* out;     // [N2, D] unit rows, global order
   const uint16_t* out_f16;  // the same rows as fp16 (operands of the tcgen05 kernels); may be null for SIMT
   const int* rows;      // [n_loc] global row ids handled here
+  int q_row0, q_row1;   // tcgen05 kernels: rows[0 .. n_loc/2) = q_row0 + i, rows[n_loc/2 .. n_loc) = q_row1 + (i - n_loc/2)
   const float* z_all;   // [N2] (pass 2)
   int N2, D, n_loc;
   float inv_T;

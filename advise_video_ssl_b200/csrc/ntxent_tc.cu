@@ -55,12 +55,19 @@ struct NtCfg {
   static constexpr int kKB = D / 64;                 // 128-byte boxes (64 fp16) per row
   static constexpr int kBoxBytes = kBJ * 128;        // one TMA box: 64 rows x 128 B
   static constexpr int kTileBytes = kKB * kBoxBytes; // 32 KiB at D = 256
-  static constexpr int kColQ = 0, kColS = D / 2, kColAcc = D / 2 + 2 * kBJ;
-  static constexpr int kColsNeeded = D / 2 + 2 * kBJ + (kGrad ? D : 0);
+  // Q (the CTA's 128 rows, fp16) lives in SHARED memory as the K-major A operand, landed by TMA like the tiles:
+  // no per-thread row loads and no TMEM stores in the prologue (round 2, first version: 128 strided 512-byte row
+  // reads per CTA, ~2 us before the first MMA of both passes)
+  static constexpr int kQBoxBytes = kMt * 128;          // one TMA box of Q: 128 rows x 128 B
+  static constexpr int kQBytes = kKB * kQBoxBytes;      // 64 KiB at D = 256
+  static constexpr int kColS = 0, kColAcc = 2 * kBJ;
+  static constexpr int kColsNeeded = 2 * kBJ + (kGrad ? D : 0);
   static constexpr int kTmemCols = kColsNeeded <= 128 ? 128 : (kColsNeeded <= 256 ? 256 : 512);
   static_assert(kColsNeeded <= 512, "TMEM budget");
-  static constexpr int kSlots = (192 * 1024 / kTileBytes) < kMaxSlots ? (192 * 1024 / kTileBytes) : kMaxSlots;
-  static constexpr size_t kSmemBytes = 1024 + (size_t)kSlots * kTileBytes + 8 * kHalfCols * 4 + 512;
+  static constexpr int kRingBudget = 208 * 1024 - kQBytes;
+  static constexpr int kSlots = (kRingBudget / kTileBytes) < kMaxSlots ? (kRingBudget / kTileBytes) : kMaxSlots;
+  static_assert(kSlots >= 2, "at least a double buffer");
+  static constexpr size_t kSmemBytes = 1024 + (size_t)kQBytes + (size_t)kSlots * kTileBytes + 8 * kHalfCols * 4 + 512;
 };
 
 struct NtBarriers {
@@ -72,14 +79,15 @@ struct NtBarriers {
 
 template <int D, bool kGrad>
 __global__ void __launch_bounds__(kNtThreads, 1)
-ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap) {
+ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_q) {
   using C = NtCfg<D, kGrad>;
   constexpr int kSlots = C::kSlots;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
-  uint8_t* ring = smem;
-  float* invz_c = reinterpret_cast<float*>(smem + kSlots * C::kTileBytes);  // [8 softmax warps][32]: 1/Z of the warp's columns
-  NtBarriers* bar = reinterpret_cast<NtBarriers*>(smem + kSlots * C::kTileBytes + 8 * kHalfCols * 4);
+  uint8_t* q_smem = smem;
+  uint8_t* ring = smem + C::kQBytes;
+  float* invz_c = reinterpret_cast<float*>(ring + kSlots * C::kTileBytes);  // [8 softmax warps][32]: 1/Z of the warp's columns
+  NtBarriers* bar = reinterpret_cast<NtBarriers*>(ring + kSlots * C::kTileBytes + 8 * kHalfCols * 4);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int split = blockIdx.x;
@@ -87,9 +95,14 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap) {
   const int j_begin = split * a.cols_per_split;
   const int j_end = min(a.N2, j_begin + a.cols_per_split);
   const int n_tiles = (j_end - j_begin + kBJ - 1) / kBJ;
+  // local rows [0, half) are global rows q_row0.., local rows [half, n_loc) global rows q_row1..: a CTA whose 128 rows
+  // stay inside one of the two blocks gets Q by TMA; one that straddles them copies the rows itself (same layout)
+  const int half = a.n_loc / 2;
+  const bool q_by_tma = (i_base + kMt <= half) || (i_base >= half);
 
   if (warp == 0 && lane == 0) {
     ptx::tma_prefetch_desc(&tmap);
+    ptx::tma_prefetch_desc(&tmap_q);
     for (int s = 0; s < kSlots; ++s) {
       ptx::mbar_init(&bar->s_full[s], 1);
       ptx::mbar_init(&bar->s_free[s], 1);
@@ -98,7 +111,7 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap) {
       ptx::mbar_init(&bar->s_ready[b], 1);
       ptx::mbar_init(&bar->p_ready[b], kSoftmax);
     }
-    ptx::mbar_init(&bar->q_ready, kSoftmax);
+    ptx::mbar_init(&bar->q_ready, 1);
     ptx::mbar_init(&bar->acc_done, 1);
     ptx::mbar_fence_init();
   }
@@ -111,6 +124,14 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap) {
   if (warp == 0) {
     // ================================================================ TMA producer
     if (lane == 0) {
+      // Q: the CTA's 128 local rows are consecutive global rows (a.q_row0 + i_base ... within one of the two
+      // B-row blocks; the host guarantees it), out-of-range rows of the last block are zero-filled by TMA
+      if (q_by_tma) {
+        ptx::mbar_arrive_expect_tx(&bar->q_ready, C::kQBytes);
+        const int qrow = (i_base < half ? a.q_row0 : a.q_row1 - half) + i_base;
+#pragma unroll
+        for (int kb = 0; kb < C::kKB; ++kb) ptx::tma_load_2d(q_smem + kb * C::kQBoxBytes, &tmap_q, &bar->q_ready, kb * 64, qrow);
+      }
       for (int t = 0; t < n_tiles; ++t) {
         const int sl = t % kSlots;
         if (t >= kSlots) ptx::mbar_wait(&bar->s_free[sl], ((t / kSlots) - 1) & 1);
@@ -127,8 +148,10 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap) {
     constexpr uint32_t idesc_pv = umma_idesc_f16(kMt, D, 0, 1);   // B = the same tile, MN-major
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
     const uint32_t ring0 = __shfl_sync(0xffffffffu, ptx::smem_u32(ring), 0);
-    ptx::mbar_wait_relaxed(&bar->q_ready, 0);
+    const uint32_t q0 = __shfl_sync(0xffffffffu, ptx::smem_u32(q_smem), 0);
+    ptx::mbar_wait(&bar->q_ready, 0);
     ptx::tc_fence_after();
+    const uint64_t qd0 = ptx::umma_smem_desc(q0, 16, 1024, ptx::kUmmaSwizzle128B);  // A = Q, K-major, 128-byte swizzle
     auto issue_pv = [&](int t) {
       const int sl = t % kSlots, b = t & 1;
       ptx::mbar_wait(&bar->p_ready[b], (t >> 1) & 1);
@@ -160,8 +183,8 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap) {
       if (ptx::elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < D / 16; ++ks)
-          ptx::mma_f16_ts(d_s, tm + C::kColQ + ks * 8, sd0 + (uint64_t)(((ks >> 2) * C::kBoxBytes + (ks & 3) * 32) >> 4), idesc_s,
-                          ks > 0 ? 1u : 0u);
+          ptx::mma_f16_ss(d_s, qd0 + (uint64_t)(((ks >> 2) * C::kQBoxBytes + (ks & 3) * 32) >> 4),
+                          sd0 + (uint64_t)(((ks >> 2) * C::kBoxBytes + (ks & 3) * 32) >> 4), idesc_s, ks > 0 ? 1u : 0u);
         ptx::tc_commit(&bar->s_ready[b]);
         if (!kGrad) ptx::tc_commit(&bar->s_free[sl]);
       }
@@ -182,41 +205,40 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap) {
     const float invz_r = (kGrad && row_valid) ? 1.f / __ldg(a.z_all + rid) : 0.f;
     float* iz = invz_c + sw * kHalfCols;        // this warp's staging of 1/Z_c (private: __syncwarp suffices)
 
-    // ---- A operand: this row of `out` in fp16 into TMEM, two consecutive elements per 32-bit column (the
-    // memory image of the row); the pair splits the 32-column chunks
-    {
-      const uint4* src = reinterpret_cast<const uint4*>(a.out_f16 + (size_t)(row_valid ? rid : 0) * D);
-      constexpr int kChunks = (D / 2 + 31) / 32;     // chunks of 32 TMEM columns = 64 elements = 8 uint4
-      constexpr int kWords = D / 2 < 32 ? D / 2 : 32;  // columns per chunk (D = 64: one chunk of 32)
-      static_assert(kWords == 32, "D >= 64");
-#pragma unroll 1
-      for (int ch = hc; ch < kChunks; ch += 2) {
-        uint32_t v[32];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          uint4 x = make_uint4(0u, 0u, 0u, 0u);
-          if (row_valid) x = __ldg(src + ch * 8 + k);
-          v[4 * k + 0] = x.x;
-          v[4 * k + 1] = x.y;
-          v[4 * k + 2] = x.z;
-          v[4 * k + 3] = x.w;
-        }
-        ptx::tmem_st32(lane_base + C::kColQ + ch * 32, v);
+    if (!q_by_tma) {
+      // the CTA's rows straddle the two blocks: copy them into the K-major 128-byte-swizzled layout TMA would
+      // have produced (16-byte chunk c of row r sits at chunk c ^ (r & 7) of its 128-byte line)
+      constexpr int kChunksPerRow = D / 8;  // 16-byte chunks of 8 fp16
+      const int st = tid - 64;              // 0..255
+      for (int e = st; e < kMt * kChunksPerRow; e += kSoftmax) {
+        const int rr = e / kChunksPerRow, c = e % kChunksPerRow;
+        const int li = i_base + rr;
+        uint4 x = make_uint4(0u, 0u, 0u, 0u);
+        if (li < a.n_loc) x = __ldg(reinterpret_cast<const uint4*>(a.out_f16 + (size_t)__ldg(a.rows + li) * D) + c);
+        *reinterpret_cast<uint4*>(q_smem + (c >> 3) * C::kQBoxBytes + rr * 128 + (((c & 7) ^ (rr & 7)) << 4)) = x;
       }
-      ptx::tc_wait_st();
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&bar->q_ready);
+      ptx::fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (st == 0) ptx::mbar_arrive(&bar->q_ready);
     }
     const float scale2 = a.inv_T * kLog2eT;
     float zs[4] = {0.f, 0.f, 0.f, 0.f};
+    // 1/Z of this warp's 32 columns of the NEXT tile is requested one tile ahead (one L2 round trip per tile otherwise)
+    float z_next = 1.f;
+    if (kGrad && n_tiles > 0) {
+      const int j = j_begin + hc * kHalfCols + lane;
+      z_next = j < j_end ? __ldg(a.z_all + j) : 0.f;
+    }
 
     for (int t = 0; t < n_tiles; ++t) {
       const int b = t & 1;
       const int j0 = j_begin + t * kBJ + hc * kHalfCols;  // first column of this warp's half tile
-      if (kGrad) {  // 1/Z of this warp's 32 columns, staged while S(t) is still being computed
+      if (kGrad) {
         __syncwarp();
-        iz[lane] = (j0 + lane < j_end) ? 1.f / __ldg(a.z_all + j0 + lane) : 0.f;
+        iz[lane] = (j0 + lane < j_end) ? 1.f / z_next : 0.f;
         __syncwarp();
+        const int jn = j0 + kBJ + lane;
+        z_next = (t + 1 < n_tiles && jn < j_end) ? __ldg(a.z_all + jn) : 1.f;
       }
       ptx::mbar_wait(&bar->s_ready[b], (t >> 1) & 1);
       ptx::tc_fence_after();
@@ -307,7 +329,7 @@ EncodeTiledFn nt_encode_fn() {
 struct NtTmapCache {
   const void* out = nullptr;
   int N2 = 0, D = 0;
-  CUtensorMap s;
+  CUtensorMap s, q;
 };
 
 template <int D, bool kGrad>
@@ -325,6 +347,11 @@ int launch_nt(const NtxArgs& a, cudaStream_t st) {
                      estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     AVSSL_REQUIRE(r == CUDA_SUCCESS, AVSSL_ERR_CUDA, "ntxent: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    const cuuint32_t qbox[2] = {64u, (cuuint32_t)kMt};  // the CTA's 128 rows, one box per 64 fp16
+    r = enc(&cache.q, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<uint16_t*>(a.out_f16), gdim, gstride, qbox, estride,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    AVSSL_REQUIRE(r == CUDA_SUCCESS, AVSSL_ERR_CUDA, "ntxent: cuTensorMapEncodeTiled (Q) failed (%d)", (int)r);
     cache.out = a.out_f16;
     cache.N2 = a.N2;
     cache.D = D;
@@ -334,7 +361,7 @@ int launch_nt(const NtxArgs& a, cudaStream_t st) {
     AVSSL_CUDA_OK(cudaFuncSetAttribute(ntxent_tc_kernel<D, kGrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes));
   }
   dim3 grid(a.n_splits, (a.n_loc + kMt - 1) / kMt);
-  ntxent_tc_kernel<D, kGrad><<<grid, kNtThreads, C::kSmemBytes, st>>>(a, cache.s);
+  ntxent_tc_kernel<D, kGrad><<<grid, kNtThreads, C::kSmemBytes, st>>>(a, cache.s, cache.q);
   AVSSL_LAUNCH_OK("ntxent_tc_kernel");
   return AVSSL_OK;
 }

@@ -691,7 +691,7 @@ def ntxent(feat1, feat2, T, gather=None, impl=_lib.IMPL_AUTO):
     n_loc = 2 * B
     ws = _workspace(dev, lib.avssl_ntxent_workspace_bytes(2 * N, D, n_loc), "ntxent")
     z_loc = torch.empty(n_loc, dtype=_f32, device=dev)
-    check(lib.avssl_ntxent_rowsum(out.data_ptr(), out_r.data_ptr(), rows.data_ptr(), 2 * N, D, n_loc, float(T),
+    check(lib.avssl_ntxent_rowsum(out.data_ptr(), out_r.data_ptr(), rows.data_ptr(), rank * B, N + rank * B, 2 * N, D, n_loc, float(T),
                                   z_loc.data_ptr(), ws.data_ptr(), ws.numel(), int(impl), _stream()), "avssl_ntxent_rowsum")
     if world > 1:
         zg = torch.empty(world, 2, B, dtype=_f32, device=dev)
@@ -701,7 +701,7 @@ def ntxent(feat1, feat2, T, gather=None, impl=_lib.IMPL_AUTO):
         z_all = z_loc
     loss = torch.empty(1, dtype=_f32, device=dev)
     dfeat = torch.empty(n_loc, D, dtype=_f32, device=dev)
-    check(lib.avssl_ntxent_grad(out.data_ptr(), out_r.data_ptr(), rows.data_ptr(), z_all.data_ptr(), nrm.data_ptr(),
+    check(lib.avssl_ntxent_grad(out.data_ptr(), out_r.data_ptr(), rows.data_ptr(), rank * B, N + rank * B, z_all.data_ptr(), nrm.data_ptr(),
                                 2 * N, D, n_loc, float(T), float(world), loss.data_ptr(), dfeat.data_ptr(), ws.data_ptr(),
                                 ws.numel(), int(impl), _stream()), "avssl_ntxent_grad")
     return loss, dfeat[:B], dfeat[B:]

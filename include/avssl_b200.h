@@ -215,6 +215,9 @@ AVSSL_API int avssl_ce_target0_bwd(const float* logits, const float* row_lse, in
  *   the 11 significant bits of round-to-nearest tf32 -- with fp32 accumulation: loss ~1e-5, gradient ~3e-4
  *   relative, inside the 1e-3 fp32 tolerance) when D is 64/128/256 and out_f16 is given; AVSSL_IMPL_SIMT
  *   forces the exact-fp32 CUDA-core kernels (out_f16 may then be NULL), which also serve every other D.
+ * row0_first, row1_first: the tcgen05 kernels take this rank's rows as two blocks of n_loc/2 consecutive global rows
+ *   (its q rows and its q2 rows): rows[i] = row0_first + i for i < n_loc/2, row1_first + (i - n_loc/2) after.  Pass -1
+ *   when `rows` has another structure (CUDA-core kernels then).
  * out_f16: `out` as IEEE fp16 ([N2, D], 2 bytes per element), the operand the tensor cores stream (written
  *   together with `out` by avssl_ntxent_prepare, so the conversion costs no extra pass).
  * workspace: avssl_ntxent_workspace_bytes(), zero-filled once, reusable.
@@ -226,10 +229,12 @@ AVSSL_API int avssl_ce_target0_bwd(const float* logits, const float* row_lse, in
 AVSSL_API size_t avssl_ntxent_workspace_bytes(int N2, int D, int n_loc);
 AVSSL_API int avssl_ntxent_prepare(const float* gathered, int world, int B, int D, float* out, void* out_f16,
                          void* stream);
-AVSSL_API int avssl_ntxent_rowsum(const float* out, const void* out_f16, const int* rows, int N2, int D, int n_loc,
+AVSSL_API int avssl_ntxent_rowsum(const float* out, const void* out_f16, const int* rows, int row0_first,
+                        int row1_first, int N2, int D, int n_loc,
                         float T, float* z_loc_out, void* workspace, size_t workspace_bytes, int impl,
                         void* stream);
-AVSSL_API int avssl_ntxent_grad(const float* out, const void* out_f16, const int* rows, const float* z_all,
+AVSSL_API int avssl_ntxent_grad(const float* out, const void* out_f16, const int* rows, int row0_first,
+                      int row1_first, const float* z_all,
                       const float* norm_loc,
                       int N2, int D, int n_loc, float T, float grad_scale, float* loss_out,
                       float* dfeat_out, void* workspace, size_t workspace_bytes, int impl, void* stream);

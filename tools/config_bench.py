@@ -115,9 +115,9 @@ for B, W in ((512, 1), (512, 8)):
 
         def rank_work():
             check(lib.avssl_ntxent_prepare(gathered.data_ptr(), W, B, D, out.data_ptr(), out_r.data_ptr(), st), "prepare")
-            check(lib.avssl_ntxent_rowsum(out.data_ptr(), out_r.data_ptr(), rows.data_ptr(), 2 * N, D, n_loc, T, z.data_ptr(),
+            check(lib.avssl_ntxent_rowsum(out.data_ptr(), out_r.data_ptr(), rows.data_ptr(), 0, N, 2 * N, D, n_loc, T, z.data_ptr(),
                                           ws.data_ptr(), ws.numel(), IMPL, st), "rowsum")
-            check(lib.avssl_ntxent_grad(out.data_ptr(), out_r.data_ptr(), rows.data_ptr(), zall.data_ptr(), nrm.data_ptr(),
+            check(lib.avssl_ntxent_grad(out.data_ptr(), out_r.data_ptr(), rows.data_ptr(), 0, N, zall.data_ptr(), nrm.data_ptr(),
                                         2 * N, D, n_loc, T, float(W), loss.data_ptr(), dfe.data_ptr(), ws.data_ptr(),
                                         ws.numel(), IMPL, st), "grad")
         report("K6 NT-Xent per-rank work of cfg3: 2B=%d local rows x 2N=%d cols, D=%d" % (2 * B, 2 * N, D), rank_work,

@@ -15,7 +15,7 @@ loss = torch.empty(1, device=dev); dfe = torch.empty(n_loc, D, device=dev)
 st = torch.cuda.current_stream().cuda_stream
 for _ in range(4):
     check(lib.avssl_ntxent_prepare(gathered.data_ptr(), W, B, D, out.data_ptr(), out_r.data_ptr(), st), "prepare")
-    check(lib.avssl_ntxent_rowsum(out.data_ptr(), out_r.data_ptr(), rows.data_ptr(), 2 * N, D, n_loc, T, z.data_ptr(), ws.data_ptr(), ws.numel(), 0, st), "rowsum")
-    check(lib.avssl_ntxent_grad(out.data_ptr(), out_r.data_ptr(), rows.data_ptr(), zall.data_ptr(), nrm.data_ptr(), 2 * N, D, n_loc, T, float(W), loss.data_ptr(), dfe.data_ptr(), ws.data_ptr(), ws.numel(), 0, st), "grad")
+    check(lib.avssl_ntxent_rowsum(out.data_ptr(), out_r.data_ptr(), rows.data_ptr(), 0, N, 2 * N, D, n_loc, T, z.data_ptr(), ws.data_ptr(), ws.numel(), 0, st), "rowsum")
+    check(lib.avssl_ntxent_grad(out.data_ptr(), out_r.data_ptr(), rows.data_ptr(), 0, N, zall.data_ptr(), nrm.data_ptr(), 2 * N, D, n_loc, T, float(W), loss.data_ptr(), dfe.data_ptr(), ws.data_ptr(), ws.numel(), 0, st), "grad")
 torch.cuda.synchronize()
 print("done")

@@ -27,8 +27,8 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 def seq():
     st = torch.cuda.current_stream().cuda_stream
     check(lib.avssl_ntxent_prepare(gathered.data_ptr(), W, B, D, out.data_ptr(), out_h.data_ptr(), st), "prepare")
-    check(lib.avssl_ntxent_rowsum(out.data_ptr(), out_h.data_ptr(), rows.data_ptr(), 2 * N, D, n_loc, T, z.data_ptr(), ws.data_ptr(), ws.numel(), 0, st), "rowsum")
-    check(lib.avssl_ntxent_grad(out.data_ptr(), out_h.data_ptr(), rows.data_ptr(), zall.data_ptr(), nrm.data_ptr(), 2 * N, D, n_loc, T, float(W), loss.data_ptr(), dfe.data_ptr(), ws.data_ptr(), ws.numel(), 0, st), "grad")
+    check(lib.avssl_ntxent_rowsum(out.data_ptr(), out_h.data_ptr(), rows.data_ptr(), 0, N, 2 * N, D, n_loc, T, z.data_ptr(), ws.data_ptr(), ws.numel(), 0, st), "rowsum")
+    check(lib.avssl_ntxent_grad(out.data_ptr(), out_h.data_ptr(), rows.data_ptr(), 0, N, zall.data_ptr(), nrm.data_ptr(), 2 * N, D, n_loc, T, float(W), loss.data_ptr(), dfe.data_ptr(), ws.data_ptr(), ws.numel(), 0, st), "grad")
 
 
 for _ in range(3):
