@@ -181,7 +181,7 @@ ntxent_finish_kernel(const NtxArgs a, const float* __restrict__ norm_loc, float 
     float4 g0 = zero4, g1 = zero4;
     const float4* pg = reinterpret_cast<const float4*>(a.part_g + (size_t)i * D);
     const size_t sstride4 = (size_t)a.n_loc * D / 4;
-    constexpr int kS = 8;
+    constexpr int kS = 9;  // split rows in flight per lane: two rounds for the 18 splits of cfg3
     for (int s0 = 0; s0 < a.n_splits; s0 += kS) {  // fixed order: deterministic
       float4 v0[kS], v1[kS];
 #pragma unroll
@@ -342,20 +342,33 @@ static int ntx_setup(NtxArgs& a, const float* out, const void* out_f16, const in
 __global__ void __launch_bounds__(256)
 ntxent_prepare_kernel(const float4* __restrict__ gathered, int W, int B, int D4, float4* __restrict__ out,
                       uint2* __restrict__ out_f16) {
-  // one warp per destination row (v * W + w) * B + b; the row index arithmetic is per warp, not per element
+  // one warp per destination row (v * W + w) * B + b; the row index arithmetic is per warp, not per element, and
+  // all of a row's loads are issued before its first store
   const int lane = threadIdx.x & 31;
   const int n_rows = 2 * W * B;
+  constexpr int kMaxPerLane = 4;  // D <= 512 in one go (D4 <= 128)
   for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n_rows; row += gridDim.x * (blockDim.x >> 5)) {
     const int b = row % B, vw = row / B;
     const int w = vw % W, v = vw / W;
     const float4* src = gathered + ((size_t)(w * 2 + v) * B + b) * D4;
     float4* o = out + (size_t)row * D4;
     uint2* oh = out_f16 + (size_t)row * D4;
-    for (int c = lane; c < D4; c += 32) {
-      const float4 x = __ldg(src + c);
-      o[c] = x;
-      const __half2 lo = __floats2half2_rn(x.x, x.y), hi = __floats2half2_rn(x.z, x.w);
-      oh[c] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+    for (int c0 = 0; c0 < D4; c0 += 32 * kMaxPerLane) {
+      float4 x[kMaxPerLane];
+#pragma unroll
+      for (int u = 0; u < kMaxPerLane; ++u) {
+        const int c = c0 + lane + 32 * u;
+        if (c < D4) x[u] = ldg_stream(src + c);
+      }
+#pragma unroll
+      for (int u = 0; u < kMaxPerLane; ++u) {
+        const int c = c0 + lane + 32 * u;
+        if (c < D4) {
+          o[c] = x[u];
+          const __half2 lo = __floats2half2_rn(x[u].x, x[u].y), hi = __floats2half2_rn(x[u].z, x[u].w);
+          oh[c] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+        }
+      }
     }
   }
 }
@@ -411,8 +424,8 @@ extern "C" int avssl_ntxent_grad(const float* out, const void* out_f16, const in
   unsigned* counter = static_cast<unsigned*>(workspace);
   float* row_term = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
   const int comb_blocks = (n_loc + kFinWarps - 1) / kFinWarps;
-  int loss_blocks = (N2 / 2 + kFinWarps - 1) / kFinWarps;  // a few pairs per warp: about one CTA per SM
-  if (loss_blocks > (sm_count() > 0 ? sm_count() : 148)) loss_blocks = sm_count() > 0 ? sm_count() : 148;
+  int loss_blocks = (N2 / 2 + kFinWarps - 1) / kFinWarps;  // a few pairs per warp: about two CTAs per SM
+  if (loss_blocks > 2 * (sm_count() > 0 ? sm_count() : 148)) loss_blocks = 2 * (sm_count() > 0 ? sm_count() : 148);
   ntxent_finish_kernel<<<comb_blocks + loss_blocks, kFinWarps * 32, 0, s>>>(a, norm_loc, gscale, dfeat_out, comb_blocks,
                                                                            loss_out, row_term, counter);
   AVSSL_LAUNCH_OK("ntxent_finish_kernel");

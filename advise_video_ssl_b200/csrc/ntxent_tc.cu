@@ -60,11 +60,15 @@ struct NtCfg {
   // reads per CTA, ~2 us before the first MMA of both passes)
   static constexpr int kQBoxBytes = kMt * 128;          // one TMA box of Q: 128 rows x 128 B
   static constexpr int kQBytes = kKB * kQBoxBytes;      // 64 KiB at D = 256
-  static constexpr int kColS = 0, kColAcc = 2 * kBJ;
-  static constexpr int kColsNeeded = 2 * kBJ + (kGrad ? D : 0);
+  // S / P is TRIPLE-buffered in TMEM (3 x 64 columns): S(t) can be issued before P.V(t-2) has even been
+  // requested, so the exponentials of tile t-1 have a whole S-issue period of slack (a double buffer forces
+  // S(t+1) behind P.V(t-1), i.e. behind softmax(t-1): the chain showed as a 16 % active tensor pipe)
+  static constexpr int kBufs = 3;
+  static constexpr int kColS = 0, kColAcc = kBufs * kBJ;
+  static constexpr int kColsNeeded = kBufs * kBJ + (kGrad ? D : 0);
   static constexpr int kTmemCols = kColsNeeded <= 128 ? 128 : (kColsNeeded <= 256 ? 256 : 512);
   static_assert(kColsNeeded <= 512, "TMEM budget");
-  static constexpr int kRingBudget = 208 * 1024 - kQBytes;
+  static constexpr int kRingBudget = 232448 /* 227 KiB per CTA */ - 1024 - kQBytes - 8 * kHalfCols * 4 - 512;
   static constexpr int kSlots = (kRingBudget / kTileBytes) < kMaxSlots ? (kRingBudget / kTileBytes) : kMaxSlots;
   static_assert(kSlots >= 2, "at least a double buffer");
   static constexpr size_t kSmemBytes = 1024 + (size_t)kQBytes + (size_t)kSlots * kTileBytes + 8 * kHalfCols * 4 + 512;
@@ -72,7 +76,7 @@ struct NtCfg {
 
 struct NtBarriers {
   uint64_t s_full[kMaxSlots], s_free[kMaxSlots];  // tile landed / both MMAs that read it have retired
-  uint64_t s_ready[2], p_ready[2];
+  uint64_t s_ready[3], p_ready[3];
   uint64_t q_ready, acc_done;
   uint32_t tmem_base;
 };
@@ -107,7 +111,7 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
       ptx::mbar_init(&bar->s_full[s], 1);
       ptx::mbar_init(&bar->s_free[s], 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < C::kBufs; ++b) {
       ptx::mbar_init(&bar->s_ready[b], 1);
       ptx::mbar_init(&bar->p_ready[b], kSoftmax);
     }
@@ -153,8 +157,8 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
     ptx::tc_fence_after();
     const uint64_t qd0 = ptx::umma_smem_desc(q0, 16, 1024, ptx::kUmmaSwizzle128B);  // A = Q, K-major, 128-byte swizzle
     auto issue_pv = [&](int t) {
-      const int sl = t % kSlots, b = t & 1;
-      ptx::mbar_wait(&bar->p_ready[b], (t >> 1) & 1);
+      const int sl = t % kSlots, b = t % C::kBufs;
+      ptx::mbar_wait(&bar->p_ready[b], (t / C::kBufs) & 1);
       ptx::tc_fence_after();
       // MN-major, 128-byte swizzle, 16-bit elements: one k-step = 16 tile rows = two 8-row atoms 1024 B apart
       // (SBO); the 64-element column blocks of N (one TMA box each) are kBoxBytes apart (LBO)
@@ -171,11 +175,11 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
       __syncwarp();
     };
     for (int t = 0; t < n_tiles; ++t) {
-      const int sl = t % kSlots, b = t & 1;
+      const int sl = t % kSlots, b = t % C::kBufs;
       ptx::mbar_wait(&bar->s_full[sl], (t / kSlots) & 1);
-      // S(t) overwrites the TMEM buffer of tile t-2: its exponentials must have been read (pass 2 gets this
-      // ordering for free from PV(t-2), which waited for the same barrier)
-      if (!kGrad && t >= 2) ptx::mbar_wait(&bar->p_ready[b], ((t - 2) >> 1) & 1);
+      // S(t) overwrites the TMEM buffer of tile t-3: its exponentials must have been read (pass 2 gets this
+      // ordering for free from PV(t-3), which waited for the same barrier and was issued earlier)
+      if (!kGrad && t >= C::kBufs) ptx::mbar_wait(&bar->p_ready[b], ((t - C::kBufs) / C::kBufs) & 1);
       ptx::tc_fence_after();
       // K-major: box ks/4 (64 fp16 = 128 B), 16 elements = 32 bytes per k-step inside the 128-byte row
       const uint64_t sd0 = ptx::umma_smem_desc(ring0 + sl * C::kTileBytes, 16, 1024, ptx::kUmmaSwizzle128B);
@@ -189,8 +193,9 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
         if (!kGrad) ptx::tc_commit(&bar->s_free[sl]);
       }
       __syncwarp();
-      if (kGrad && t > 0) issue_pv(t - 1);
+      if (kGrad && t >= 2) issue_pv(t - 2);  // two S tiles ahead of the oldest outstanding P.V
     }
+    if (kGrad && n_tiles > 1) issue_pv(n_tiles - 2);
     if (kGrad && n_tiles > 0) issue_pv(n_tiles - 1);
   } else {
     // ================= softmax + epilogue: thread = local row; warp pair (w, w+4) shares a sub-partition
@@ -231,7 +236,7 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
     }
 
     for (int t = 0; t < n_tiles; ++t) {
-      const int b = t & 1;
+      const int b = t % C::kBufs;
       const int j0 = j_begin + t * kBJ + hc * kHalfCols;  // first column of this warp's half tile
       if (kGrad) {
         __syncwarp();
@@ -240,7 +245,7 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
         const int jn = j0 + kBJ + lane;
         z_next = (t + 1 < n_tiles && jn < j_end) ? __ldg(a.z_all + jn) : 1.f;
       }
-      ptx::mbar_wait(&bar->s_ready[b], (t >> 1) & 1);
+      ptx::mbar_wait(&bar->s_ready[b], (t / C::kBufs) & 1);
       ptx::tc_fence_after();
       const uint32_t s_col = lane_base + C::kColS + b * kBJ + hc * kHalfCols;
       uint32_t sv[kHalfCols];
