@@ -29,6 +29,7 @@
 
 #include "ntxent.cuh"
 #include "sm100_ptx.cuh"
+#include "tc_trace.cuh"
 
 namespace avssl {
 
@@ -94,6 +95,7 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
   NtBarriers* bar = reinterpret_cast<NtBarriers*>(ring + kSlots * C::kTileBytes + 8 * kHalfCols * 4);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) TC_TRACE(6, 0);
   const int split = blockIdx.x;
   const int i_base = blockIdx.y * kMt;
   const int j_begin = split * a.cols_per_split;
@@ -124,6 +126,7 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = bar->tmem_base;
+  if (tid == 0) TC_TRACE(6, 1);
 
   if (warp == 0) {
     // ================================================================ TMA producer
@@ -139,6 +142,7 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
       for (int t = 0; t < n_tiles; ++t) {
         const int sl = t % kSlots;
         if (t >= kSlots) ptx::mbar_wait(&bar->s_free[sl], ((t / kSlots) - 1) & 1);
+        TC_TRACE(0, t);
         ptx::mbar_arrive_expect_tx(&bar->s_full[sl], C::kTileBytes);
         uint8_t* dst = ring + (size_t)sl * C::kTileBytes;
 #pragma unroll
@@ -155,11 +159,13 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
     const uint32_t q0 = __shfl_sync(0xffffffffu, ptx::smem_u32(q_smem), 0);
     ptx::mbar_wait(&bar->q_ready, 0);
     ptx::tc_fence_after();
+    TC_TRACE(6, 2);
     const uint64_t qd0 = ptx::umma_smem_desc(q0, 16, 1024, ptx::kUmmaSwizzle128B);  // A = Q, K-major, 128-byte swizzle
     auto issue_pv = [&](int t) {
       const int sl = t % kSlots, b = t % C::kBufs;
       ptx::mbar_wait(&bar->p_ready[b], (t / C::kBufs) & 1);
       ptx::tc_fence_after();
+      TC_TRACE(5, t);
       // MN-major, 128-byte swizzle, 16-bit elements: one k-step = 16 tile rows = two 8-row atoms 1024 B apart
       // (SBO); the 64-element column blocks of N (one TMA box each) are kBoxBytes apart (LBO)
       const uint64_t bd0 = ptx::umma_smem_desc(ring0 + sl * C::kTileBytes, C::kBoxBytes, 1024, ptx::kUmmaSwizzle128B);
@@ -181,6 +187,7 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
       // ordering for free from PV(t-3), which waited for the same barrier and was issued earlier)
       if (!kGrad && t >= C::kBufs) ptx::mbar_wait(&bar->p_ready[b], ((t - C::kBufs) / C::kBufs) & 1);
       ptx::tc_fence_after();
+      TC_TRACE(1, t);
       // K-major: box ks/4 (64 fp16 = 128 B), 16 elements = 32 bytes per k-step inside the 128-byte row
       const uint64_t sd0 = ptx::umma_smem_desc(ring0 + sl * C::kTileBytes, 16, 1024, ptx::kUmmaSwizzle128B);
       const uint32_t d_s = tm + C::kColS + b * kBJ;
@@ -193,6 +200,7 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
         if (!kGrad) ptx::tc_commit(&bar->s_free[sl]);
       }
       __syncwarp();
+      TC_TRACE(2, t);
       if (kGrad && t >= 2) issue_pv(t - 2);  // two S tiles ahead of the oldest outstanding P.V
     }
     if (kGrad && n_tiles > 1) issue_pv(n_tiles - 2);
@@ -247,6 +255,7 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
       }
       ptx::mbar_wait(&bar->s_ready[b], (t / C::kBufs) & 1);
       ptx::tc_fence_after();
+      if (sw == 0 && lane == 0) TC_TRACE(3, t);
       const uint32_t s_col = lane_base + C::kColS + b * kBJ + hc * kHalfCols;
       uint32_t sv[kHalfCols];
       ptx::tmem_ld32(s_col, sv);
@@ -276,23 +285,38 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
         ptx::tc_wait_st();
       }
       ptx::tc_fence_before();
+      if (sw == 0 && lane == 0) TC_TRACE(4, t);
       ptx::mbar_arrive(&bar->p_ready[b]);
     }
     if (kGrad) {
       // ---- the gradient partial is complete once the last PV retires; the pair splits the 32-column chunks
       ptx::mbar_wait(&bar->acc_done, 0);
       ptx::tc_fence_after();
+      if (sw == 0 && lane == 0) TC_TRACE(6, 3);
+      // The accumulator comes out of TMEM one ROW per thread; written like that, every store instruction of a warp
+      // touches 32 different 1 KiB-strided rows (half-filled sectors: the epilogue took 9300 of the kernel's 26000
+      // cycles).  Each warp therefore transposes its 32 x 32 chunk through a padded scratch in the (now idle) tile
+      // ring and stores four whole 128-byte row segments per instruction.
+      float* scratch = reinterpret_cast<float*>(ring) + sw * (32 * 33);
+      const int g_row = lane >> 3, g_c4 = (lane & 7) * 4;  // store phase: lane -> (row within a group of 4, float4 column)
 #pragma unroll 1
       for (int cb = hc; cb < D / 32; cb += 2) {
         uint32_t av[32];
         ptx::tmem_ld32(lane_base + C::kColAcc + cb * 32, av);
         ptx::tc_wait_ld();
-        if (row_valid) {
-          float4* dst = reinterpret_cast<float4*>(a.part_g + ((size_t)split * a.n_loc + i) * D + cb * 32);
+        __syncwarp();
 #pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4)
-            dst[c4] = make_float4(__uint_as_float(av[c4 * 4]) * kPUnscale, __uint_as_float(av[c4 * 4 + 1]) * kPUnscale,
-                                  __uint_as_float(av[c4 * 4 + 2]) * kPUnscale, __uint_as_float(av[c4 * 4 + 3]) * kPUnscale);
+        for (int c = 0; c < 32; ++c) scratch[lane * 33 + c] = __uint_as_float(av[c]) * kPUnscale;  // conflict-free (pitch 33)
+        __syncwarp();
+#pragma unroll
+        for (int r0 = 0; r0 < 32; r0 += 4) {
+          const int rr = r0 + g_row;                 // row of this warp's sub-partition
+          const int li = i_base + sub * 32 + rr;     // local row
+          if (li < a.n_loc) {
+            const float* sp = scratch + rr * 33 + g_c4;
+            float4* dst = reinterpret_cast<float4*>(a.part_g + ((size_t)split * a.n_loc + li) * D + cb * 32 + g_c4);
+            *dst = make_float4(sp[0], sp[1], sp[2], sp[3]);
+          }
         }
       }
       ptx::tc_fence_before();
@@ -308,6 +332,7 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (tid == 0) TC_TRACE(6, 4);
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem, C::kTmemCols);
