@@ -324,7 +324,7 @@ static int ntx_setup(NtxArgs& a, const float* out, const void* out_f16, const in
   AVSSL_REQUIRE(*use_tc || impl != AVSSL_IMPL_TC1X, AVSSL_ERR_UNSUPPORTED,
                 "%s: the tcgen05 kernel needs D in {64,128,256} and a 16-byte aligned fp16 copy of `out` "
                 "(avssl_ntxent_prepare) (D=%d)", who, D);
-  AVSSL_REQUIRE((*use_tc ? ntxent_tc_plan(N2, n_loc, &a.n_splits, &a.cols_per_split)
+  AVSSL_REQUIRE((*use_tc ? ntxent_tc_plan(N2, n_loc, z_all != nullptr, &a.n_splits, &a.cols_per_split)
                          : plan_splits(N2, n_loc, &a.n_splits, &a.cols_per_split)) == 0,
                 AVSSL_ERR_CUDA, "%s: no CUDA device", who);
   char* w = static_cast<char*>(workspace);

@@ -20,7 +20,7 @@ struct NtxArgs {
 };
 
 bool ntxent_tc_supported(int N2, int D, int n_loc);
-int ntxent_tc_plan(int N2, int n_loc, int* n_splits, int* cols_per_split);
+int ntxent_tc_plan(int N2, int n_loc, bool grad, int* n_splits, int* cols_per_split);
 int launch_ntxent_tc(const NtxArgs& a, bool grad, cudaStream_t s);
 
 }  // namespace avssl

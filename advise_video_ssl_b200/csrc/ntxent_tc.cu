@@ -35,12 +35,14 @@ namespace avssl {
 
 namespace {
 
-constexpr int kBJ = 64;    // columns of `out` per tile
+constexpr int kBJGrad = 64;   // columns of `out` per tile, gradient pass (S/P triple buffer + the D-wide accumulator fill TMEM)
+constexpr int kBJSum = 128;   // row-sum pass: no accumulator, so N = 128 MMAs fit (64 tensor cycles each: above the ~54-cycle
+                              // issue interval of one thread, which bounds the N = 64 tiles)
 constexpr int kMt = 128;   // local rows per CTA
 constexpr int kNtThreads = 320;
 constexpr int kSoftmax = 256;
 constexpr int kMaxSlots = 6;
-constexpr int kHalfCols = kBJ / 2;  // columns of a tile per softmax warp
+constexpr int kHalfCols = 32;  // columns per tcgen05.ld chunk and per 1/Z staging row
 constexpr float kLog2eT = 1.4426950408889634f;
 constexpr float kPScale = 16384.f, kPUnscale = 1.f / 16384.f;
 
@@ -53,8 +55,10 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, int a_mn_maj
 template <int D, bool kGrad>
 struct NtCfg {
   static_assert(D % 64 == 0 && D <= 256, "whole 128-byte boxes of fp16");
+  static constexpr int kBJ = kGrad ? kBJGrad : kBJSum;  // columns of `out` per tile
+  static constexpr int kHalf = kBJ / 2;              // columns of a tile per softmax warp
   static constexpr int kKB = D / 64;                 // 128-byte boxes (64 fp16) per row
-  static constexpr int kBoxBytes = kBJ * 128;        // one TMA box: 64 rows x 128 B
+  static constexpr int kBoxBytes = kBJ * 128;        // one TMA box: kBJ rows x 128 B
   static constexpr int kTileBytes = kKB * kBoxBytes; // 32 KiB at D = 256
   // Q (the CTA's 128 rows, fp16) lives in SHARED memory as the K-major A operand, landed by TMA like the tiles:
   // no per-thread row loads and no TMEM stores in the prologue (round 2, first version: 128 strided 512-byte row
@@ -100,6 +104,7 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
   const int i_base = blockIdx.y * kMt;
   const int j_begin = split * a.cols_per_split;
   const int j_end = min(a.N2, j_begin + a.cols_per_split);
+  constexpr int kBJ = C::kBJ;
   const int n_tiles = (j_end - j_begin + kBJ - 1) / kBJ;
   // local rows [0, half) are global rows q_row0.., local rows [half, n_loc) global rows q_row1..: a CTA whose 128 rows
   // stay inside one of the two blocks gets Q by TMA; one that straddles them copies the rows itself (same layout)
@@ -173,7 +178,7 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
       if (ptx::elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < kBJ / 16; ++ks)  // P of columns 32h..32h+31 sits packed in TMEM columns 32h..32h+15
-          ptx::mma_f16_ts(tm + C::kColAcc, a0 + (ks >> 1) * kHalfCols + (ks & 1) * 8, bd0 + (uint64_t)(ks * 2048 >> 4),
+          ptx::mma_f16_ts(tm + C::kColAcc, a0 + (ks >> 1) * C::kHalf + (ks & 1) * 8, bd0 + (uint64_t)(ks * 2048 >> 4),
                           idesc_pv, (t > 0 || ks > 0) ? 1u : 0u);
         ptx::tc_commit(&bar->s_free[sl]);  // S(t) retired before PV(t) was issued: the slot is free
         if (t == n_tiles - 1) ptx::tc_commit(&bar->acc_done);
@@ -239,13 +244,13 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
     // 1/Z of this warp's 32 columns of the NEXT tile is requested one tile ahead (one L2 round trip per tile otherwise)
     float z_next = 1.f;
     if (kGrad && n_tiles > 0) {
-      const int j = j_begin + hc * kHalfCols + lane;
+      const int j = j_begin + hc * C::kHalf + lane;
       z_next = j < j_end ? __ldg(a.z_all + j) : 0.f;
     }
 
     for (int t = 0; t < n_tiles; ++t) {
       const int b = t % C::kBufs;
-      const int j0 = j_begin + t * kBJ + hc * kHalfCols;  // first column of this warp's half tile
+      const int j0 = j_begin + t * kBJ + hc * C::kHalf;  // first column of this warp's half tile
       if (kGrad) {
         __syncwarp();
         iz[lane] = (j0 + lane < j_end) ? 1.f / z_next : 0.f;
@@ -256,33 +261,37 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
       ptx::mbar_wait(&bar->s_ready[b], (t / C::kBufs) & 1);
       ptx::tc_fence_after();
       if (sw == 0 && lane == 0) TC_TRACE(3, t);
-      const uint32_t s_col = lane_base + C::kColS + b * kBJ + hc * kHalfCols;
-      uint32_t sv[kHalfCols];
-      ptx::tmem_ld32(s_col, sv);
-      ptx::tc_wait_ld();
-      const int diag = rid - j0;            // column of this half tile that is the row itself (masked), if in [0, 32)
-      const int valid = row_valid ? min(kHalfCols, j_end - j0) : 0;
-      uint32_t pk[kHalfCols / 2];
 #pragma unroll
-      for (int c = 0; c < kHalfCols; c += 2) {
-        float e[2];
+      for (int ch = 0; ch < C::kHalf / kHalfCols; ++ch) {  // 32-column chunks of this warp's half tile (2 in the row-sum pass)
+        const int jc = j0 + ch * kHalfCols;
+        const uint32_t s_col = lane_base + C::kColS + b * kBJ + hc * C::kHalf + ch * kHalfCols;
+        uint32_t sv[kHalfCols];
+        ptx::tmem_ld32(s_col, sv);
+        ptx::tc_wait_ld();
+        const int diag = rid - jc;            // column of this chunk that is the row itself (masked), if in [0, 32)
+        const int valid = row_valid ? min(kHalfCols, j_end - jc) : 0;
+        uint32_t pk[kHalfCols / 2];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          // e^{(s - 1)/T}: unit rows give s <= 1, so the exponent is <= 0
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[u]) : "f"((__uint_as_float(sv[c + u]) - 1.f) * scale2));
-          e[u] = (c + u < valid && c + u != diag) ? e[u] : 0.f;
+        for (int c = 0; c < kHalfCols; c += 2) {
+          float e[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            // e^{(s - 1)/T}: unit rows give s <= 1, so the exponent is <= 0
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[u]) : "f"((__uint_as_float(sv[c + u]) - 1.f) * scale2));
+            e[u] = (c + u < valid && c + u != diag) ? e[u] : 0.f;
+          }
+          if (kGrad) {
+            const __half2 h = __floats2half2_rn(e[0] * (invz_r + iz[c]) * kPScale, e[1] * (invz_r + iz[c + 1]) * kPScale);
+            pk[c >> 1] = *reinterpret_cast<const uint32_t*>(&h);  // low half = even k
+          } else {
+            zs[c & 3] += e[0];
+            zs[(c + 1) & 3] += e[1];
+          }
         }
         if (kGrad) {
-          const __half2 h = __floats2half2_rn(e[0] * (invz_r + iz[c]) * kPScale, e[1] * (invz_r + iz[c + 1]) * kPScale);
-          pk[c >> 1] = *reinterpret_cast<const uint32_t*>(&h);  // low half = even k
-        } else {
-          zs[c & 3] += e[0];
-          zs[(c + 1) & 3] += e[1];
+          ptx::tmem_st16(s_col, pk);  // over the first 16 columns of this warp's own 32 (the pair never overlaps)
+          ptx::tc_wait_st();
         }
-      }
-      if (kGrad) {
-        ptx::tmem_st16(s_col, pk);  // over the first 16 columns of this warp's own 32 (the pair never overlaps)
-        ptx::tc_wait_st();
       }
       ptx::tc_fence_before();
       if (sw == 0 && lane == 0) TC_TRACE(4, t);
@@ -371,7 +380,7 @@ int launch_nt(const NtxArgs& a, cudaStream_t st) {
     AVSSL_REQUIRE(enc, AVSSL_ERR_CUDA, "ntxent: cuTensorMapEncodeTiled is not available from the driver");
     const cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)a.N2};
     const cuuint64_t gstride[1] = {(cuuint64_t)D * sizeof(uint16_t)};
-    const cuuint32_t box[2] = {64u, (cuuint32_t)kBJ};  // 64 fp16 = 128 bytes x 64 rows
+    const cuuint32_t box[2] = {64u, (cuuint32_t)C::kBJ};  // 64 fp16 = 128 bytes x kBJ rows
     const cuuint32_t estride[2] = {1u, 1u};
     CUresult r = enc(&cache.s, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<uint16_t*>(a.out_f16), gdim, gstride, box,
                      estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -405,9 +414,10 @@ bool ntxent_tc_supported(int N2, int D, int n_loc) {
 
 // Column split of the tcgen05 kernels: whole 64-column tiles, at most 64 splits (workspace layout),
 // about one CTA per SM.
-int ntxent_tc_plan(int N2, int n_loc, int* n_splits, int* cols_per_split) {
+int ntxent_tc_plan(int N2, int n_loc, bool grad, int* n_splits, int* cols_per_split) {
   const int sms = sm_count();
   if (sms <= 0) return -1;
+  const int kBJ = grad ? kBJGrad : kBJSum;
   const int row_blocks = (n_loc + kMt - 1) / kMt;
   const int n_tiles = (N2 + kBJ - 1) / kBJ;
   int S = sms / row_blocks;
