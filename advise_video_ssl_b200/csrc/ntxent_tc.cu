@@ -22,9 +22,11 @@
 // accumulator is scaled back in the epilogue.  The CUDA-core kernels (AVSSL_IMPL_SIMT) remain the exact-fp32
 // reference and serve every D that is not a multiple of 64.
 //
-// Warp roles (320 threads, 1 CTA / SM): 0 TMA producer | 1 MMA issuer + TMEM allocator |
+// Warp roles (352 threads, 1 CTA / SM): 0 TMA producer | 1 issuer of the S MMAs + TMEM allocator |
 // 2-9 softmax + epilogue: thread = row, and the two warps that share a TMEM sub-partition (w, w+4)
-// split every tile's 64 columns (and the accumulator read-out) between them.
+// split every tile's columns (and the accumulator read-out) between them | 10 issuer of the P.V MMAs.
+// Two issuing warps because ONE thread needs ~54 cycles per tcgen05.mma: with S (16) and P.V (4 long) MMAs of a
+// tile issued by the same thread the gradient loop ran at ~1650 cycles per tile against 1024 tensor cycles.
 #include <cuda_fp16.h>
 
 #include "ntxent.cuh"
@@ -39,7 +41,7 @@ constexpr int kBJGrad = 64;   // columns of `out` per tile, gradient pass (S/P t
 constexpr int kBJSum = 128;   // row-sum pass: no accumulator, so N = 128 MMAs fit (64 tensor cycles each: above the ~54-cycle
                               // issue interval of one thread, which bounds the N = 64 tiles)
 constexpr int kMt = 128;   // local rows per CTA
-constexpr int kNtThreads = 320;
+constexpr int kNtThreads = 352;
 constexpr int kSoftmax = 256;
 constexpr int kMaxSlots = 6;
 constexpr int kHalfCols = 32;  // columns per tcgen05.ld chunk and per 1/Z staging row
@@ -81,7 +83,7 @@ struct NtCfg {
 
 struct NtBarriers {
   uint64_t s_full[kMaxSlots], s_free[kMaxSlots];  // tile landed / both MMAs that read it have retired
-  uint64_t s_ready[3], p_ready[3];
+  uint64_t s_ready[3], p_ready[3], pv_done[3];
   uint64_t q_ready, acc_done;
   uint32_t tmem_base;
 };
@@ -121,6 +123,7 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
     for (int b = 0; b < C::kBufs; ++b) {
       ptx::mbar_init(&bar->s_ready[b], 1);
       ptx::mbar_init(&bar->p_ready[b], kSoftmax);
+      ptx::mbar_init(&bar->pv_done[b], 1);
     }
     ptx::mbar_init(&bar->q_ready, 1);
     ptx::mbar_init(&bar->acc_done, 1);
@@ -158,7 +161,6 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
   } else if (warp == 1) {
     // ================================================================== MMA issuer
     constexpr uint32_t idesc_s = umma_idesc_f16(kMt, kBJ, 0, 0);  // B = tile, K-major
-    constexpr uint32_t idesc_pv = umma_idesc_f16(kMt, D, 0, 1);   // B = the same tile, MN-major
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
     const uint32_t ring0 = __shfl_sync(0xffffffffu, ptx::smem_u32(ring), 0);
     const uint32_t q0 = __shfl_sync(0xffffffffu, ptx::smem_u32(q_smem), 0);
@@ -166,31 +168,15 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
     ptx::tc_fence_after();
     TC_TRACE(6, 2);
     const uint64_t qd0 = ptx::umma_smem_desc(q0, 16, 1024, ptx::kUmmaSwizzle128B);  // A = Q, K-major, 128-byte swizzle
-    auto issue_pv = [&](int t) {
-      const int sl = t % kSlots, b = t % C::kBufs;
-      ptx::mbar_wait(&bar->p_ready[b], (t / C::kBufs) & 1);
-      ptx::tc_fence_after();
-      TC_TRACE(5, t);
-      // MN-major, 128-byte swizzle, 16-bit elements: one k-step = 16 tile rows = two 8-row atoms 1024 B apart
-      // (SBO); the 64-element column blocks of N (one TMA box each) are kBoxBytes apart (LBO)
-      const uint64_t bd0 = ptx::umma_smem_desc(ring0 + sl * C::kTileBytes, C::kBoxBytes, 1024, ptx::kUmmaSwizzle128B);
-      const uint32_t a0 = tm + C::kColS + b * kBJ;
-      if (ptx::elect_one()) {
-#pragma unroll
-        for (int ks = 0; ks < kBJ / 16; ++ks)  // P of columns 32h..32h+31 sits packed in TMEM columns 32h..32h+15
-          ptx::mma_f16_ts(tm + C::kColAcc, a0 + (ks >> 1) * C::kHalf + (ks & 1) * 8, bd0 + (uint64_t)(ks * 2048 >> 4),
-                          idesc_pv, (t > 0 || ks > 0) ? 1u : 0u);
-        ptx::tc_commit(&bar->s_free[sl]);  // S(t) retired before PV(t) was issued: the slot is free
-        if (t == n_tiles - 1) ptx::tc_commit(&bar->acc_done);
-      }
-      __syncwarp();
-    };
     for (int t = 0; t < n_tiles; ++t) {
       const int sl = t % kSlots, b = t % C::kBufs;
       ptx::mbar_wait(&bar->s_full[sl], (t / kSlots) & 1);
-      // S(t) overwrites the TMEM buffer of tile t-3: its exponentials must have been read (pass 2 gets this
-      // ordering for free from PV(t-3), which waited for the same barrier and was issued earlier)
-      if (!kGrad && t >= C::kBufs) ptx::mbar_wait(&bar->p_ready[b], ((t - C::kBufs) / C::kBufs) & 1);
+      // S(t) overwrites the TMEM buffer of tile t-3: its exponentials must have been read (row sums), or the
+      // P.V MMAs that read them as operand A must have retired (gradient; they are issued by another warp)
+      if (t >= C::kBufs) {
+        if (kGrad) ptx::mbar_wait(&bar->pv_done[b], ((t - C::kBufs) / C::kBufs) & 1);
+        else ptx::mbar_wait(&bar->p_ready[b], ((t - C::kBufs) / C::kBufs) & 1);
+      }
       ptx::tc_fence_after();
       TC_TRACE(1, t);
       // K-major: box ks/4 (64 fp16 = 128 B), 16 elements = 32 bytes per k-step inside the 128-byte row
@@ -206,10 +192,34 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
       }
       __syncwarp();
       TC_TRACE(2, t);
-      if (kGrad && t >= 2) issue_pv(t - 2);  // two S tiles ahead of the oldest outstanding P.V
     }
-    if (kGrad && n_tiles > 1) issue_pv(n_tiles - 2);
-    if (kGrad && n_tiles > 0) issue_pv(n_tiles - 1);
+  } else if (warp == 10) {
+    // ======================================================= issuer of the P.V MMAs (gradient pass only)
+    if (kGrad) {
+      constexpr uint32_t idesc_pv = umma_idesc_f16(kMt, D, 0, 1);   // B = the same tile, MN-major
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+      const uint32_t ring0 = __shfl_sync(0xffffffffu, ptx::smem_u32(ring), 0);
+      for (int t = 0; t < n_tiles; ++t) {
+        const int sl = t % kSlots, b = t % C::kBufs;
+        ptx::mbar_wait(&bar->p_ready[b], (t / C::kBufs) & 1);
+        ptx::tc_fence_after();
+        TC_TRACE(5, t);
+        // MN-major, 128-byte swizzle, 16-bit elements: one k-step = 16 tile rows = two 8-row atoms 1024 B apart
+        // (SBO); the 64-element column blocks of N (one TMA box each) are kBoxBytes apart (LBO)
+        const uint64_t bd0 = ptx::umma_smem_desc(ring0 + sl * C::kTileBytes, C::kBoxBytes, 1024, ptx::kUmmaSwizzle128B);
+        const uint32_t a0 = tm + C::kColS + b * kBJ;
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < kBJ / 16; ++ks)  // P of columns 32h..32h+31 sits packed in TMEM columns 32h..32h+15
+            ptx::mma_f16_ts(tm + C::kColAcc, a0 + (ks >> 1) * C::kHalf + (ks & 1) * 8, bd0 + (uint64_t)(ks * 2048 >> 4),
+                            idesc_pv, (t > 0 || ks > 0) ? 1u : 0u);
+          ptx::tc_commit(&bar->s_free[sl]);   // S(t) retired before its exponentials were read: the slot is free
+          ptx::tc_commit(&bar->pv_done[b]);   // the S/P buffer may be overwritten
+          if (t == n_tiles - 1) ptx::tc_commit(&bar->acc_done);
+        }
+        __syncwarp();
+      }
+    }
   } else {
     // ================= softmax + epilogue: thread = local row; warp pair (w, w+4) shares a sub-partition
     const int sw = warp - 2;                    // 0..7
