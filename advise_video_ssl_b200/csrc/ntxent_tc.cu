@@ -37,9 +37,11 @@ namespace avssl {
 
 namespace {
 
-constexpr int kBJGrad = 64;   // columns of `out` per tile, gradient pass (S/P triple buffer + the D-wide accumulator fill TMEM)
-constexpr int kBJSum = 128;   // row-sum pass: no accumulator, so N = 128 MMAs fit (64 tensor cycles each: above the ~54-cycle
-                              // issue interval of one thread, which bounds the N = 64 tiles)
+// Columns of `out` per tile: 128 in both passes.  An N = 64 kind::f16 MMA costs ~54 cycles whatever it computes (the
+// S MMAs of a 64-column tile took 870 cycles for 512 cycles of tensor work); N = 128 MMAs cost ~70 for twice the work.
+// TMEM: row sums 3 x 128 columns of S; gradient 2 x 128 of S/P + the D-wide accumulator = 512 at D = 256.
+constexpr int kBJGrad = 128;
+constexpr int kBJSum = 128;
 constexpr int kMt = 128;   // local rows per CTA
 constexpr int kNtThreads = 352;
 constexpr int kSoftmax = 256;
@@ -70,15 +72,15 @@ struct NtCfg {
   // S / P is TRIPLE-buffered in TMEM (3 x 64 columns): S(t) can be issued before P.V(t-2) has even been
   // requested, so the exponentials of tile t-1 have a whole S-issue period of slack (a double buffer forces
   // S(t+1) behind P.V(t-1), i.e. behind softmax(t-1): the chain showed as a 16 % active tensor pipe)
-  static constexpr int kBufs = 3;
+  static constexpr int kBufs = (3 * kBJ + (kGrad ? D : 0)) <= 512 ? 3 : 2;
   static constexpr int kColS = 0, kColAcc = kBufs * kBJ;
   static constexpr int kColsNeeded = kBufs * kBJ + (kGrad ? D : 0);
   static constexpr int kTmemCols = kColsNeeded <= 128 ? 128 : (kColsNeeded <= 256 ? 256 : 512);
   static_assert(kColsNeeded <= 512, "TMEM budget");
-  static constexpr int kRingBudget = 232448 /* 227 KiB per CTA */ - 1024 - kQBytes - 8 * kHalfCols * 4 - 512;
+  static constexpr int kRingBudget = 232448 /* 227 KiB per CTA */ - 1024 - kQBytes - 8 * kHalf * 4 - 512;
   static constexpr int kSlots = (kRingBudget / kTileBytes) < kMaxSlots ? (kRingBudget / kTileBytes) : kMaxSlots;
   static_assert(kSlots >= 2, "at least a double buffer");
-  static constexpr size_t kSmemBytes = 1024 + (size_t)kQBytes + (size_t)kSlots * kTileBytes + 8 * kHalfCols * 4 + 512;
+  static constexpr size_t kSmemBytes = 1024 + (size_t)kQBytes + (size_t)kSlots * kTileBytes + 8 * kHalf * 4 + 512;
 };
 
 struct NtBarriers {
@@ -97,8 +99,8 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   uint8_t* q_smem = smem;
   uint8_t* ring = smem + C::kQBytes;
-  float* invz_c = reinterpret_cast<float*>(ring + kSlots * C::kTileBytes);  // [8 softmax warps][32]: 1/Z of the warp's columns
-  NtBarriers* bar = reinterpret_cast<NtBarriers*>(ring + kSlots * C::kTileBytes + 8 * kHalfCols * 4);
+  float* invz_c = reinterpret_cast<float*>(ring + kSlots * C::kTileBytes);  // [8 softmax warps][kHalf]: 1/Z of the warp's columns
+  NtBarriers* bar = reinterpret_cast<NtBarriers*>(ring + kSlots * C::kTileBytes + 8 * C::kHalf * 4);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) TC_TRACE(6, 0);
@@ -210,8 +212,8 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
         const uint32_t a0 = tm + C::kColS + b * kBJ;
         if (ptx::elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < kBJ / 16; ++ks)  // P of columns 32h..32h+31 sits packed in TMEM columns 32h..32h+15
-            ptx::mma_f16_ts(tm + C::kColAcc, a0 + (ks >> 1) * C::kHalf + (ks & 1) * 8, bd0 + (uint64_t)(ks * 2048 >> 4),
+          for (int ks = 0; ks < kBJ / 16; ++ks)  // P of columns 32c..32c+31 sits packed in TMEM columns 32c..32c+15
+            ptx::mma_f16_ts(tm + C::kColAcc, a0 + (ks >> 1) * kHalfCols + (ks & 1) * 8, bd0 + (uint64_t)(ks * 2048 >> 4),
                             idesc_pv, (t > 0 || ks > 0) ? 1u : 0u);
           ptx::tc_commit(&bar->s_free[sl]);   // S(t) retired before its exponentials were read: the slot is free
           ptx::tc_commit(&bar->pv_done[b]);   // the S/P buffer may be overwritten
@@ -231,7 +233,7 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
     const uint32_t lane_base = tmem + ((uint32_t)(sub * 32) << 16);
     const int rid = row_valid ? __ldg(a.rows + i) : -1;  // global row id: the diagonal column of this row
     const float invz_r = (kGrad && row_valid) ? 1.f / __ldg(a.z_all + rid) : 0.f;
-    float* iz = invz_c + sw * kHalfCols;        // this warp's staging of 1/Z_c (private: __syncwarp suffices)
+    float* iz = invz_c + sw * C::kHalf;         // this warp's staging of 1/Z_c (private: __syncwarp suffices)
 
     if (!q_by_tma) {
       // the CTA's rows straddle the two blocks: copy them into the K-major 128-byte-swizzled layout TMA would
@@ -252,10 +254,12 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
     const float scale2 = a.inv_T * kLog2eT;
     float zs[4] = {0.f, 0.f, 0.f, 0.f};
     // 1/Z of this warp's 32 columns of the NEXT tile is requested one tile ahead (one L2 round trip per tile otherwise)
-    float z_next = 1.f;
-    if (kGrad && n_tiles > 0) {
-      const int j = j_begin + hc * C::kHalf + lane;
-      z_next = j < j_end ? __ldg(a.z_all + j) : 0.f;
+    constexpr int kZ = C::kHalf / 32;  // values per lane
+    float z_next[kZ];
+#pragma unroll
+    for (int u = 0; u < kZ; ++u) {
+      const int j = j_begin + hc * C::kHalf + u * 32 + lane;
+      z_next[u] = (kGrad && n_tiles > 0 && j < j_end) ? __ldg(a.z_all + j) : 1.f;
     }
 
     for (int t = 0; t < n_tiles; ++t) {
@@ -263,10 +267,13 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
       const int j0 = j_begin + t * kBJ + hc * C::kHalf;  // first column of this warp's half tile
       if (kGrad) {
         __syncwarp();
-        iz[lane] = (j0 + lane < j_end) ? 1.f / z_next : 0.f;
+#pragma unroll
+        for (int u = 0; u < kZ; ++u) {
+          iz[u * 32 + lane] = (j0 + u * 32 + lane < j_end) ? 1.f / z_next[u] : 0.f;
+          const int jn = j0 + kBJ + u * 32 + lane;
+          z_next[u] = (t + 1 < n_tiles && jn < j_end) ? __ldg(a.z_all + jn) : 1.f;
+        }
         __syncwarp();
-        const int jn = j0 + kBJ + lane;
-        z_next = (t + 1 < n_tiles && jn < j_end) ? __ldg(a.z_all + jn) : 1.f;
       }
       ptx::mbar_wait(&bar->s_ready[b], (t / C::kBufs) & 1);
       ptx::tc_fence_after();
@@ -291,7 +298,8 @@ ntxent_tc_kernel(const NtxArgs a, const __grid_constant__ CUtensorMap tmap, cons
             e[u] = (c + u < valid && c + u != diag) ? e[u] : 0.f;
           }
           if (kGrad) {
-            const __half2 h = __floats2half2_rn(e[0] * (invz_r + iz[c]) * kPScale, e[1] * (invz_r + iz[c + 1]) * kPScale);
+            const float* izc = iz + ch * kHalfCols;
+            const __half2 h = __floats2half2_rn(e[0] * (invz_r + izc[c]) * kPScale, e[1] * (invz_r + izc[c + 1]) * kPScale);
             pk[c >> 1] = *reinterpret_cast<const uint32_t*>(&h);  // low half = even k
           } else {
             zs[c & 3] += e[0];
