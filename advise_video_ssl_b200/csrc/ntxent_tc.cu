@@ -37,10 +37,13 @@ namespace avssl {
 
 namespace {
 
-// Columns of `out` per tile: 128 in both passes.  An N = 64 kind::f16 MMA costs ~54 cycles whatever it computes (the
-// S MMAs of a 64-column tile took 870 cycles for 512 cycles of tensor work); N = 128 MMAs cost ~70 for twice the work.
-// TMEM: row sums 3 x 128 columns of S; gradient 2 x 128 of S/P + the D-wide accumulator = 512 at D = 256.
-constexpr int kBJGrad = 128;
+// Columns of `out` per tile.  An N = 64 kind::f16 MMA costs ~54 cycles whatever it computes (the S MMAs of a 64-column
+// tile take 870 cycles for 512 cycles of tensor work); N = 128 MMAs cost ~70 for twice the work, so the row-sum pass
+// (TMEM: 3 x 128 columns of S) uses 128-column tiles.  The gradient pass was measured both ways (the code handles
+// either): with 128-column tiles TMEM only holds a double buffer of S/P beside the D = 256 accumulator and shared
+// memory two 64 KiB tile slots, and the longer softmax per tile (16 exp2 per clock and SM) serialises with the slot
+// release: 14.4 us against 13.9 us with 64-column tiles, three S/P buffers and five slots.
+constexpr int kBJGrad = 64;
 constexpr int kBJSum = 128;
 constexpr int kMt = 128;   // local rows per CTA
 constexpr int kNtThreads = 352;

@@ -18,7 +18,7 @@ int main() {
   cudaMalloc(&a.part_z, (size_t)64 * n_loc * 4); cudaMalloc(&a.part_g, (size_t)64 * n_loc * D * 4);
   for (int grad = 0; grad < 2; ++grad) {
     ntxent_tc_plan(N2, n_loc, grad != 0, &a.n_splits, &a.cols_per_split);
-    printf("splits %d cols/split %d tiles/CTA %d\n", a.n_splits, a.cols_per_split, a.cols_per_split / 128);
+    printf("splits %d cols/split %d tiles/CTA %d\n", a.n_splits, a.cols_per_split, a.cols_per_split / (grad ? 64 : 128));
     for (int rep = 0; rep < 3; ++rep) {
       int rc = launch_ntxent_tc(a, grad != 0, 0);
       cudaError_t e = cudaDeviceSynchronize();
@@ -28,7 +28,7 @@ int main() {
     const long long t0 = tr[6][0];
     printf("pass %d: entry=0 setup_done=%lld q_ready=%lld acc_done_seen=%lld teardown=%lld\n", grad, tr[6][1] - t0, tr[6][2] - t0,
            grad ? tr[6][3] - t0 : -1, tr[6][4] - t0);
-    for (int t = 0; t < a.cols_per_split / 128; ++t)
+    for (int t = 0; t < a.cols_per_split / (grad ? 64 : 128); ++t)
       printf("  tile %d: tma_issue=%lld S_issue=%lld S_issued=%lld S_seen=%lld P_done=%lld PV_issue=%lld\n", t, tr[0][t] - t0,
              tr[1][t] - t0, tr[2][t] - t0, tr[3][t] - t0, tr[4][t] - t0, grad ? tr[5][t] - t0 : -1);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0);
