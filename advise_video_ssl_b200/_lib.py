@@ -65,6 +65,7 @@ SIGNATURES = {
     "avssl_ce_target0_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "avssl_ntxent_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "avssl_ntxent_prepare": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "avssl_ntxent_prepare_peer": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "avssl_ntxent_rowsum": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_size_t,
                                     c_int, c_void_p]),
     "avssl_ntxent_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float,

@@ -85,15 +85,16 @@ class NtXentRows(torch.autograd.Function):
     models/contrastive.py:770-792, utils/distributed.py:131-155)."""
 
     @staticmethod
-    def forward(ctx, feat1, feat2, T, impl):
-        loss, d1, d2 = ops.ntxent(feat1.detach().contiguous(), feat2.detach().contiguous(), T, impl=impl)
+    def forward(ctx, feat1, feat2, T, impl, xchg=None, status=None):
+        loss, d1, d2 = ops.ntxent(feat1.detach().contiguous(), feat2.detach().contiguous(), T, impl=impl, xchg=xchg,
+                                  status=status)
         ctx.save_for_backward(d1, d2)
         return loss.reshape(())
 
     @staticmethod
     def backward(ctx, g):
         d1, d2 = ctx.saved_tensors
-        return _scaled(d1, g), _scaled(d2, g), None, None
+        return _scaled(d1, g), _scaled(d2, g), None, None, None, None
 
 
 class SwavSwappedCe(torch.autograd.Function):

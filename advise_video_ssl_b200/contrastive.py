@@ -362,7 +362,8 @@ class ContrastiveModel(nn.Module):
         self._peer_exchange_on = bool(on)
         if not on:
             for ex in self._peer_xchgs.values():
-                ex.close()
+                for one in (ex if isinstance(ex, tuple) else (ex,)):
+                    one.close()
             self._peer_xchgs = {}
         return self
 
@@ -785,10 +786,27 @@ class ContrastiveModel(nn.Module):
         feat_q2 = self.backbone(clips[1])
         # K6 + C4/C5: normalise, gather, NT-Xent over this rank's rows, gradient with the reference's
         # world-size factor (utils/distributed.py:142-155)
-        loss = NtXentRows.apply(feat_q, feat_q2, self.T, self.ntxent_impl)
-        with torch.no_grad():
-            self.knn_mem_update(self.l2_norm(feat_q.detach()), index)
+        loss = NtXentRows.apply(feat_q, feat_q2, self.T, self.ntxent_impl, self._simclr_exchanges(feat_q), self._status)
+        if self.knn_on:
+            with torch.no_grad():
+                self.knn_mem_update(self.l2_norm(feat_q.detach()), index)
         return self._cached_dummy_logits(len(index), feat_q.device), loss
+
+    def _simclr_exchanges(self, feat):
+        """NVLink exchanges for the two gathers of the SimCLR branch (C4: rows and row sums over WORLD), or None
+        when the ranks do not share a box / CUDA IPC is unavailable (NCCL all_gather then)."""
+        if self.num_gpus <= 1 or not torch.distributed.is_initialized() or int(_opt(self.cfg, "NUM_SHARDS", 1)) != 1:
+            return None
+        B, D = feat.shape
+        if not (feat.is_cuda and feat.dtype == torch.float32 and D % 4 == 0 and B % 4 == 0):
+            return None
+        if torch.distributed.get_world_size() > _lib.MAX_PEERS or not self._peer_transport_on():
+            return None
+        key = ("simclr", B, D)
+        ex = self._peer_xchgs.get(key)
+        if ex is None:
+            ex = self._peer_xchgs[key] = (ops.PeerExchange(2 * B, D), ops.PeerExchange(2, B))
+        return ex
 
     # ------------------------------------------------------------------ SwAV helpers
     def run_swav_orig_encoder_q(self, x):

@@ -14,8 +14,10 @@
 // Both passes are split over column ranges; partials are reduced in a fixed order.
 // CUDA-core kernels (fp32 exact) = AVSSL_IMPL_SIMT; the tcgen05 kernels are in ntxent_tc.cu.
 #include <cuda_fp16.h>
+#include <string.h>
 
 #include "ntxent.cuh"
+#include "peer.cuh"
 #include "simt_tile.cuh"
 
 namespace avssl {
@@ -339,9 +341,21 @@ static int ntx_setup(NtxArgs& a, const float* out, const void* out_f16, const in
 
 // out[(v * W + w) * B + b] = gathered[w][v][b] ([q_all ; q2_all], models/contrastive.py:771-775) and its
 // fp16 copy (round to nearest), one pass: 128-bit loads, a 128-bit and a 64-bit store per element group.
+// kPeer: the gathered rows sit in this rank's NVLink exchange buffer (every rank pushed its [2B, D] block, C4 without
+// a collective kernel): wait for all flags of the current epoch first, then read the slot.
+template <bool kPeer>
 __global__ void __launch_bounds__(256)
-ntxent_prepare_kernel(const float4* __restrict__ gathered, int W, int B, int D4, float4* __restrict__ out,
-                      uint2* __restrict__ out_f16) {
+ntxent_prepare_kernel(const float4* __restrict__ gathered, const avssl_peer_xchg x, uint32_t* status, int W, int B, int D4,
+                      float4* __restrict__ out, uint2* __restrict__ out_f16) {
+  if (kPeer) {
+    __shared__ int s_slot;
+    if (threadIdx.x < 32) {
+      const int slot = peer_wait_all_warp(x, status);
+      if (threadIdx.x == 0) s_slot = slot;
+    }
+    __syncthreads();
+    gathered = reinterpret_cast<const float4*>(peer_payload(x.base[x.rank], s_slot, x));
+  }
   // one warp per destination row (v * W + w) * B + b; the row index arithmetic is per warp, not per element, and
   // all of a row's loads are issued before its first store
   const int lane = threadIdx.x & 31;
@@ -354,18 +368,18 @@ ntxent_prepare_kernel(const float4* __restrict__ gathered, int W, int B, int D4,
     float4* o = out + (size_t)row * D4;
     uint2* oh = out_f16 + (size_t)row * D4;
     for (int c0 = 0; c0 < D4; c0 += 32 * kMaxPerLane) {
-      float4 x[kMaxPerLane];
+      float4 xv[kMaxPerLane];
 #pragma unroll
       for (int u = 0; u < kMaxPerLane; ++u) {
         const int c = c0 + lane + 32 * u;
-        if (c < D4) x[u] = ldg_stream(src + c);
+        if (c < D4) xv[u] = kPeer ? __ldcg(src + c) : ldg_stream(src + c);  // peer rows were written by other GPUs: through L2
       }
 #pragma unroll
       for (int u = 0; u < kMaxPerLane; ++u) {
         const int c = c0 + lane + 32 * u;
         if (c < D4) {
-          o[c] = x[u];
-          const __half2 lo = __floats2half2_rn(x[u].x, x[u].y), hi = __floats2half2_rn(x[u].z, x[u].w);
+          o[c] = xv[u];
+          const __half2 lo = __floats2half2_rn(xv[u].x, xv[u].y), hi = __floats2half2_rn(xv[u].z, xv[u].w);
           oh[c] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
         }
       }
@@ -373,9 +387,27 @@ ntxent_prepare_kernel(const float4* __restrict__ gathered, int W, int B, int D4,
   }
 }
 
+static int ntx_prepare(const float* gathered, const avssl_peer_xchg* x, uint32_t* status, int world, int B, int D, float* out,
+                       void* out_f16, void* stream);
+
+extern "C" int avssl_ntxent_prepare_peer(const avssl_peer_xchg* x, uint32_t* status_dev, int B, int D, float* out,
+                                         void* out_f16, void* stream) {
+  int rc = peer_check(x, "ntxent_prepare_peer");
+  if (rc != AVSSL_OK) return rc;
+  AVSSL_REQUIRE(x->rows_per_rank == 2 * B && x->D == D, AVSSL_ERR_INVALID_ARGUMENT,
+                "ntxent_prepare_peer: the exchange carries [%d x %d] per rank, expected [%d x %d]", x->rows_per_rank, x->D, 2 * B, D);
+  return ntx_prepare(nullptr, x, status_dev, x->world, B, D, out, out_f16, stream);
+}
+
 extern "C" int avssl_ntxent_prepare(const float* gathered, int world, int B, int D, float* out, void* out_f16,
                                     void* stream) {
-  AVSSL_REQUIRE(gathered && out && out_f16 && world > 0 && B > 0 && D > 0 && D % 4 == 0, AVSSL_ERR_INVALID_ARGUMENT,
+  AVSSL_REQUIRE(gathered, AVSSL_ERR_INVALID_ARGUMENT, "ntxent_prepare: gathered is null");
+  return ntx_prepare(gathered, nullptr, nullptr, world, B, D, out, out_f16, stream);
+}
+
+static int ntx_prepare(const float* gathered, const avssl_peer_xchg* x, uint32_t* status, int world, int B, int D, float* out,
+                       void* out_f16, void* stream) {
+  AVSSL_REQUIRE((gathered || x) && out && out_f16 && world > 0 && B > 0 && D > 0 && D % 4 == 0, AVSSL_ERR_INVALID_ARGUMENT,
                 "ntxent_prepare: bad arguments (world=%d B=%d D=%d, D %% 4 == 0)", world, B, D);
   AVSSL_REQUIRE(((reinterpret_cast<uintptr_t>(gathered) | reinterpret_cast<uintptr_t>(out) |
                   reinterpret_cast<uintptr_t>(out_f16)) & 15u) == 0,
@@ -383,9 +415,15 @@ extern "C" int avssl_ntxent_prepare(const float* gathered, int world, int B, int
   int grid = (2 * world * B + 7) / 8;  // 8 warps = 8 rows per CTA
   const int cap = 16 * (sm_count() > 0 ? sm_count() : 148);
   if (grid > cap) grid = cap;
-  ntxent_prepare_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const float4*>(gathered), world, B, D / 4, reinterpret_cast<float4*>(out),
-      reinterpret_cast<uint2*>(out_f16));
+  avssl_peer_xchg none;
+  memset(&none, 0, sizeof(none));
+  if (x)
+    ntxent_prepare_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        nullptr, *x, status, world, B, D / 4, reinterpret_cast<float4*>(out), reinterpret_cast<uint2*>(out_f16));
+  else
+    ntxent_prepare_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(gathered), none, nullptr, world, B, D / 4, reinterpret_cast<float4*>(out),
+        reinterpret_cast<uint2*>(out_f16));
   AVSSL_LAUNCH_OK("ntxent_prepare_kernel");
   return AVSSL_OK;
 }

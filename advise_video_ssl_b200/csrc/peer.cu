@@ -25,6 +25,38 @@ l2norm_push_kernel(const avssl_peer_xchg x, const float* __restrict__ feat, floa
   peer_push_cta<true>(x, feat, blockIdx.x, &s_epoch, eps, y_local);
 }
 
+// push for LARGE blocks (the SimCLR row gather, C4: 1 MiB per rank and destination at cfg3): M CTAs per destination
+// split the block's bytes; the last of them (counter per destination in the header) publishes the flag, the last CTA
+// of the whole grid advances the local epoch.
+__global__ void __launch_bounds__(512)
+peer_push_wide_kernel(const avssl_peer_xchg x, const float4* __restrict__ rows, int M) {
+  __shared__ unsigned long long s_epoch;
+  PeerHdr* me = static_cast<PeerHdr*>(x.base[x.rank]);
+  if (threadIdx.x == 0) s_epoch = *reinterpret_cast<volatile unsigned long long*>(&me->epoch) + 1ull;
+  __syncthreads();
+  const unsigned long long e = s_epoch;
+  const int d = blockIdx.x / M, m = blockIdx.x % M;
+  const size_t n4 = (size_t)x.rows_per_rank * x.D / 4;
+  const size_t lo = n4 * m / M, hi = n4 * (m + 1) / M;
+  float4* out = reinterpret_cast<float4*>(peer_payload(x.base[d], (int)(e & 1ull), x) + (size_t)x.rank * x.rows_per_rank * x.D);
+#pragma unroll 4
+  for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) out[i] = __ldg(rows + i);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    if (atomicAdd(&me->pad_[d], 1u) == (unsigned)M - 1u) {  // last CTA of destination d
+      me->pad_[d] = 0u;
+      __threadfence_system();
+      st_release_sys_u64(&static_cast<PeerHdr*>(x.base[d])->flags[x.rank], e);
+    }
+    if (atomicAdd(&me->done, 1u) == gridDim.x - 1u) {
+      me->done = 0u;
+      *reinterpret_cast<volatile unsigned long long*>(&me->epoch) = e;
+      __threadfence();
+    }
+  }
+}
+
 // out[i] = gathered[row_idx ? row_idx[i] : rank * rows_per_rank + i]; bit-exact copy.
 __global__ void __launch_bounds__(256)
 peer_wait_gather_kernel(const avssl_peer_xchg x, const long long* __restrict__ row_idx, int n_out,
@@ -229,8 +261,18 @@ extern "C" int avssl_peer_push_rows(const avssl_peer_xchg* x, const float* rows,
   if (rc != AVSSL_OK) return rc;
   AVSSL_REQUIRE(rows && (reinterpret_cast<uintptr_t>(rows) & 15u) == 0, AVSSL_ERR_INVALID_ARGUMENT,
                 "peer_push_rows: rows is null or not 16-byte aligned");
-  peer_push_kernel<<<x->world, 256, 0, static_cast<cudaStream_t>(stream)>>>(*x, rows);
-  AVSSL_LAUNCH_OK("peer_push_kernel");
+  const size_t bytes = (size_t)x->rows_per_rank * x->D * 4;
+  if (bytes <= 65536) {  // small blocks (the MoCo keys): one CTA per destination, the shortest dependent chain
+    peer_push_kernel<<<x->world, 256, 0, static_cast<cudaStream_t>(stream)>>>(*x, rows);
+    AVSSL_LAUNCH_OK("peer_push_kernel");
+    return AVSSL_OK;
+  }
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  int M = (int)((bytes + 32767) / 32768);  // ~32 KiB per CTA
+  const int cap = 4 * sms / x->world > 1 ? 4 * sms / x->world : 1;
+  if (M > cap) M = cap;
+  peer_push_wide_kernel<<<x->world * M, 512, 0, static_cast<cudaStream_t>(stream)>>>(*x, reinterpret_cast<const float4*>(rows), M);
+  AVSSL_LAUNCH_OK("peer_push_wide_kernel");
   return AVSSL_OK;
 }
 

@@ -656,11 +656,35 @@ def ce_target0_bwd(logits, lse, grad_out):
 
 
 # ----------------------------------------------------------------------------- K6
-def ntxent(feat1, feat2, T, gather=None, impl=_lib.IMPL_AUTO):
+_ntx_const = {}
+
+
+def _ntx_rows(rank, B, N, dev):
+    """Global row ids of this rank's 2B rows of [q_all ; q2_all] (int32, cached)."""
+    key = ("rows", rank, B, N, dev)
+    t = _ntx_const.get(key)
+    if t is None:
+        t = _ntx_const[key] = torch.cat([torch.arange(rank * B, (rank + 1) * B, dtype=torch.int32, device=dev),
+                                         torch.arange(N + rank * B, N + (rank + 1) * B, dtype=torch.int32, device=dev)])
+    return t
+
+
+def _ntx_zperm(world, dev):
+    """Row gather that turns the exchanged [W][2][B] row sums into [2][W][B] (the order of [q_all ; q2_all])."""
+    key = ("zperm", world, dev)
+    t = _ntx_const.get(key)
+    if t is None:
+        t = _ntx_const[key] = torch.tensor([w * 2 + v for v in range(2) for w in range(world)], dtype=torch.int64, device=dev)
+    return t
+
+
+def ntxent(feat1, feat2, T, gather=None, impl=_lib.IMPL_AUTO, xchg=None, status=None):
     """SimCLR NT-Xent (K6) with the cross-rank gather (C4) and the reduce-scatter-
     equivalent gradient (C5) folded in.  feat1/feat2: this rank's raw [B, D] features.
     Returns (loss[1], dfeat1, dfeat2); the gradients carry the reference's world-size
-    factor (utils/distributed.py:142-155)."""
+    factor (utils/distributed.py:142-155).
+    `xchg` = (PeerExchange(2B, D), PeerExchange(2, B)) over WORLD: both gathers (rows, row sums) go over NVLink
+    peer stores instead of NCCL all_gather kernels (one box)."""
     import torch.distributed as dist
     _req(feat1, "feat1")
     _req(feat2, "feat2")
@@ -675,25 +699,37 @@ def ntxent(feat1, feat2, T, gather=None, impl=_lib.IMPL_AUTO):
         world = 1
     rank = dist.get_rank() if world > 1 else 0
     y, nrm = l2norm_fwd(torch.cat([feat1, feat2], 0), 0.0)  # [2B, D] unit rows, local
-    if world > 1:
-        allq = torch.empty(world, 2, B, D, dtype=_f32, device=dev)
-        dist.all_gather_into_tensor(allq.view(world * 2 * B, D), y)
-    else:
-        allq = y
-    # [q_all ; q2_all] and its fp16 copy (the tensor cores' operand) in one pass over the gathered rows
     N = world * B
     out = torch.empty(2 * N, D, dtype=_f32, device=dev)
     out_r = torch.empty(2 * N, D, dtype=torch.float16, device=dev)
-    check(lib.avssl_ntxent_prepare(allq.data_ptr(), world, B, D, out.data_ptr(), out_r.data_ptr(), _stream()),
-          "avssl_ntxent_prepare")
-    rows = torch.cat([torch.arange(rank * B, (rank + 1) * B, dtype=torch.int32, device=dev),
-                      torch.arange(N + rank * B, N + (rank + 1) * B, dtype=torch.int32, device=dev)])
+    peer = world > 1 and xchg is not None
+    if peer:
+        rows_x, z_x = xchg
+        if rows_x.world != world or z_x.world != world:
+            raise ValueError("the exchanges span %d ranks, the gather %d" % (rows_x.world, world))
+        rows_x.push(y)
+        # wait for every rank's block, then [q_all ; q2_all] and its fp16 copy in one pass over the exchange buffer
+        check(lib.avssl_ntxent_prepare_peer(ctypes.addressof(rows_x.desc), status.data_ptr() if status is not None else None,
+                                            B, D, out.data_ptr(), out_r.data_ptr(), _stream()), "avssl_ntxent_prepare_peer")
+    else:
+        if world > 1:
+            allq = torch.empty(world, 2, B, D, dtype=_f32, device=dev)
+            dist.all_gather_into_tensor(allq.view(world * 2 * B, D), y)
+        else:
+            allq = y
+        # [q_all ; q2_all] and its fp16 copy (the tensor cores' operand) in one pass over the gathered rows
+        check(lib.avssl_ntxent_prepare(allq.data_ptr(), world, B, D, out.data_ptr(), out_r.data_ptr(), _stream()),
+              "avssl_ntxent_prepare")
+    rows = _ntx_rows(rank, B, N, dev)
     n_loc = 2 * B
     ws = _workspace(dev, lib.avssl_ntxent_workspace_bytes(2 * N, D, n_loc), "ntxent")
     z_loc = torch.empty(n_loc, dtype=_f32, device=dev)
     check(lib.avssl_ntxent_rowsum(out.data_ptr(), out_r.data_ptr(), rows.data_ptr(), rank * B, N + rank * B, 2 * N, D, n_loc, float(T),
                                   z_loc.data_ptr(), ws.data_ptr(), ws.numel(), int(impl), _stream()), "avssl_ntxent_rowsum")
-    if world > 1:
+    if peer:
+        z_x.push(z_loc.view(2, B))
+        z_all = z_x.wait_gather(_ntx_zperm(world, dev), status=status).view(-1)
+    elif world > 1:
         zg = torch.empty(world, 2, B, dtype=_f32, device=dev)
         dist.all_gather_into_tensor(zg.view(-1), z_loc)
         z_all = zg.permute(1, 0, 2).reshape(-1).contiguous()

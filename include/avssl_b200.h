@@ -229,6 +229,9 @@ AVSSL_API int avssl_ce_target0_bwd(const float* logits, const float* row_lse, in
 AVSSL_API size_t avssl_ntxent_workspace_bytes(int N2, int D, int n_loc);
 AVSSL_API int avssl_ntxent_prepare(const float* gathered, int world, int B, int D, float* out, void* out_f16,
                          void* stream);
+/* Same, reading the gathered rows out of this rank's NVLink exchange buffer (every rank pushed its [2B, D] block of
+ * unit rows with avssl_peer_push_rows: C4 without a collective kernel); the launch waits for every rank's flag first.
+ * Declared after avssl_peer_xchg below. */
 AVSSL_API int avssl_ntxent_rowsum(const float* out, const void* out_f16, const int* rows, int row0_first,
                         int row1_first, int N2, int D, int n_loc,
                         float T, float* z_loc_out, void* workspace, size_t workspace_bytes, int impl,
@@ -291,7 +294,7 @@ AVSSL_API int avssl_peer_alloc(size_t bytes, void** dev_ptr_out, void* ipc_handl
 AVSSL_API int avssl_peer_open(const void* ipc_handle_host, void** dev_ptr_out);
 AVSSL_API int avssl_peer_close(void* dev_ptr);
 AVSSL_API int avssl_peer_free(void* dev_ptr);
-/* push: `world` CTAs, one per destination rank (stand-alone launch). */
+/* push (stand-alone launch): one CTA per destination rank for blocks up to 64 KiB, several per destination beyond. */
 AVSSL_API int avssl_peer_push_rows(const avssl_peer_xchg* x, const float* rows, void* stream);
 /* push with Normalize fused in (models/contrastive.py:923-934 applied to the key features, :350):
  * what travels is feat / max(||feat||, eps), bit-identical to avssl_l2norm_fwd followed by
@@ -345,6 +348,9 @@ AVSSL_API int avssl_moco_infonce_fwd_bwd_enqueue_peer(const float* feat_q, const
                                             float* loss_out, float* dfeat_out, float* row_lse_out,
                                             float* logits_out, void* workspace, size_t workspace_bytes,
                                             int impl, void* stream);
+
+AVSSL_API int avssl_ntxent_prepare_peer(const avssl_peer_xchg* x, uint32_t* status_dev, int B, int D, float* out,
+                              void* out_f16, void* stream);
 
 /* K2+K3+K4 with the un-shuffle (and optionally the key Normalize) folded in, for keys that live on THIS
  * device (one GPU, or after an NCCL gather): key_rows is [n_key_rows, D]; query row i meets

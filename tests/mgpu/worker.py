@@ -134,16 +134,21 @@ def check_simclr(rank, world, dev, C, O, make_cfg, report):
         b = torch.cat(f2).requires_grad_(True)
         ref = O.ntxent(O.l2_normalize(a), O.l2_normalize(b), T)
         ref.backward()
-        for impl, lt, gt in ((_lib.IMPL_SIMT, 1e-5, 1e-4), (_lib.IMPL_AUTO, 2e-4, 1e-3)):
-            model.ntxent_impl = impl
-            x1 = f1[rank].to(dev).requires_grad_(True)
-            x2 = f2[rank].to(dev).requires_grad_(True)
-            _, loss = model([[x1], [x2]], torch.arange(B, device=dev), None, 0.0)
-            loss.backward()
-            sl = slice(rank * B, (rank + 1) * B)
-            e = (rel_err(loss.detach(), ref.detach()), rel_err(x1.grad, world * a.grad[sl]), rel_err(x2.grad, world * b.grad[sl]))
-            assert e[0] < lt and e[1] < gt and e[2] < gt, (B, D, impl, e)
-            out["B%d_D%d_impl%d" % (B, D, impl)] = {"loss": e[0], "grad": max(e[1:])}
+        for peer in (True, False):  # both gathers over NVLink peer stores / over NCCL
+            model.enable_peer_exchange(peer)
+            for impl, lt, gt in ((_lib.IMPL_SIMT, 1e-5, 1e-4), (_lib.IMPL_AUTO, 2e-4, 1e-3)):
+                model.ntxent_impl = impl
+                x1 = f1[rank].to(dev).requires_grad_(True)
+                x2 = f2[rank].to(dev).requires_grad_(True)
+                _, loss = model([[x1], [x2]], torch.arange(B, device=dev), None, 0.0)
+                loss.backward()
+                sl = slice(rank * B, (rank + 1) * B)
+                e = (rel_err(loss.detach(), ref.detach()), rel_err(x1.grad, world * a.grad[sl]), rel_err(x2.grad, world * b.grad[sl]))
+                assert e[0] < lt and e[1] < gt and e[2] < gt, (B, D, impl, peer, e)
+                out["B%d_D%d_impl%d_%s" % (B, D, impl, "peer" if peer else "nccl")] = {"loss": e[0], "grad": max(e[1:])}
+            assert bool(model._peer_xchgs) == peer
+        assert model.check_device_status() == 0
+        model.enable_peer_exchange(False)
     report["simclr"] = out
 
 
