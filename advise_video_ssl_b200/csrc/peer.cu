@@ -39,7 +39,7 @@ peer_push_wide_kernel(const avssl_peer_xchg x, const float4* __restrict__ rows, 
   const size_t n4 = (size_t)x.rows_per_rank * x.D / 4;
   const size_t lo = n4 * m / M, hi = n4 * (m + 1) / M;
   float4* out = reinterpret_cast<float4*>(peer_payload(x.base[d], (int)(e & 1ull), x) + (size_t)x.rank * x.rows_per_rank * x.D);
-#pragma unroll 4
+#pragma unroll 8
   for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) out[i] = __ldg(rows + i);
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -268,8 +268,10 @@ extern "C" int avssl_peer_push_rows(const avssl_peer_xchg* x, const float* rows,
     return AVSSL_OK;
   }
   const int sms = sm_count() > 0 ? sm_count() : 148;
-  int M = (int)((bytes + 32767) / 32768);  // ~32 KiB per CTA
-  const int cap = 4 * sms / x->world > 1 ? 4 * sms / x->world : 1;
+  // ~128 KiB per CTA: every CTA ends with a system-scope fence that waits for the GPU's outstanding NVLink writes, so
+  // few fat CTAs beat many thin ones (256 CTAs of 32 KiB: 32 us for 8 x 1 MiB at N = 8)
+  int M = (int)((bytes + 131071) / 131072);
+  const int cap = 2 * sms / x->world > 1 ? 2 * sms / x->world : 1;
   if (M > cap) M = cap;
   peer_push_wide_kernel<<<x->world * M, 512, 0, static_cast<cudaStream_t>(stream)>>>(*x, reinterpret_cast<const float4*>(rows), M);
   AVSSL_LAUNCH_OK("peer_push_wide_kernel");
