@@ -91,6 +91,8 @@ SIGNATURES = {
                                                            c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
                                                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                                            c_size_t, c_int, c_void_p]),
+    "avssl_moco_infonce_sweep": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_size_t,
+                                         c_int, c_int, c_void_p]),
     "avssl_multi_l2norm_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "avssl_multi_l2norm": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "avssl_swav_ce_workspace_bytes": (c_size_t, [c_int]),
@@ -99,6 +101,11 @@ SIGNATURES = {
 }
 
 IMPL_AUTO, IMPL_SIMT, IMPL_TC3X, IMPL_TC1X = 0, 1, 2, 3
+
+
+def head_swept(sweep_ctas):
+    """AVSSL_HEAD_SWEPT(sweep_ctas): or-ed into `impl` of a head call that follows avssl_moco_infonce_sweep."""
+    return 0x100 | (int(sweep_ctas) << 16)
 MAX_KEYS = 8
 DEVFLAG_QUEUE_OVERRUN = 1
 DEVFLAG_BAD_INDEX = 2

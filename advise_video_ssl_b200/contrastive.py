@@ -30,6 +30,7 @@ Backbones are not part of this package: `_MODEL_TYPES` is filled from the host a
 """
 import logging
 import math
+import os
 
 import numpy as np
 import torch
@@ -131,6 +132,11 @@ class ContrastiveModel(nn.Module):
         # ---- knobs of the B200 path (absent from the reference)
         self.materialize_logits = True
         self.infonce_impl = _lib.IMPL_AUTO
+        # MoCo head in two launches (ops.moco_infonce_sweep): the sweep of q against the queue starts right after the
+        # query encoder, on its own stream, and runs beside the momentum update / shuffle / key encoder that the
+        # reference issues next (:462 then :478).  sweep_ctas: None = sized against the momentum update, 0 = every SM.
+        self.overlap_sweep = True
+        self.sweep_ctas = int(os.environ["AVSSL_SWEEP_CTAS"]) if os.environ.get("AVSSL_SWEEP_CTAS") else None
         self.ntxent_impl = _lib.IMPL_AUTO  # tcgen05 tf32 when D allows it; IMPL_SIMT = exact fp32
         self.queue_mode = str(_opt(ct, "QUEUE_MODE", "reference"))
         assert self.queue_mode in QUEUE_MODES, "CONTRASTIVE.QUEUE_MODE must be one of %s" % (QUEUE_MODES,)
@@ -626,6 +632,7 @@ class ContrastiveModel(nn.Module):
         n_k = 1 if own_keys and len(clips_k) == 1 else (len(clips_k) if own_keys else len(keys))
         head_kw = dict(want_logits=self.materialize_logits, impl=self.infonce_impl,
                        workspace=self._head_workspace(B, D, n_k, feat_q.device))
+        sweep_stream = self._sweep_ahead(feat_q, n_k, own_keys, head_kw)
         # the fused ring write rides in the head launch when exactly keys[0] is enqueued (the default) and
         # the kernel's vector path applies; anything else goes through _dequeue_and_enqueue afterwards
         can_fuse = (own_keys and not self.cfg.CONTRASTIVE.MOCO_MULTI_VIEW_QUEUE and D % 4 == 0)
@@ -656,11 +663,59 @@ class ContrastiveModel(nn.Module):
             if fused:
                 head_kw["enqueue"] = (self.ptr, self._status)
             plan = {"keys": [k.detach().contiguous() for k in keys], "kw": head_kw}
+        if sweep_stream is not None:
+            torch.cuda.current_stream(feat_q.device).wait_stream(sweep_stream)
         loss, logits, q = MocoInfoNce.apply(feat_q, self.queue_x, self.T, plan)
         if own_keys and not fused:
             self._dequeue_and_enqueue(keys)
         self.knn_mem_update(q, index)
         return (logits if self.materialize_logits else None), loss
+
+    def _sweep_ahead(self, feat_q, n_keys, own_keys, head_kw):
+        """Launch the sweep of q against the queue NOW, on its own stream: it needs neither the keys nor the momentum
+        encoder, and the reference's order puts the whole key path (:478 -> :314 momentum update, :338 shuffle, key
+        encoder) between the query encoder (:462) and the logits (:490).  The head launch that follows the key path
+        then only merges the sweep's partials with the key term.  Returns the stream to wait for, or None."""
+        B, D = feat_q.shape
+        if not (self.overlap_sweep and feat_q.is_cuda and self._tc_head_ok(B, D)):
+            return None
+        dev = feat_q.device
+        ctas = self.sweep_ctas
+        if ctas is None:  # sized against the momentum update that `compute_key_feat` launches next; None: not worth it
+            ctas = self._sweep_ctas_beside_ema(B, dev) if own_keys else None
+            if ctas is None:
+                return None
+        logits = torch.empty(n_keys * B, self.k + 1, dtype=torch.float32, device=dev) if self.materialize_logits else None
+        fq = feat_q.detach().contiguous()
+        main = torch.cuda.current_stream(dev)
+        side = self._cached(("sweep_stream", dev), lambda: torch.cuda.Stream(device=dev, priority=-1))
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            ops.moco_infonce_sweep(fq, self.queue_x, self.T, head_kw["workspace"], n_keys=n_keys, logits=logits,
+                                   impl=self.infonce_impl, sweep_ctas=ctas)
+        # (fq, logits and the workspace stay referenced until the head launch, which the main stream orders behind the sweep)
+        head_kw.update(swept=ctas, out={"logits": logits} if logits is not None else None)
+        return side
+
+    def _sweep_ctas_beside_ema(self, B, device):
+        """CTAs for a sweep that shares the GPU with the momentum update, or None when the single-launch head is the
+        better choice.  The tcgen05 sweep owns every register of the SMs it runs on; the momentum update is HBM-bound
+        and a flat grid of small CTAs that fills whatever is left.  Give the sweep just enough SMs to end well before
+        the update does (measured on B200, DESIGN.md 4 K3: ~2 us per 64-row tile beside the update, ~20 us before its
+        first CTA is placed); when the update is short compared with the sweep there is nothing to hide it under."""
+        def size():
+            sms = ops.sm_count()
+            n_params = sum(p.numel() for p in self.backbone_hist.parameters()) if hasattr(self, "backbone_hist") else 0
+            ema_us = 12.0 * n_params / 6.5e6                      # 12 bytes per parameter at ~6.5 TB/s
+            row_blocks = (B + 127) // 128
+            tiles = (self.k + 63) // 64 * row_blocks
+            alone_us = 4.0 + 1.2 * -(-tiles // sms)                # the sweep with every SM to itself
+            if ema_us < 2.0 * alone_us + 20.0:
+                return -1
+            tiles_per_cta = max(1, int((0.8 * ema_us - 20.0) / 2.0))
+            return int(min(sms, max(row_blocks, -(-tiles // tiles_per_cta))))
+        ctas = self._cached(("sweep_ctas", B, device), size)
+        return None if ctas < 0 else ctas
 
     def _head_workspace(self, B, D, n_keys, device):
         """Scratch of the head launch (split partials + barrier words), owned by the module and zero-filled once:

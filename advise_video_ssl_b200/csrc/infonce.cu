@@ -20,7 +20,7 @@ int max_splits() {
 }
 
 struct Carve {
-  size_t counter, row_loss, part_m, part_l, part_acc, total;
+  size_t counter, row_loss, part_m, part_l, part_acc, one_m, one_l, one_acc, total;
 };
 Carve carve(int B, int D, int n_keys, int S) {
   Carve c;
@@ -35,6 +35,13 @@ Carve carve(int B, int D, int n_keys, int S) {
   off += align_up(sizeof(float) * (size_t)S * B);
   c.part_acc = off;
   off += align_up(sizeof(float) * (size_t)S * B * D);
+  // two-launch form: the partials of every row merged to one (infonce_merge_partials_kernel)
+  c.one_m = off;
+  off += align_up(sizeof(float) * (size_t)B);
+  c.one_l = off;
+  off += align_up(sizeof(float) * (size_t)B);
+  c.one_acc = off;
+  off += align_up(sizeof(float) * (size_t)B * D);
   c.total = off;
   return c;
 }
@@ -55,7 +62,12 @@ int moco_infonce_run(const float* feat_q, const float* const* keys_host, int n_k
                      const avssl_peer_xchg* peer = nullptr, const int64_t* peer_row_idx = nullptr,
                      const int64_t* enq_row_idx = nullptr, int n_enq = 0, int n_key_rows = 0, int keys_raw = 0,
                      const float* push_feat = nullptr) {
-  AVSSL_REQUIRE(feat_q && (keys_host || peer) && queue && q_out && loss_out && dfeat_out && workspace,
+  // impl carries the two-launch form in its upper bits (avssl_b200.h: AVSSL_HEAD_SWEPT, avssl_moco_infonce_sweep)
+  const int phase = (impl & 0x100) ? kPhaseFinish : ((impl & 0x200) ? kPhaseSweep : kPhaseFused);
+  const int sweep_ctas = (impl >> 16) & 0xffff;
+  impl &= 0xff;
+  AVSSL_REQUIRE(feat_q && queue && workspace, AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: null pointer");
+  AVSSL_REQUIRE(phase == kPhaseSweep || ((keys_host || peer) && q_out && loss_out && dfeat_out),
                 AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: null pointer");
   AVSSL_REQUIRE(B > 0 && D > 0 && K > 0, AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: bad sizes B=%d D=%d K=%d", B, D, K);
   AVSSL_REQUIRE(n_keys >= 1 && n_keys <= AVSSL_MAX_KEYS, AVSSL_ERR_INVALID_ARGUMENT,
@@ -70,8 +82,8 @@ int moco_infonce_run(const float* feat_q, const float* const* keys_host, int n_k
 
   InfoNceParams p;
   p.feat_q = feat_q;
-  for (int k = 0; k < AVSSL_MAX_KEYS; ++k) p.keys[k] = (k < n_keys && !peer) ? keys_host[k] : nullptr;
-  for (int k = 0; k < n_keys && !peer; ++k)
+  for (int k = 0; k < AVSSL_MAX_KEYS; ++k) p.keys[k] = (k < n_keys && !peer && keys_host) ? keys_host[k] : nullptr;
+  for (int k = 0; k < n_keys && !peer && phase != kPhaseSweep; ++k)
     AVSSL_REQUIRE(p.keys[k], AVSSL_ERR_INVALID_ARGUMENT, "moco_infonce: keys[%d] is null", k);
   p.use_peer = peer ? 1 : 0;
   p.peer_row_idx = reinterpret_cast<const long long*>(peer_row_idx);
@@ -79,7 +91,8 @@ int moco_infonce_run(const float* feat_q, const float* const* keys_host, int n_k
   p.n_enq = (ptr_dev && n_enq > 0) ? n_enq : B;
   p.n_key_rows = n_key_rows > 0 ? n_key_rows : B;
   p.keys_raw = keys_raw ? 1 : 0;
-  p.push_feat = push_feat;
+  p.push_feat = phase == kPhaseSweep ? nullptr : push_feat;
+  p.phase = phase;
   p.push_eps = 0.f;  // Normalize has no epsilon (models/contrastive.py:929-934)
   AVSSL_REQUIRE(!push_feat || (peer && (reinterpret_cast<uintptr_t>(push_feat) & 15u) == 0), AVSSL_ERR_INVALID_ARGUMENT,
                 "moco_infonce_peer: push_feat needs an exchange descriptor and 16-byte alignment");
@@ -126,6 +139,8 @@ int moco_infonce_run(const float* feat_q, const float* const* keys_host, int n_k
   AVSSL_REQUIRE(!indexed || use != AVSSL_IMPL_SIMT, AVSSL_ERR_UNSUPPORTED,
                 "moco_infonce_indexed: row indices / raw keys need the tcgen05 kernel (D in {32,64,96,128}); normalise and "
                 "gather the keys first and call the plain entry point instead");
+  AVSSL_REQUIRE(phase == kPhaseFused || use != AVSSL_IMPL_SIMT, AVSSL_ERR_UNSUPPORTED,
+                "moco_infonce: the two-launch form (sweep, then AVSSL_HEAD_SWEPT) needs the tcgen05 kernel (D in {32,64,96,128})");
   AVSSL_REQUIRE(!peer || use != AVSSL_IMPL_SIMT, AVSSL_ERR_UNSUPPORTED,
                 "moco_infonce_peer: the fused exchange wait needs the tcgen05 kernel (D in {32,64,96,128}); "
                 "call avssl_peer_wait_gather and the plain entry point instead");
@@ -135,7 +150,9 @@ int moco_infonce_run(const float* feat_q, const float* const* keys_host, int n_k
   const int n_tiles = (K + tile - 1) / tile;
   const int row_blocks = (use == AVSSL_IMPL_SIMT) ? (B + 63) / 64 : (B + 127) / 128;
   // (the fused key push takes one more column of CTAs: leave it an SM, the launch is cooperative)
-  int S = (push_feat ? sms - row_blocks : sms) / row_blocks;
+  // (two launches: the caller may give the sweep fewer CTAs than SMs, leaving the rest to whatever runs beside it)
+  int S = (push_feat && phase == kPhaseFused ? sms - row_blocks : sms) / row_blocks;
+  if (phase != kPhaseFused && sweep_ctas > 0 && sweep_ctas / row_blocks < S) S = sweep_ctas / row_blocks;
   if (S < 1) S = 1;
   if (S > n_tiles) S = n_tiles;
   const int tiles_per_split = (n_tiles + S - 1) / S;
@@ -154,7 +171,21 @@ int moco_infonce_run(const float* feat_q, const float* const* keys_host, int n_k
   p.part_acc = reinterpret_cast<float*>(w + c.part_acc);
 
   if (use != AVSSL_IMPL_SIMT) {
-    // one cooperative launch: sweep + grid barrier + merge (+ the queue ring write of K4)
+    float* one_m = reinterpret_cast<float*>(w + c.one_m);
+    float* one_l = reinterpret_cast<float*>(w + c.one_l);
+    float* one_acc = reinterpret_cast<float*>(w + c.one_acc);
+    if (phase == kPhaseSweep) {  // the sweep, then (same stream) its partials reduced to one per query row
+      const int rc = launch_infonce_tc(p, use == AVSSL_IMPL_TC3X ? 1 : 0, s);
+      return rc != AVSSL_OK ? rc : launch_infonce_merge_partials(p, one_m, one_l, one_acc, s);
+    }
+    if (phase == kPhaseFinish) {  // key term, loss, gradient, enqueue against the one merged partial per row
+      p.part_m = one_m;
+      p.part_l = one_l;
+      p.part_acc = one_acc;
+      p.n_splits = 1;
+      return launch_infonce_finish(p, s);
+    }
+    // kPhaseFused: one cooperative launch: sweep + grid barrier + merge (+ the queue ring write of K4)
     return launch_infonce_tc(p, use == AVSSL_IMPL_TC3X ? 1 : 0, s);
   }
   int rc = launch_infonce_simt(p, s);
@@ -165,6 +196,15 @@ int moco_infonce_run(const float* feat_q, const float* const* keys_host, int n_k
 }
 
 }  // namespace
+
+extern "C" int avssl_moco_infonce_sweep(const float* feat_q, const float* queue, int B, int D, int K, float T, int n_keys,
+                                        float* logits_out, void* workspace, size_t workspace_bytes, int impl,
+                                        int sweep_ctas, void* stream) {
+  AVSSL_REQUIRE(impl >= 0 && impl <= 0xff && sweep_ctas >= 0 && sweep_ctas <= 0xffff, AVSSL_ERR_INVALID_ARGUMENT,
+                "moco_infonce_sweep: bad impl %d / sweep_ctas %d", impl, sweep_ctas);
+  return moco_infonce_run(feat_q, nullptr, n_keys, queue, nullptr, nullptr, nullptr, B, D, K, T, nullptr, nullptr, nullptr,
+                          nullptr, logits_out, workspace, workspace_bytes, impl | 0x200 | (sweep_ctas << 16), stream);
+}
 
 extern "C" int avssl_moco_infonce_fwd_bwd(const float* feat_q, const float* const* keys_host, int n_keys,
                                           const float* queue, int B, int D, int K, float T, float* q_out,

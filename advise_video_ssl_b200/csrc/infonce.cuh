@@ -59,7 +59,13 @@ struct InfoNceParams {
   const float* push_feat;
   float push_eps;
   avssl_peer_xchg peer;
+  // tcgen05 path in two steps (kPhaseSweep: the sweep kernel + infonce_merge_partials_kernel; kPhaseFinish:
+  // infonce_finish_kernel on the same workspace): the sweep only needs feat_q and the queue, so it can run on another
+  // stream while the key path (momentum update, shuffle, key encoder) is still in flight; kPhaseFused is the single
+  // cooperative launch with the grid barrier in between.
+  int phase;
 };
+constexpr int kPhaseFused = 0, kPhaseSweep = 1, kPhaseFinish = 2;
 
 // 1 / ||row|| computed by ONE warp with a fixed summation order, so that every
 // kernel that normalises the same row obtains the same bits.
@@ -71,6 +77,10 @@ int launch_infonce_simt(const InfoNceParams& p, cudaStream_t s);
 int launch_infonce_combine(const InfoNceParams& p, cudaStream_t s);
 // tcgen05 path; returns AVSSL_ERR_UNSUPPORTED when the shape does not fit.
 int launch_infonce_tc(const InfoNceParams& p, int three_term, cudaStream_t s);
+// Two-launch form, behind the sweep on its stream: reduce the n_splits partials of every query row to ONE partial
+// (m, l, acc) in (m_out[B], l_out[B], acc_out[B, D]), which kPhaseFinish then reads with n_splits = 1.
+int launch_infonce_finish(const InfoNceParams& p, cudaStream_t s);  // kPhaseFinish: p.part_* = the merged partials, n_splits = 1
+int launch_infonce_merge_partials(const InfoNceParams& p, float* m_out, float* l_out, float* acc_out, cudaStream_t s);
 bool infonce_tc_supported(int B, int D, int K);
 
 }  // namespace avssl

@@ -65,6 +65,7 @@ constexpr int kMaxSlots = 3;
 constexpr int kStageRows = 64;            // query rows per CTA whose logits go through the staging tiles
 constexpr int kStagePitch = kBlockJ + 1;  // floats; odd pitch: row- and column-wise accesses conflict-free
 constexpr int kDrainWarps = 4;            // warps 10, 11 (softmax warps without rows), 14, 15
+constexpr int kLogitsWarps = 4;           // helper warps 4, 5, 8, 9: the ones that may read TMEM lanes 0..63
 
 template <int D, bool kThreeTerm>
 struct TcCfg {
@@ -82,7 +83,7 @@ struct TcCfg {
   static constexpr int kTmemCols = 512;
   static_assert(3 * D + 2 * kBlockJ <= 512, "TMEM budget");
   static_assert(kSRingBytes >= (int)sizeof(CombineSmem<kTcThreads>), "merge scratch aliases the S ring");
-  static constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kSRingBytes + kVRingBytes + kScratchBytes + 512;
+  static constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kSRingBytes + kVRingBytes + kScratchBytes + 1024;
 };
 
 struct TcBarriers {
@@ -91,13 +92,106 @@ struct TcBarriers {
   uint64_t s_ready[2], p_ready[2], pv_done[2];
   uint64_t q_ready, acc_done;
   uint64_t stage_full[2], stage_free[2];
+  uint64_t s_read[2];        // staged CTAs: the logits warps have read S(t) out of TMEM, P may overwrite it
   uint32_t tmem_base;
+  float lscale[kStageRows];  // staged CTAs: 1 / (T ||f_r||) of the CTA's rows, for the logits warps
 };
+static_assert(sizeof(TcBarriers) <= 1024, "barrier block");
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+
+// Everything behind the sweep: one query row per CTA -- its partials merged, the key term added, loss terms, lse, q, the
+// gradient through the normalisation, logits column 0 -- then the queue ring write of K4 and the mean over the rows by
+// the CTA that arrives last.  Called by all threads of every CTA: in the cooperative kernel after the grid barrier,
+// or as the body of infonce_finish_kernel (two-launch form).  `cta` of `n_ctas`.
+template <int kThreads>
+__device__ __forceinline__ void infonce_tail(const InfoNceParams& p, CombineSmem<kThreads>& csm, int cta, unsigned n_ctas) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int D = p.D;
+  // ------------------------------------------- merge: one query row per CTA, then the mean
+  if (tid == 0) TC_TRACE(14, 3);
+  const float* key_base = p.keys[0];
+  const long long n_key_rows = p.use_peer ? (long long)p.peer.world * p.peer.rows_per_rank : (long long)p.n_key_rows;
+  const long long own_base = p.use_peer ? (long long)p.peer.rank * p.peer.rows_per_rank : 0ll;
+  // the first row indices of this CTA and the ring pointer in ONE round trip (everything here is L2-cold in the
+  // two-launch form: the momentum update has streamed through L2 since the data was written)
+  long long krow_first = own_base + cta, erow_first = own_base + cta;
+  if (p.peer_row_idx && cta < p.B) krow_first = __ldg(p.peer_row_idx + cta);
+  if (p.enq_row_idx && p.enq_ptr && cta < p.n_enq) erow_first = __ldg(p.enq_row_idx + cta);
+  long long enq_ptr = 0;
+  bool enq_ok = false;
+  if (p.enq_ptr) {
+    enq_ptr = *reinterpret_cast<volatile long long*>(p.enq_ptr);  // advanced only after every CTA arrived below
+    enq_ok = enq_ptr >= 0 && enq_ptr + p.n_enq <= p.K;           // models/contrastive.py:285
+  }
+  if (p.use_peer && (cta < p.B || (enq_ok && cta < p.n_enq))) {  // C3: the keys come from the peer exchange buffer (peer.cuh)
+    if (warp == 0) {  // long since landed: the sweep took ~15 us
+      const int slot = peer_wait_all_warp(p.peer, p.enq_status);
+      if (lane == 0) csm.peer_slot = slot;
+    }
+    __syncthreads();
+    key_base = peer_payload(p.peer.base[p.peer.rank], csm.peer_slot, p.peer);
+  }
+  for (int i = cta; i < p.B; i += (int)n_ctas) {
+    long long krow = i == cta ? krow_first : (p.peer_row_idx ? p.peer_row_idx[i] : own_base + i);  // un-shuffle by index (:216-230)
+    if (krow < 0 || krow >= n_key_rows) {  // uniform over the CTA
+      if (tid == 0 && p.enq_status) atomicOr(p.enq_status, AVSSL_DEVFLAG_BAD_INDEX);
+      krow = 0;
+    }
+    infonce_combine_row<kThreads, 1>(p, i, csm, key_base + (size_t)krow * D);
+  }
+  if (enq_ok) {
+    // K4 (+ C9): queue[ptr + e] = the e-th row of the enqueue list -- keys[0][e], or key rows picked by enq_row_idx
+    // (rank 0's block of the gathered buffer on every rank keeps the queues of all ranks identical, as the
+    // reference's DDP buffer broadcast does; all world*B rows = canonical MoCo).  No CTA reads the queue after
+    // the grid barrier.
+    for (int e = cta; e < p.n_enq; e += (int)n_ctas) {
+      const long long krow = e == cta ? erow_first : (p.enq_row_idx ? p.enq_row_idx[e] : own_base + e);
+      if (krow < 0 || krow >= n_key_rows) {
+        if (tid == 0 && p.enq_status) atomicOr(p.enq_status, AVSSL_DEVFLAG_BAD_INDEX);
+        continue;
+      }
+      const float* src_row = key_base + (size_t)krow * D;
+      float4* dst = reinterpret_cast<float4*>(p.queue_rw + (size_t)(enq_ptr + e) * D);
+      if (p.keys_raw) {  // Normalize on the way in: x / ||x||, the bits l2norm_fwd_kernel writes
+        __syncthreads();
+        if (warp == 0) {
+          const float knrm = warp_row_norm(src_row, D, lane);
+          if (lane == 0) csm.bcast[1] = knrm;
+        }
+        __syncthreads();
+        const float knrm = csm.bcast[1];
+        for (int c4 = tid; c4 < D / 4; c4 += kThreads) {
+          const float4 v = __ldcg(reinterpret_cast<const float4*>(src_row) + c4);
+          dst[c4] = make_float4(v.x / knrm, v.y / knrm, v.z / knrm, v.w / knrm);
+        }
+      } else {
+        for (int c4 = tid; c4 < D / 4; c4 += kThreads) dst[c4] = __ldcg(reinterpret_cast<const float4*>(src_row) + c4);
+      }
+    }
+  }
+  if (tid == 0) TC_TRACE(14, 4);
+  const bool last_cta = infonce_finish<kThreads>(p, n_ctas, csm);
+  if (tid == 0) TC_TRACE(14, 5);
+  if (last_cta) {
+    if (tid == 0) {
+      p.counter[1] = 0u;  // every CTA is past the barrier: it incremented counter[0] afterwards
+      p.counter[2] = 0u;  // (infonce_finish_kernel: and past its wait for the push CTAs)
+      if (p.enq_ptr) {
+        if (enq_ok) {
+          long long np = enq_ptr + p.n_enq;
+          if (np == p.K) np = 0;  // wrap only when landing exactly on K (:290-291)
+          *p.enq_ptr = np;
+        } else if (p.enq_status) {
+          atomicOr(p.enq_status, AVSSL_DEVFLAG_QUEUE_OVERRUN);
+        }
+      }
+    }
+  }
 }
 
 template <int D, bool kThreeTerm>
@@ -171,8 +265,9 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
     ptx::mbar_init(&bar->q_ready, kGroupThreads);
     ptx::mbar_init(&bar->acc_done, 1);
     for (int b = 0; b < 2; ++b) {
-      ptx::mbar_init(&bar->stage_full[b], 2 * 32);            // the two softmax warps of rows 0..63 of the CTA tile
-      ptx::mbar_init(&bar->stage_free[b], kDrainWarps * 32);  // the warps that store the staged logits
+      ptx::mbar_init(&bar->stage_full[b], kLogitsWarps * 32);  // the helper warps that read S and stage logits / T
+      ptx::mbar_init(&bar->stage_free[b], kDrainWarps * 32);   // the warps that store the staged logits
+      ptx::mbar_init(&bar->s_read[b], kLogitsWarps * 32);
     }
     ptx::mbar_fence_init();
   }
@@ -184,10 +279,13 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
   if (tid == 0) TC_TRACE(14, 1);
 
   // Logits of a CTA tile with at most 64 query rows (the MoCo case) go through two padded staging
-  // tiles: the two softmax warps that own rows write their 64 values per row, and kDrainWarps
-  // other warps (the two softmax warps whose rows do not exist + warps 14, 15) store tile t as
-  // whole 128-byte row segments while the softmax already works on tile t+1.  Larger CTA tiles
-  // store directly from the softmax threads.
+  // tiles.  The two softmax warps that own the rows are the critical path of the sweep (per tile: 64
+  // exp2, max, sum and the P store per thread), so they do NOT touch the logits: four of the helper
+  // warps -- 4, 5, 8, 9, the ones whose TMEM sub-partition holds lanes 0..63 -- read S(t) themselves
+  // (32 columns each), scale it and write the staging tile, and kDrainWarps other warps (the two
+  // softmax warps whose rows do not exist + warps 14, 15) store it as whole 128-byte row segments.
+  // (Round 1 staged from the softmax threads: 1300 of their 2100 cycles per tile.)  Larger CTA
+  // tiles store directly from the softmax threads.
   const bool staged_cta = p.logits_out != nullptr && (p.B - i_base) <= kStageRows;
   auto drain_tile = [&](int t, int dw) {  // dw = 0..kDrainWarps-1; logits / T of tile t (models/contrastive.py:498)
     const int b = t & 1;
@@ -236,8 +334,20 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
         for (int kb = 0; kb < C::kKB; ++kb)
           ptx::tma_load_2d(dst + kb * C::kBoxBytes, &tmap_v, &bar->v_full[vs], kb * 32, j_begin + t * kBlockJ);
       };
+      // The S ring holds two tiles, so a TMA load is in flight for at most one tile time: enough when the queue comes
+      // out of L2 or an idle HBM, not when the sweep shares HBM with a bandwidth-bound kernel (the momentum update
+      // of the two-launch form: loaded latency of several microseconds).  The split's rows are contiguous in the
+      // queue: pull them into L2 kPrefetchTiles tiles ahead, which costs no shared memory.
+      constexpr int kPrefetchTiles = 6;
+      auto prefetch = [&](int t) {
+        const int j0 = j_begin + t * kBlockJ;
+        if (t < n_tiles && j0 < j_end)
+          ptx::bulk_prefetch_l2(p.queue + (size_t)j0 * D, (uint32_t)(min(kBlockJ, j_end - j0) * D * 4));
+      };
+      for (int t = 2; t < 2 + kPrefetchTiles; ++t) prefetch(t);
       if (n_tiles > 0) load_s(0);
       for (int t = 0; t < n_tiles; ++t) {
+        prefetch(t + 2 + kPrefetchTiles);
         if (t + 1 < n_tiles) load_s(t + 1);
         if (!kThreeTerm) {
           if (t == 0) ptx::mbar_wait(&bar->q_ready, 0);  // the V ring doubles as the q staging area
@@ -318,6 +428,29 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
   } else if (warp < 10) {
     // ============================ helper warps 2..9 (3-term only): one read of the raw tile ->
     // correction tile [bf16(k) | bf16(k_lo)] and, from registers, the V tile rn_tf32(k)
+    // + (staged CTAs, warps 4, 5, 8, 9) the logits of tile u: S(u) out of TMEM, scaled, into the staging tile
+    const bool logits_duty = staged_cta && (warp == 4 || warp == 5 || warp == 8 || warp == 9);
+    auto logits_tile = [&](int u) {
+      const int b = u & 1, lsub = warp & 3, lhc = warp >> 3;  // sub-partition 0 / 1, column half 0 / 1
+      ptx::mbar_wait(&bar->s_ready[b], (u >> 1) & 1);
+      ptx::tc_fence_after();
+      uint32_t sv[32];
+      ptx::tmem_ld32(tmem + ((uint32_t)(lsub * 32) << 16) + C::kColS + b * kBlockJ + lhc * 32, sv);
+      ptx::tc_wait_ld();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&bar->s_read[b]);  // the softmax warps may overwrite S(u) with P(u)
+      if (u >= 2) ptx::mbar_wait(&bar->stage_free[b], ((u >> 1) - 1) & 1);  // tile u-2 has left this buffer
+      const int r = lsub * 32 + lane;
+      if (r < p.B - i_base) {
+        const float sc = bar->lscale[r];
+        float* st_row = stage + b * (kStageRows * kStagePitch) + r * kStagePitch + lhc * 32;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) st_row[c] = __uint_as_float(sv[c]) * sc;
+      }
+      ptx::mbar_arrive(&bar->stage_full[b]);
+    };
+    if (!kThreeTerm && logits_duty)
+      for (int u = 0; u < n_tiles; ++u) logits_tile(u);
     if (kThreeTerm) {
       // st in [0,256) indexes the float4 this thread owns: a warp takes rows {w, w+4, w+8, w+12} of a
       // 16-row group (8 lanes per row) so that its 8-byte correction-tile stores land in both 64-byte
@@ -362,6 +495,7 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
         ptx::fence_proxy_async_smem();
         if (st == 0) TC_TRACE(2, t);
         ptx::mbar_arrive(&bar->s_op[ss]);
+        if (logits_duty && t >= 1) logits_tile(t - 1);  // S(t-1) is ready or about to be: the split runs one tile ahead
         // V tile = rn_tf32(k) in the 32B-atom layout, written from registers once PV(t - kVSlots)
         // has released the slot (and, for the first tiles, once q has left the aliased staging area)
         if (t == 0) ptx::mbar_wait_relaxed(&bar->q_ready, 0);
@@ -372,6 +506,7 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&bar->v_op[vs]);
       }
+      if (logits_duty && n_tiles > 0) logits_tile(n_tiles - 1);
     }
   } else if (warp >= 14) {
     // ============================================================ logits writers 14, 15
@@ -445,10 +580,11 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
       }
       ptx::tc_wait_st();
       if (r == 0) TC_TRACE(15, 6);
+      inv_norm = row_valid ? 1.f / sqrtf((ss.x + ss.y) + (ss.z + ss.w)) : 0.f;
+      if (r < kStageRows) bar->lscale[r] = p.inv_T * inv_norm;  // for the logits warps (ordered by q_ready -> S(0) -> s_ready)
       ptx::tc_fence_before();
       if (r == 0) TC_TRACE(12, 0);
       ptx::mbar_arrive(&bar->q_ready);
-      inv_norm = row_valid ? 1.f / sqrtf((ss.x + ss.y) + (ss.z + ss.w)) : 0.f;
       if (r == 0) TC_TRACE(11, 0);
     }
     const float scale2 = p.inv_T * kLog2e * inv_norm;  // log2-domain logit scale of this row (>= 0)
@@ -480,13 +616,7 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
       }
       if (p.logits_out) {  // logits / T (models/contrastive.py:498)
         if (staged_cta) {
-          if (t >= 2) ptx::mbar_wait(&bar->stage_free[b], ((t >> 1) - 1) & 1);  // tile t-2 has left this buffer
-          if (warp_valid) {
-            float* st_row = stage + b * (kStageRows * kStagePitch) + r * kStagePitch;
-#pragma unroll
-            for (int c = 0; c < kBlockJ; ++c) st_row[c] = __uint_as_float(sv[c]) * logit_scale;
-          }
-          ptx::mbar_arrive(&bar->stage_full[b]);
+          // the logits warps read S(t) themselves (see above); nothing to do here
         } else if (row_valid) {
           for (int k = 0; k < p.n_keys; ++k) {
             float* dst = p.logits_out + ((size_t)k * p.B + i) * (size_t)(p.K + 1) + 1 + j0;
@@ -548,6 +678,7 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
             sv[c + u] = __float_as_uint(ptx::round_tf32(pv));
           }
         }
+        if (staged_cta) ptx::mbar_wait(&bar->s_read[b], (t >> 1) & 1);  // S(t) has been read for the logits
         ptx::tmem_st32(s_col, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
         ptx::tmem_st32(s_col + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
         l_run += (ps[0] + ps[1]) + (ps[2] + ps[3]);
@@ -593,6 +724,8 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
 
   }  // !exch_cta
 
+  if (p.phase == kPhaseSweep) return;  // the partials are complete when the launch is; infonce_finish_kernel follows
+
   // --------------------------------------------------------------------- grid barrier
   // Cooperative launch: all CTAs are co-resident, so spinning on a global counter is safe.
   const unsigned n_ctas = gridDim.x * gridDim.y;
@@ -604,81 +737,66 @@ infonce_tc_kernel(const InfoNceParams p, const __grid_constant__ CUtensorMap tma
   }
   __syncthreads();
 
-  // ------------------------------------------- merge: one query row per CTA, then the mean
   CombineSmem<kTcThreads>& csm = *reinterpret_cast<CombineSmem<kTcThreads>*>(smem);  // the rings are dead
-  if (tid == 0) TC_TRACE(14, 3);
-  const int cta = blockIdx.y * gridDim.x + blockIdx.x;
-  long long enq_ptr = 0;
-  bool enq_ok = false;
-  if (p.enq_ptr) {
-    enq_ptr = *reinterpret_cast<volatile long long*>(p.enq_ptr);  // advanced only after every CTA arrived below
-    enq_ok = enq_ptr >= 0 && enq_ptr + p.n_enq <= p.K;           // models/contrastive.py:285
+  infonce_tail<kTcThreads>(p, csm, blockIdx.y * gridDim.x + blockIdx.x, n_ctas);
+}
+
+// One CTA per query row: M = max_s m_s, w_s = 2^(m_s - M), L = sum_s w_s l_s, acc = sum_s w_s acc_s -- the first half of
+// infonce_combine_row, in a fixed order (deterministic).  Runs under the momentum update in the two-launch form, so
+// that the launch behind the key path has one partial per row left to read.
+constexpr int kMergeThreads = 256;
+__global__ void __launch_bounds__(kMergeThreads)
+infonce_merge_partials_kernel(const InfoNceParams p, float* __restrict__ m_out, float* __restrict__ l_out,
+                              float* __restrict__ acc_out) {
+  __shared__ float s_w[kMaxSplits];
+  __shared__ float s_red[32];
+  __shared__ __align__(16) float s_acc[kMergeThreads / 32][256];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int i = blockIdx.x, S = p.n_splits, B = p.B, D = p.D;
+  float mloc = -INFINITY;
+  for (int s = tid; s < S; s += kMergeThreads) mloc = fmaxf(mloc, __ldcg(p.part_m + (size_t)s * B + i));
+  mloc = warp_max(mloc);
+  if (lane == 0) s_red[warp] = mloc;
+  __syncthreads();
+  float M = s_red[0];
+#pragma unroll
+  for (int w = 1; w < kMergeThreads / 32; ++w) M = fmaxf(M, s_red[w]);
+  float lloc = 0.f;
+  for (int s = tid; s < S; s += kMergeThreads) {
+    const float w = fast_ex2(__ldcg(p.part_m + (size_t)s * B + i) - M);
+    s_w[s] = w;
+    lloc = fmaf(w, __ldcg(p.part_l + (size_t)s * B + i), lloc);
   }
-  const float* key_base = p.keys[0];
-  const long long n_key_rows = p.use_peer ? (long long)p.peer.world * p.peer.rows_per_rank : (long long)p.n_key_rows;
-  const long long own_base = p.use_peer ? (long long)p.peer.rank * p.peer.rows_per_rank : 0ll;
-  if (p.use_peer && (cta < p.B || (enq_ok && cta < p.n_enq))) {  // C3: the keys come from the peer exchange buffer (peer.cuh)
-    if (warp == 0) {  // long since landed: the sweep took ~15 us
-      const int slot = peer_wait_all_warp(p.peer, p.enq_status);
-      if (lane == 0) csm.peer_slot = slot;
-    }
-    __syncthreads();
-    key_base = peer_payload(p.peer.base[p.peer.rank], csm.peer_slot, p.peer);
-  }
-  for (int i = cta; i < p.B; i += (int)n_ctas) {
-    long long krow = p.peer_row_idx ? p.peer_row_idx[i] : own_base + i;  // un-shuffle by index (:216-230)
-    if (krow < 0 || krow >= n_key_rows) {  // uniform over the CTA
-      if (tid == 0 && p.enq_status) atomicOr(p.enq_status, AVSSL_DEVFLAG_BAD_INDEX);
-      krow = 0;
-    }
-    infonce_combine_row<kTcThreads, 1>(p, i, csm, key_base + (size_t)krow * D);
-  }
-  if (enq_ok) {
-    // K4 (+ C9): queue[ptr + e] = the e-th row of the enqueue list -- keys[0][e], or key rows picked by enq_row_idx
-    // (rank 0's block of the gathered buffer on every rank keeps the queues of all ranks identical, as the
-    // reference's DDP buffer broadcast does; all world*B rows = canonical MoCo).  No CTA reads the queue after
-    // the grid barrier.
-    for (int e = cta; e < p.n_enq; e += (int)n_ctas) {
-      const long long krow = p.enq_row_idx ? p.enq_row_idx[e] : own_base + e;
-      if (krow < 0 || krow >= n_key_rows) {
-        if (tid == 0 && p.enq_status) atomicOr(p.enq_status, AVSSL_DEVFLAG_BAD_INDEX);
-        continue;
+  const float L = block_sum(lloc, s_red);  // (its barriers publish s_w)
+  // warp g takes splits g, g + 8, ...; lane l owns columns 4l..4l+3 (and 128 + 4l.. for D > 128)
+  const size_t stride = (size_t)B * D;
+  for (int c0 = 0; c0 < D; c0 += 128) {
+    const int c = c0 + lane * 4;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < D) {
+      const float* src = p.part_acc + (size_t)i * D + c;
+#pragma unroll 4
+      for (int s = warp; s < S; s += kMergeThreads / 32) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(src + (size_t)s * stride));
+        const float w = s_w[s];
+        a.x = fmaf(w, v.x, a.x);
+        a.y = fmaf(w, v.y, a.y);
+        a.z = fmaf(w, v.z, a.z);
+        a.w = fmaf(w, v.w, a.w);
       }
-      const float* src_row = key_base + (size_t)krow * D;
-      float4* dst = reinterpret_cast<float4*>(p.queue_rw + (size_t)(enq_ptr + e) * D);
-      if (p.keys_raw) {  // Normalize on the way in: x / ||x||, the bits l2norm_fwd_kernel writes
-        __syncthreads();
-        if (warp == 0) {
-          const float knrm = warp_row_norm(src_row, D, lane);
-          if (lane == 0) csm.bcast[1] = knrm;
-        }
-        __syncthreads();
-        const float knrm = csm.bcast[1];
-        for (int c4 = tid; c4 < D / 4; c4 += kTcThreads) {
-          const float4 v = __ldcg(reinterpret_cast<const float4*>(src_row) + c4);
-          dst[c4] = make_float4(v.x / knrm, v.y / knrm, v.z / knrm, v.w / knrm);
-        }
-      } else {
-        for (int c4 = tid; c4 < D / 4; c4 += kTcThreads) dst[c4] = __ldcg(reinterpret_cast<const float4*>(src_row) + c4);
-      }
+      *reinterpret_cast<float4*>(&s_acc[warp][c]) = a;
     }
   }
-  if (tid == 0) TC_TRACE(14, 4);
-  const bool last_cta = infonce_finish<kTcThreads>(p, n_ctas, csm);
-  if (tid == 0) TC_TRACE(14, 5);
-  if (last_cta) {
-    if (tid == 0) {
-      p.counter[1] = 0u;  // every CTA is past the barrier: it incremented counter[0] afterwards
-      if (p.enq_ptr) {
-        if (enq_ok) {
-          long long np = enq_ptr + p.n_enq;
-          if (np == p.K) np = 0;  // wrap only when landing exactly on K (:290-291)
-          *p.enq_ptr = np;
-        } else if (p.enq_status) {
-          atomicOr(p.enq_status, AVSSL_DEVFLAG_QUEUE_OVERRUN);
-        }
-      }
-    }
+  __syncthreads();
+  for (int c = tid; c < D; c += kMergeThreads) {
+    float a = s_acc[0][c];
+#pragma unroll
+    for (int g = 1; g < kMergeThreads / 32; ++g) a += s_acc[g][c];
+    acc_out[(size_t)i * D + c] = a;
+  }
+  if (tid == 0) {
+    m_out[i] = M;
+    l_out[i] = L;
   }
 }
 
@@ -735,10 +853,19 @@ int launch_tc(const InfoNceParams& p, cudaStream_t s) {
                                        (int)C::kSmemBytes));
   }
   dim3 grid(p.n_splits + (p.push_feat ? 1 : 0), (p.B + kM - 1) / kM);
+  InfoNceParams pc = p;
+  if (p.phase == kPhaseSweep) {  // no grid barrier: a plain launch, any number of CTAs
+    infonce_tc_kernel<D, kThreeTerm><<<grid, kTcThreads, C::kSmemBytes, s>>>(pc, cache.s, cache.v);
+    const cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) {
+      set_error("launch of infonce_tc_kernel (sweep) failed: %s", cudaGetErrorString(le));
+      return AVSSL_ERR_CUDA;
+    }
+    return AVSSL_OK;
+  }
   AVSSL_REQUIRE((int)(grid.x * grid.y) <= sm_count(), AVSSL_ERR_INVALID_ARGUMENT,
                 "moco_infonce: %u CTAs cannot be co-resident on %d SMs", grid.x * grid.y, sm_count());
   // cooperative: the kernel contains a grid-wide barrier (all CTAs must be co-resident)
-  InfoNceParams pc = p;
   void* args[] = {&pc, &cache.s, &cache.v};
 #ifdef AVSSL_TC_TRACE
   if (getenv("AVSSL_TC_PLAIN_LAUNCH")) {  // developer probe: cost of the cooperative launch itself
@@ -756,6 +883,61 @@ int launch_tc(const InfoNceParams& p, cudaStream_t s) {
 }
 
 }  // namespace
+
+int launch_infonce_merge_partials(const InfoNceParams& p, float* m_out, float* l_out, float* acc_out, cudaStream_t s) {
+  AVSSL_REQUIRE(p.D % 4 == 0 && p.D <= 256 && p.n_splits <= kMaxSplits, AVSSL_ERR_UNSUPPORTED,
+                "moco_infonce: cannot merge %d partials of width %d", p.n_splits, p.D);
+  infonce_merge_partials_kernel<<<p.B, kMergeThreads, 0, s>>>(p, m_out, l_out, acc_out);
+  const cudaError_t le = cudaGetLastError();
+  if (le != cudaSuccess) {
+    set_error("launch of infonce_merge_partials_kernel failed: %s", cudaGetErrorString(le));
+    return AVSSL_ERR_CUDA;
+  }
+  return AVSSL_OK;
+}
+
+// Second launch of the two-launch form: the tail of the cooperative kernel as a small kernel of its own (one CTA per
+// query row / enqueued row; with push_feat one more CTA that performs this rank's key push first).  p.part_* hold
+// ONE merged partial per row (n_splits == 1).
+constexpr int kFinishThreads = 256;
+__global__ void __launch_bounds__(kFinishThreads) infonce_finish_kernel(const InfoNceParams p) {
+  __shared__ CombineSmem<kFinishThreads> csm;
+  // With push_feat the FIRST `world` CTAs perform this rank's key push (C3: Normalize + stores into rank d's buffer +
+  // flag, CTA d -> rank d).  The wait in the tail reads the local epoch, which the last push CTA advances: every CTA
+  // first waits for the `world` pushes of its own launch (counter[2]; the push CTAs have the lowest block indices, so
+  // they are resident before any CTA that spins on them).
+  const int n_push = p.push_feat != nullptr ? p.peer.world : 0;
+  if ((int)blockIdx.x < n_push) {
+    __shared__ unsigned long long s_epoch;
+    peer_push_cta<true>(p.peer, p.push_feat, (int)blockIdx.x, &s_epoch, p.push_eps);
+    if (threadIdx.x == 0) {  // (thread 0 published the flag and, in the last CTA, advanced the epoch just above)
+      __threadfence();
+      atomicAdd(p.counter + 2, 1u);
+    }
+  }
+  if (n_push > 0) {
+    if (threadIdx.x == 0)
+      while (ld_acquire_u32(p.counter + 2) < (unsigned)n_push) __nanosleep(20);
+    __syncthreads();
+  }
+  const int cta = ((int)blockIdx.x - n_push + (int)gridDim.x) % (int)gridDim.x;  // the push CTAs take the last rows, if any
+  infonce_tail<kFinishThreads>(p, csm, cta, gridDim.x);
+}
+
+int launch_infonce_finish(const InfoNceParams& p, cudaStream_t s) {
+  AVSSL_REQUIRE(p.D % 4 == 0 && p.D <= kCombineCols && p.n_splits == 1, AVSSL_ERR_UNSUPPORTED,
+                "moco_infonce: finish launch needs one merged partial per row and D <= %d", kCombineCols);
+  const int rows = p.enq_ptr && p.n_enq > p.B ? p.n_enq : p.B;
+  const int cap = 4 * sm_count();
+  const unsigned grid = (unsigned)(rows < cap ? rows : cap) + (p.push_feat ? (unsigned)p.peer.world : 0u);
+  infonce_finish_kernel<<<grid, kFinishThreads, 0, s>>>(p);
+  const cudaError_t le = cudaGetLastError();
+  if (le != cudaSuccess) {
+    set_error("launch of infonce_finish_kernel failed: %s", cudaGetErrorString(le));
+    return AVSSL_ERR_CUDA;
+  }
+  return AVSSL_OK;
+}
 
 bool infonce_tc_supported(int B, int D, int K) {
   // one CTA per 128 query rows and queue split; the cooperative grid must fit the SMs

@@ -68,6 +68,11 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// Bulk prefetch of a contiguous global range into L2 (no destination, no completion): 16-byte aligned, size % 16 == 0
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gmem_src)), "r"(bytes) : "memory");
+}
+
 // 1-D bulk copy global -> shared (no tensor map): 16-byte aligned addresses, size % 16 == 0
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

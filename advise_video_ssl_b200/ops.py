@@ -394,8 +394,27 @@ def _workspace(device, nbytes, op):
     return ws
 
 
+def moco_infonce_sweep(feat_q, queue, T, workspace, n_keys=1, logits=None, impl=_lib.IMPL_AUTO, sweep_ctas=0):
+    """First launch of the two-launch head (avssl_moco_infonce_sweep): q against the queue on the current stream --
+    per-CTA softmax partials into `workspace`, logits[:, 1:] into `logits` ([n_keys*B, K+1] or None).  Needs neither
+    the keys nor the momentum encoder; `moco_infonce(..., swept=sweep_ctas)` with the same tensors finishes the head
+    on a stream ordered behind this one.  `sweep_ctas`: 0 = every SM, fewer leaves SMs to a kernel running beside it."""
+    _req(feat_q, "feat_q")
+    _req(queue, "queue")
+    _req(workspace, "workspace", torch.uint8)
+    B, D = feat_q.shape
+    K = queue.shape[0]
+    if logits is not None:
+        _req(logits, "logits")
+        if tuple(logits.shape) != (n_keys * B, K + 1):
+            raise ValueError("logits must be [%d, %d], got %s" % (n_keys * B, K + 1, tuple(logits.shape)))
+    check(lib.avssl_moco_infonce_sweep(feat_q.data_ptr(), queue.data_ptr(), B, D, K, float(T), int(n_keys),
+                                       logits.data_ptr() if logits is not None else None, workspace.data_ptr(),
+                                       workspace.numel(), int(impl), int(sweep_ctas), _stream()), "avssl_moco_infonce_sweep")
+
+
 def moco_infonce(feat_q, keys, queue, T, want_logits=True, impl=_lib.IMPL_AUTO, out=None, enqueue=None, workspace=None,
-                 peer=None, peer_row_idx=None, enq_row_idx=None, key_rows=None, keys_raw=False, push_rows=None):
+                 peer=None, peer_row_idx=None, enq_row_idx=None, key_rows=None, keys_raw=False, push_rows=None, swept=None):
     """Fused l2-norm + logits + InfoNCE forward/backward (K2+K3).
 
     Returns dict(loss[1], dfeat[B,D], q[B,D], lse[n_keys*B], logits[n_keys*B,K+1] or None).
@@ -417,7 +436,13 @@ def moco_infonce(feat_q, keys, queue, T, want_logits=True, impl=_lib.IMPL_AUTO, 
     encoder's row order -- query row i meets key_rows[peer_row_idx[i]] and the queue receives
     key_rows[enq_row_idx[e]] (the un-shuffle folded into the launch); with `keys_raw` they are the
     encoder's raw output and Normalize is applied inside the kernel as well.
+    `swept` (int): `moco_infonce_sweep(..., sweep_ctas=swept)` has already run on these tensors (`workspace`, and
+    `out["logits"]` when logits are wanted): this call only merges its partials with the key term.
     """
+    if swept is not None:
+        if workspace is None or (want_logits and "logits" not in (out or {})):
+            raise ValueError("swept: pass the workspace (and out['logits']) the sweep wrote")
+        impl = int(impl) | _lib.head_swept(swept)
     _req(feat_q, "feat_q")
     _req(queue, "queue")
     if feat_q.dim() != 2 or queue.dim() != 2 or queue.shape[1] != feat_q.shape[1]:

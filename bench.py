@@ -495,8 +495,9 @@ def gpu_arm(args):
     # also yields the duration of the dominant kernel (the EMA): CUDA events around its launch inside the eager
     # two-launch sequence, where the host keeps ahead of the GPU (event records cannot be timed inside a captured
     # graph, and the eager MODULE step is host-bound, so events there would time launch gaps, not the kernel)
-    ops_ms, ema_ms = ops_level(args, ops, dist, dev, world, rank, impl, queue0, feats_h, kfeat_h, model, sync_all)
+    ops_ms, ema_ms, beside = ops_level(args, ops, dist, dev, world, rank, impl, queue0, feats_h, kfeat_h, model, sync_all)
     ops_note = None if ops_ms is not None else "--no-ops-level"
+    two_launch = beside is not None
 
     # max over ranks
     if world > 1:
@@ -519,6 +520,8 @@ def gpu_arm(args):
     # own kernels per step: EMA, head(+Normalize of the keys, un-shuffle, enqueue) on one GPU; across GPUs one more
     # launch normalises the keys and stores them into every rank's exchange buffer (or: Normalize, then NCCL)
     own_launches = 2 if (world == 1 or deferred_path) else 3
+    if two_launch:
+        own_launches += 2  # the head is sweep + merge of its partials (own stream, beside the EMA) + finish
     if world > 1:
         own_launches += 1  # the NVLink scatter of the key-encoder input rows (side stream, under the EMA)
 
@@ -563,8 +566,11 @@ def gpu_arm(args):
                        "what": "EMA[+push] launch -> head launch driven through ops.* (no module, no autograd), CUDA-graph replay"}
                       if ops_ms is not None else {"skipped": ops_note or "--no-ops-level"}),
         "gpu_launches": own_launches * args.steps,
-        "gpu_launches_note": "own kernels per step: EMA, head(+key Normalize, [N>1: key push over NVLink + wait,] un-shuffle, "
-                             "enqueue) [, N>1: row scatter of the shuffle, side stream]; plus torch's row gather of the "
+        "gpu_launches_note": ("own kernels per step: head sweep + merge of its partials (own stream, beside the EMA), EMA, "
+                              "head finish(+key Normalize, [N>1: key push over NVLink + wait,] un-shuffle, enqueue)"
+                              if two_launch else
+                              "own kernels per step: EMA, head(+key Normalize, [N>1: key push over NVLink + wait,] un-shuffle, "
+                              "enqueue)") + " [, N>1: row scatter of the shuffle, side stream]; plus torch's row gather of the "
                              "shuffle on one GPU and autograd's ones-fill and elementwise multiply in backward",
         "clocks": clocks,
         "roofline": {"kernel": "ema_multi_tensor_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
@@ -573,6 +579,13 @@ def gpu_arm(args):
                                        "(profiles/r2_ema_ncu.md)",
                      "bytes_per_launch": ema_bytes, "us_per_launch": ema_ms * 1e3, "peak_source": peak_src},
         "step_roofline": {"bytes_per_step": step_bytes, "floor_us": floor_us, "frac": floor_us / (ms_per_step * 1e3)},
+        "roofline_in_step": ({
+            "what": "the module step runs the head's sweep of the queue (tcgen05, %d CTAs, own stream) BESIDE the EMA kernel: "
+                    "EMA launch duration with the sweep sharing HBM, CUDA events in an eager ops-level sequence" % beside["ctas"],
+            "ema_us_beside_sweep": beside["ema_ms"] * 1e3, "ema_us_alone": ema_ms * 1e3,
+            "bytes": ema_bytes + beside["sweep_bytes"], "unit": "GB/s", "peak": peak,
+            "achieved": (ema_bytes + beside["sweep_bytes"]) / (beside["ema_ms"] * 1e-3) / 1e9,
+            "frac": (ema_bytes + beside["sweep_bytes"]) / (beside["ema_ms"] * 1e-3) / 1e9 / peak} if two_launch else None),
         "loss": loss_val,
     }
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
@@ -781,8 +794,40 @@ def ops_level(args, ops, dist, dev, world, rank, impl, queue0, feats_h, kfeat_h,
         step(i % POOL, ema_t)
     sync_all()
     ema_ms = sum(t.ms() for t in ema_t) / len(ema_t)
+    # ---- the EMA kernel as the MODULE step runs it: beside the head's sweep (two-launch head), same eager timing
+    beside = None
+    ctas = model.sweep_ctas if model.sweep_ctas is not None else model._sweep_ctas_beside_ema(B_PER_GPU, dev)
+    if ctas is not None and model.overlap_sweep and args.kernel != "simt":
+        side = torch.cuda.Stream(device=dev, priority=-1)
+        lg = None if args.no_logits else torch.empty(B_PER_GPU, QUEUE_LEN + 1, device=dev)
+
+        def step2(slot, timers):
+            f, k = feats[slot], keys[slot]
+            main = torch.cuda.current_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                ops.moco_infonce_sweep(f, queue, TEMP, ws, logits=lg, impl=impl, sweep_ctas=ctas)
+            tm = Timer()
+            tm.a.record()
+            plan.run(MOMENTUM, it, bump_iter=True, first_iter=False)
+            tm.b.record()
+            timers.append(tm)
+            main.wait_stream(side)
+            ops.moco_infonce(f, [k], queue, TEMP, want_logits=lg is not None, impl=impl,
+                             out={"logits": lg} if lg is not None else None, enqueue=(ptr, status), workspace=ws, swept=ctas)
+
+        for i in range(5):
+            step2(i % POOL, [])
+        sync_all()
+        t2 = []
+        for i in range(min(args.steps, 100)):
+            step2(i % POOL, t2)
+        sync_all()
+        ptr.zero_()
+        beside = {"ctas": ctas, "ema_ms": sum(t.ms() for t in t2) / len(t2),
+                  "sweep_bytes": 4 * QUEUE_LEN * DIM + (0 if lg is None else 4 * B_PER_GPU * QUEUE_LEN)}
     if args.no_ops_level:
-        return None, ema_ms
+        return None, ema_ms, beside
     one, many = step, None
     if not args.no_graph:
         pool_graph = torch.cuda.CUDAGraph()
@@ -813,7 +858,7 @@ def ops_level(args, ops, dist, dev, world, rank, impl, queue0, feats_h, kfeat_h,
     t.b.record()
     sync_all()
     assert int(status.item()) == 0, "device status word set in the ops-level run: %d" % int(status.item())
-    return t.ms(), ema_ms
+    return t.ms(), ema_ms, beside
 
 
 def main():

@@ -365,6 +365,24 @@ AVSSL_API int avssl_moco_infonce_fwd_bwd_enqueue_indexed(const float* feat_q, co
                                                float* dfeat_out, float* row_lse_out, float* logits_out,
                                                void* workspace, size_t workspace_bytes, int impl, void* stream);
 
+/* K2+K3 in two launches.  The sweep of q against the queue -- 99.9% of the head's work, and all of logits[:, 1:] --
+ * depends only on the query encoder's output and the queue, not on the keys: in the reference's own order
+ * (models/contrastive.py:462 query encoder, then :478 compute_key_feat = :314 momentum update, :338 shuffle, key
+ * encoder, :356 un-shuffle) it can start before the key path does.  avssl_moco_infonce_sweep() launches it alone (any
+ * stream); any avssl_moco_infonce_fwd_bwd* entry called afterwards with AVSSL_HEAD_SWEPT(sweep_ctas) or-ed into `impl`
+ * -- same B, D, K, n_keys, T, logits_out, workspace and sweep_ctas, on a stream ordered behind the sweep -- then only
+ * merges the partials with the key term (loss, gradient, logits[:, 0], enqueue, fused exchange push / wait).
+ * sweep_ctas: 0 = one CTA per SM; a smaller count leaves SMs (the kernel owns all registers of the SMs it runs on) to
+ * a bandwidth-bound kernel running beside it, e.g. the momentum update.  tcgen05 kernels only
+ * (AVSSL_ERR_UNSUPPORTED otherwise).  The sweep call is two launches: the sweep, then the per-CTA partials of every
+ * query row reduced to one, so that the call behind the key path reads one partial per row.  logits and q_out are
+ * bit-identical to the single-launch form; loss, lse and gradient differ by the (fixed, deterministic) order in
+ * which the partials are merged. */
+#define AVSSL_HEAD_SWEPT(sweep_ctas) (0x100 | ((int)(sweep_ctas) << 16))
+AVSSL_API int avssl_moco_infonce_sweep(const float* feat_q, const float* queue, int B, int D, int K, float T, int n_keys,
+                             float* logits_out, void* workspace, size_t workspace_bytes, int impl, int sweep_ctas,
+                             void* stream);
+
 /* ------------------------------------------- multi-tensor L2 norm
  * Replaces get_grad_norm_ (models/optimizer.py:375-397; one torch.norm per parameter, a stack and a
  * .cpu() sync every step from utils/solver.py:109-111) and the torch.norm pairs of LARS.step

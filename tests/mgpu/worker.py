@@ -64,13 +64,18 @@ def check_moco(rank, world, dev, C, O, make_cfg, report):
     from helpers import rel_err
     B, D, K, T, m = 32, 128, 2048, 0.1, 0.9
     out = {}
-    for mode, peer in (("reference", True), ("reference", False), ("canonical", True), ("canonical", False), ("local", True)):
+    # sweep: None = the single-launch head; 3 = the two-launch head (sweep on its own stream with 3 CTAs, the key
+    # push over NVLink by the first CTAs of the finish launch)
+    for mode, peer, sweep in (("reference", True, None), ("reference", False, None), ("canonical", True, None),
+                              ("canonical", False, None), ("local", True, None), ("reference", True, 3),
+                              ("canonical", True, 3), ("reference", False, 3), ("local", True, 0)):
         cfg = make_cfg(CONTRASTIVE__TYPE="moco", CONTRASTIVE__T=T, CONTRASTIVE__DIM=D, CONTRASTIVE__QUEUE_LEN=K,
                        CONTRASTIVE__MOMENTUM=m, NUM_GPUS=world)
         cfg.CONTRASTIVE.QUEUE_MODE = mode
         torch.manual_seed(0)  # identical replicas, as DDP would make them
         model = C.ContrastiveModel(cfg).to(dev).train()
         model.enable_peer_exchange(peer)
+        model.sweep_ctas = sweep
         assert model._batch_shuffle_on
         W_on = model.backbone.proj.weight.detach().cpu().clone()
         W_hi = model.backbone_hist.proj.weight.detach().cpu().clone()
@@ -112,7 +117,8 @@ def check_moco(rank, world, dev, C, O, make_cfg, report):
             assert (qs[rank] - queue).abs().max().item() < 2e-7
         assert worst["loss"] < 2e-5 and worst["grad"] < 5e-4, worst
         assert model.check_device_status() == 0
-        out["%s/%s" % (mode, "peer" if peer else "nccl")] = dict(worst, queues_identical=mode != "local", ptr=ptr)
+        out["%s/%s%s" % (mode, "peer" if peer else "nccl", "" if sweep is None else "/two_launch")] = dict(
+            worst, queues_identical=mode != "local", ptr=ptr)
         model.enable_peer_exchange(False)
     report["moco"] = out
 

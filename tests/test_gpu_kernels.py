@@ -339,6 +339,52 @@ def test_infonce_indexed_keys(raw, B, D, K, n_rows, n_enq):
     assert int(status.item()) & _lib.DEVFLAG_BAD_INDEX
 
 
+@pytest.mark.parametrize("impl_name", ["tc3x", "tc1x"])
+@pytest.mark.parametrize("B,D,K,n_keys,sweep_ctas", [(64, 128, 65536, 1, 0), (64, 128, 65536, 1, 24), (64, 128, 4096, 2, 7),
+                                                      (200, 64, 2048, 1, 5), (16, 32, 1024, 1, 1)])
+def test_infonce_two_launch_form(impl_name, B, D, K, n_keys, sweep_ctas):
+    """avssl_moco_infonce_sweep on a side stream, then the head call with AVSSL_HEAD_SWEPT on the main one: the
+    logits and q are bit-identical to the single cooperative launch; loss and gradient (whose per-CTA partials are
+    merged in a different, still fixed, order) are within the kernel's tolerance of the oracle and repeat bit for bit."""
+    ops = _ops()
+    from advise_video_ssl_b200 import _lib
+    impl = {"tc3x": _lib.IMPL_TC3X, "tc1x": _lib.IMPL_TC1X}[impl_name]
+    g = torch.Generator().manual_seed(B + K + sweep_ctas)
+    T = 0.07
+    queue_c = O.l2_normalize(torch.randn(K, D, generator=g))
+    keys_c = [O.l2_normalize(torch.randn(B, D, generator=g)) for _ in range(n_keys)]
+    feat = torch.randn(B, D, generator=g)
+    fq, queue, keys = feat.cuda(), queue_c.cuda(), [k.cuda() for k in keys_c]
+    ref = ops.moco_infonce(fq, keys, queue, T, True, impl)
+    ws = torch.zeros(ops.moco_infonce_workspace_bytes(B, D, K, n_keys), dtype=torch.uint8, device="cuda")
+    logits = torch.full((n_keys * B, K + 1), float("nan"), device="cuda")
+    side = torch.cuda.Stream()
+    main = torch.cuda.current_stream()
+    for rep in range(2):  # the workspace is reusable
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            ops.moco_infonce_sweep(fq, queue, T, ws, n_keys=n_keys, logits=logits, impl=impl, sweep_ctas=sweep_ctas)
+        main.wait_stream(side)
+        ptr = torch.zeros(1, dtype=torch.int64, device="cuda")
+        status = torch.zeros(1, dtype=torch.int32, device="cuda")
+        queue2 = queue.clone()
+        out = ops.moco_infonce(fq, keys, queue2, T, True, impl, out={"logits": logits}, workspace=ws, swept=sweep_ctas,
+                               enqueue=(ptr, status) if K % B == 0 else None)
+        assert torch.equal(out["logits"], ref["logits"])
+        assert torch.equal(out["q"], ref["q"])
+        if rep == 0:
+            first = {k: out[k].clone() for k in ("loss", "dfeat", "lse")}
+        else:
+            for k in first:
+                assert torch.equal(out[k], first[k]), k
+        _check_infonce(out, feat, keys_c, queue_c, T, *TOL[impl_name])
+        if K % B == 0:
+            assert torch.equal(queue2[:B], keys[0]) and torch.equal(queue2[B:], queue[B:]) and int(ptr.item()) == B % K
+            assert int(status.item()) == 0
+    with pytest.raises(Exception, match="tcgen05"):
+        ops.moco_infonce_sweep(fq, queue, T, ws, n_keys=n_keys, logits=logits, impl=_lib.IMPL_SIMT)
+
+
 def test_l2norm_push_is_bit_identical_to_normalize_then_push():
     ops = _ops()
     x = ops.PeerExchange(48, 64)  # no process group: world 1, the exchange targets its own buffer

@@ -34,8 +34,11 @@ def _set(p, v):
 
 
 # ------------------------------------------------------------------------------ MoCo
+@pytest.mark.parametrize("sweep_ctas", [None, 0, 3])
 @pytest.mark.parametrize("shuffle", [False, True])
-def test_moco_small_golden(golden, shuffle):
+def test_moco_small_golden(golden, shuffle, sweep_ctas):
+    """sweep_ctas None: the single-launch head (the update of this tiny encoder is too short to hide a sweep under);
+    0 / 3: the two-launch head -- sweep on its own stream before the momentum update, finish behind the key path."""
     g = golden("moco_small")
     B, D, K, T, m_ = int(g.scalar("B")), int(g.scalar("D")), int(g.scalar("K")), g.scalar("T"), g.scalar("m")
     cfg = make_cfg(CONTRASTIVE__TYPE="moco", CONTRASTIVE__T=T, CONTRASTIVE__DIM=D, CONTRASTIVE__QUEUE_LEN=K,
@@ -43,6 +46,8 @@ def test_moco_small_golden(golden, shuffle):
     C, model = _model(cfg)
     assert model._batch_shuffle_on  # reference default at 1 GPU without sync BN
     model._batch_shuffle_on = shuffle
+    assert model.sweep_ctas is None and model._sweep_ctas_beside_ema(B, torch.device("cuda", 0)) is None
+    model.sweep_ctas = sweep_ctas
     _set(model.queue_x, g["queue0"])
     _set(model.backbone_hist.proj.weight, g["Whist0"])
     tap = Tap(model.backbone)
@@ -473,8 +478,9 @@ def test_ema_plan_follows_rebound_parameter_storage():
     assert torch.equal(w_hi.detach().cpu(), ref)
 
 
+@pytest.mark.parametrize("sweep_ctas", [None, 5])
 @pytest.mark.parametrize("shuffle", [False, True])
-def test_module_step_captures_into_a_cuda_graph(shuffle):
+def test_module_step_captures_into_a_cuda_graph(shuffle, sweep_ctas):
     """contrastive_forward + backward (the call tools/train.py makes) is capturable: no host synchronisation,
     allocation-stable, and replays reproduce the eager step (same kernels, same order)."""
     B, D, K, T = 32, 128, 1024, 0.1
@@ -488,6 +494,7 @@ def test_module_step_captures_into_a_cuda_graph(shuffle):
     ref = C.ContrastiveModel(cfg).cuda().train()
     ref._batch_shuffle_on = shuffle
     ref.load_state_dict(model.state_dict())
+    model.sweep_ctas = ref.sweep_ctas = sweep_ctas  # 5: the two-launch head (sweep stream forked inside the capture)
     xq = torch.randn(B, D).cuda().requires_grad_(True)
     xk = torch.randn(B, D).cuda()
     index, time = torch.arange(B).cuda(), torch.zeros(B, 2, 1).cuda()
