@@ -95,6 +95,14 @@ SIGNATURES = {
                                          c_int, c_int, c_void_p]),
     "avssl_multi_l2norm_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "avssl_multi_l2norm": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "avssl_linear_l2norm_max_dout": (c_int, []),
+    "avssl_linear_l2norm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p,
+                                        c_void_p]),
+    "avssl_linear_l2norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int,
+                                        c_void_p, c_void_p, c_void_p, c_void_p]),
+    "avssl_topk_rows_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "avssl_topk_rows": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                c_size_t, c_void_p]),
     "avssl_swav_ce_workspace_bytes": (c_size_t, [c_int]),
     "avssl_swav_ce_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_size_t, c_void_p]),

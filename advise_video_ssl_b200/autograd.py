@@ -39,6 +39,27 @@ def l2norm_lastdim(x, eps=0.0):
     return L2NormRows.apply(x.reshape(-1, shape[-1]), eps).reshape(shape)
 
 
+class LinearNormalize(torch.autograd.Function):
+    """q = Normalize(x W^T + b): the projection MLP's last Linear (models/head_helper.py:52-58) with the head's
+    Normalize (models/contrastive.py:923-934) as its epilogue; one launch forward, one launch backward."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, normalize):
+        xd, wd = x.detach().contiguous(), weight.detach().contiguous()
+        q, nrm = ops.linear_l2norm_fwd(xd, wd, None if bias is None else bias.detach().contiguous(), eps, normalize)
+        ctx.save_for_backward(xd, wd, q, nrm)
+        ctx.eps, ctx.normalize, ctx.has_bias = eps, normalize, bias is not None
+        return q
+
+    @staticmethod
+    def backward(ctx, grad_q):
+        x, w, q, nrm = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        dx, dw, db = ops.linear_l2norm_bwd(x, w, q, nrm, grad_q, ctx.eps, ctx.normalize, need_dx=need[0], need_dw=need[1],
+                                           need_db=ctx.has_bias and need[2])
+        return dx, dw, db, None, None
+
+
 class MocoInfoNce(torch.autograd.Function):
     """K2 + K3 (+ K4, + C3 wait): q = f/||f||, logits against [key; queue], InfoNCE, d loss / d f
     (models/contrastive.py:462-503, models/losses.py:20-25).

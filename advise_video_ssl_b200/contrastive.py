@@ -263,8 +263,12 @@ class ContrastiveModel(nn.Module):
     def eval_knn(self, q_knn, knn_k=200):
         """Similarity of the queries to every bank row and its top-k (:232-241); eval only."""
         bank = self.knn_mem.memory
-        sims = q_knn.reshape(q_knn.size(0), -1) @ bank.reshape(bank.size(0), -1).t()
-        return sims.topk(knn_k, dim=1, largest=True, sorted=True)
+        q = q_knn.reshape(q_knn.size(0), -1)
+        bank = bank.reshape(bank.size(0), -1)
+        if q.is_cuda and q.dtype == torch.float32 and ops.topk_rows_supported(q.size(0), bank.size(0), knn_k):
+            # similarities from the head's tcgen05 mainloop, exact top-k behind it (csrc/knn.cu)
+            return ops.knn_similarity_topk(q.detach().contiguous(), bank.contiguous(), knn_k)
+        return (q @ bank.t()).topk(knn_k, dim=1, largest=True, sorted=True)  # k > 1024 or a bank beyond the plan
 
     # ------------------------------------------------------------------- K1: momentum update
     def _ema_state(self):

@@ -619,6 +619,61 @@ def membank_gather_dot(bank, q, ind, time, T, interp=False, status=None):
     return prod
 
 
+# ------------------------------------------------------------------------- kNN evaluation (eval_knn)
+def topk_rows_supported(N, M, k):
+    return 1 <= k <= M and N >= 1 and int(lib.avssl_topk_rows_workspace_bytes(int(N), int(M), int(k))) > 0
+
+
+def topk_rows(dist, k, q_scale_rows=None):
+    """Exact row-wise top-k (largest, sorted, ties towards the smaller index) of a [N, M] fp32 matrix whose rows are
+    contiguous (stride(1) == 1; a column-offset view such as logits[:, 1:] is fine).  `q_scale_rows` [N, D]: the
+    values are multiplied by ||q_row|| (similarities computed on normalised queries).  Returns (yd [N, k] fp32,
+    yi [N, k] int64) like torch.topk (models/contrastive.py:240)."""
+    if not isinstance(dist, torch.Tensor) or not dist.is_cuda:
+        raise RuntimeError("dist must be a CUDA tensor: the contrastive hot path has no CPU fallback")
+    if dist.dtype != _f32 or dist.dim() != 2 or dist.stride(1) != 1:
+        raise ValueError("topk_rows: dist must be a 2-D fp32 tensor with contiguous rows")
+    N, M = dist.shape
+    ld = dist.stride(0) if N > 1 else max(M, dist.stride(0))
+    k = int(k)
+    if not 1 <= k <= M:
+        raise RuntimeError("topk_rows: k = %d not in [1, %d]" % (k, M))  # torch.topk raises here as well
+    q_ptr, D = None, 0
+    if q_scale_rows is not None:
+        _req(q_scale_rows, "q_scale_rows")
+        if q_scale_rows.dim() != 2 or q_scale_rows.shape[0] != N:
+            raise ValueError("topk_rows: q_scale_rows must be [N, D]")
+        q_ptr, D = q_scale_rows.data_ptr(), q_scale_rows.shape[1]
+    nbytes = int(lib.avssl_topk_rows_workspace_bytes(N, M, k))
+    if nbytes == 0:
+        raise _lib.AvsslError("topk_rows: k=%d over M=%d is outside the two-pass plan" % (k, M))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dist.device)
+    yd = torch.empty(N, k, dtype=_f32, device=dist.device)
+    yi = torch.empty(N, k, dtype=torch.int64, device=dist.device)
+    check(lib.avssl_topk_rows(dist.data_ptr(), int(ld), N, M, k, q_ptr, int(D), yd.data_ptr(), yi.data_ptr(), ws.data_ptr(),
+                              nbytes, _stream()), "avssl_topk_rows")
+    return yd, yi
+
+
+def knn_similarity_topk(q, bank, k, impl=_lib.IMPL_AUTO):
+    """eval_knn (models/contrastive.py:232-241): top-k of q bank^T.  The similarity matrix is produced by the head's
+    tcgen05 mainloop (avssl_moco_infonce_sweep with the bank in the queue's place and T = 1: fp32-grade 3-term split,
+    logits[:, 1:]); shapes it does not take (D outside {32, 64, 96, 128}) go through a library GEMM.  The top-k is
+    `topk_rows` either way."""
+    _req(q, "q")
+    _req(bank, "bank")
+    N, D = q.shape
+    M = bank.shape[0]
+    if bank.dim() != 2 or bank.shape[1] != D:
+        raise ValueError("knn_similarity_topk: q [N, D] and bank [M, D] expected")
+    if D in (32, 64, 96, 128) and impl != _lib.IMPL_SIMT and q.data_ptr() % 16 == 0 and bank.data_ptr() % 16 == 0:
+        logits = torch.empty(N, M + 1, dtype=_f32, device=q.device)
+        ws = _workspace(q.device, moco_infonce_workspace_bytes(N, D, M, 1), "knn")
+        moco_infonce_sweep(q, bank, 1.0, ws, n_keys=1, logits=logits, impl=impl, sweep_ctas=0)
+        return topk_rows(logits[:, 1:], k, q_scale_rows=q)
+    return topk_rows(q @ bank.t(), k)
+
+
 # ------------------------------------------------------------------------- K2 / K7
 def l2norm_fwd(x, eps=0.0):
     _req(x, "x")
@@ -639,6 +694,57 @@ def l2norm_bwd(y, nrm, dy, eps=0.0):
     check(lib.avssl_l2norm_bwd(y.data_ptr(), nrm.data_ptr(), dy.data_ptr(), n, D, float(eps), dx.data_ptr(),
                                _stream()), "avssl_l2norm_bwd")
     return dx
+
+
+def linear_l2norm_supported(in_features, out_features):
+    """Shapes the fused projection tail handles (avssl_linear_l2norm_fwd): Dout <= 256, Kin % 4 == 0."""
+    return out_features <= lib.avssl_linear_l2norm_max_dout() and in_features % 4 == 0
+
+
+def linear_l2norm_fwd(x, weight, bias=None, eps=0.0, normalize=True):
+    """q = Normalize(x W^T + b) in one launch, the raw projection is never written (projection tail,
+    models/head_helper.py:52-58 + models/contrastive.py:923-934).  Returns (q [B, Dout], ||y|| [B])."""
+    _req(x, "x")
+    _req(weight, "weight")
+    if bias is not None:
+        _req(bias, "bias")
+    if x.dim() != 2 or weight.dim() != 2 or x.shape[1] != weight.shape[1]:
+        raise ValueError("linear_l2norm: x [B, Kin] and weight [Dout, Kin] expected, got %s and %s"
+                         % (tuple(x.shape), tuple(weight.shape)))
+    B, Kin = x.shape
+    Dout = weight.shape[0]
+    if bias is not None and tuple(bias.shape) != (Dout,):
+        raise ValueError("linear_l2norm: bias must be [%d]" % Dout)
+    q = torch.empty(B, Dout, dtype=_f32, device=x.device)
+    nrm = torch.empty(B, dtype=_f32, device=x.device)
+    check(lib.avssl_linear_l2norm_fwd(x.data_ptr(), weight.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                      B, Kin, Dout, float(eps), 1 if normalize else 0, q.data_ptr(), nrm.data_ptr(),
+                                      _stream()), "avssl_linear_l2norm_fwd")
+    return q, nrm
+
+
+def linear_l2norm_bwd(x, weight, q, nrm, grad_q, eps=0.0, normalize=True, need_dx=True, need_dw=True, need_db=True):
+    """Backward of `linear_l2norm_fwd` in one launch: the gradient of the normalisation is applied where grad_q is
+    read, then dx = dy W, dW = dy^T x, db = sum_b dy.  Returns (dx, dW, db), None where not requested."""
+    _req(x, "x")
+    _req(weight, "weight")
+    _req(q, "q")
+    _req(nrm, "norm")
+    grad_q = _req(grad_q.contiguous(), "grad_q")
+    B, Kin = x.shape
+    Dout = weight.shape[0]
+    if tuple(grad_q.shape) != (B, Dout) or tuple(q.shape) != (B, Dout) or nrm.numel() != B:
+        raise ValueError("linear_l2norm_bwd: shape mismatch")
+    dx = torch.empty_like(x) if need_dx else None
+    dW = torch.empty_like(weight) if need_dw else None
+    db = torch.empty(Dout, dtype=_f32, device=x.device) if need_db else None
+    if B == 0:
+        return (dx, dW.zero_() if dW is not None else None, db.zero_() if db is not None else None)
+    ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+    check(lib.avssl_linear_l2norm_bwd(x.data_ptr(), weight.data_ptr(), q.data_ptr(), nrm.data_ptr(), grad_q.data_ptr(),
+                                      B, Kin, Dout, float(eps), 1 if normalize else 0, ptr(dx), ptr(dW), ptr(db),
+                                      _stream()), "avssl_linear_l2norm_bwd")
+    return dx, dW, db
 
 
 def byol_simloss(pred, key, T, normalize=True, want_grad=True):

@@ -399,6 +399,39 @@ AVSSL_API int avssl_multi_l2norm(const avssl_ema_chunk* table_dev, int64_t n_chu
                        int n_tensors, float* per_tensor_norm_out, float* total_norm_out, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------- projection tail
+ * The last Linear of the projection MLP (models/head_helper.py:52-58, `MLPHead.projection[-1]`: y = x W^T + b,
+ * W [Dout, Kin] as nn.Linear stores it) with the head's Normalize (models/contrastive.py:923-934, applied to the
+ * backbone output at :462 / :350 / :757) as its epilogue:
+ *     q = y / max(||y||, eps)        norm_out[b] = ||y_b||            (eps = 0 reproduces Normalize)
+ * y itself is never written.  normalize = 0 gives the plain Linear (q = y).  Exact fp32, deterministic.
+ * Backward, one launch: grad_q = dL/dq ->  dy = (grad_q - (grad_q . q) q) / ||y||   (the arithmetic of avssl_l2norm_bwd),
+ *     dx = dy W      dW = dy^T x      db = sum_b dy          (any of the three outputs may be NULL)
+ * Limits: Dout <= avssl_linear_l2norm_max_dout() (256), Kin % 4 == 0, 16-byte aligned tensors; AVSSL_ERR_UNSUPPORTED
+ * otherwise (the caller keeps nn.Linear + Normalize for such a layer).
+ */
+AVSSL_API int avssl_linear_l2norm_max_dout(void);
+AVSSL_API int avssl_linear_l2norm_fwd(const float* x, const float* W, const float* bias, int B, int Kin, int Dout, float eps,
+                            int normalize, float* q_out, float* norm_out, void* stream);
+AVSSL_API int avssl_linear_l2norm_bwd(const float* x, const float* W, const float* q, const float* norm, const float* grad_q,
+                            int B, int Kin, int Dout, float eps, int normalize, float* dx_out, float* dW_out,
+                            float* db_out, void* stream);
+
+/* ------------------------------------------- kNN evaluation top-k
+ * eval_knn (models/contrastive.py:232-241): dist = q bank^T, then dist.topk(knn_k, dim=1, largest=True, sorted=True).
+ * The similarities come from the head's tcgen05 mainloop -- avssl_moco_infonce_sweep(q, bank, ..., T = 1) writes them
+ * as logits[:, 1:], computed on q / ||q|| -- and avssl_topk_rows() is the top-k behind it: exact, every row of `dist`
+ * read once, sorted descending, ties towards the smaller index, deterministic.
+ *   dist: [N, ld] fp32, the M candidates of a row start at dist + row * ld (pass logits + 1, ld = M + 1);
+ *   q_scale_rows: NULL, or the [N, D] queries the similarities were normalised by: yd is multiplied by ||q_row||;
+ *   yd_out [N, k] fp32, yi_out [N, k] int64 (the dtype torch.topk returns).
+ * k <= min(M, 1024); AVSSL_ERR_UNSUPPORTED when M is too long for the two-pass plan at this k (M > ~1.5 M at k = 200:
+ * avssl_topk_rows_workspace_bytes() returns 0 for such a shape).  workspace: no initialisation needed.
+ */
+AVSSL_API size_t avssl_topk_rows_workspace_bytes(int N, int M, int k);
+AVSSL_API int avssl_topk_rows(const float* dist, int64_t ld, int N, int M, int k, const float* q_scale_rows, int D,
+                    float* yd_out, int64_t* yi_out, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

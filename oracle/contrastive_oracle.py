@@ -380,6 +380,13 @@ def knn_topk(q, bank, k=200):
     return d.topk(k, dim=1, largest=True, sorted=True)
 
 
+# ---------------------------------------------------------------- projection tail
+def projection_tail(x, weight, bias=None):
+    """Last Linear of MLPHead (models/head_helper.py:52-58, nn.Linear: x W^T + b) followed by the head's
+    Normalize (models/contrastive.py:923-934, applied to the backbone output at :462 / :350 / :757)."""
+    return l2_normalize(torch.nn.functional.linear(x, weight, bias), dim=1)
+
+
 # ---------------------------------------------------------------- shuffle (A6, C1-C3)
 def shuffle_plan(perm, world):
     """_batch_shuffle index math, models/contrastive.py:203-211: rank r keeps the

@@ -340,3 +340,17 @@ def test_grad_norm(golden):
     grads = [g["grad%d" % i] for i in range(int(g.scalar("n")))]
     assert torch.equal(O.grad_norm(grads), g["total"])
     assert O.grad_norm([]).item() == g["empty"].item() == 0.0
+
+
+def test_projection_tail(golden):
+    """projtail.npz comes from the reference's own MLPHead + Normalize (make_golden_projtail.py): the oracle's
+    restatement of the tail (last Linear + Normalize) on the tapped input reproduces q bit for bit."""
+    g = golden("projtail")
+    for case in ("a", "b"):
+        layers = int(g[case + "_cfg"][4])
+        last = "projection.%d" % (3 * (layers - 1) if int(g[case + "_cfg"][5]) else 2 * (layers - 1))
+        W = g["%s_sd_%s.weight" % (case, last)]
+        key_b = "%s_sd_%s.bias" % (case, last)
+        b = g[key_b] if key_b in g.keys() else None
+        assert torch.equal(torch.nn.functional.linear(g[case + "_tail_x"], W, b), g[case + "_tail_y"])
+        assert torch.equal(O.projection_tail(g[case + "_tail_x"], W, b), g[case + "_q"])
