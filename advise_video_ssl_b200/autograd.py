@@ -43,10 +43,21 @@ class LinearNormalize(torch.autograd.Function):
     """q = Normalize(x W^T + b): the projection MLP's last Linear (models/head_helper.py:52-58) with the head's
     Normalize (models/contrastive.py:923-934) as its epilogue; one launch forward, one launch backward."""
 
+    # The fused launches are a latency play: exact fp32 on the CUDA cores, split-K over a cluster forward, every CTA
+    # re-deriving dy backward.  Measured on B200 (profiles/r2_next_bench.jsonl): they win at the head's batch (B = 64,
+    # Kin 2048 -> 128: 10.7 / 12.6 us against 27.0 / 24.9 us for cuBLAS + the Normalize kernels) and up to 128 rows;
+    # at B = 512 the GEMMs are flop-bound and belong to the library (cuBLAS, then the Normalize kernels).
+    FUSED_MAX_ROWS = 128
+
     @staticmethod
     def forward(ctx, x, weight, bias, eps, normalize):
         xd, wd = x.detach().contiguous(), weight.detach().contiguous()
-        q, nrm = ops.linear_l2norm_fwd(xd, wd, None if bias is None else bias.detach().contiguous(), eps, normalize)
+        bd = None if bias is None else bias.detach().contiguous()
+        if xd.shape[0] <= LinearNormalize.FUSED_MAX_ROWS:
+            q, nrm = ops.linear_l2norm_fwd(xd, wd, bd, eps, normalize)
+        else:
+            y = torch.nn.functional.linear(xd, wd, bd)
+            q, nrm = ops.l2norm_fwd(y, eps) if normalize else (y, y.new_empty(y.shape[0]))
         ctx.save_for_backward(xd, wd, q, nrm)
         ctx.eps, ctx.normalize, ctx.has_bias = eps, normalize, bias is not None
         return q
@@ -55,9 +66,13 @@ class LinearNormalize(torch.autograd.Function):
     def backward(ctx, grad_q):
         x, w, q, nrm = ctx.saved_tensors
         need = ctx.needs_input_grad
-        dx, dw, db = ops.linear_l2norm_bwd(x, w, q, nrm, grad_q, ctx.eps, ctx.normalize, need_dx=need[0], need_dw=need[1],
-                                           need_db=ctx.has_bias and need[2])
-        return dx, dw, db, None, None
+        want_db = ctx.has_bias and need[2]
+        if x.shape[0] <= LinearNormalize.FUSED_MAX_ROWS:
+            dx, dw, db = ops.linear_l2norm_bwd(x, w, q, nrm, grad_q, ctx.eps, ctx.normalize, need_dx=need[0],
+                                               need_dw=need[1], need_db=want_db)
+            return dx, dw, db, None, None
+        dy = ops.l2norm_bwd(q, nrm, grad_q, ctx.eps) if ctx.normalize else grad_q.contiguous()
+        return (dy @ w if need[0] else None, dy.t() @ x if need[1] else None, dy.sum(0) if want_db else None, None, None)
 
 
 class MocoInfoNce(torch.autograd.Function):

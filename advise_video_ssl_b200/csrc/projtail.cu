@@ -171,11 +171,14 @@ __global__ void __launch_bounds__(kPtThreads, 1) linear_l2norm_bwd_kernel(const 
   const int Kin = a.Kin, Dout = a.Dout;
   const int k0 = blockIdx.x * kPbKS;  // Kin % 4 == 0: every 4-column group is entirely inside or outside
 
-  // W slice, zero-padded rows / columns
-  for (int idx = t; idx < DP * (kPbKS / 4); idx += kPtThreads) {
+  // W slice (zero-padded rows / columns) into registers: its latency overlaps the first pass's g / q loads below
+  constexpr int WV = 2 * CPT;  // DP * 4 float4 / 256 threads
+  float4 wreg[WV];
+#pragma unroll
+  for (int i = 0; i < WV; ++i) {
+    const int idx = t + i * kPtThreads;
     const int c = idx >> 2, k = k0 + ((idx & 3) << 2);
-    const float4 v = (c < Dout && k < Kin) ? __ldg(reinterpret_cast<const float4*>(a.W + (int64_t)c * Kin + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    *reinterpret_cast<float4*>(W_s + c * kPbKS + ((idx & 3) << 2)) = v;
+    wreg[i] = (c < Dout && k < Kin) ? __ldg(reinterpret_cast<const float4*>(a.W + (int64_t)c * Kin + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 
   const int c0 = t & 127, kg = t >> 7;   // dW: columns c0 (+128) of Dout, Kin columns kg*8 .. +7 of the slice
@@ -188,36 +191,57 @@ __global__ void __launch_bounds__(kPtThreads, 1) linear_l2norm_bwd_kernel(const 
   float accb = 0.f;  // CTA 0: db[t], rows added in order
 
   for (int b0 = 0; b0 < a.B; b0 += kPbRows) {
-    __syncthreads();  // the previous pass no longer reads dy_s / x_s (and W_s is complete)
-    // dy rows of this pass: one warp per row, arithmetic of l2norm_bwd_kernel (rowops.cu)
-    for (int r = warp; r < kPbRows; r += kPtThreads / 32) {
-      const int row = b0 + r;
-      float* out = dy_s + r * DYS;
-      if (row < a.B) {
-        const float* gr = a.g + (int64_t)row * Dout;
-        if (a.normalize) {
-          const float* qr = a.q + (int64_t)row * Dout;
-          const float nrm = a.norm[row];
-          if (nrm > a.eps) {
-            float dot = 0.f;
-            for (int c = lane; c < Dout; c += 32) dot = fmaf(gr[c], qr[c], dot);
-            dot = warp_sum(dot);
-            for (int c = lane; c < DP; c += 32) out[c] = (c < Dout) ? (gr[c] - dot * qr[c]) / nrm : 0.f;
-          } else {
-            for (int c = lane; c < DP; c += 32) out[c] = (c < Dout) ? gr[c] / a.eps : 0.f;
-          }
-        } else {
-          for (int c = lane; c < DP; c += 32) out[c] = (c < Dout) ? gr[c] : 0.f;
+    // x slice of this pass: 64 rows x 4 float4 = one per thread (in flight under the dy arithmetic)
+    float4 xreg;
+    {
+      const int r = t >> 2, k = k0 + ((t & 3) << 2);
+      xreg = (b0 + r < a.B && k < Kin) ? __ldg(reinterpret_cast<const float4*>(a.x + (int64_t)(b0 + r) * Kin + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();  // the previous pass no longer reads dy_s / x_s
+    // dy rows of this pass: one warp per row, eight rows per warp, the loads of four rows issued together;
+    // arithmetic of l2norm_bwd_kernel (rowops.cu): same summation order, true division
+    constexpr int RPB = 4, NV = 4 * CPT;
+    for (int rb = 0; rb < kPbRows / 8; rb += RPB) {
+      float gv[RPB][NV], qv[RPB][NV], nr[RPB];
+#pragma unroll
+      for (int u = 0; u < RPB; ++u) {
+        const int row = b0 + warp + 8 * (rb + u);
+        const bool ok = row < a.B;
+        nr[u] = (ok && a.normalize) ? a.norm[row] : 1.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = lane + 32 * i;
+          gv[u][i] = (ok && c < Dout) ? a.g[(int64_t)row * Dout + c] : 0.f;
+          qv[u][i] = (ok && a.normalize && c < Dout) ? a.q[(int64_t)row * Dout + c] : 0.f;
         }
-      } else {
-        for (int c = lane; c < DP; c += 32) out[c] = 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < RPB; ++u) {
+        float* out = dy_s + (warp + 8 * (rb + u)) * DYS;
+        if (!a.normalize || b0 + warp + 8 * (rb + u) >= a.B) {
+#pragma unroll
+          for (int i = 0; i < NV; ++i) out[lane + 32 * i] = gv[u][i];  // plain Linear; rows past B hold zeros
+        } else if (nr[u] > a.eps) {
+          float dot = 0.f;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) dot = fmaf(gv[u][i], qv[u][i], dot);
+          dot = warp_sum(dot);
+#pragma unroll
+          for (int i = 0; i < NV; ++i) out[lane + 32 * i] = (lane + 32 * i < Dout) ? (gv[u][i] - dot * qv[u][i]) / nr[u] : 0.f;
+        } else {
+#pragma unroll
+          for (int i = 0; i < NV; ++i) out[lane + 32 * i] = (lane + 32 * i < Dout) ? gv[u][i] / a.eps : 0.f;
+        }
       }
     }
-    {  // x slice of this pass: 64 rows x 4 float4 = one per thread
-      const int r = t >> 2, k = k0 + ((t & 3) << 2);
-      const float4 v = (b0 + r < a.B && k < Kin) ? __ldg(reinterpret_cast<const float4*>(a.x + (int64_t)(b0 + r) * Kin + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(x_s + r * kPbKS + ((t & 3) << 2)) = v;
+    if (b0 == 0) {
+#pragma unroll
+      for (int i = 0; i < WV; ++i) {
+        const int idx = t + i * kPtThreads;
+        *reinterpret_cast<float4*>(W_s + (idx >> 2) * kPbKS + ((idx & 3) << 2)) = wreg[i];
+      }
     }
+    *reinterpret_cast<float4*>(x_s + (t >> 2) * kPbKS + ((t & 3) << 2)) = xreg;
     __syncthreads();
 
     if (a.dW) {  // dW[c][k] += sum_b dy[b][c] x[b][k]

@@ -4,6 +4,9 @@
 //   swap-prediction CE  models/contrastive.py:672-679, KLDivLoss :912-916
 #include <cooperative_groups.h>
 
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -459,130 +462,148 @@ __global__ void __launch_bounds__(256) swav_ce_reg_kernel(const SwavCeArgs a) {
 }
 
 
-// Persistent, pipelined variant of the register-resident kernel (the hot one at cfg5): about three CTAs per SM
-// walk the score rows; while a CTA reduces row i out of shared memory, ONE elected thread has the bulk-copy
-// engine (cp.async.bulk, completion on an mbarrier) landing row i+1 -- its scores and the code rows it needs --
-// in the other stage.  The one-CTA-per-row kernel only had loads in flight at the start of each CTA's short life
-// (load -> reduce -> reduce -> store, 1536 CTAs: 0.33 of HBM); here the loads of the next row overlap the two
-// block reductions and the store of the current one.  Per-thread arithmetic and the shape of every reduction are
-// those of swav_ce_reg_kernel, so the results are bit-identical to it.
+// Sample-major variant (the hot one at cfg5): one CTA per (sample r, group of crops).  The score rows of ONE sample
+// across the crops all meet the same code rows codes[as][r], so the CTA lands those once (bulk copy into shared
+// memory, then registers, their sums reduced once) and streams the sample's score rows through a two-stage bulk-copy
+// pipeline: L2 -> SM traffic is the algorithmic 1 + n_assign / crops_per_cta rows per score row.
+// ncu on the first version (per-thread arithmetic of swav_ce_reg_kernel, profiles/r2_k11_ncu.md) showed the kernel
+// ISSUE-bound, not memory-bound: ~800 instructions per warp and row, 22 per element.  Hence the arithmetic diet:
+// scores go to the log2 domain with one multiply (exp = one FADD + MUFU.EX2), the code sums are taken once per CTA
+// instead of once per row, zero weights need no select (they multiply every use), and 1/T is folded into the two
+// factors of the gradient.  Same mathematics as the reference's -(q * log_softmax(s / T)).sum(); rounding differs
+// from swav_ce_reg_kernel in the last bits (the test bounds it).
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int kA>
-__global__ void __launch_bounds__(256) swav_ce_pipe_kernel(const SwavCeArgs a) {
+__global__ void __launch_bounds__(256) swav_ce_sample_kernel(const SwavCeArgs a, int crops_per_cta) {
   extern __shared__ __align__(16) uint8_t pipe_smem[];
-  __shared__ float s_red[32 * (1 + 2 * kA)];
+  __shared__ float s_red[32 * (1 + kA)];
   __shared__ unsigned s_last;
   __shared__ __align__(8) uint64_t full[2];
+  __shared__ __align__(8) uint64_t codes_full;
+  constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
   const int tid = threadIdx.x;
   const int P4 = a.P >> 2;
   const int n_rows = a.n_crops * a.bs;
   const uint32_t row_bytes = (uint32_t)a.P * 4u;
-  auto stage_ptr = [&](int st, int which) {  // which: 0 = scores, 1 + as = code set as
-    return reinterpret_cast<float4*>(pipe_smem + ((size_t)st * (1 + kA) + which) * row_bytes);
-  };
-  auto issue = [&](int row, int st) {  // thread 0 only
-    const int v = row / a.bs, r = row % a.bs;
-    uint32_t bytes = row_bytes;
-#pragma unroll
-    for (int as = 0; as < kA; ++as)
-      if (as < a.n_assign && a.w[as * a.n_crops + v] != 0.f) bytes += row_bytes;
-    ptx::mbar_arrive_expect_tx(&full[st], bytes);
-    ptx::bulk_load(stage_ptr(st, 0), a.scores + (size_t)row * a.P, row_bytes, &full[st]);
-#pragma unroll
-    for (int as = 0; as < kA; ++as)
-      if (as < a.n_assign && a.w[as * a.n_crops + v] != 0.f)
-        ptx::bulk_load(stage_ptr(st, 1 + as), a.codes + ((size_t)as * a.bs + r) * a.P, row_bytes, &full[st]);
-  };
+  const int r = blockIdx.x % a.bs;
+  const int v0 = (blockIdx.x / a.bs) * crops_per_cta;
+  const int v1 = min(v0 + crops_per_cta, a.n_crops);
+  auto code_ptr = [&](int as) { return reinterpret_cast<float4*>(pipe_smem + (size_t)as * row_bytes); };
+  auto stage_ptr = [&](int st) { return reinterpret_cast<float4*>(pipe_smem + (size_t)(kA + st) * row_bytes); };
   if (tid == 0) {
     ptx::mbar_init(&full[0], 1);
     ptx::mbar_init(&full[1], 1);
+    ptx::mbar_init(&codes_full, 1);
     ptx::mbar_fence_init();
-    if ((int)blockIdx.x < n_rows) issue(blockIdx.x, 0);
+    // the first score row before the code rows: the max reduction only needs the scores
+    ptx::mbar_arrive_expect_tx(&full[0], row_bytes);
+    ptx::bulk_load(stage_ptr(0), a.scores + ((size_t)v0 * a.bs + r) * a.P, row_bytes, &full[0]);
+    ptx::mbar_arrive_expect_tx(&codes_full, row_bytes * (uint32_t)min(a.n_assign, kA));
+    for (int as = 0; as < kA && as < a.n_assign; ++as)
+      ptx::bulk_load(code_ptr(as), a.codes + ((size_t)as * a.bs + r) * a.P, row_bytes, &codes_full);
   }
   __syncthreads();
 
+  const float to_log2 = a.inv_T * kLog2e;
+  float4 cd[kA][kCeVec];  // this sample's code rows, resident in registers across the crops
+  float csum[kA];         // ... and their sums
+  bool have_codes = false;
   int it = 0;
-  for (int row = blockIdx.x; row < n_rows; row += gridDim.x, ++it) {
+  for (int v = v0; v < v1; ++v, ++it) {
     const int st = it & 1;
-    const int v = row / a.bs;
-    if (tid == 0 && row + (int)gridDim.x < n_rows) issue(row + gridDim.x, st ^ 1);  // stage st^1 was released by the barrier below
+    const int row = v * a.bs + r;
+    if (tid == 0 && v + 1 < v1) {  // stage st^1 was released by the barriers of the previous iteration
+      ptx::mbar_arrive_expect_tx(&full[st ^ 1], row_bytes);
+      ptx::bulk_load(stage_ptr(st ^ 1), a.scores + ((size_t)(v + 1) * a.bs + r) * a.P, row_bytes, &full[st ^ 1]);
+    }
     ptx::mbar_wait(&full[st], (it >> 1) & 1);
 
-    const float4* xs = stage_ptr(st, 0);
-    float4 x[kCeVec];
+    const float4* xs = stage_ptr(st);
+    float4 x[kCeVec];  // s / T in log2 units
     float mx = -INFINITY;
 #pragma unroll
     for (int j = 0; j < kCeVec; ++j) {
       const int c = tid + j * 256;
       if (c < P4) {
         x[j] = xs[c];
-        x[j].x *= a.inv_T; x[j].y *= a.inv_T; x[j].z *= a.inv_T; x[j].w *= a.inv_T;
+        x[j].x *= to_log2; x[j].y *= to_log2; x[j].z *= to_log2; x[j].w *= to_log2;
         mx = fmaxf(mx, fmaxf(fmaxf(x[j].x, x[j].y), fmaxf(x[j].z, x[j].w)));
       } else {
         x[j] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
       }
     }
-    float wa[kA];
-    float4 cd[kA][kCeVec];
+    if (!have_codes) {  // uniform: first row of the CTA
+      ptx::mbar_wait(&codes_full, 0);
 #pragma unroll
-    for (int as = 0; as < kA; ++as) {
-      wa[as] = as < a.n_assign ? a.w[as * a.n_crops + v] : 0.f;
-      const float4* c4 = stage_ptr(st, 1 + as);
+      for (int as = 0; as < kA; ++as) {
+        const float4* c4 = code_ptr(as);
+        csum[as] = 0.f;
 #pragma unroll
-      for (int j = 0; j < kCeVec; ++j) {
-        const int c = tid + j * 256;
-        cd[as][j] = (wa[as] != 0.f && c < P4) ? c4[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < kCeVec; ++j) {
+          const int c = tid + j * 256;
+          cd[as][j] = (as < a.n_assign && c < P4) ? c4[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+          csum[as] += (cd[as][j].x + cd[as][j].y) + (cd[as][j].z + cd[as][j].w);
+        }
       }
+      block_sum_n<kA>(csum, s_red);
+      have_codes = true;
     }
     mx = warp_max(mx);
-    __syncthreads();  // s_red of the previous row is dead
+    __syncthreads();  // s_red of the previous reduction is dead
     if ((tid & 31) == 0) s_red[tid >> 5] = mx;
-    __syncthreads();  // ... and every thread has read stage st: it may be refilled after the next iteration's issue
+    __syncthreads();  // ... and every thread has read stage st: it may be refilled by the next iteration's issue
     mx = s_red[0];
 #pragma unroll
     for (int w = 1; w < 8; ++w) mx = fmaxf(mx, s_red[w]);
 
-    float red[1 + 2 * kA];
+    // one reduction for: sum of 2^(x - mx), and per code set the dot product with x
+    float red[1 + kA];
 #pragma unroll
-    for (int i = 0; i < 1 + 2 * kA; ++i) red[i] = 0.f;
+    for (int i = 0; i < 1 + kA; ++i) red[i] = 0.f;
     float4 e[kCeVec];
 #pragma unroll
     for (int j = 0; j < kCeVec; ++j) {
-      e[j] = make_float4(__expf(x[j].x - mx), __expf(x[j].y - mx), __expf(x[j].z - mx), __expf(x[j].w - mx));
-      red[0] += (e[j].x + e[j].y) + (e[j].z + e[j].w);
-      const bool in = tid + j * 256 < P4;
+      e[j] = make_float4(ex2_approx(x[j].x - mx), ex2_approx(x[j].y - mx), ex2_approx(x[j].z - mx), ex2_approx(x[j].w - mx));
+      red[0] += (e[j].x + e[j].y) + (e[j].z + e[j].w);  // padding columns: 2^(-inf) = 0
+      if (tid + j * 256 < P4) {
 #pragma unroll
-      for (int as = 0; as < kA; ++as) {
-        const float4 c = cd[as][j];
-        if (in) {
-          red[1 + 2 * as] = fmaf(c.x, x[j].x, fmaf(c.y, x[j].y, fmaf(c.z, x[j].z, fmaf(c.w, x[j].w, red[1 + 2 * as]))));
-          red[2 + 2 * as] += (c.x + c.y) + (c.z + c.w);
+        for (int as = 0; as < kA; ++as) {
+          const float4 c = cd[as][j];
+          red[1 + as] = fmaf(c.x, x[j].x, fmaf(c.y, x[j].y, fmaf(c.z, x[j].z, fmaf(c.w, x[j].w, red[1 + as]))));
         }
       }
     }
-    block_sum_n<1 + 2 * kA>(red, s_red);
-    const float lse = mx + logf(red[0]);
-    float loss = 0.f, wsum = 0.f;
+    block_sum_n<1 + kA>(red, s_red);
+    const float lse = (mx + log2f(red[0])) * kLn2;
+    float loss = 0.f, wsum = 0.f, wn[kA];  // wsum = sum_a w * sum_k code
 #pragma unroll
     for (int as = 0; as < kA; ++as) {
-      loss += wa[as] * (lse * red[2 + 2 * as] - red[1 + 2 * as]);
-      wsum += wa[as] * red[2 + 2 * as];
+      const float w = as < a.n_assign ? a.w[as * a.n_crops + v] : 0.f;
+      loss += w * (lse * csum[as] - red[1 + as] * kLn2);
+      wsum += w * csum[as];
+      wn[as] = -w * a.inv_T;
     }
     if (a.dscores) {
       float4* d4 = reinterpret_cast<float4*>(a.dscores + (size_t)row * a.P);
-      const float pscale = wsum / red[0];
+      const float ps = wsum / red[0] * a.inv_T;  // softmax_k * wsum / T = e_k * ps
 #pragma unroll
       for (int j = 0; j < kCeVec; ++j) {
         const int c = tid + j * 256;
         if (c < P4) {
-          float4 g = make_float4(e[j].x * pscale, e[j].y * pscale, e[j].z * pscale, e[j].w * pscale);
+          float4 g = make_float4(e[j].x * ps, e[j].y * ps, e[j].z * ps, e[j].w * ps);
 #pragma unroll
           for (int as = 0; as < kA; ++as) {
-            g.x = fmaf(-wa[as], cd[as][j].x, g.x);
-            g.y = fmaf(-wa[as], cd[as][j].y, g.y);
-            g.z = fmaf(-wa[as], cd[as][j].z, g.z);
-            g.w = fmaf(-wa[as], cd[as][j].w, g.w);
+            g.x = fmaf(wn[as], cd[as][j].x, g.x);
+            g.y = fmaf(wn[as], cd[as][j].y, g.y);
+            g.z = fmaf(wn[as], cd[as][j].z, g.z);
+            g.w = fmaf(wn[as], cd[as][j].w, g.w);
           }
-          st_stream(d4 + c, make_float4(g.x * a.inv_T, g.y * a.inv_T, g.z * a.inv_T, g.w * a.inv_T));
+          st_stream(d4 + c, g);
         }
       }
     }
@@ -742,18 +763,21 @@ extern "C" int avssl_swav_ce_fwd_bwd(const float* scores, const float* codes, in
                         ((reinterpret_cast<uintptr_t>(scores) | reinterpret_cast<uintptr_t>(codes) |
                           reinterpret_cast<uintptr_t>(dscores_out)) & 15u) == 0;
   // more than two code sets (never produced by the reference: two global crops) take the generic kernel
-  const size_t pipe_smem = (size_t)2 * 3 * P * 4;  // two stages x (scores + two code rows)
-  if (reg_path && n_assign <= 2 && pipe_smem <= 200 * 1024 && n_crops * bs >= 2 * sm_count()) {
-    // persistent + bulk-copy pipeline: as many CTAs as fit (about three per SM at P = 3000)
+  // AVSSL_SWAV_CE_KERNEL=reg: developer knob for A/B measurements (tools/next_bench.py); default: sample-major when large
+  const char* knob = getenv("AVSSL_SWAV_CE_KERNEL");
+  const bool big = reg_path && n_assign <= 2 && n_crops * bs >= 2 * sm_count();
+  const size_t sample_smem = (size_t)(2 + 2) * P * 4;  // two code rows + two score stages
+  if (big && n_crops >= 2 && sample_smem <= 200 * 1024 && !(knob && !strcmp(knob, "reg"))) {
+    // code rows resident per CTA, the sample's score rows streamed; enough CTAs for ~3 per SM
     static unsigned long long configured = 0ull;
     if (first_use_on_device(configured))
-      AVSSL_CUDA_OK(cudaFuncSetAttribute(swav_ce_pipe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    int per_sm = (int)((220 * 1024) / (pipe_smem + 2048));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;
-    int grid = sm_count() * per_sm;
-    if (grid > n_crops * bs) grid = n_crops * bs;
-    swav_ce_pipe_kernel<2><<<grid, 256, pipe_smem, static_cast<cudaStream_t>(stream)>>>(a);
+      AVSSL_CUDA_OK(cudaFuncSetAttribute(swav_ce_sample_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    int groups = (3 * sm_count() + bs - 1) / bs;
+    if (groups < 1) groups = 1;
+    if (groups > n_crops) groups = n_crops;
+    const int per = (n_crops + groups - 1) / groups;
+    groups = (n_crops + per - 1) / per;
+    swav_ce_sample_kernel<2><<<bs * groups, 256, sample_smem, static_cast<cudaStream_t>(stream)>>>(a, per);
   } else if (reg_path && n_assign <= 2)
     swav_ce_reg_kernel<2><<<n_crops * bs, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   else

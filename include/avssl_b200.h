@@ -421,12 +421,12 @@ AVSSL_API int avssl_linear_l2norm_bwd(const float* x, const float* W, const floa
  * eval_knn (models/contrastive.py:232-241): dist = q bank^T, then dist.topk(knn_k, dim=1, largest=True, sorted=True).
  * The similarities come from the head's tcgen05 mainloop -- avssl_moco_infonce_sweep(q, bank, ..., T = 1) writes them
  * as logits[:, 1:], computed on q / ||q|| -- and avssl_topk_rows() is the top-k behind it: exact, every row of `dist`
- * read once, sorted descending, ties towards the smaller index, deterministic.
+ * fetched from HBM once, sorted descending, ties towards the smaller index, deterministic.
  *   dist: [N, ld] fp32, the M candidates of a row start at dist + row * ld (pass logits + 1, ld = M + 1);
  *   q_scale_rows: NULL, or the [N, D] queries the similarities were normalised by: yd is multiplied by ||q_row||;
  *   yd_out [N, k] fp32, yi_out [N, k] int64 (the dtype torch.topk returns).
- * k <= min(M, 1024); AVSSL_ERR_UNSUPPORTED when M is too long for the two-pass plan at this k (M > ~1.5 M at k = 200:
- * avssl_topk_rows_workspace_bytes() returns 0 for such a shape).  workspace: no initialisation needed.
+ * k <= min(M, 1024), otherwise AVSSL_ERR_UNSUPPORTED (avssl_topk_rows_workspace_bytes() returns 0 for such a shape);
+ * M is not limited (the rows are streamed).  workspace: no initialisation needed.
  */
 AVSSL_API size_t avssl_topk_rows_workspace_bytes(int N, int M, int k);
 AVSSL_API int avssl_topk_rows(const float* dist, int64_t ld, int N, int M, int k, const float* q_scale_rows, int D,

@@ -7,6 +7,7 @@ import torch
 import torch.nn.functional as F
 
 import recipes
+from helpers import rel_err
 from oracle import contrastive_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -420,3 +421,35 @@ def test_no_cpu_fallback():
     ops = _ops()
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.moco_infonce(torch.randn(4, 8), [torch.randn(4, 8)], torch.randn(16, 8), 0.1)
+
+
+@pytest.mark.parametrize("crops,bs,P", [(6, 256, 3000), (4, 200, 1000), (2, 300, 52), (8, 64, 3072)])
+def test_swav_ce_sample_major_kernel(crops, bs, P, monkeypatch):
+    """K11: the sample-major kernel (code rows resident per CTA, log2-domain softmax; default for large problems)
+    against the one-CTA-per-row register kernel (AVSSL_SWAV_CE_KERNEL=reg, the developer knob) and the closed form
+    in fp64.  Both are deterministic: a second launch repeats the bits and leaves the workspace counter at zero."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(crops * bs + P)
+    scores = (torch.randn(crops * bs, P, generator=g) * 0.1).cuda()
+    codes = torch.softmax(torch.randn(2, bs, P, generator=g), -1).cuda()
+    outs = {}
+    for name in ("sample", "reg"):
+        monkeypatch.setenv("AVSSL_SWAV_CE_KERNEL", name)
+        loss, d = ops.swav_ce(scores, codes, crops, bs, 0.1)
+        loss2, d2 = ops.swav_ce(scores, codes, crops, bs, 0.1)
+        assert torch.equal(loss, loss2) and torch.equal(d, d2)
+        outs[name] = (loss.clone(), d.clone())
+    monkeypatch.delenv("AVSSL_SWAV_CE_KERNEL")
+    assert rel_err(outs["sample"][0], outs["reg"][0]) < 2e-6
+    assert rel_err(outs["sample"][1], outs["reg"][1]) < 2e-5
+    x = scores.double().cpu() / 0.1
+    lsm = torch.log_softmax(x, -1).view(crops, bs, P)
+    w = torch.from_numpy(ops.swav_pair_weights(crops, 2, bs)).double()
+    cdd = codes.double().cpu()
+    ref = -sum(w[a, v] * (cdd[a] * lsm[v]).sum() for a in range(2) for v in range(crops))
+    sm = torch.softmax(x, -1).view(crops, bs, P)
+    dref = torch.stack([sum(w[a, v] * (sm[v] * cdd[a].sum(-1, keepdim=True) - cdd[a]) for a in range(2)) / 0.1
+                        for v in range(crops)]).view(crops * bs, P)
+    for name in outs:
+        assert abs(outs[name][0].item() - ref.item()) < 2e-5 * abs(ref.item()), name
+        assert rel_err(outs[name][1], dref) < 5e-5, name

@@ -221,3 +221,22 @@ def test_fused_tail_captures_into_a_cuda_graph():
     graph.replay()
     torch.cuda.synchronize()
     assert torch.equal(q_g, q_e) and torch.equal(x.grad, gx_e) and torch.equal(tail.weight.grad, gw_e)
+
+
+@pytest.mark.parametrize("B", [128, 200])
+def test_linear_normalize_module_both_backward_routes(B):
+    """Up to 128 rows forward and backward are the fused launches; above, library GEMMs + the Normalize kernels
+    (autograd.LinearNormalize.FUSED_MAX_ROWS).  Both against the oracle."""
+    from advise_video_ssl_b200 import head_helper as H
+    torch.manual_seed(B)
+    tail = H.LinearNormalize(260, 96).cuda()
+    x = torch.randn(B, 260).relu_()
+    G = torch.randn(B, 96)
+    xd = x.cuda().requires_grad_(True)
+    (tail(xd) * G.cuda()).sum().backward()
+    xr = x.clone().requires_grad_(True)
+    Wr = tail.weight.detach().cpu().clone().requires_grad_(True)
+    br = tail.bias.detach().cpu().clone().requires_grad_(True)
+    (O.projection_tail(xr, Wr, br) * G).sum().backward()
+    assert rel_err(xd.grad, xr.grad) < GRAD_RTOL and rel_err(tail.weight.grad, Wr.grad) < GRAD_RTOL
+    assert rel_err(tail.bias.grad, br.grad) < GRAD_RTOL
