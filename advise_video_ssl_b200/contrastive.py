@@ -706,7 +706,14 @@ class ContrastiveModel(nn.Module):
         better choice.  The tcgen05 sweep owns every register of the SMs it runs on; the momentum update is HBM-bound
         and a flat grid of small CTAs that fills whatever is left.  Give the sweep just enough SMs to end well before
         the update does (measured on B200, DESIGN.md 4 K3: ~2 us per 64-row tile beside the update, ~20 us before its
-        first CTA is placed); when the update is short compared with the sweep there is nothing to hide it under."""
+        first CTA is placed); when the update is short compared with the sweep there is nothing to hide it under.
+        Across GPUs the single launch stays: there the sweep, placed BEHIND the key encoder, is what hides the key
+        exchange (push over NVLink, wait for every rank's rows); with the sweep moved ahead that round trip and the
+        ranks' skew sit bare on the critical path (measured at N = 2: 109.4 us per step against 100.9 us)."""
+        if self.num_gpus > 1 and torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size() > 1:
+            return None
+
         def size():
             sms = ops.sm_count()
             n_params = sum(p.numel() for p in self.backbone_hist.parameters()) if hasattr(self, "backbone_hist") else 0
