@@ -28,6 +28,7 @@ What deliberately differs from the reference:
 Backbones are not part of this package: `_MODEL_TYPES` is filled from the host application's
 `models.video_model_builder` when importable (inside the reference tree), or by the caller.
 """
+import contextlib
 import logging
 import math
 import os
@@ -785,26 +786,42 @@ class ContrastiveModel(nn.Module):
             head.weight.copy_(unit)
 
         bs = clips[0][0].size(0)
-        encoded = [self.run_swav_orig_encoder_q(c) for c in clips]
-        q_knn = encoded[0][0]
-        embedding = torch.cat([e for e, _ in encoded], dim=0)
-        scores = torch.cat([s for _, s in encoded], dim=0)
+        # the reference encodes, normalises and scores crop by crop (:623-631, run_swav_orig_encoder_q) and concatenates
+        # afterwards; the crops differ in resolution, so the backbone runs per crop, but Normalize and the prototype
+        # scores are row-wise: ONE Normalize launch and ONE score GEMM over all crops (and one pair of backward GEMMs
+        # instead of twelve) give the same rows
+        feats = [self.backbone(c) for c in clips]
+        embedding = l2norm_lastdim(torch.cat(feats, dim=0), 1e-12)
+        scores = head(embedding)
+        q_knn = embedding[:bs]
 
         # the first two crops (the large ones) get codes; every crop is scored against them (:633-679)
         self.swav_crops_for_assign = np.arange(min(2, n_crops))
         queue_live = self.cfg.CONTRASTIVE.SWAV_QEUE_LEN > 0 and epoch_exact >= 15.0
         codes = []
         with torch.no_grad():
+            # the assign crops' Sinkhorn problems are independent (one 16-CTA cluster each at cfg5): the second one
+            # runs on a side stream beside the first
+            side = None
+            if scores.is_cuda and self.cfg.NUM_SHARDS <= 1 and len(self.swav_crops_for_assign) > 1:
+                main = torch.cuda.current_stream(scores.device)
+                side = self._cached(("sinkhorn_stream", scores.device), lambda: torch.cuda.Stream(device=scores.device))
+                side.wait_stream(main)
             for slot, crop in enumerate(self.swav_crops_for_assign):
                 rows = slice(bs * crop, bs * (crop + 1))
-                out = scores[rows].detach()
-                if queue_live:
-                    out = self._swav_queue_step(slot, embedding[rows].detach(), out, head.weight)
-                if self.cfg.NUM_SHARDS > 1:
-                    q = self.distributed_sinkhorn(torch.exp(out / self.swav_eps_sinkhorn).t(), 3)[-bs:]
-                else:  # K10
-                    q = ops.sinkhorn(out.contiguous(), self.swav_eps_sinkhorn, 3, keep_last=bs)
+                with torch.cuda.stream(side) if (side is not None and slot == 1) else contextlib.nullcontext():
+                    out = scores[rows].detach()
+                    if queue_live:
+                        out = self._swav_queue_step(slot, embedding[rows].detach(), out, head.weight)
+                    if self.cfg.NUM_SHARDS > 1:
+                        q = self.distributed_sinkhorn(torch.exp(out / self.swav_eps_sinkhorn).t(), 3)[-bs:]
+                    else:  # K10
+                        q = ops.sinkhorn(out.contiguous(), self.swav_eps_sinkhorn, 3, keep_last=bs, lane=slot)
+                if side is not None and slot == 1:
+                    q.record_stream(main)
                 codes.append(q)
+            if side is not None:
+                main.wait_stream(side)
         loss = SwavSwappedCe.apply(scores, torch.stack(codes, 0), n_crops, bs, self.T)  # K11
         self.knn_mem_update(q_knn, index)
         return self._cached_dummy_logits(len(index), scores.device), loss

@@ -875,14 +875,15 @@ def ntxent(feat1, feat2, T, gather=None, impl=_lib.IMPL_AUTO, xchg=None, status=
 
 
 # ---------------------------------------------------------------------- K10 / K11
-def sinkhorn(scores, eps, iters, keep_last=None):
+def sinkhorn(scores, eps, iters, keep_last=None, lane=0):
     """codes = sinkhorn(exp(scores/eps)) (K10).  scores [Btot, P]; returns the last
-    `keep_last` rows (default all), each summing to 1."""
+    `keep_last` rows (default all), each summing to 1.  `lane`: calls that may run concurrently
+    (different streams) pass different lanes and get separate scratch."""
     _req(scores, "scores")
     Btot, P = scores.shape
     keep = Btot if keep_last is None else int(keep_last)
     out = torch.empty(keep, P, dtype=_f32, device=scores.device)
-    ws = _workspace(scores.device, lib.avssl_sinkhorn_workspace_bytes(Btot, P), "sinkhorn")
+    ws = _workspace(scores.device, lib.avssl_sinkhorn_workspace_bytes(Btot, P), "sinkhorn" if lane == 0 else "sinkhorn/%d" % lane)
     check(lib.avssl_sinkhorn(scores.data_ptr(), Btot, P, float(eps), int(iters), keep, out.data_ptr(),
                              ws.data_ptr(), ws.numel(), _stream()), "avssl_sinkhorn")
     return out

@@ -30,6 +30,7 @@ and forwards the synthetic [B, D] embedding it is given (backbone compute is exc
 """
 import argparse
 import json
+import math
 import os
 import sys
 import threading
@@ -607,13 +608,161 @@ def gpu_arm(args):
     return 0
 
 
-def simclr_arm(args):
-    """--workload simclr: BASELINE configs[2] (SimCLR, global all_gather negatives, 512 clips per GPU -> total batch
-    4096 at 8 GPUs, dim 256, T = 0.1) through the same module API: ContrastiveModel(simclr)([[f1], [f2]], index) +
-    loss.backward(), the two all_gathers (C4: rows, row sums) inside the timed region, CUDA-graph replay.
-    Not the headline (that is the MoCo step); one JSON line of the same shape, `roofline` on the tensor pipe."""
-    import torch.distributed as dist
+def _setup_simclr(C, cfg, dev, rank, world):
+    """BASELINE configs[2]: SimCLR, global all_gather negatives, 512 clips per GPU (total batch 4096 at 8 GPUs), dim 256."""
     import torch.nn as nn
+    B, D, T = 512, 256, 0.1
+
+    class Identity(nn.Module):
+        def __init__(self, cfg):
+            super().__init__()
+            self.dummy = nn.Parameter(torch.zeros(4))
+
+        def forward(self, x):
+            return x[0] if isinstance(x, (list, tuple)) else x
+
+    C._MODEL_TYPES["identity_embed"] = Identity
+    cfg.MODEL.ARCH = "identity_embed"
+    cfg.CONTRASTIVE.TYPE, cfg.CONTRASTIVE.DIM, cfg.CONTRASTIVE.T = "simclr", D, T
+    cfg.CONTRASTIVE.QUEUE_LEN = 64
+    cfg.TRAIN.BATCH_SIZE = B * world
+    model = C.ContrastiveModel(cfg).to(dev).train()
+    g = torch.Generator().manual_seed(2000 + rank)
+    f1 = [torch.randn(B, D, generator=g).to(dev).requires_grad_(True) for _ in range(POOL)]
+    f2 = [torch.randn(B, D, generator=g).to(dev).requires_grad_(True) for _ in range(POOL)]
+    index = torch.arange(B, device=dev)
+
+    def step(slot):
+        f1[slot].grad, f2[slot].grad = None, None
+        _, loss = model([[f1[slot]], [f2[slot]]], index, None, 0.0)
+        loss.backward()
+        return loss
+
+    N = B * world
+    flops = 3 * 2 * (2 * B) * (2 * N) * D  # this rank's rows: S for the row sums, S again and P.V for the gradient
+    return dict(
+        B=B, step=step, dtype="f32 (kind::f16 operands on unit rows, fp32 accumulate)",
+        workload="configs[2] head: SimCLR NT-Xent, global all_gather negatives, 512 clips/GPU (total batch %d), dim 256, "
+                 "T 0.1; l2norm + all_gather + row sums + all_gather + gradient + finalise; backbone excluded" % N,
+        api="ContrastiveModel(simclr).forward + loss.backward()",
+        collectives="2 gathers per step (rows, row sums) inside the timed region, NVLink peer stores on one box" if world > 1 else "none",
+        parallelism="dp%d, rows sharded: each rank computes its 2B rows against all 2N columns" % world,
+        launches=6, launches_note="l2norm, prepare, rowsum, sum_z, grad, finish per step (+ torch cat / mul)",
+        roofline=lambda per_ms, peaks: {
+            "kernel": "ntxent step (per-rank useful flops 3*2*(2B)(2N)D)", "bound": "tensor",
+            "achieved": flops / (per_ms * 1e-3) / 1e12, "peak": float(peaks.get("bf16_tflops", 1590.0)), "unit": "TFLOP/s",
+            "frac": flops / (per_ms * 1e-3) / 1e12 / float(peaks.get("bf16_tflops", 1590.0)), "traffic": None,
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops (kind::f16 runs at the bf16 rate)"})
+
+
+def _setup_byol(C, cfg, dev, rank, world):
+    """BASELINE configs[3]: BYOL, momentum EMA over the Slow-R50 + projection + predictor list (169 tensors, 37.4 M fp32,
+    dim 256, PREDICTOR_DEPTHS [2]) + the symmetric predictor loss over 2 views, batch 64 per GPU."""
+    import torch.nn as nn
+    B, D, T = 64, 256, 0.1
+    shapes = param_shapes("slow_r50_byol_dim256_pred2")
+
+    class ByolStub(nn.Module):
+        """Owns the reference's parameter list so that the momentum update streams the real thing; hands the synthetic
+        projection / prediction pair through as [feat, pred] (models/head_helper.py:232-235)."""
+
+        def __init__(self, cfg):
+            super().__init__()
+            g = torch.Generator().manual_seed(1234)
+            self.weights = nn.ParameterList([nn.Parameter(torch.randn(s, generator=g) * 0.02) for s in shapes])
+
+        def forward(self, x):
+            return [x[0], x[1]]
+
+    C._MODEL_TYPES["stub_byol"] = ByolStub
+    cfg.MODEL.ARCH = "stub_byol"
+    cfg.CONTRASTIVE.TYPE, cfg.CONTRASTIVE.DIM, cfg.CONTRASTIVE.T = "byol", D, T
+    cfg.CONTRASTIVE.PREDICTOR_DEPTHS, cfg.CONTRASTIVE.MOMENTUM = [2], 0.996
+    cfg.TRAIN.BATCH_SIZE = B * world
+    model = C.ContrastiveModel(cfg).to(dev).train()
+    g = torch.Generator().manual_seed(3000 + rank)
+    views = [[[torch.randn(B, D, generator=g).to(dev), torch.randn(B, D, generator=g).to(dev).requires_grad_(True)]
+              for _ in range(2)] for _ in range(POOL)]
+    index = torch.arange(B, device=dev)
+
+    def step(slot):
+        for v in views[slot]:
+            v[1].grad = None
+        _, loss = model(views[slot], index, None, 0.0)
+        loss.backward()
+        return loss
+
+    n_params = sum(math.prod(s) for s in shapes)
+    step_bytes = 12 * n_params + 2 * 4 * B * D * 3  # EMA + the two sim_loss pairs (SURVEY.md 8(d))
+    return dict(
+        B=B, step=step, dtype="f32",
+        workload="configs[3] head: BYOL, EMA(%d tensors, %.1fM fp32) + Normalize of the keys + symmetric predictor loss over "
+                 "2 views (2 x sim_loss fwd/bwd), batch %d/GPU, dim %d; backbone excluded" % (len(shapes), n_params / 1e6, B, D),
+        api="ContrastiveModel(byol).forward + loss.backward()", collectives="none (BYOL has no exchange in the head)",
+        parallelism="dp%d (EMA replicated, batch sharded)" % world,
+        launches=5, launches_note="EMA, 2 x Normalize(keys), 2 x sim_loss per step (+ torch cat / split of the batched key pass, autograd adds)",
+        roofline=lambda per_ms, peaks: {
+            "kernel": "step (EMA-dominated: 12 B per parameter)", "bound": "hbm", "achieved": step_bytes / (per_ms * 1e-3) / 1e9,
+            "peak": float(peaks.get("hbm_gbs", 6650.0)), "unit": "GB/s",
+            "frac": step_bytes / (per_ms * 1e-3) / 1e9 / float(peaks.get("hbm_gbs", 6650.0)), "traffic": None,
+            "bytes_per_step": step_bytes, "peak_source": "MEASURED_PEAKS.json hbm_gbs"})
+
+
+def _setup_swav(C, cfg, dev, rank, world):
+    """BASELINE configs[4]: SwAV multi-crop (2 + 4 crops), 3000 prototypes, 3 Sinkhorn iterations, batch 256 per GPU."""
+    import torch.nn as nn
+    B, D, T, P, crops = 256, 128, 0.1, 3000, 6
+
+    class Identity(nn.Module):
+        def __init__(self, cfg):
+            super().__init__()
+            self.dummy = nn.Parameter(torch.zeros(4))
+
+        def forward(self, x):
+            return x[0] if isinstance(x, (list, tuple)) else x
+
+    C._MODEL_TYPES["identity_embed"] = Identity
+    cfg.MODEL.ARCH = "identity_embed"
+    cfg.CONTRASTIVE.TYPE, cfg.CONTRASTIVE.DIM, cfg.CONTRASTIVE.T = "swav", D, T
+    cfg.CONTRASTIVE.SWAV_NUM_PROTOTYPES = P
+    cfg.CONTRASTIVE.QUEUE_LEN = 64
+    cfg.TRAIN.BATCH_SIZE = B * world
+    model = C.ContrastiveModel(cfg).to(dev).train()
+    g = torch.Generator().manual_seed(4000 + rank)
+    embs = [[torch.randn(B, D, generator=g).to(dev).requires_grad_(True) for _ in range(crops)] for _ in range(POOL)]
+    index = torch.arange(B, device=dev)
+
+    def step(slot):
+        for e in embs[slot]:
+            e.grad = None
+        model.swav_prototypes.weight.grad = None
+        _, loss = model([[e] for e in embs[slot]], index, None, 0.0)
+        loss.backward()
+        return loss
+
+    # SURVEY.md 8(d): the score rows cross HBM for the loss kernel (read + gradient write), the codes for Sinkhorn
+    step_bytes = 4 * P * (crops * B * 2 + 2 * B) + 2 * 8 * P * B
+    return dict(
+        B=B, step=step, dtype="f32",
+        workload="configs[4] head: SwAV, %d crops x %d clips/GPU, %d prototypes, eps 0.05, 3 Sinkhorn iterations, T %.1f: prototype "
+                 "renorm + per-crop Normalize + scores (library GEMM) + 2 x Sinkhorn + swapped-prediction CE fwd/bwd + the "
+                 "gradients back to embeddings and prototypes; backbone excluded" % (crops, B, P, T),
+        api="ContrastiveModel(swav).forward + loss.backward()", collectives="none on one box (NUM_SHARDS = 1)",
+        parallelism="dp%d (prototypes replicated, batch sharded)" % world,
+        launches=3 + crops * 2, launches_note="prototype renorm, 6 x Normalize fwd (+ 6 x bwd in backward), 2 x Sinkhorn, swapped CE "
+                                               "per step (+ cuBLAS score GEMMs and their backward, torch cat)",
+        roofline=lambda per_ms, peaks: {
+            "kernel": "step (K10 + K11 algorithmic bytes; the step is launch- and latency-bound: ~40 kernels)", "bound": "hbm",
+            "achieved": step_bytes / (per_ms * 1e-3) / 1e9, "peak": float(peaks.get("hbm_gbs", 6650.0)), "unit": "GB/s",
+            "frac": step_bytes / (per_ms * 1e-3) / 1e9 / float(peaks.get("hbm_gbs", 6650.0)), "traffic": None,
+            "bytes_per_step": step_bytes, "peak_source": "MEASURED_PEAKS.json hbm_gbs"})
+
+
+def extra_arm(args):
+    """--workload simclr | byol | swav: BASELINE configs[2..4] through the same module API as the headline
+    (ContrastiveModel.forward + loss.backward(), exchanges inside the timed region, CUDA-graph replay).  Not the headline
+    (that is the MoCo step); one JSON line of the same shape."""
+    import torch.distributed as dist
     from advise_video_ssl_b200 import contrastive as C
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -629,39 +778,14 @@ def simclr_arm(args):
         json_out = os.fdopen(os.dup(1), "w")
         os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
-    B, D, T = 512, 256, 0.1
-
-    class Identity(nn.Module):
-        def __init__(self, cfg):
-            super().__init__()
-            self.dummy = nn.Parameter(torch.zeros(4))
-
-        def forward(self, x):
-            return x[0] if isinstance(x, (list, tuple)) else x
-
-    C._MODEL_TYPES["identity_embed"] = Identity
-    cfg = head_cfg(world)
-    cfg.MODEL.ARCH = "identity_embed"
-    cfg.CONTRASTIVE.TYPE, cfg.CONTRASTIVE.DIM, cfg.CONTRASTIVE.T = "simclr", D, T
-    cfg.CONTRASTIVE.QUEUE_LEN = 64
-    cfg.TRAIN.BATCH_SIZE = B * world
-    model = C.ContrastiveModel(cfg).to(dev).train()
-    g = torch.Generator().manual_seed(2000 + rank)
-    f1 = [torch.randn(B, D, generator=g).to(dev).requires_grad_(True) for _ in range(POOL)]
-    f2 = [torch.randn(B, D, generator=g).to(dev).requires_grad_(True) for _ in range(POOL)]
-    index = torch.arange(B, device=dev)
+    w = {"simclr": _setup_simclr, "byol": _setup_byol, "swav": _setup_swav}[args.workload](C, head_cfg(world), dev, rank, world)
+    step, B = w["step"], w["B"]
 
     def sync_all():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
-
-    def step(slot):
-        f1[slot].grad, f2[slot].grad = None, None
-        _, loss = model([[f1[slot]], [f2[slot]]], index, None, 0.0)
-        loss.backward()
-        return loss
 
     for i in range(args.warmup):
         step(i % POOL)
@@ -703,32 +827,20 @@ def simclr_arm(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
     per = ms / steps
-    N = B * world
-    flops = 3 * 2 * (2 * B) * (2 * N) * D  # this rank's rows: S for the row sums, S again and P.V for the gradient
     peaks = {}
     pth = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pth):
         with open(pth) as f:
             peaks = json.load(f)
-    peak_tf = float(peaks.get("bf16_tflops", 1590.0))
-    ach = flops / (per * 1e-3) / 1e12
     if rank == 0:
         json_out.write(json.dumps({
             "metric": METRIC, "value": world * B / (per * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
             "warmup": args.warmup, "ms_per_step": per, "step_us": per * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 (kind::f16 operands on unit rows, fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": "configs[2] head: SimCLR NT-Xent, global all_gather negatives, 512 clips/GPU (total batch "
-                                   "%d), dim 256, T 0.1; l2norm + all_gather + row sums + all_gather + gradient + finalise; "
-                                   "backbone excluded" % N,
-                       "api": "ContrastiveModel(simclr).forward + loss.backward()", "cuda_graph": graph is not None,
-                       "cuda_graph_error": graph_err, "collectives": "2 x ncclAllGather per step inside the timed region" if world > 1 else "none",
-                       "parallelism": "dp%d, rows sharded: each rank computes its 2B rows against all 2N columns" % world},
-            "gpu_launches": 6 * steps,
-            "gpu_launches_note": "l2norm, prepare, rowsum, sum_z, grad, finish per step (+ torch cat / mul, NCCL)",
-            "clocks": clocks,
-            "roofline": {"kernel": "ntxent step (per-rank useful flops 3*2*(2B)(2N)D)", "bound": "tensor", "achieved": ach,
-                         "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
-                         "peak_source": "MEASURED_PEAKS.json bf16_tflops (kind::f16 runs at the bf16 rate)"},
+            "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
+            "config": {"workload": w["workload"], "api": w["api"], "cuda_graph": graph is not None,
+                       "cuda_graph_error": graph_err, "collectives": w["collectives"], "parallelism": w["parallelism"]},
+            "gpu_launches": w["launches"] * steps, "gpu_launches_note": w["launches_note"],
+            "clocks": clocks, "roofline": w["roofline"](per, peaks),
             "loss": float(loss_t.item()) if loss_t is not None else None}) + "\n")
         json_out.flush()
     if world > 1:
@@ -872,8 +984,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ops-level", action="store_true", help="skip the secondary kernel-only (ops.*) measurement")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
-    ap.add_argument("--workload", default="moco", choices=["moco", "simclr"],
-                    help="moco = BASELINE configs[1] (the headline); simclr = configs[2], an extra line")
+    ap.add_argument("--workload", default="moco", choices=["moco", "simclr", "byol", "swav"],
+                    help="moco = BASELINE configs[1] (the headline); simclr / byol / swav = configs[2] / [3] / [4], extra lines")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: cross-GPU key gather over NVLink peer memory (default) or NCCL all_gather")
     args = ap.parse_args()
@@ -881,8 +993,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         return reference_arm(args)
-    if args.workload == "simclr":
-        return simclr_arm(args)
+    if args.workload != "moco":
+        return extra_arm(args)
     return gpu_arm(args)
 
 

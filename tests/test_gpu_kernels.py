@@ -7,7 +7,7 @@ import torch
 import torch.nn.functional as F
 
 import recipes
-from helpers import rel_err
+from helpers import rel_err, rel_err_above_floor
 from oracle import contrastive_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -209,6 +209,8 @@ def test_infonce_cfg1_full_size(golden, name, impl):
     lt, gt, at = TOL[name]
     assert abs(out["loss"].item() - g["loss"].item()) <= lt * abs(g["loss"].item())
     assert _grad_close(out["dfeat"], g["dfeatq"], gt)
+    # element-wise, on the 82 % of the entries that reach 5 % of the largest one (measured: 6e-7 / 2.1e-5 / 2.9e-4)
+    assert rel_err_above_floor(out["dfeat"], g["dfeatq"], 0.05) < {"simt": 5e-6, "tc3x": 1e-4, "tc1x": 1e-3}[name]
     lg = out["logits"].cpu()
     assert (lg[:, :16] - g["logits_head"]).abs().max().item() <= at
     assert (lg[:, -16:] - g["logits_tail"]).abs().max().item() <= at

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import Tap, make_cfg, register_backbones, rel_err
+from helpers import Tap, make_cfg, register_backbones, rel_err, rel_err_above_floor
 from oracle import contrastive_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -216,6 +216,12 @@ def test_ntxent_shapes_vs_closed_form(B, D, T, impl_name):
     lt, gt = (5e-6, 1e-4) if impl_name == "simt" else (2e-4, 1e-3)
     assert abs(loss.item() - cl.item()) < lt * abs(cl.item())
     assert rel_err(torch.cat([d1, d2]), df) < gt
+    # element-wise on the entries that reach 5 % (exact-fp32 kernels, measured 6e-7) / 10 % (fp16-operand tensor-core
+    # kernels, measured <= 4.7e-4) of the largest one
+    if impl_name == "simt":
+        assert rel_err_above_floor(torch.cat([d1, d2]), df, 0.05) < 2e-5
+    else:
+        assert rel_err_above_floor(torch.cat([d1, d2]), df, 0.1) < 2e-3
 
 
 # ------------------------------------------------------------------------------ SwAV
