@@ -199,3 +199,73 @@ def test_shuffle_plan_matches_gather_then_select(world, bsz):
             recv.append(parts[s_rank].index_select(0, sp.send_rows)[off:off + sp.send_counts[r]])
         got = torch.cat(recv).index_select(0, plan.place)
         assert torch.equal(got, ref_x[r])
+
+
+# ------------------------------------------------------------------ projection tail, host side
+def test_fuse_projection_tail_swaps_only_the_last_linear_and_shares_parameters():
+    import torch.nn as nn
+    from advise_video_ssl_b200 import head_helper as H
+
+    class MLP(nn.Module):  # layout of the reference's MLPHead (models/head_helper.py:36-59)
+        def __init__(self, dout):
+            super().__init__()
+            self.projection = nn.Sequential(nn.Linear(32, 64, bias=False), nn.BatchNorm1d(64), nn.ReLU(inplace=True),
+                                            nn.Linear(64, dout))
+
+    class Head(nn.Module):  # ... and of ResNetBasicHead (:135-182)
+        def __init__(self, dout, n_pred=0):
+            super().__init__()
+            self.projection = MLP(dout)
+            self.predictors = nn.ModuleList([MLP(dout) for _ in range(n_pred)])
+
+    class Net(nn.Module):
+        def __init__(self, **kw):
+            super().__init__()
+            self.stem = nn.Linear(8, 32)
+            self.head = Head(**kw)
+
+    class Pair(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.backbone, self.backbone_hist = Net(dout=128), Net(dout=128)
+
+    pair = Pair()
+    keys = list(pair.state_dict().keys())
+    params = [id(p) for p in pair.parameters()]
+    last = pair.backbone.head.projection.projection[3]
+    assert H.fuse_projection_tail(pair) == 2
+    new = pair.backbone.head.projection.projection[3]
+    assert isinstance(new, H.LinearNormalize) and new.weight is last.weight and new.bias is last.bias
+    assert isinstance(pair.backbone.head.projection.projection[0], nn.Linear)       # only the tail
+    assert list(pair.state_dict().keys()) == keys and [id(p) for p in pair.parameters()] == params
+    assert H.fuse_projection_tail(pair) == 0                                         # idempotent
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        new(torch.randn(4, 64))                                                      # the kernel is the only path
+    # left alone: heads with predictors (BYOL), outputs wider than the kernel takes, in_features % 4 != 0
+    assert H.fuse_projection_tail(Net(dout=128, n_pred=1)) == 0
+    assert H.fuse_projection_tail(Net(dout=300)) == 0
+    assert H.fuse_projection_tail(nn.Sequential(nn.Linear(8, 6), nn.ReLU(), nn.Linear(6, 16))) == 0
+    # a bare Sequential and a single-Linear projection (SSL.NUM_MLP_LAYERS == 1, :135-136) are recognised
+    seq = nn.Sequential(nn.Linear(8, 16), nn.ReLU(), nn.Linear(16, 32, bias=False))
+    assert H.fuse_projection_tail(seq) == 1 and seq[2].bias is None and "2.bias" not in seq.state_dict()
+
+    class OneLayerHead(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.projection = nn.Linear(16, 128)
+    one = OneLayerHead()
+    assert H.fuse_projection_tail(one) == 1 and isinstance(one.projection, H.LinearNormalize)
+    with pytest.raises(ValueError):
+        H.LinearNormalize(16, 512)
+
+
+def test_topk_plan_limits():
+    """avssl_topk_rows_workspace_bytes doubles as the capability query of the kNN top-k: k <= min(M, 1024), any M."""
+    from advise_video_ssl_b200._lib import lib
+    assert lib.avssl_topk_rows_workspace_bytes(64, 239975, 200) > 0
+    assert lib.avssl_topk_rows_workspace_bytes(1, 10_000_000, 1024) > 0
+    assert lib.avssl_topk_rows_workspace_bytes(64, 239975, 1025) == 0     # beyond the candidate lists
+    assert lib.avssl_topk_rows_workspace_bytes(64, 100, 101) == 0         # k > M: torch.topk raises as well
+    assert lib.avssl_topk_rows_workspace_bytes(0, 100, 10) == 0
+    # workspace = N x G x KP composites, G <= 32 lists
+    assert lib.avssl_topk_rows_workspace_bytes(1, 10_000_000, 200) <= 1 * 32 * 256 * 8
