@@ -1,5 +1,5 @@
 """Developer probe (GPU box): runs ONE kernel family a few times so that `ncu --set full -k regex:<name>` can capture it.
-Usage: python tools/profile_one.py k11|knn|projtail"""
+Usage: python tools/profile_one.py k11|knn|projtail|sinkhorn|byol"""
 import os
 import sys
 
@@ -32,5 +32,13 @@ elif what == "projtail":
     for _ in range(3):
         q, nrm = ops.linear_l2norm_fwd(x, W, b)
         ops.linear_l2norm_bwd(x, W, q, nrm, G)
+elif what == "sinkhorn":
+    scores = torch.randn(256, 3000, device=dev) * 0.1
+    for _ in range(3):
+        ops.sinkhorn(scores, 0.05, 3)
+elif what == "byol":
+    pred, key = torch.randn(64, 256, device=dev), torch.nn.functional.normalize(torch.randn(64, 256, device=dev), dim=1)
+    for _ in range(3):
+        ops.byol_simloss(pred, key, 0.1)
 torch.cuda.synchronize()
 print("ok", what)
