@@ -60,7 +60,12 @@ class LinearNormalize(nn.Module):
         return m
 
     def forward(self, x):
-        assert x.dim() == 2 and x.shape[1] == self.in_features, "LinearNormalize expects [B, %d]" % self.in_features
+        assert x.shape[-1] == self.in_features, "LinearNormalize expects [..., %d]" % self.in_features
+        if x.is_cuda and (x.dim() != 2 or x.dtype != torch.float32):
+            # fully-convolutional inference (a [N, T, H, W, C] input that the head averages AFTER the projection,
+            # models/head_helper.py:222-228) and autocast inputs keep the plain Linear: the contrastive model
+            # normalises whatever the backbone returns, so an un-normalised output is always valid
+            return torch.nn.functional.linear(x, self.weight.to(x.dtype), None if self.bias is None else self.bias.to(x.dtype))
         return _LinearNormalizeFn.apply(x, self.weight, self.bias, self.eps, self.normalize)
 
     def extra_repr(self):

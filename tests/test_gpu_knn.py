@@ -90,6 +90,37 @@ def test_knn_similarity_topk_against_oracle(N, M, D, scale):
     assert torch.equal(yi.cpu()[gap_ok], ri[gap_ok])
 
 
+def _same_neighbours(yd, yi, rd, ri, tol):
+    """Sorted values within tol; indices identical wherever the neighbouring reference values are further apart."""
+    assert (yd.cpu() - rd).abs().max().item() < tol
+    ok = torch.ones_like(ri, dtype=torch.bool)
+    gap = (rd[:, :-1] - rd[:, 1:]) > 2 * tol
+    ok[:, 1:] &= gap
+    ok[:, :-1] &= gap
+    assert torch.equal(yi.cpu()[ok], ri[ok]) and ok.float().mean().item() > 0.9
+
+
+def test_eval_knn_golden(golden):
+    """knn.npz: the reference's own eval_knn (k = 200 and 5) and the eval branch of forward, on a 1500-row bank."""
+    from advise_video_ssl_b200 import ops
+    g = golden("knn")
+    for k in (200, 5):
+        yd, yi = ops.knn_similarity_topk(g["q"].cuda(), g["bank"].cuda(), k)
+        assert yi.dtype == torch.int64
+        _same_neighbours(yd, yi, g["yd%d" % k], g["yi%d" % k], 2e-5)
+    C = register_backbones()
+    N, D, L = int(g.scalar("N")), int(g.scalar("D")), int(g.scalar("L"))
+    cfg = make_cfg(CONTRASTIVE__TYPE="moco", CONTRASTIVE__T=0.1, CONTRASTIVE__DIM=D, CONTRASTIVE__QUEUE_LEN=64,
+                   CONTRASTIVE__KNN_ON=True, CONTRASTIVE__LENGTH=L)
+    model = C.ContrastiveModel(cfg).cuda().eval()
+    with torch.no_grad():
+        model.backbone.proj.weight.copy_(g["W"])
+        model.knn_mem.memory.copy_(g["bank"].view(L, 1, D))
+    x = g["x"].cuda()
+    yd, yi = model([[x], [x]], torch.arange(N).cuda(), torch.zeros(N, 2, 1).cuda())
+    _same_neighbours(yd, yi, g["fwd_yd"], g["fwd_yi"], 2e-5)
+
+
 def test_eval_knn_through_the_module():
     """ContrastiveModel in eval mode returns (yd, yi) of the kNN bank (:232-241, :469-474)."""
     C = register_backbones()

@@ -240,3 +240,16 @@ def test_linear_normalize_module_both_backward_routes(B):
     (O.projection_tail(xr, Wr, br) * G).sum().backward()
     assert rel_err(xd.grad, xr.grad) < GRAD_RTOL and rel_err(tail.weight.grad, Wr.grad) < GRAD_RTOL
     assert rel_err(tail.bias.grad, br.grad) < GRAD_RTOL
+
+
+def test_linear_normalize_leaves_other_inputs_to_the_plain_linear():
+    """5-D inputs (fully-convolutional inference averages AFTER the projection) and non-fp32 inputs are projected
+    without the epilogue: ContrastiveModel normalises the backbone output itself."""
+    from advise_video_ssl_b200 import head_helper as H
+    torch.manual_seed(0)
+    tail = H.LinearNormalize(64, 32).cuda()
+    x5 = torch.randn(2, 1, 3, 3, 64).cuda()
+    ref = torch.nn.functional.linear(x5, tail.weight, tail.bias)
+    assert torch.equal(tail(x5), ref)
+    xh = torch.randn(4, 64).cuda().half()
+    assert tail(xh).dtype == torch.float16

@@ -354,3 +354,14 @@ def test_projection_tail(golden):
         b = g[key_b] if key_b in g.keys() else None
         assert torch.equal(torch.nn.functional.linear(g[case + "_tail_x"], W, b), g[case + "_tail_y"])
         assert torch.equal(O.projection_tail(g[case + "_tail_x"], W, b), g[case + "_q"])
+
+
+def test_knn_topk(golden):
+    """knn.npz comes from the reference's own eval_knn and the eval branch of forward (make_golden_knn.py)."""
+    g = golden("knn")
+    for k in (200, 5):
+        yd, yi = O.knn_topk(g["q"], g["bank"], k)
+        assert torch.equal(yd, g["yd%d" % k]) and torch.equal(yi, g["yi%d" % k])
+    q = O.l2_normalize(torch.nn.functional.linear(g["x"], g["W"]))
+    yd, yi = O.knn_topk(q, g["bank"], 200)
+    assert torch.equal(yd, g["fwd_yd"]) and torch.equal(yi, g["fwd_yi"])
