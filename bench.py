@@ -154,8 +154,8 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    steps = min(args.steps, 40)
-    warmup = min(args.warmup, 3)
+    steps = min(args.steps, 1000)    # ~13 ms per step on 16 cores; the time budget below bounds the run either way
+    warmup = min(args.warmup, 50)    # the same --warmup the GPU arm gets
     dt, done = run_cpu(steps, warmup, budget_s=120.0)
     val = B_PER_GPU / dt
     cores = torch.get_num_threads()
@@ -164,7 +164,9 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": done, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU oracle port (torch CPU ops = the reference's own op sequence, pinned to the "
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B_PER_GPU, "global_batch": B_PER_GPU, "queue_len": QUEUE_LEN, "dim": DIM,
+                   "T": TEMP, "ema_tensors": len(param_shapes()), "ema_params": sum(math.prod(s) for s in param_shapes()),
+                   "note": "CPU oracle port (torch CPU ops = the reference's own op sequence, pinned to the "
                                                  "unmodified reference by tests/golden; the reference itself cannot travel to "
                                                  "the GPU box), rank 0 only"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
