@@ -773,6 +773,7 @@ extern "C" int avssl_swav_ce_fwd_bwd(const float* scores, const float* codes, in
     if (first_use_on_device(configured))
       AVSSL_CUDA_OK(cudaFuncSetAttribute(swav_ce_sample_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int groups = (3 * sm_count() + bs - 1) / bs;
+    if (const char* gk = getenv("AVSSL_SWAV_CE_GROUPS")) groups = atoi(gk);  // developer knob (tools/k11_groups.py)
     if (groups < 1) groups = 1;
     if (groups > n_crops) groups = n_crops;
     const int per = (n_crops + groups - 1) / groups;
