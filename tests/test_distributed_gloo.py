@@ -111,6 +111,9 @@ def _body_shuffle(rank, world):
     y = x.flatten(1).sum(1, keepdim=True)
     back = model._batch_unshuffle(y, restore)
     assert torch.equal(back, parts[rank].flatten(1).sum(1, keepdim=True))
+    # across ranks the head stays one launch behind the key encoder (its sweep hides the key exchange):
+    # the automatic sizing of a sweep beside the momentum update declines
+    assert model.overlap_sweep and model._sweep_ctas_beside_ema(64, torch.device("cpu")) is None
 
 
 def _body_shuffle_local_group(rank, world):
