@@ -365,3 +365,57 @@ def test_knn_topk(golden):
     q = O.l2_normalize(torch.nn.functional.linear(g["x"], g["W"]))
     yd, yi = O.knn_topk(q, g["bank"], 200)
     assert torch.equal(yd, g["fwd_yd"]) and torch.equal(yi, g["fwd_yi"])
+
+
+# ------------------------------------------------------------------ oracle self-consistency (size-independent properties)
+@pytest.mark.parametrize("B,D,K,nk,T", [(5, 16, 40, 1, 0.1), (9, 32, 100, 3, 0.07), (1, 4, 1, 2, 0.5)])
+def test_moco_closed_form_agrees_with_autograd(B, D, K, nk, T):
+    """The independent fp64 closed form (what the GPU tests use at sizes autograd would be slow for) reproduces the
+    autograd gradient of the restated forward (models/contrastive.py:462-500, losses.py:20-25)."""
+    g = torch.Generator().manual_seed(B + K)
+    f = torch.randn(B, D, generator=g, dtype=torch.float64).requires_grad_(True)
+    keys = [O.l2_normalize(torch.randn(B, D, generator=g, dtype=torch.float64)) for _ in range(nk)]
+    queue = O.l2_normalize(torch.randn(K, D, generator=g, dtype=torch.float64))
+    _, logits, loss = O.moco_head(f, keys, queue, T)
+    loss.backward()
+    cl, cdf, _ = O.moco_head_closed_form(f.detach(), keys, queue, T)
+    assert abs(cl.item() - loss.item()) < 1e-12 * max(1.0, abs(loss.item()))
+    assert (cdf - f.grad).abs().max().item() < 1e-12
+    assert tuple(logits.shape) == (nk * B, K + 1)
+
+
+@pytest.mark.parametrize("N,D,T", [(4, 8, 0.5), (11, 16, 0.1)])
+def test_ntxent_closed_form_agrees_with_autograd(N, D, T):
+    g = torch.Generator().manual_seed(N)
+    a = O.l2_normalize(torch.randn(N, D, generator=g, dtype=torch.float64)).requires_grad_(True)
+    b = O.l2_normalize(torch.randn(N, D, generator=g, dtype=torch.float64)).requires_grad_(True)
+    loss = O.ntxent(a, b, T)
+    loss.backward()
+    cl, G, _ = O.ntxent_closed_form(a.detach(), b.detach(), T)
+    assert abs(cl.item() - loss.item()) < 1e-12
+    assert (G - torch.cat([a.grad, b.grad])).abs().max().item() < 1e-12
+
+
+def test_enqueue_ring_properties():
+    """:263-292: the pointer stays a multiple of the batch inside [0, K), wraps exactly at K, and after K / n pushes
+    every row of the queue has been rewritten, oldest first."""
+    K, n, D = 24, 4, 3
+    queue = torch.zeros(K, D)
+    ptr = 0
+    for step in range(2 * K // n + 1):
+        ptr = O.enqueue(queue, ptr, [torch.full((n, D), float(step + 1))], K)
+        assert 0 <= ptr < K and ptr % n == 0 and ptr == ((step + 1) * n) % K
+    assert torch.equal(queue[:n], torch.full((n, D), float(2 * K // n + 1)))      # the newest block
+    assert torch.equal(queue[n:2 * n], torch.full((n, D), float(K // n + 2)))     # the oldest surviving block
+    with pytest.raises(AssertionError):
+        O.enqueue(queue, 0, [torch.zeros(5, D)], K)                               # K % n != 0 (:284)
+
+
+def test_ema_limits():
+    """:158-172: m = 1 keeps the history bits, m = 0 copies the online weights, iteration 0 copies first (Q11)."""
+    on = [torch.randn(7, 3), torch.randn(5)]
+    hi = [torch.randn(7, 3), torch.randn(5)]
+    assert all(torch.equal(a, b) for a, b in zip(O.ema_update(on, [h.clone() for h in hi], 1.0, 3), hi))
+    assert all(torch.equal(a, b) for a, b in zip(O.ema_update(on, [h.clone() for h in hi], 0.0, 3), on))
+    first = O.ema_update(on, [h.clone() for h in hi], 0.9, 0)
+    assert all(torch.equal(a, o * (1.0 - 0.9) + o * 0.9) for a, o in zip(first, on))
